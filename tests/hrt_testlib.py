@@ -1,0 +1,218 @@
+"""Test-side plumbing: loads the CPU checkers (oracle/liboracle.so and, when
+present, oracle/_ref/libhrt_ref.so) and runs them through the reference ABI.
+Only tests/, smoke() and bench.py's CPU-baseline legs may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from hrt_b200 import abi
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+SCENES = os.path.join(ROOT, "scenes")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+NONE = 0xFFFFFFFF
+IDLE = 0xFFFFFFFE
+
+
+def scene_path(name: str) -> str:
+    return os.path.join(SCENES, name if name.endswith(".hrt") else name + ".hrt")
+
+
+class OrcTrace(C.Structure):
+    _fields_ = [("hit_tri", C.c_void_p), ("hit_t", C.c_void_p), ("hit_theta", C.c_void_p),
+                ("slot_state", C.c_void_p), ("shadow_tri", C.c_void_p),
+                ("theta_used", C.c_void_p)]
+
+
+_oracle = None
+_ref = None
+
+
+def oracle_lib() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        so = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(so):
+            subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so"], check=True,
+                           capture_output=True)
+        lib = C.CDLL(so)
+        lib.scene_load.restype = abi.Scene
+        lib.scene_load.argtypes = [C.c_char_p]
+        lib.oracle_compute_paths.restype = C.c_int
+        lib.oracle_compute_paths.argtypes = [
+            C.POINTER(abi.Scene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_float, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+            C.POINTER(abi.ChannelInfo), C.POINTER(abi.RaysInfo),
+            C.POINTER(abi.ChannelInfo), C.POINTER(abi.RaysInfo), C.POINTER(OrcTrace)]
+        lib.oracle_closest_hits.restype = C.c_int
+        lib.oracle_closest_hits.argtypes = [C.POINTER(abi.Scene), C.c_void_p, C.c_size_t,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_launch_dirs.restype = None
+        lib.oracle_launch_dirs.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+        _oracle = lib
+    return _oracle
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libhrt_ref.so"))
+
+
+def ref_lib() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libhrt_ref.so"))
+        abi.bind_compute_paths(lib)
+        _ref = lib
+    return _ref
+
+
+def run_ref(scene, rx, tx, rxv, txv, f_ghz, P, B, fill=0):
+    """The unmodified reference, outputs pre-filled with `fill` bytes."""
+    lib = ref_lib()
+    sc = lib.scene_load(scene_path(scene).encode())
+    try:
+        return abi.call_compute_paths(lib, sc, rx, tx, rxv, txv, f_ghz, P, B, fill=fill)
+    finally:
+        abi.free_scene(sc)
+
+
+def run_oracle(scene, rx, tx, rxv, txv, f_ghz, P, B, fill=0, trace=True):
+    """Our CPU restatement.  Returns (Outputs, trace dict)."""
+    lib = oracle_lib()
+    sc = lib.scene_load(scene_path(scene).encode())
+    rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
+    R, T = rx.shape[0], tx.shape[0]
+    rxv = abi.vec3_array(rxv, R); txv = abi.vec3_array(txv, T)
+    o = abi.alloc_outputs(R, T, P, B, fill)
+    tr = {}
+    ot = OrcTrace()
+    if trace:
+        tr["hit_tri"] = np.full((T, B, P), IDLE, np.uint32)
+        tr["hit_t"] = np.zeros((T, B, P), np.float32)
+        tr["hit_theta"] = np.zeros((T, B, P), np.float32)
+        tr["slot_state"] = np.zeros((R, T, B, P), np.uint8)
+        tr["shadow_tri"] = np.full((R, T, B, P), NONE, np.uint32)
+        tr["theta_used"] = np.zeros((R, T, B, P), np.float32)
+        for k in tr:
+            setattr(ot, k, tr[k].ctypes.data)
+    los = abi.chan_struct(o.los, 1)
+    scs = abi.chan_struct(o.scat, B * P)
+    rl = abi.RaysInfo(1, 1, o.los_rays.ctypes.data, o.los_active.ctypes.data)
+    rs = abi.RaysInfo(B + 1, P, o.scat_rays.ctypes.data, o.scat_active.ctypes.data)
+    try:
+        rc = lib.oracle_compute_paths(C.byref(sc), rx.ctypes.data, tx.ctypes.data,
+                                      rxv.ctypes.data, txv.ctypes.data, C.c_float(f_ghz),
+                                      R, T, P, B, C.byref(los), C.byref(rl),
+                                      C.byref(scs), C.byref(rs),
+                                      C.byref(ot) if trace else None)
+        assert rc == 0
+    finally:
+        abi.free_scene(sc)
+    return o, tr
+
+
+def outputs_words(o: abi.Outputs) -> dict:
+    """Every output array of a call as a flat uint32/uint8 view, keyed by name."""
+    w = {}
+    for k in abi.CHAN_FIELDS:
+        w["los." + k] = o.los[k].view(np.uint32).reshape(-1)
+        w["scat." + k] = o.scat[k].view(np.uint32).reshape(-1)
+    w["los_rays"] = o.los_rays.view(np.uint32).reshape(-1)
+    w["scat_rays"] = o.scat_rays.view(np.uint32).reshape(-1)
+    w["los_active"] = o.los_active.reshape(-1)
+    w["scat_active"] = o.scat_active.reshape(-1)
+    return w
+
+
+def written_mask(a: abi.Outputs, b: abi.Outputs) -> dict:
+    """Words identical in two runs that differed only in the pre-fill pattern
+    are the ones the callee determines ('How to compare')."""
+    wa, wb = outputs_words(a), outputs_words(b)
+    return {k: wa[k] == wb[k] for k in wa}
+
+
+# Geometry of the named configurations ("Concrete inputs").
+CONFIGS = {
+    # name: (scene, rx, tx, f_GHz)
+    "reflector_testc": ("simple_reflector", [[0, 0, .5]], [[0, 0, .5]], 3.0),
+    "reflector_testpy": ("simple_reflector", [[0, 0, .15]], [[0, 0, .151]], 3.0),
+    "box_axis": ("box", [[0, 0, 1]], [[0, 0, 2.5]], 3.0),
+    "box_generic": ("box", [[-3, 1.5, 1]], [[1, -2, 2.5]], 3.0),
+    "2cars_origin": ("2cars", [[0, 0, 0]], [[0, 0, 0]], 70.0),
+    "2cars_raised": ("2cars", [[2, -1, 1.5]], [[0, 0, 1.5]], 70.0),
+    "canyon_1x1": ("simple_street_canyon_with_cars", [[0, 0, 1.5]], [[0, 0, 10]], 3.5),
+}
+
+
+def canyon_c4_positions(num_tx=4, num_rx=64):
+    """BASELINE config 4: TX i at (-45+30i, 0, 10); RX on a 16x4
+    grid x=-60+8j, y in {-3,-1,1,3}, z=1.5."""
+    tx = [[-45.0 + 30.0 * i, 0.0, 10.0] for i in range(num_tx)]
+    rx = [[-60.0 + 8.0 * j, y, 1.5] for y in (-3.0, -1.0, 1.0, 3.0) for j in range(16)]
+    return np.asarray(rx[:num_rx], np.float32), np.asarray(tx, np.float32)
+
+
+# ---------------------------------------------------------------- goldens
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_NAMES = ("reflector_testc", "reflector_testpy", "box_generic", "2cars_raised",
+                "canyon_3rx")
+
+
+def load_golden(name: str) -> dict:
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["scene"] = str(g["scene"])
+    g["P"] = int(g["P"]); g["B"] = int(g["B"]); g["f"] = float(g["f"])
+    for k in list(g):
+        if k.startswith("mask."):
+            n = g["out." + k[5:]].size
+            g[k] = np.unpackbits(g[k])[:n].astype(bool)
+    return g
+
+
+# Output words that must be BIT-EXACT on the GPU (they depend only on exactly
+# rounded fp32 + - * / sqrt in a fixed order) ...
+EXACT_KEYS = ("scat.tau", "scat.directions_rx", "scat.freq_shift", "scat_rays", "scat_active",
+              "los_rays", "los_active") + tuple("los." + k for k in abi.CHAN_FIELDS)
+# ... and the complex gains, which pass through sinf/cosf/expf/acosf and are
+# compared with the north star's fp32 relative tolerance.
+GAIN_KEYS = ("scat.a_te_re", "scat.a_te_im", "scat.a_tm_re", "scat.a_tm_im")
+GAIN_RTOL = 1e-4
+
+
+def f32(words: np.ndarray) -> np.ndarray:
+    return words.view(np.float32)
+
+
+def assert_exact(ref_words, mask, test_words, keys=EXACT_KEYS):
+    """Bit equality on reference-determined words (+0 == -0 tolerated: the
+    reference's `x += 0*v` Doppler no-op can flip the sign of a zero)."""
+    for k in keys:
+        m = mask[k]
+        a, b = ref_words[k][m], test_words[k][m]
+        if a.dtype == np.uint32:
+            bad = (a != b) & ~(((a | b) & 0x7FFFFFFF) == 0)
+        else:
+            bad = a != b
+        assert not bad.any(), f"{k}: {int(bad.sum())} of {a.size} words differ " \
+                              f"(first at {int(np.flatnonzero(bad)[0])})"
+
+
+def assert_gains_close(ref_words, mask, test_words, rtol=GAIN_RTOL):
+    """|delta a| <= rtol * |a| as complex numbers, per polarisation and slot."""
+    for pol in ("te", "tm"):
+        m = mask[f"scat.a_{pol}_re"]
+        ar = f32(ref_words[f"scat.a_{pol}_re"])[m].astype(np.float64)
+        ai = f32(ref_words[f"scat.a_{pol}_im"])[m].astype(np.float64)
+        br = f32(test_words[f"scat.a_{pol}_re"])[m].astype(np.float64)
+        bi = f32(test_words[f"scat.a_{pol}_im"])[m].astype(np.float64)
+        err = np.hypot(ar - br, ai - bi)
+        mag = np.hypot(ar, ai)
+        bad = err > rtol * mag + 1e-38
+        assert not bad.any(), f"a_{pol}: {int(bad.sum())} of {ar.size} gains off, " \
+                              f"worst rel {float((err / np.maximum(mag, 1e-300)).max()):.3e}"
