@@ -1,0 +1,132 @@
+/* hrt_bvh.cuh -- element functions of the GPU BVH builder (LBVH: Morton sort,
+ * Karras radix-tree, bottom-up boxes, leaf cut, padded node emission).
+ *
+ * Replaces the reference's "for every mesh, for every triangle" loop
+ * (src/compute_paths.c:246-255, "TODO BVH") with a structure that returns the
+ * same answer.  As with hrt_core.cuh, the functions are __host__ __device__ so
+ * that tests/emul can run the identical build serially on the CPU; the
+ * product builds on the GPU only (kernels in hrt_cuda.cu).
+ */
+#pragma once
+
+#include "hrt_core.cuh"
+
+/* ---- triangle set-up: corners -> record + bounds (reference :208-224) ---- */
+
+struct HrtTriSetup {
+  float4 q0, q1, q2;      /* record, see hrt_core.cuh */
+  V3 lo, hi;              /* exact bounds of the three corners */
+};
+
+HRT_HD HrtTriSetup hrt_tri_setup(V3 a, V3 b, V3 c)
+{
+  HrtTriSetup r;
+  const V3 ab = v3_sub(b, a);                 /* :217 / :259 */
+  const V3 ac = v3_sub(c, a);                 /* :218 / :260 */
+  const V3 n  = v3_normalize(v3_cross(ab, ac)); /* :219-220 */
+  r.q0.x = a.x;  r.q0.y = a.y;  r.q0.z = a.z;  r.q0.w = ab.x;
+  r.q1.x = ab.y; r.q1.y = ab.z; r.q1.z = ac.x; r.q1.w = ac.y;
+  r.q2.x = ac.z; r.q2.y = n.x;  r.q2.z = n.y;  r.q2.w = n.z;
+  r.lo = v3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+  r.hi = v3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+  return r;
+}
+
+/* ---- Morton keys ---- */
+
+HRT_HD uint32_t hrt_expand10(uint32_t v)   /* 10 bits -> every third bit */
+{
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+/* 64-bit sort key: 30-bit Morton code of the box centre (relative to the scene
+ * bounds) in the high word, triangle id in the low word -> all keys distinct. */
+HRT_HD uint64_t hrt_morton_key(V3 lo, V3 hi, V3 scene_lo, V3 scene_inv_ext, uint32_t id)
+{
+  const float cx = (0.5f * (lo.x + hi.x) - scene_lo.x) * scene_inv_ext.x;
+  const float cy = (0.5f * (lo.y + hi.y) - scene_lo.y) * scene_inv_ext.y;
+  const float cz = (0.5f * (lo.z + hi.z) - scene_lo.z) * scene_inv_ext.z;
+  const uint32_t x = (uint32_t)fminf(fmaxf(cx * 1024.f, 0.f), 1023.f);
+  const uint32_t y = (uint32_t)fminf(fmaxf(cy * 1024.f, 0.f), 1023.f);
+  const uint32_t z = (uint32_t)fminf(fmaxf(cz * 1024.f, 0.f), 1023.f);
+  const uint32_t code = (hrt_expand10(x) << 2) | (hrt_expand10(y) << 1) | hrt_expand10(z);
+  return ((uint64_t)code << 32) | id;
+}
+
+/* ---- Karras 2012 radix tree over sorted distinct keys ---- */
+
+HRT_HD int hrt_clz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
+HRT_HD int hrt_delta(const uint64_t *keys, int n, int i, int j)
+{
+  if (j < 0 || j >= n) return -1;
+  return hrt_clz64(keys[i] ^ keys[j]);
+}
+
+/* Inner node i (0 <= i < n-1) of the tree over n >= 2 leaves.
+ * Children are returned as indices into a combined numbering:
+ * [0, n-1) inner nodes, n-1+k for leaf k.  Also the covered leaf range. */
+HRT_HD void hrt_karras_node(const uint64_t *keys, int n, int i,
+                            int *left, int *right, int *first, int *last)
+{
+  const int d = (hrt_delta(keys, n, i, i + 1) - hrt_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = hrt_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (hrt_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (hrt_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = hrt_delta(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) / 2;
+    if (hrt_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + (d < 0 ? d : 0);
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  *left  = (lo == gamma)     ? (n - 1 + gamma)     : gamma;
+  *right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
+  *first = lo; *last = hi;
+}
+
+/* ---- node emission ----
+ * Karras inner node i becomes a traversal node iff it covers more than
+ * leaf_max triangles; smaller subtrees (and single leaves) become leaf refs of
+ * their parent.  Boxes are padded by `pad` on every side (conservative
+ * culling: see DESIGN.md, "exact hits behind inexact boxes"). */
+HRT_HD int hrt_child_ref(int child, int n, const int *first, const int *last,
+                         const int *new_index, int leaf_max)
+{
+  if (child >= n - 1) return hrt_leaf_ref((uint32_t)(child - (n - 1)), 1u);   /* single leaf */
+  const int cnt = last[child] - first[child] + 1;
+  if (cnt <= leaf_max) return hrt_leaf_ref((uint32_t)first[child], (uint32_t)cnt);
+  return new_index[child];
+}
+
+HRT_HD void hrt_emit_node(float4 *out, int ref_l, int ref_r, V3 llo, V3 lhi, V3 rlo, V3 rhi, float pad)
+{
+  out[0].x = llo.x - pad; out[0].y = lhi.x + pad; out[0].z = llo.y - pad; out[0].w = lhi.y + pad;
+  out[1].x = rlo.x - pad; out[1].y = rhi.x + pad; out[1].z = rlo.y - pad; out[1].w = rhi.y + pad;
+  out[2].x = llo.z - pad; out[2].y = lhi.z + pad; out[2].z = rlo.z - pad; out[2].w = rhi.z + pad;
+  out[3].x = hrt_int_as_float(ref_l); out[3].y = hrt_int_as_float(ref_r);
+  out[3].z = 0.f; out[3].w = 0.f;
+}
+
+/* Padding rule: `ulps` fp32 epsilons of the largest coordinate magnitude any
+ * ray origin or vertex can have. */
+HRT_HD float hrt_box_pad(float max_abs_coord, float ulps)
+{
+  return ulps * FLT_EPSILON * fmaxf(max_abs_coord, 1.0f);
+}

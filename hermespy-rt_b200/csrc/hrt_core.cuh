@@ -1,0 +1,512 @@
+/* hrt_core.cuh -- per-ray arithmetic of compute_paths(), written once as
+ * __host__ __device__ code.
+ *
+ * The product only ever runs it on the GPU (kernels in hrt_cuda.cu).  The host
+ * instantiation exists for one purpose: tests/emul/ compiles it into a serial
+ * CPU driver so the kernel logic can be checked against the oracle in the
+ * GPU-less authoring container.  No product entry point reaches a host path.
+ *
+ * Exactness contract: everything that decides WHICH
+ * triangle is hit, and the whole delay/direction chain, uses separately
+ * rounded fp32 + - * / sqrt in the reference's operation order
+ * (inc/vec3.h:10-43, src/compute_paths.c:259-276, :650-659).  Those operations
+ * are spelled with the HRT_* macros below, which map to the __f*_rn intrinsics
+ * on the device -- nvcc never contracts those into FMA, whatever -fmad says.
+ * FMA is used only where a conservative answer suffices (ray/box culling).
+ */
+#pragma once
+
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HRT_HD __host__ __device__ __forceinline__
+#else
+#define HRT_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define HRT_MUL(a, b) __fmul_rn((a), (b))
+#define HRT_ADD(a, b) __fadd_rn((a), (b))
+#define HRT_SUB(a, b) __fsub_rn((a), (b))
+#define HRT_DIV(a, b) __fdiv_rn((a), (b))
+#define HRT_SQRT(a)   __fsqrt_rn((a))
+#define HRT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+#define HRT_MUL(a, b) ((a) * (b))
+#define HRT_ADD(a, b) ((a) + (b))
+#define HRT_SUB(a, b) ((a) - (b))
+#define HRT_DIV(a, b) ((a) / (b))
+#define HRT_SQRT(a)   sqrtf((a))
+#define HRT_FMA(a, b, c) fmaf((a), (b), (c))
+#endif
+
+#define HRT_PI    3.14159265358979323846f  /* reference src/compute_paths.c:18 */
+#define HRT_C0    299792458.0f             /* reference src/compute_paths.c:19 */
+#define HRT_EPS   FLT_EPSILON              /* reference :251, :263-275 */
+#define HRT_T_MAX 1e9f                     /* reference :251 */
+#define HRT_NONE  0xFFFFFFFFu              /* query found nothing */
+#define HRT_IDLE  0xFFFFFFFEu              /* ray already dead, not traced */
+
+#if !defined(__CUDACC__)
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+#endif
+
+struct V3 { float x, y, z; };
+
+HRT_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+/* reference inc/vec3.h:10-43, same operand order */
+HRT_HD V3 v3_sub(V3 a, V3 b) { return v3(HRT_SUB(a.x, b.x), HRT_SUB(a.y, b.y), HRT_SUB(a.z, b.z)); }
+HRT_HD V3 v3_add(V3 a, V3 b) { return v3(HRT_ADD(a.x, b.x), HRT_ADD(a.y, b.y), HRT_ADD(a.z, b.z)); }
+HRT_HD V3 v3_scale(V3 a, float s) { return v3(HRT_MUL(a.x, s), HRT_MUL(a.y, s), HRT_MUL(a.z, s)); }
+HRT_HD float v3_dot(V3 a, V3 b)
+{ return HRT_ADD(HRT_ADD(HRT_MUL(a.x, b.x), HRT_MUL(a.y, b.y)), HRT_MUL(a.z, b.z)); }
+HRT_HD V3 v3_cross(V3 a, V3 b)
+{
+  return v3(HRT_SUB(HRT_MUL(a.y, b.z), HRT_MUL(a.z, b.y)),
+            HRT_SUB(HRT_MUL(a.z, b.x), HRT_MUL(a.x, b.z)),
+            HRT_SUB(HRT_MUL(a.x, b.y), HRT_MUL(a.y, b.x)));
+}
+HRT_HD V3 v3_normalize(V3 a)
+{
+  float len = HRT_SQRT(v3_dot(a, a));
+  return v3(HRT_DIV(a.x, len), HRT_DIV(a.y, len), HRT_DIV(a.z, len));
+}
+
+/* -------------------------------------------------------------------------
+ * Scene records in HBM / shared memory.
+ *
+ * Triangle record, 48 B = 3 x float4, in BVH leaf order:
+ *   q0 = (a.x, a.y, a.z, ab.x)   a  = first corner
+ *   q1 = (ab.y, ab.z, ac.x, ac.y) ab = b - a, ac = c - a  (the reference forms
+ *   q2 = (ac.z, n.x, n.y, n.z)        them per test, :259-260; same rounding)
+ * n is the unit normal of reference :208-224.
+ *
+ * BVH2 node, 64 B = 4 x float4, children's boxes stored in the parent:
+ *   n0 = (L.lo.x, L.hi.x, L.lo.y, L.hi.y)
+ *   n1 = (R.lo.x, R.hi.x, R.lo.y, R.hi.y)
+ *   n2 = (L.lo.z, L.hi.z, R.lo.z, R.hi.z)
+ *   n3 = bit patterns (L.ref, R.ref, -, -)
+ * ref >= 0: inner node index.  ref < 0: leaf, ~ref = (first_slot << 3) | (count-1).
+ * ------------------------------------------------------------------------- */
+#define HRT_LEAF_MAX_CAP 8
+
+HRT_HD int   hrt_leaf_ref(uint32_t first, uint32_t count) { return ~(int)((first << 3) | (count - 1u)); }
+HRT_HD float hrt_int_as_float(int v)
+{
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(v);
+#else
+  float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+HRT_HD int hrt_float_as_int(float f)
+{
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int v; memcpy(&v, &f, 4); return v;
+#endif
+}
+
+struct HrtHit {
+  float    t;      /* distance, reference *t                           */
+  uint32_t gid;    /* triangle id in (mesh, face) order; HRT_NONE: miss */
+  uint32_t slot;   /* position of that triangle in BVH leaf order       */
+};
+
+/* One Moeller-Trumbore test with the reference's accept/reject decisions
+ * (src/compute_paths.c:259-276), against the running best (t, gid).
+ *
+ * The quotients u, v, t are only formed when a division-free bound cannot
+ * already prove the reference's test rejects: |N/det| compared against
+ * thresholds that sit 1e-5 away from the reference's, while IEEE division is
+ * monotonic and off by at most 2^-24 relative -- so the shortcut never changes
+ * a decision, it only skips divisions. */
+HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
+                        float best, uint32_t best_gid, uint32_t gid, float *t_out)
+{
+  const V3 a  = v3(q0.x, q0.y, q0.z);
+  const V3 ab = v3(q0.w, q1.x, q1.y);
+  const V3 ac = v3(q1.z, q1.w, q2.x);
+  const V3 pv = v3_cross(d, ac);                         /* :261 */
+  const float det = v3_dot(ab, pv);                      /* :262 */
+  if (det > -HRT_EPS && det < HRT_EPS) return false;     /* :263 (NaN passes, as there) */
+  const float ad  = fabsf(det);
+  const float sgn = det < 0.f ? -1.f : 1.f;
+  const float lo  = HRT_MUL(ad, -1e-5f), hi = HRT_MUL(ad, 1.00001f);
+  const V3 sv = v3_sub(o, a);                            /* :264 */
+  const float nu = v3_dot(sv, pv);
+  const float snu = nu * sgn;                            /* exact sign flip */
+  if (snu < lo || snu > hi) return false;                /* u clearly outside */
+  const float u = HRT_DIV(nu, det);                      /* :265 */
+  if ((u < 0.f && -u > HRT_EPS) || (u > 1.f && HRT_SUB(u, 1.f) > HRT_EPS)) return false; /* :266 */
+  const V3 qv = v3_cross(sv, ab);                        /* :269 */
+  const float nv = v3_dot(d, qv);
+  const float snv = nv * sgn;
+  if (snv < lo || snv > hi) return false;                /* v clearly outside */
+  const float v = HRT_DIV(nv, det);                      /* :270 */
+  const float uv = HRT_ADD(u, v);
+  if ((v < 0.f && -v > HRT_EPS) || (uv > 1.f && HRT_SUB(uv, 1.f) > HRT_EPS)) return false; /* :271 */
+  const float nt = v3_dot(ac, qv);
+  if (!(nt * sgn > 0.f) && nt == nt) return false;       /* t <= 0 */
+  const float t = HRT_DIV(nt, det);                      /* :274 */
+  if (!(t > HRT_EPS)) return false;                      /* :275 */
+  if (t < best || (t == best && gid < best_gid)) { *t_out = t; return true; }
+  return false;
+}
+
+/* Ray/box culling state.  Conservative by construction: boxes are padded by
+ * the builder, the far bound carries slack, NaNs never reject. */
+struct HrtRayCull {
+  V3 inv;    /* 1/d with tiny components clamped */
+  V3 ood;    /* -o * inv */
+};
+
+HRT_HD float hrt_safe_inv(float d)
+{
+  const float tiny = 1e-20f;
+  if (fabsf(d) < tiny) d = (hrt_float_as_int(d) < 0) ? -tiny : tiny;
+  return 1.0f / d;
+}
+
+HRT_HD HrtRayCull hrt_ray_cull(V3 o, V3 d)
+{
+  HrtRayCull c;
+  c.inv = v3(hrt_safe_inv(d.x), hrt_safe_inv(d.y), hrt_safe_inv(d.z));
+  c.ood = v3(-o.x * c.inv.x, -o.y * c.inv.y, -o.z * c.inv.z);
+  return c;
+}
+
+/* entry distance of the ray into [lo,hi]; returns false when the slab interval
+ * is empty within [0, tmax] */
+HRT_HD bool hrt_slab(const HrtRayCull &c, float lox, float hix, float loy, float hiy,
+                     float loz, float hiz, float tmax, float *t_near)
+{
+  const float x0 = HRT_FMA(lox, c.inv.x, c.ood.x), x1 = HRT_FMA(hix, c.inv.x, c.ood.x);
+  const float y0 = HRT_FMA(loy, c.inv.y, c.ood.y), y1 = HRT_FMA(hiy, c.inv.y, c.ood.y);
+  const float z0 = HRT_FMA(loz, c.inv.z, c.ood.z), z1 = HRT_FMA(hiz, c.inv.z, c.ood.z);
+  const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+  const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+  *t_near = tn;
+  return tn <= tf;
+}
+
+/* Scene view handed to the traversal: how to fetch node / triangle words.
+ * `Mem` provides node(i,k) and tri(slot,k) returning float4 -- from shared
+ * memory when the scene was staged there, else from global memory. */
+struct HrtGlobalMem {
+  const float4 *nodes;
+  const float4 *tris;
+  HRT_HD float4 node(int i, int k) const
+  {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&nodes[4 * i + k]);
+#else
+    return nodes[4 * i + k];
+#endif
+  }
+  HRT_HD float4 tri(uint32_t s, int k) const
+  {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&tris[3 * s + k]);
+#else
+    return tris[3 * s + k];
+#endif
+  }
+};
+
+#define HRT_STACK 64
+
+/* Closest hit over the BVH == the reference's loop over every triangle
+ * (moeller_trumbore, :237-287): minimum t, ties to the lowest (mesh, face).
+ * root_ref: inner node index, a leaf ref, or 0 with num_tris == 0. */
+template <class Mem>
+HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_ref,
+                              uint32_t num_tris, V3 o, V3 d)
+{
+  HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
+  if (num_tris == 0) return h;
+  const HrtRayCull c = hrt_ray_cull(o, d);
+  float tmax = HRT_T_MAX * 1.0001f;          /* far bound with slack */
+  int   stack_ref[HRT_STACK];
+  float stack_tn[HRT_STACK];
+  int sp = 0, cur = root_ref;
+  for (;;) {
+    if (cur >= 0) {
+      const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1);
+      const float4 n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
+      float tl, tr;
+      const bool hl = hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl);
+      const bool hr = hrt_slab(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr);
+      const int rl = hrt_float_as_int(n3.x), rr = hrt_float_as_int(n3.y);
+      if (hl && hr) {
+        const bool left_first = tl <= tr;
+        stack_ref[sp] = left_first ? rr : rl;
+        stack_tn[sp]  = left_first ? tr : tl;
+        ++sp;
+        cur = left_first ? rl : rr;
+        continue;
+      }
+      if (hl) { cur = rl; continue; }
+      if (hr) { cur = rr; continue; }
+    } else {
+      const uint32_t code = (uint32_t)~cur;
+      const uint32_t first = code >> 3, cnt = (code & 7u) + 1u;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t s = first + k;
+        float t;
+        const uint32_t gid = tri_gid[s];
+        if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t)) {
+          h.t = t; h.gid = gid; h.slot = s;
+          tmax = HRT_FMA(t, 1.0001f, 1e-30f);
+        }
+      }
+    }
+    /* pop, skipping subtrees that start beyond the current best */
+    for (;;) {
+      if (sp == 0) return h;
+      --sp;
+      if (stack_tn[sp] <= tmax) { cur = stack_ref[sp]; break; }
+    }
+  }
+}
+
+/* Brute force over every triangle in leaf order -- debug/validation path of
+ * the kernels (HRT_FLAG_BRUTE_FORCE), same decisions by construction. */
+template <class Mem>
+HRT_HD HrtHit hrt_closest_hit_brute(const Mem &mem, const uint32_t *tri_gid,
+                                    uint32_t num_tris, V3 o, V3 d)
+{
+  HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
+  for (uint32_t s = 0; s < num_tris; ++s) {
+    float t;
+    const uint32_t gid = tri_gid[s];
+    if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t)) {
+      h.t = t; h.gid = gid; h.slot = s;
+    }
+  }
+  return h;
+}
+
+/* Folded incidence angle, reference :280-283: acos in double of the fp32 dot
+ * product (normal first), rounded to float, then folded into [0, pi/2]. */
+HRT_HD float hrt_theta_fold(V3 n, V3 d)
+{
+  float th = (float)acos((double)v3_dot(n, d));
+  if ((double)th > (double)HRT_PI / 2.) th = HRT_SUB(HRT_PI, th);
+  return th;
+}
+
+/* ------------------------------------------------------------- materials
+ * Derived per-material constants, computed on the HOST with the host libm
+ * (powf) exactly as the reference does (:171-206) and uploaded; the raw
+ * scattering parameters of g_materials ride along. */
+struct HrtMaterial {
+  float eta_abs2, eta_abs_inv_sqrt;
+  float sqrt_re, sqrt_im;
+  float inv_re, inv_im;
+  float r;            /* 1 - s */
+  float s;            /* scattering coefficient */
+  float s1_alpha;     /* (float)uint8 */
+  float pad_[3];
+};
+struct HrtMaterialTable { HrtMaterial m[17]; };
+
+HRT_HD void hrt_cdiv(float ar, float ai, float br, float bi, float *cr, float *ci)
+{
+  const float den = HRT_ADD(HRT_MUL(br, br), HRT_MUL(bi, bi));                 /* :161 */
+  *cr = HRT_DIV(HRT_ADD(HRT_MUL(ar, br), HRT_MUL(ai, bi)), den);               /* :162 */
+  *ci = HRT_DIV(HRT_SUB(HRT_MUL(ai, br), HRT_MUL(ar, bi)), den);               /* :163 */
+}
+
+/* reference refl_coefs :300-344; out = (te_re, te_im, tm_re, tm_im) */
+HRT_HD void hrt_refl_coefs(const HrtMaterial &m, float th, float out[4])
+{
+  const float s1 = sinf(th);                                                   /* :310 */
+  if (HRT_MUL(m.eta_abs_inv_sqrt, s1) > 1.f - HRT_EPS) {                       /* :311 */
+    out[0] = out[2] = 1.f; out[1] = out[3] = 0.f; return;
+  }
+  const float s1sq = HRT_MUL(s1, s1);                                          /* :318 */
+  const float c2r = HRT_SQRT(HRT_ADD(1.f, HRT_MUL(HRT_DIV(m.inv_re, m.eta_abs2), s1sq))); /* :319 */
+  const float c2i = HRT_SQRT(HRT_SUB(1.f, HRT_MUL(HRT_DIV(m.inv_im, m.eta_abs2), s1sq))); /* :320 */
+  const float pr = HRT_SUB(HRT_MUL(m.sqrt_re, c2r), HRT_MUL(m.sqrt_im, c2i));  /* :323 */
+  const float pi = HRT_ADD(HRT_MUL(m.sqrt_re, c2i), HRT_MUL(m.sqrt_im, c2r));  /* :324 */
+  const float c1 = cosf(th);                                                   /* :325 */
+  hrt_cdiv(HRT_SUB(c1, pr), -pi, HRT_ADD(c1, pr), pi, &out[0], &out[1]);       /* :326 */
+  const float qr = HRT_MUL(m.sqrt_re, c1), qi = HRT_MUL(m.sqrt_im, c1);        /* :331 */
+  hrt_cdiv(HRT_SUB(qr, c2r), HRT_SUB(qi, c2i), HRT_ADD(qr, c2r), HRT_ADD(qi, c2i),
+           &out[2], &out[3]);                                                  /* :333 */
+  out[0] = HRT_MUL(out[0], m.r); out[1] = HRT_MUL(out[1], m.r);                /* :340 */
+  out[2] = HRT_MUL(out[2], m.r); out[3] = HRT_MUL(out[3], m.r);
+}
+
+/* reference scat_coefs :359-415 */
+HRT_HD void hrt_scat_coefs(const HrtMaterial &m, float th_s, float th_i, float out[4])
+{
+  const float cs = cosf(th_s), ci = cosf(th_i), si = sinf(th_i);               /* :372 */
+  const float lobe = HRT_MUL(m.s, expf(HRT_MUL(-m.s1_alpha, fabsf(HRT_SUB(th_s, th_i))))); /* :378 */
+  const float rough = HRT_DIV(1.0f, HRT_ADD(1.0f, m.s1_alpha));                /* :382 */
+  const float spec = HRT_MUL(rough, cs);                                       /* :383 */
+  const float diff = HRT_MUL(HRT_SUB(1.0f, rough), cs);                        /* :384 */
+  float te_r = HRT_MUL(lobe, HRT_ADD(spec, diff));                             /* :388 */
+  float tm_r = HRT_MUL(lobe, HRT_ADD(HRT_MUL(spec, ci), diff));                /* :390 */
+  const float ph = HRT_MUL(HRT_MUL(m.s1_alpha, si), 0.1f);                     /* :394 */
+  const float sp = sinf(ph);
+  float te_i = HRT_MUL(te_r, sp);                                              /* :395 */
+  float tm_i = HRT_MUL(tm_r, sp);                                              /* :396 */
+  const float nrm = HRT_SQRT(HRT_ADD(HRT_ADD(HRT_ADD(HRT_MUL(te_r, te_r), HRT_MUL(te_i, te_i)),
+                                             HRT_MUL(tm_r, tm_r)), HRT_MUL(tm_i, tm_i))); /* :399 */
+  if (nrm > 1e-6f) {                                                           /* :401 */
+    te_r = HRT_DIV(te_r, nrm); te_i = HRT_DIV(te_i, nrm);
+    tm_r = HRT_DIV(tm_r, nrm); tm_i = HRT_DIV(tm_i, nrm);
+  }
+  out[0] = te_r; out[1] = te_i; out[2] = tm_r; out[3] = tm_i;
+}
+
+/* ----------------------------------------------------- launch directions
+ * Fibonacci sphere, reference :444-451.  fp32 index math, double trig rounded
+ * to fp32.  CUDA's double acos/sin/cos are within 2 ulp, glibc's within 1, so
+ * after rounding to fp32 the two can differ only when the double value sits
+ * within ~2^-50 (relative) of an fp32 rounding boundary.  `*ambiguous` is set
+ * when a value is within 2^-46 of one; the host then recomputes those few rays
+ * (about 1 in 5e5) with its own libm, which makes launch directions bit-exact
+ * for every ray (hrt_cuda.cu, fix_ambiguous_dirs). */
+HRT_HD float hrt_round_checked(double x, bool *ambiguous)
+{
+  const float f = (float)x;
+  const double k = 1.4210854715202004e-14;  /* 2^-46 */
+  if ((float)(x * (1.0 - k)) != f || (float)(x * (1.0 + k)) != f) *ambiguous = true;
+  return f;
+}
+
+HRT_HD V3 hrt_launch_dir(uint64_t path, uint64_t num_paths, bool *ambiguous)
+{
+  const float k = HRT_ADD((float)path, .5f);                                   /* :444 */
+  const float arg = HRT_SUB(1.f, HRT_DIV(HRT_MUL(2.f, k), (float)num_paths));
+  const float phi = hrt_round_checked(acos((double)arg), ambiguous);           /* :445 */
+  const float th = HRT_MUL(HRT_MUL(HRT_PI, HRT_ADD(1.f, HRT_SQRT(5.f))), k);   /* :446 */
+  const double sphi = sin((double)phi);
+  V3 d;
+  d.x = hrt_round_checked(cos((double)th) * sphi, ambiguous);                  /* :448 */
+  d.y = hrt_round_checked(sin((double)th) * sphi, ambiguous);                  /* :449 */
+  d.z = hrt_round_checked(cos((double)phi), ambiguous);                        /* :450 */
+  return d;
+}
+
+/* ------------------------------------------------------------ one bounce
+ * Everything the reference does to a ray that hit something (:621-659),
+ * except the closest-hit query itself. */
+struct HrtRunConst {
+  float fsl_k;   /* 4*pi*f/c, reference :484 */
+  float dop_k;   /* f/c,      reference :488 */
+};
+
+struct HrtRayState {
+  V3 o, d;
+  float te_r, te_i, tm_r, tm_i;
+  float tau;
+};
+
+HRT_HD void hrt_bounce_update(HrtRayState &s, const HrtMaterial &m, const HrtRunConst &k,
+                              float t, V3 n, float theta)
+{
+  float rc[4];
+  hrt_refl_coefs(m, theta, rc);                                                /* :623 */
+  float fsl = HRT_MUL(k.fsl_k, t);                                             /* :627 */
+  fsl = HRT_MUL(fsl, fsl);                                                     /* :628 */
+  if (fsl > 1.f) {                                                             /* :629 */
+    rc[0] = HRT_DIV(rc[0], fsl); rc[1] = HRT_DIV(rc[1], fsl);
+    rc[2] = HRT_DIV(rc[2], fsl); rc[3] = HRT_DIV(rc[3], fsl);
+  }
+  const float a = HRT_SUB(HRT_MUL(s.te_r, rc[0]), HRT_MUL(s.te_i, rc[1]));     /* :636 */
+  const float b = HRT_ADD(HRT_MUL(s.te_r, rc[1]), HRT_MUL(s.te_i, rc[0]));
+  const float c = HRT_SUB(HRT_MUL(s.tm_r, rc[2]), HRT_MUL(s.tm_i, rc[3]));
+  const float e = HRT_ADD(HRT_MUL(s.tm_r, rc[3]), HRT_MUL(s.tm_i, rc[2]));
+  s.te_r = a; s.te_i = b; s.tm_r = c; s.tm_i = e;
+  s.tau = HRT_ADD(s.tau, HRT_DIV(t, HRT_C0));                                  /* :645 */
+  V3 step = v3_scale(s.d, t);                                                  /* :650 */
+  s.o = v3_add(step, s.o);                                                     /* :651 */
+  const float dn = v3_dot(s.d, n);                                             /* :654 */
+  step = v3_scale(n, HRT_MUL(2.f, dn));                                        /* :655 */
+  s.d = v3_sub(s.d, step);                                                     /* :656 */
+  step = v3_scale(s.d, 1e-4f);                                                 /* :658 */
+  s.o = v3_add(s.o, step);                                                     /* :659 */
+}
+
+/* ------------------------------------------------------- scatter to one RX
+ * reference :676-722 after the shadow query has been resolved. */
+struct HrtScatterOut {
+  float te_r, te_i, tm_r, tm_i, tau, dfreq;   /* dfreq: amount SUBTRACTED from freq_shift */
+  V3 dir_rx;
+};
+
+/* geometry of the shadow ray: direction (unit) and distance to the receiver */
+HRT_HD V3 hrt_shadow_dir(V3 o, V3 rx, float *dist)
+{
+  const V3 dv = v3_sub(rx, o);                                                 /* :676 */
+  const float len = HRT_SQRT(v3_dot(dv, dv));                                  /* :677 */
+  *dist = len;
+  return v3(HRT_DIV(dv.x, len), HRT_DIV(dv.y, len), HRT_DIV(dv.z, len));       /* :678 */
+}
+
+HRT_HD HrtScatterOut hrt_scatter_path(const HrtRayState &s, const HrtMaterial &m,
+                                      const HrtRunConst &k, V3 n, V3 mesh_vel,
+                                      V3 sd, float dist, float theta_i)
+{
+  HrtScatterOut r;
+  const float th_s = acosf(v3_dot(sd, n));                                     /* :694 */
+  float sc[4];
+  hrt_scat_coefs(m, th_s, theta_i, sc);                                        /* :696 */
+  r.te_r = HRT_SUB(HRT_MUL(s.te_r, sc[0]), HRT_MUL(s.te_i, sc[1]));            /* :698 */
+  r.te_i = HRT_ADD(HRT_MUL(s.te_r, sc[1]), HRT_MUL(s.te_i, sc[0]));
+  r.tm_r = HRT_SUB(HRT_MUL(s.tm_r, sc[2]), HRT_MUL(s.tm_i, sc[3]));
+  r.tm_i = HRT_ADD(HRT_MUL(s.tm_r, sc[3]), HRT_MUL(s.tm_i, sc[2]));
+  r.dir_rx = v3(-sd.x, -sd.y, -sd.z);                                          /* :707 */
+  r.tau = HRT_ADD(s.tau, HRT_DIV(dist, HRT_C0));                               /* :709 */
+  float l2 = HRT_MUL(k.fsl_k, dist);                                           /* :711 */
+  l2 = HRT_MUL(l2, l2);
+  if (l2 > 1.f) {                                                              /* :713 */
+    r.te_r = HRT_DIV(r.te_r, l2); r.te_i = HRT_DIV(r.te_i, l2);
+    r.tm_r = HRT_DIV(r.tm_r, l2); r.tm_i = HRT_DIV(r.tm_i, l2);
+  }
+  const V3 dd = v3_sub(sd, s.d);                                               /* :720 */
+  r.dfreq = HRT_MUL(v3_dot(dd, mesh_vel), k.dop_k);                            /* :721 */
+  return r;
+}
+
+/* ------------------------------------------------------------------ LoS
+ * reference :520-577 for one (rx, tx) pair, query result passed in. */
+struct HrtLosOut {
+  V3 dir_tx, dir_rx;
+  float a, tau, freq;
+  int state;      /* 0 blocked, 1 clear, 2 co-located */
+};
+
+HRT_HD HrtLosOut hrt_los_finish(V3 d, bool hit, float t_hit, V3 tx_vel0, V3 rx_vel0,
+                                const HrtRunConst &k, float f_over_c)
+{
+  HrtLosOut r;
+  r.dir_tx = r.dir_rx = v3(0.f, 0.f, 0.f); r.a = 0.f; r.tau = 0.f; r.freq = 0.f;
+  if (hit && t_hit <= 1.f) { r.state = 0; return r; }                          /* :548 */
+  const float len = HRT_SQRT(v3_dot(d, d));                                    /* :558 */
+  const V3 u = v3(HRT_DIV(d.x, len), HRT_DIV(d.y, len), HRT_DIV(d.z, len));    /* :560 */
+  r.dir_tx = u; r.dir_rx = v3(-u.x, -u.y, -u.z);
+  const float fsl = HRT_MUL(k.fsl_k, len);                                     /* :564 */
+  r.a = fsl > 1.f ? HRT_DIV(1.f, fsl) : 1.f;
+  r.tau = HRT_DIV(len, HRT_C0);                                                /* :571 */
+  r.freq = HRT_MUL(HRT_SUB(v3_dot(tx_vel0, u), v3_dot(rx_vel0, u)), f_over_c); /* :573-574 */
+  r.state = 1;
+  return r;
+}
+
+/* 64-bit mixer for the order-independent checksums of summary mode */
+HRT_HD uint64_t hrt_mix64(uint64_t x)
+{
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}

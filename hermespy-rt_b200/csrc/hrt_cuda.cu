@@ -1,0 +1,1373 @@
+/* hrt_cuda.cu -- CUDA (sm_100a) implementation behind include/hrt_cuda.h.
+ *
+ * Kernels (DESIGN.md has the data layout and the roofline of each):
+ *   k_tri_setup / k_morton / k_gather / k_karras / k_refit / k_emit
+ *        scene -> SoA triangle records + LBVH, replaces the reference's scene
+ *        walk (src/compute_paths.c:208-224, :253-258)
+ *   k_raygen     Fibonacci launch directions            (reference :443-451)
+ *   k_init       per-ray state + output initialisation  (reference :460-508)
+ *   k_los        line-of-sight pairs                    (reference :514-577)
+ *   k_bounce     one wavefront step per bounce depth: closest hit, Fresnel,
+ *                gain/delay update, reflection, ballot/prefix-sum compaction
+ *                of the survivors                       (reference :599-664)
+ *   k_scatter    per-(hit, rx) shadow query + scattering coefficients +
+ *                outputs / reductions                   (reference :670-723)
+ *
+ * The arithmetic lives in hrt_core.cuh; this file is launch logic, memory
+ * management and the C ABI.  Nothing here computes paths on the CPU.
+ */
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/hrt_cuda.h"
+#include "hrt_bvh.cuh"
+
+/* host C helpers (host_math.c): glibc double trig, as the reference uses */
+extern "C" void hrt_host_launch_dir(uint64_t path, uint64_t num_paths, float out[3]);
+
+static_assert(sizeof(HrtMaterialDerived) == sizeof(HrtMaterial), "material ABI");
+static_assert(sizeof(Ray) == 24 && sizeof(Vec3) == 12, "reference ABI");
+static_assert(sizeof(HrtPairSummary) == 48 && sizeof(HrtBounceSummary) == 32, "summary ABI");
+
+#define HRT_BLOCK 128
+#define HRT_SMEM_SCENE_LIMIT (96 * 1024)   /* stage nodes+triangles in shared memory below this */
+#define HRT_AMB_CAP 65536
+
+static char g_create_error[256] = "";
+
+struct SceneDev {
+  const float4 *nodes;
+  const float4 *tris;
+  const uint32_t *tri_gid;
+  const uint32_t *mesh_of;     /* by triangle id */
+  const uint32_t *mesh_mat;    /* by mesh */
+  const float *mesh_vel;       /* 3 per mesh */
+  uint32_t num_tris, num_nodes;
+  int root_ref;
+};
+
+struct RunDev {
+  uint32_t R, T, B;
+  uint32_t n;            /* paths per TX in this chunk      */
+  uint32_t n_alloc;      /* row pitch of all per-path arrays */
+  uint64_t P;            /* num_paths of the whole job       */
+  uint64_t l0;           /* first shard-local path index of the chunk */
+  uint32_t rank, world;
+  uint64_t blk;
+  HrtRunConst k;
+  const float *rx_pos, *tx_pos, *rx_vel, *tx_vel;
+  float *dirs;           /* [n_alloc][3] launch directions of the chunk */
+  Ray *rays;             /* [rows][T][n_alloc] */
+  float4 *gain;          /* [T][n_alloc] te_r te_i tm_r tm_i */
+  float *tau, *theta;    /* [T][n_alloc] */
+  uint32_t *hslot;       /* [T][n_alloc] leaf slot of the last primary hit */
+  uint8_t *dead_at;      /* [T][n_alloc] bounce at which the ray left the scene, 255 alive */
+  uint32_t *queue[2];    /* [T][n_alloc] active path indices */
+  uint32_t *qcount;      /* [B+1][T] */
+  float *out_f[6];       /* [R][T][B][n_alloc] te_re te_im tm_re tm_im tau freq */
+  float *out_dir;        /* [R][T][B][n_alloc][3] */
+  uint32_t *tr_hit;      /* [T][B][n_alloc] */
+  float *tr_t;
+  uint8_t *tr_state;     /* [R][T][B][n_alloc] */
+  HrtPairSummary *pair;  /* [R][T][B] */
+  HrtBounceSummary *bounce; /* [T][B] */
+  uint32_t *amb_list, *amb_count;
+  unsigned long long *counters;  /* [16] instrumented build */
+  uint32_t flags;
+};
+
+/* global path index of shard-local index L (blocks dealt round-robin) */
+__host__ __device__ static inline uint64_t hrt_gpath(uint64_t L, uint32_t rank, uint32_t world, uint64_t blk)
+{
+  if (world <= 1) return L;
+  const uint64_t q = L / blk, r = L - q * blk;
+  return (q * world + rank) * blk + r;
+}
+
+/* ------------------------------------------------------------------ context */
+
+struct hrt_ctx {
+  int device;
+  cudaStream_t stream;
+  cudaEvent_t ev[8];
+  char err[512];
+  int leaf_max;
+  float pad_ulps;
+
+  /* scene */
+  bool have_scene;
+  uint32_t num_tris, num_meshes, num_nodes;
+  int root_ref;
+  float pad, scene_max_abs;
+  float4 *d_tris; uint32_t *d_tri_gid; uint32_t *d_mesh_of; uint32_t *d_mesh_mat; float *d_mesh_vel;
+  float4 *d_nodes;
+  /* builder arrays kept for re-padding */
+  int *d_kl, *d_kr, *d_kfirst, *d_klast, *d_newidx;
+  float *d_box;            /* [(2n-1)][6] lo.xyz hi.xyz; inner nodes then leaves */
+
+  bool have_mats;
+  HrtMaterialTable mats;
+
+  /* run buffers */
+  size_t cap_n, cap_T, cap_R, cap_B; uint32_t cap_flags;
+  RunDev rd;
+  float *d_pos;            /* rx_pos, tx_pos, rx_vel, tx_vel */
+  size_t cap_pos;
+  void *d_los;             /* HrtLosOut[R*T] */
+  size_t cap_los;
+  HrtRunStats stats;
+};
+
+static int fail(hrt_ctx *c, int code, const char *fmt, ...)
+{
+  va_list ap; va_start(ap, fmt);
+  if (c) vsnprintf(c->err, sizeof c->err, fmt, ap);
+  else   vsnprintf(g_create_error, sizeof g_create_error, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                   \
+  do { cudaError_t e_ = (call);                                                    \
+       if (e_ != cudaSuccess)                                                      \
+         return fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                     cudaGetErrorString(e_)); } while (0)
+
+template <class T> static cudaError_t dev_alloc(T **p, size_t count)
+{ *p = nullptr; return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T)); }
+template <class T> static void dev_free(T *&p) { if (p) cudaFree((void *)p); p = nullptr; }
+
+/* ---------------------------------------------------------- build kernels */
+
+__device__ __forceinline__ unsigned enc_f(float f)
+{ unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__host__ __device__ __forceinline__ float dec_f(unsigned u)
+{
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  float f; memcpy(&f, &u, 4); return f;
+}
+
+/* verts: all meshes' vertices concatenated; idx: 3 per triangle, already offset */
+__global__ void k_tri_setup(const float *verts, const uint32_t *idx, uint32_t n,
+                            float4 *recs, float *boxes, unsigned *bounds /* lo xyz, hi xyz */)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const uint32_t ia = idx[3 * g], ib = idx[3 * g + 1], ic = idx[3 * g + 2];
+  const V3 a = v3(verts[3 * ia], verts[3 * ia + 1], verts[3 * ia + 2]);
+  const V3 b = v3(verts[3 * ib], verts[3 * ib + 1], verts[3 * ib + 2]);
+  const V3 c = v3(verts[3 * ic], verts[3 * ic + 1], verts[3 * ic + 2]);
+  const HrtTriSetup s = hrt_tri_setup(a, b, c);
+  recs[3 * g] = s.q0; recs[3 * g + 1] = s.q1; recs[3 * g + 2] = s.q2;
+  float *bx = boxes + 6 * (size_t)g;
+  bx[0] = s.lo.x; bx[1] = s.lo.y; bx[2] = s.lo.z; bx[3] = s.hi.x; bx[4] = s.hi.y; bx[5] = s.hi.z;
+  atomicMin(&bounds[0], enc_f(s.lo.x)); atomicMin(&bounds[1], enc_f(s.lo.y)); atomicMin(&bounds[2], enc_f(s.lo.z));
+  atomicMax(&bounds[3], enc_f(s.hi.x)); atomicMax(&bounds[4], enc_f(s.hi.y)); atomicMax(&bounds[5], enc_f(s.hi.z));
+}
+
+__global__ void k_morton(const float *boxes, uint32_t n, const unsigned *bounds, uint64_t *keys)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const V3 slo = v3(dec_f(bounds[0]), dec_f(bounds[1]), dec_f(bounds[2]));
+  const V3 shi = v3(dec_f(bounds[3]), dec_f(bounds[4]), dec_f(bounds[5]));
+  const V3 inv = v3(1.f / fmaxf(shi.x - slo.x, 1e-30f), 1.f / fmaxf(shi.y - slo.y, 1e-30f),
+                    1.f / fmaxf(shi.z - slo.z, 1e-30f));
+  const float *bx = boxes + 6 * (size_t)g;
+  keys[g] = hrt_morton_key(v3(bx[0], bx[1], bx[2]), v3(bx[3], bx[4], bx[5]), slo, inv, g);
+}
+
+/* leaf order: triangle records, ids and leaf boxes follow the sorted keys */
+__global__ void k_gather(const uint64_t *keys, uint32_t n, const float4 *recs, const float *boxes,
+                         float4 *tris, uint32_t *tri_gid, float *node_box)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t g = (uint32_t)(keys[s] & 0xFFFFFFFFull);
+  tris[3 * s] = recs[3 * g]; tris[3 * s + 1] = recs[3 * g + 1]; tris[3 * s + 2] = recs[3 * g + 2];
+  tri_gid[s] = g;
+  float *dst = node_box + 6 * (size_t)(n - 1 + s);
+  const float *src = boxes + 6 * (size_t)g;
+  for (int k = 0; k < 6; ++k) dst[k] = src[k];
+}
+
+__global__ void k_karras(const uint64_t *keys, int n, int *kl, int *kr, int *kfirst, int *klast,
+                         int *parent)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int l, r, f, la;
+  hrt_karras_node(keys, n, i, &l, &r, &f, &la);
+  kl[i] = l; kr[i] = r; kfirst[i] = f; klast[i] = la;
+  parent[l] = i; parent[r] = i;
+  if (i == 0) parent[0] = -1;   /* written by nobody else: node 0 is never a child */
+}
+
+/* bottom-up boxes: the second thread to reach a node merges its children */
+__global__ void k_refit(int n, const int *kl, const int *kr, const int *parent, float *node_box,
+                        unsigned *arrive)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int cur = parent[n - 1 + s];
+  while (cur >= 0) {
+    __threadfence();
+    if (atomicAdd(&arrive[cur], 1u) == 0u) return;
+    const volatile float *a = node_box + 6 * (size_t)kl[cur];
+    const volatile float *b = node_box + 6 * (size_t)kr[cur];
+    float *o = node_box + 6 * (size_t)cur;
+    for (int k = 0; k < 3; ++k) o[k] = fminf(a[k], b[k]);
+    for (int k = 3; k < 6; ++k) o[k] = fmaxf(a[k], b[k]);
+    cur = parent[cur];
+  }
+}
+
+__global__ void k_mark(int n, const int *kfirst, const int *klast, int leaf_max, int *used)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  used[i] = (klast[i] - kfirst[i] + 1) > leaf_max ? 1 : 0;
+}
+
+__global__ void k_emit(int n, const int *kl, const int *kr, const int *kfirst, const int *klast,
+                       const int *used, const int *newidx, const float *node_box, int leaf_max,
+                       float pad, float4 *nodes)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1 || !used[i]) return;
+  const int l = kl[i], r = kr[i];
+  const float *bl = node_box + 6 * (size_t)l, *br = node_box + 6 * (size_t)r;
+  hrt_emit_node(nodes + 4 * (size_t)newidx[i],
+                hrt_child_ref(l, n, kfirst, klast, newidx, leaf_max),
+                hrt_child_ref(r, n, kfirst, klast, newidx, leaf_max),
+                v3(bl[0], bl[1], bl[2]), v3(bl[3], bl[4], bl[5]),
+                v3(br[0], br[1], br[2]), v3(br[3], br[4], br[5]), pad);
+}
+
+/* ------------------------------------------------------- scene in shared */
+
+struct HrtSharedMem {
+  const float4 *nodes;
+  const float4 *tris;
+  __device__ __forceinline__ float4 node(int i, int k) const { return nodes[4 * i + k]; }
+  __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return tris[3 * s + k]; }
+};
+
+extern __shared__ float4 hrt_smem4[];
+
+/* copies nodes, triangle records and ids into shared memory; returns the
+ * first free float4 slot after them */
+__device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
+{
+  const uint32_t nn = sc.num_nodes * 4u, nt = sc.num_tris * 3u;
+  for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.nodes[i];
+  for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) hrt_smem4[nn + i] = sc.tris[i];
+  uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
+  for (uint32_t i = threadIdx.x; i < sc.num_tris; i += blockDim.x) gid[i] = sc.tri_gid[i];
+  return nn + nt + (sc.num_tris + 3u) / 4u;
+}
+
+static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris)
+{ return (size_t)num_nodes * 64 + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
+
+template <bool SMEM, bool BRUTE>
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d)
+{
+  if (SMEM) {
+    HrtSharedMem m;
+    m.nodes = hrt_smem4;
+    m.tris = hrt_smem4 + sc.num_nodes * 4u;
+    const uint32_t *gid = (const uint32_t *)(hrt_smem4 + sc.num_nodes * 4u + sc.num_tris * 3u);
+    if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d);
+    return hrt_closest_hit(m, gid, sc.root_ref, sc.num_tris, o, d);
+  } else {
+    HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
+    if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d);
+    return hrt_closest_hit(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d);
+  }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
+{
+  const float4 q2 = SMEM ? hrt_smem4[sc.num_nodes * 4u + 3u * slot + 2u] : __ldg(&sc.tris[3 * slot + 2]);
+  return v3(q2.y, q2.z, q2.w);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
+{
+  if (SMEM) return ((const uint32_t *)(hrt_smem4 + sc.num_nodes * 4u + sc.num_tris * 3u))[slot];
+  return sc.tri_gid[slot];
+}
+
+__device__ __forceinline__ V3 ld3(const float *p, uint32_t i) { return v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+
+/* ------------------------------------------------------------ run kernels */
+
+/* launch directions of the chunk (reference :443-451) + list of the ones the
+ * host must recompute (see hrt_launch_dir) */
+__global__ void k_raygen(RunDev rd)
+{
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
+    bool amb = false;
+    const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+    const V3 d = hrt_launch_dir(path, rd.P, &amb);
+    rd.dirs[3 * l] = d.x; rd.dirs[3 * l + 1] = d.y; rd.dirs[3 * l + 2] = d.z;
+    if (amb) {
+      const uint32_t k = atomicAdd(rd.amb_count, 1u);
+      if (k < HRT_AMB_CAP) rd.amb_list[k] = l;
+    }
+  }
+}
+
+/* per-ray state (reference :453-472) and output initialisation: gains/tau
+ * zero, freq_shift = Doppler base value with the reference's index algebra
+ * (:494-508) */
+__global__ void k_init(RunDev rd)
+{
+  const uint32_t T = rd.T, B = rd.B, R = rd.R;
+  const size_t np = rd.n_alloc;
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
+    const V3 d = ld3(rd.dirs, l);
+    for (uint32_t t = 0; t < T; ++t) {
+      const size_t i = t * np + l;
+      const V3 o = ld3(rd.tx_pos, t);
+      float2 *ry = (float2 *)(rd.rays + i);
+      ry[0] = make_float2(o.x, o.y); ry[1] = make_float2(o.z, d.x); ry[2] = make_float2(d.y, d.z);
+      rd.gain[i] = make_float4(1.f, 0.f, 1.f, 0.f);
+      rd.tau[i] = 0.f;
+      rd.dead_at[i] = 255;
+      rd.queue[0][i] = l;
+      if (rd.flags & HRT_FLAG_TRACE)
+        for (uint32_t b = 0; b < B; ++b) {
+          rd.tr_hit[(t * B + b) * np + l] = HRT_IDLE;
+          rd.tr_t[(t * B + b) * np + l] = -1.f;
+        }
+    }
+    if (rd.flags & HRT_FLAG_DENSE) {
+      for (uint32_t t = 0; t < T; ++t)
+        for (uint32_t b = 0; b < B; ++b) {
+          /* which TX's Doppler base the reference leaves in row (t, b) */
+          const uint32_t j = (t * B + b) % T;
+          const uint32_t src = (j % B == 0) ? j / B : t;
+          float base = v3_dot(ld3(rd.tx_vel, src), d);
+          base = HRT_MUL(base, rd.k.dop_k);
+          for (uint32_t r = 0; r < R; ++r) {
+            const size_t s = ((size_t)(r * T + t) * B + b) * np + l;
+            rd.out_f[0][s] = 0.f; rd.out_f[1][s] = 0.f; rd.out_f[2][s] = 0.f; rd.out_f[3][s] = 0.f;
+            rd.out_f[4][s] = 0.f; rd.out_f[5][s] = base;
+            rd.out_dir[3 * s] = 0.f; rd.out_dir[3 * s + 1] = 0.f; rd.out_dir[3 * s + 2] = 0.f;
+            if (rd.flags & HRT_FLAG_TRACE) rd.tr_state[s] = 0;
+          }
+        }
+    } else if (rd.flags & HRT_FLAG_TRACE) {
+      for (uint32_t t = 0; t < T; ++t)
+        for (uint32_t b = 0; b < B; ++b)
+          for (uint32_t r = 0; r < R; ++r) rd.tr_state[((size_t)(r * T + t) * B + b) * np + l] = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < T) rd.qcount[threadIdx.x] = rd.n;
+}
+
+/* line of sight (reference :520-577), one thread per (rx, tx) pair */
+template <bool SMEM, bool BRUTE>
+__global__ void k_los(RunDev rd, SceneDev sc, HrtLosOut *out)
+{
+  if (SMEM) { stage_scene(sc); __syncthreads(); }
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rd.R * rd.T) return;
+  const uint32_t r = k / rd.T, t = k % rd.T;
+  const V3 o = ld3(rd.tx_pos, t);
+  const V3 d = v3_sub(ld3(rd.rx_pos, r), o);                                   /* :528 */
+  HrtLosOut res;
+  if (v3_dot(d, d) < HRT_EPS) {                                                /* :531 */
+    res.dir_rx = v3(1.f, 0.f, 0.f); res.dir_tx = v3(-1.f, 0.f, 0.f);
+    res.a = 1.f; res.tau = 0.f; res.freq = 0.f; res.state = 2;
+  } else {
+    const HrtHit h = query<SMEM, BRUTE>(sc, o, d);
+    res = hrt_los_finish(d, h.gid != HRT_NONE, h.t, ld3(rd.tx_vel, 0), ld3(rd.rx_vel, 0),
+                         rd.k, rd.k.dop_k);
+  }
+  out[k] = res;
+}
+
+/* One bounce depth of the wavefront (reference :599-664): a thread per active
+ * ray of TX blockIdx.y.  Survivors are appended to the next queue with one
+ * atomicAdd per warp (ballot + prefix popcount). */
+template <bool SMEM, bool BRUTE>
+__global__ void __launch_bounds__(HRT_BLOCK)
+k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
+{
+  if (SMEM) { stage_scene(sc); __syncthreads(); }
+  const uint32_t t = blockIdx.y, T = rd.T, B = rd.B;
+  const size_t np = rd.n_alloc;
+  const uint32_t cnt = rd.qcount[depth * T + t];
+  const uint32_t *qin = rd.queue[depth & 1] + t * np;
+  uint32_t *qout = rd.queue[(depth + 1) & 1] + t * np;
+  const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
+  const Ray *rin = rd.rays + (rows ? (size_t)depth * T * np : 0) + t * np;
+  Ray *rout = rd.rays + (rows ? (size_t)(depth + 1) * T * np : 0) + t * np;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long hash_acc = 0, tbits_acc = 0;
+
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t end = (cnt + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+    const bool valid = i < cnt;
+    bool hit = false;
+    uint32_t l = 0;
+    if (valid) {
+      l = qin[i];
+      const float2 *rp = (const float2 *)(rin + l);
+      const float2 a = rp[0], b = rp[1], c = rp[2];
+      HrtRayState s;
+      s.o = v3(a.x, a.y, b.x); s.d = v3(b.y, c.x, c.y);
+      const HrtHit h = query<SMEM, BRUTE>(sc, s.o, s.d);                       /* :615 */
+      hit = h.gid != HRT_NONE;
+      const size_t si = t * np + l;
+      if (rd.flags & HRT_FLAG_TRACE) {
+        rd.tr_hit[(t * B + depth) * np + l] = h.gid;
+        rd.tr_t[(t * B + depth) * np + l] = hit ? h.t : -1.f;
+      }
+      if (!hit) {
+        rd.dead_at[si] = (uint8_t)depth;                                       /* :616-620 */
+      } else {
+        const V3 n = tri_normal<SMEM>(sc, h.slot);
+        const float theta = hrt_theta_fold(n, s.d);                            /* :281-283 */
+        const uint32_t mat = sc.mesh_mat[sc.mesh_of[h.gid]];                   /* :622 */
+        const float4 g = rd.gain[si];
+        s.te_r = g.x; s.te_i = g.y; s.tm_r = g.z; s.tm_i = g.w;
+        s.tau = rd.tau[si];
+        hrt_bounce_update(s, mats.m[mat], rd.k, h.t, n, theta);                /* :623-659 */
+        float2 *wp = (float2 *)(rout + l);
+        wp[0] = make_float2(s.o.x, s.o.y); wp[1] = make_float2(s.o.z, s.d.x);
+        wp[2] = make_float2(s.d.y, s.d.z);
+        rd.gain[si] = make_float4(s.te_r, s.te_i, s.tm_r, s.tm_i);
+        rd.tau[si] = s.tau;
+        rd.theta[si] = theta;
+        rd.hslot[si] = h.slot;
+        if (rd.flags & HRT_FLAG_SUMMARY) {
+          const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+          hash_acc += hrt_mix64((path << 32) | h.gid);
+          tbits_acc += (unsigned long long)__float_as_uint(h.t);
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&rd.qcount[(depth + 1) * T + t], (uint32_t)__popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (hit) qout[base + __popc(m & ((1u << lane) - 1u))] = l;
+    }
+  }
+  if (rd.flags & HRT_FLAG_SUMMARY) {
+    for (int o = 16; o; o >>= 1) {
+      hash_acc += __shfl_xor_sync(0xFFFFFFFFu, hash_acc, o);
+      tbits_acc += __shfl_xor_sync(0xFFFFFFFFu, tbits_acc, o);
+    }
+    if (lane == 0 && (hash_acc | tbits_acc)) {
+      atomicAdd((unsigned long long *)&rd.bounce[t * B + depth].hit_hash, hash_acc);
+      atomicAdd((unsigned long long *)&rd.bounce[t * B + depth].t_bits, tbits_acc);
+    }
+  }
+}
+
+/* Shared-memory reduction table of k_scatter: one record per receiver. */
+struct PairAcc {
+  unsigned long long hash, tau_bits;
+  double p_te, p_tm;
+  unsigned n_valid, n_occl;
+};
+
+/* Per-(hit, rx) scatter step (reference :670-723) for the rays that hit at
+ * `depth` (they are exactly the next queue).
+ *   WARP = true : one warp per hit, lanes across receivers in tiles of 32; the
+ *                 incidence-angle carry-over is an
+ *                 inclusive "last lane that hit" scan over ballot bits, carried
+ *                 from tile to tile.
+ *   WARP = false: one thread per hit, receivers in sequence (small num_rx). */
+template <bool SMEM, bool BRUTE, bool WARP>
+__global__ void __launch_bounds__(HRT_BLOCK)
+k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
+{
+  uint32_t used4 = 0;
+  if (SMEM) used4 = stage_scene(sc);
+  const uint32_t R = rd.R, T = rd.T, B = rd.B, t = blockIdx.y;
+  /* receivers (and, in summary mode, the reduction table) in shared memory */
+  float *s_rx = (float *)(hrt_smem4 + used4);
+  PairAcc *s_acc = (PairAcc *)(hrt_smem4 + used4 + (smem_rx_ok ? (3u * R + 3u) / 4u : 0u));
+  const bool summary = (rd.flags & HRT_FLAG_SUMMARY) != 0;
+  if (smem_rx_ok) {
+    for (uint32_t i = threadIdx.x; i < 3u * R; i += blockDim.x) s_rx[i] = rd.rx_pos[i];
+    if (summary)
+      for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) {
+        PairAcc z; z.hash = 0; z.tau_bits = 0; z.p_te = 0.0; z.p_tm = 0.0; z.n_valid = 0; z.n_occl = 0;
+        s_acc[i] = z;
+      }
+  }
+  if (SMEM || smem_rx_ok) __syncthreads();
+  const float *rxp = smem_rx_ok ? s_rx : rd.rx_pos;
+
+  const size_t np = rd.n_alloc;
+  const uint32_t cnt = rd.qcount[(depth + 1) * T + t];
+  const uint32_t *q = rd.queue[(depth + 1) & 1] + t * np;
+  const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
+  const Ray *rays = rd.rays + (rows ? (size_t)(depth + 1) * T * np : 0) + t * np;
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool dense = (rd.flags & HRT_FLAG_DENSE) != 0, trace = (rd.flags & HRT_FLAG_TRACE) != 0;
+
+  const uint32_t unit = WARP ? (blockIdx.x * blockDim.x + threadIdx.x) >> 5 : blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nunits = WARP ? (gridDim.x * blockDim.x) >> 5 : gridDim.x * blockDim.x;
+
+  for (uint32_t hi = unit; hi < cnt; hi += nunits) {
+    const uint32_t l = q[hi];
+    const size_t si = t * np + l;
+    const float2 *rp = (const float2 *)(rays + l);
+    const float2 a = rp[0], b = rp[1], c = rp[2];
+    HrtRayState s;
+    s.o = v3(a.x, a.y, b.x); s.d = v3(b.y, c.x, c.y);
+    const float4 g = rd.gain[si];
+    s.te_r = g.x; s.te_i = g.y; s.tm_r = g.z; s.tm_i = g.w;
+    s.tau = rd.tau[si];
+    const uint32_t slot = rd.hslot[si];
+    const V3 n = tri_normal<SMEM>(sc, slot);
+    const uint32_t gid = tri_gid_of<SMEM>(sc, slot);
+    const uint32_t mesh = sc.mesh_of[gid];
+    const HrtMaterial &mat = mats.m[sc.mesh_mat[mesh]];
+    const V3 mv = ld3(sc.mesh_vel, mesh);
+    float theta_carry = rd.theta[si];
+    const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+    const uint64_t hkey = hrt_mix64((path << 32) | gid);
+
+    const uint32_t step = WARP ? 32u : 1u;
+    for (uint32_t r0 = 0; r0 < R; r0 += step) {
+      const uint32_t r = WARP ? r0 + lane : r0;
+      const bool act = r < R;
+      float dist = 0.f, th_sh = 0.f;
+      V3 sd = v3(0.f, 0.f, 1.f);
+      HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
+      if (act) {
+        sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
+        h = query<SMEM, BRUTE>(sc, s.o, sd);                                   /* :682 */
+        if (h.gid != HRT_NONE) th_sh = hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), sd);
+      }
+      const bool shit = act && h.gid != HRT_NONE;
+      float theta_i;
+      if (WARP) {
+        /* theta handed to scat_coefs: the fold angle of the most recent shadow
+         * query (this receiver included) that hit anything, else the primary
+         * incidence angle (appendix A-4) */
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, shit);
+        const unsigned below = m & (0xFFFFFFFFu >> (31u - lane));
+        const int src = below ? 31 - __clz((int)below) : 0;
+        const float from = __shfl_sync(0xFFFFFFFFu, th_sh, src);
+        theta_i = below ? from : theta_carry;
+        if (m) theta_carry = __shfl_sync(0xFFFFFFFFu, th_sh, 31 - __clz((int)m));
+      } else {
+        if (shit) theta_carry = th_sh;
+        theta_i = theta_carry;
+      }
+      if (!act) continue;
+      const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;            /* :674 */
+      if (shit && h.t <= 1.f) {                                                /* :683-691 */
+        if (dense) {
+          rd.out_f[0][so] = 0.f; rd.out_f[1][so] = 0.f; rd.out_f[2][so] = 0.f;
+          rd.out_f[3][so] = 0.f; rd.out_f[4][so] = 0.f;
+        }
+        if (trace) rd.tr_state[so] = 2;
+        if (summary) {
+          if (smem_rx_ok) atomicAdd(&s_acc[r].n_occl, 1u);
+          else atomicAdd((unsigned long long *)&rd.pair[(r * T + t) * B + depth].n_occluded, 1ull);
+        }
+        continue;
+      }
+      const HrtScatterOut p = hrt_scatter_path(s, mat, rd.k, n, mv, sd, dist, theta_i); /* :694-721 */
+      if (dense) {
+        rd.out_f[0][so] = p.te_r; rd.out_f[1][so] = p.te_i;
+        rd.out_f[2][so] = p.tm_r; rd.out_f[3][so] = p.tm_i;
+        rd.out_f[4][so] = p.tau;
+        rd.out_f[5][so] = HRT_SUB(rd.out_f[5][so], p.dfreq);                   /* :722 */
+        rd.out_dir[3 * so] = p.dir_rx.x; rd.out_dir[3 * so + 1] = p.dir_rx.y;
+        rd.out_dir[3 * so + 2] = p.dir_rx.z;
+      }
+      if (trace) rd.tr_state[so] = 1;
+      if (summary) {
+        const double pte = (double)p.te_r * p.te_r + (double)p.te_i * p.te_i;
+        const double ptm = (double)p.tm_r * p.tm_r + (double)p.tm_i * p.tm_i;
+        if (smem_rx_ok) {
+          atomicAdd(&s_acc[r].n_valid, 1u);
+          atomicAdd(&s_acc[r].hash, (unsigned long long)hkey);
+          atomicAdd(&s_acc[r].tau_bits, (unsigned long long)__float_as_uint(p.tau));
+          atomicAdd(&s_acc[r].p_te, pte);
+          atomicAdd(&s_acc[r].p_tm, ptm);
+        } else {
+          HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+          atomicAdd((unsigned long long *)&ps->n_valid, 1ull);
+          atomicAdd((unsigned long long *)&ps->hit_hash, (unsigned long long)hkey);
+          atomicAdd((unsigned long long *)&ps->tau_bits, (unsigned long long)__float_as_uint(p.tau));
+          atomicAdd(&ps->power_te, pte);
+          atomicAdd(&ps->power_tm, ptm);
+        }
+      }
+    }
+  }
+  if (summary && smem_rx_ok) {
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
+      const PairAcc a = s_acc[r];
+      if (a.n_valid | a.n_occl) {
+        HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+        atomicAdd((unsigned long long *)&ps->n_valid, (unsigned long long)a.n_valid);
+        atomicAdd((unsigned long long *)&ps->n_occluded, (unsigned long long)a.n_occl);
+        atomicAdd((unsigned long long *)&ps->hit_hash, a.hash);
+        atomicAdd((unsigned long long *)&ps->tau_bits, a.tau_bits);
+        atomicAdd(&ps->power_te, a.p_te);
+        atomicAdd(&ps->power_tm, a.p_tm);
+      }
+    }
+  }
+}
+
+/* adds the per-depth queue sizes of a chunk into the bounce summary */
+__global__ void k_fold_counts(RunDev rd)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rd.T * rd.B) return;
+  const uint32_t t = k / rd.B, b = k % rd.B;
+  rd.bounce[k].n_traced += rd.qcount[b * rd.T + t];
+  rd.bounce[k].n_hit += rd.qcount[(b + 1) * rd.T + t];
+}
+
+__global__ void k_add_u64(unsigned long long *dst, const unsigned long long *src, size_t n, const unsigned char *is_double)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is_double && is_double[i]) ((double *)dst)[i] += ((const double *)src)[i];
+  else dst[i] += src[i];
+}
+
+/* batch closest hit for hrt_closest_hits() */
+template <bool SMEM, bool BRUTE>
+__global__ void k_closest(SceneDev sc, const Ray *rays, uint32_t n, uint32_t *tri, float *t, float *theta)
+{
+  if (SMEM) { stage_scene(sc); __syncthreads(); }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float2 *rp = (const float2 *)(rays + i);
+    const float2 a = rp[0], b = rp[1], c = rp[2];
+    const V3 o = v3(a.x, a.y, b.x), d = v3(b.y, c.x, c.y);
+    const HrtHit h = query<SMEM, BRUTE>(sc, o, d);
+    const bool hit = h.gid != HRT_NONE;
+    tri[i] = h.gid; t[i] = hit ? h.t : -1.f;
+    theta[i] = hit ? hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), d) : 0.f;
+  }
+}
+
+/* ------------------------------------------------------------------- API */
+
+extern "C" int hrt_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char *hrt_last_error(const hrt_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+extern "C" int hrt_ctx_create(int device, hrt_ctx **out)
+{
+  hrt_ctx *ctx = nullptr;
+  if (!out) return HRT_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, HRT_E_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(nullptr, HRT_E_ARG, "device %d out of range (0..%d)", device, n - 1);
+  hrt_ctx *c = (hrt_ctx *)calloc(1, sizeof(hrt_ctx));
+  if (!c) return fail(nullptr, HRT_E_NOMEM, "out of host memory");
+  c->device = device;
+  c->leaf_max = 4;
+  c->pad_ulps = 64.f;
+  if (const char *s = getenv("HRT_LEAF_MAX")) { int v = atoi(s); if (v >= 1 && v <= HRT_LEAF_MAX_CAP) c->leaf_max = v; }
+  if (const char *s = getenv("HRT_BVH_PAD_ULPS")) { float v = strtof(s, nullptr); if (v >= 1.f) c->pad_ulps = v; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    fail(nullptr, HRT_E_CUDA, "cannot initialise device %d: %s", device, cudaGetErrorString(e));
+    free(c); return HRT_E_CUDA;
+  }
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+  *out = c;
+  (void)ctx;
+  return HRT_OK;
+}
+
+static void free_scene_dev(hrt_ctx *c)
+{
+  dev_free(c->d_tris); dev_free(c->d_tri_gid); dev_free(c->d_mesh_of); dev_free(c->d_mesh_mat);
+  dev_free(c->d_mesh_vel); dev_free(c->d_nodes); dev_free(c->d_kl); dev_free(c->d_kr);
+  dev_free(c->d_kfirst); dev_free(c->d_klast); dev_free(c->d_newidx); dev_free(c->d_box);
+  c->have_scene = false;
+}
+
+static void free_run_dev(hrt_ctx *c)
+{
+  RunDev &r = c->rd;
+  dev_free(r.dirs); dev_free(r.rays); dev_free(r.gain); dev_free(r.tau); dev_free(r.theta);
+  dev_free(r.hslot); dev_free(r.dead_at); dev_free(r.queue[0]); dev_free(r.queue[1]);
+  dev_free(r.qcount);
+  for (int k = 0; k < 6; ++k) dev_free(r.out_f[k]);
+  dev_free(r.out_dir); dev_free(r.tr_hit); dev_free(r.tr_t); dev_free(r.tr_state);
+  dev_free(r.pair); dev_free(r.bounce); dev_free(r.amb_list); dev_free(r.amb_count);
+  dev_free(r.counters);
+  c->cap_n = 0;
+}
+
+extern "C" void hrt_ctx_destroy(hrt_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_scene_dev(c); free_run_dev(c);
+  dev_free(c->d_pos);
+  if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->stream);
+  free(c);
+}
+
+static inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+/* (re)emit traversal nodes with the given padding */
+static int emit_nodes(hrt_ctx *ctx, float pad)
+{
+  const int n = (int)ctx->num_tris;
+  ctx->pad = pad;
+  if (ctx->num_nodes == 0) return HRT_OK;
+  k_emit<<<nblk(n - 1), 256, 0, ctx->stream>>>(n, ctx->d_kl, ctx->d_kr, ctx->d_kfirst, ctx->d_klast,
+                                               ctx->d_newidx + n /* used flags live behind newidx */,
+                                               ctx->d_newidx, ctx->d_box, ctx->leaf_max, pad, ctx->d_nodes);
+  CK(cudaGetLastError());
+  return HRT_OK;
+}
+
+extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_out)
+{
+  if (!ctx || !scene || !scene->meshes || scene->num_meshes == 0) return fail(ctx, HRT_E_ARG, "scene is empty");
+  CK(cudaSetDevice(ctx->device));
+  free_scene_dev(ctx);
+
+  /* host: concatenate vertices / indices (indices rebased), validate */
+  size_t nv = 0, nt = 0;
+  for (uint32_t m = 0; m < scene->num_meshes; ++m) { nv += scene->meshes[m].num_vertices; nt += scene->meshes[m].num_triangles; }
+  if (nt >= (1u << 28)) return fail(ctx, HRT_E_ARG, "too many triangles (%zu)", nt);
+  const uint32_t M = scene->num_meshes;
+  float *h_v = (float *)malloc((nv ? nv : 1) * 12);
+  uint32_t *h_i = (uint32_t *)malloc((nt ? nt : 1) * 12);
+  uint32_t *h_mesh_of = (uint32_t *)malloc((nt ? nt : 1) * 4);
+  uint32_t *h_mat = (uint32_t *)malloc(M * 4);
+  float *h_vel = (float *)malloc(M * 12);
+  if (!h_v || !h_i || !h_mesh_of || !h_mat || !h_vel) { free(h_v); free(h_i); free(h_mesh_of); free(h_mat); free(h_vel); return fail(ctx, HRT_E_NOMEM, "out of host memory"); }
+  size_t vo = 0, to = 0; float max_abs = 0.f; int bad = 0;
+  for (uint32_t m = 0; m < M && !bad; ++m) {
+    const Mesh *me = &scene->meshes[m];
+    if (me->material_index >= NUM_G_MATERIALS) { bad = 1; break; }
+    memcpy(h_v + 3 * vo, me->vs, (size_t)me->num_vertices * 12);
+    for (size_t k = 0; k < (size_t)3 * me->num_vertices; ++k) { const float a = fabsf(h_v[3 * vo + k]); if (a > max_abs) max_abs = a; if (!(a == a)) bad = 2; }
+    for (size_t k = 0; k < (size_t)3 * me->num_triangles; ++k) {
+      const uint32_t ix = me->is[k];
+      if (ix >= me->num_vertices) { bad = 3; break; }
+      h_i[3 * to + k] = ix + (uint32_t)vo;
+    }
+    for (uint32_t f = 0; f < me->num_triangles; ++f) h_mesh_of[to + f] = m;
+    h_mat[m] = me->material_index;
+    h_vel[3 * m] = me->velocity.x; h_vel[3 * m + 1] = me->velocity.y; h_vel[3 * m + 2] = me->velocity.z;
+    vo += me->num_vertices; to += me->num_triangles;
+  }
+  if (bad) {
+    free(h_v); free(h_i); free(h_mesh_of); free(h_mat); free(h_vel);
+    return fail(ctx, HRT_E_ARG, bad == 1 ? "material index out of range" : bad == 2 ? "NaN vertex" : "vertex index out of range");
+  }
+
+  const uint32_t n = (uint32_t)nt;
+  ctx->num_tris = n; ctx->num_meshes = M; ctx->scene_max_abs = max_abs;
+  float *d_v = nullptr; uint32_t *d_i = nullptr; float4 *d_recs = nullptr; float *d_boxes = nullptr;
+  unsigned *d_bounds = nullptr; uint64_t *d_keys = nullptr, *d_keys2 = nullptr; int *d_parent = nullptr;
+  unsigned *d_arrive = nullptr; void *d_tmp = nullptr; size_t tmp_bytes = 0;
+  int rc = HRT_OK;
+#define CKG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
+  {
+    cudaStream_t st = ctx->stream;
+    CKG(dev_alloc(&d_v, nv * 3)); CKG(dev_alloc(&d_i, (size_t)n * 3));
+    CKG(dev_alloc(&d_recs, (size_t)n * 3)); CKG(dev_alloc(&d_boxes, (size_t)n * 6));
+    CKG(dev_alloc(&d_bounds, 6)); CKG(dev_alloc(&d_keys, n)); CKG(dev_alloc(&d_keys2, n));
+    CKG(dev_alloc(&ctx->d_tris, (size_t)n * 3)); CKG(dev_alloc(&ctx->d_tri_gid, n));
+    CKG(dev_alloc(&ctx->d_mesh_of, n)); CKG(dev_alloc(&ctx->d_mesh_mat, M)); CKG(dev_alloc(&ctx->d_mesh_vel, (size_t)M * 3));
+    const size_t nn = n > 1 ? n - 1 : 1;
+    CKG(dev_alloc(&ctx->d_kl, nn)); CKG(dev_alloc(&ctx->d_kr, nn)); CKG(dev_alloc(&ctx->d_kfirst, nn));
+    CKG(dev_alloc(&ctx->d_klast, nn)); CKG(dev_alloc(&ctx->d_newidx, 2 * (size_t)n + 2));
+    CKG(dev_alloc(&ctx->d_box, (2 * (size_t)n) * 6)); CKG(dev_alloc(&d_parent, 2 * (size_t)n));
+    CKG(dev_alloc(&d_arrive, nn));
+    CKG(cudaMemcpyAsync(d_v, h_v, nv * 12, cudaMemcpyHostToDevice, st));
+    CKG(cudaMemcpyAsync(d_i, h_i, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CKG(cudaMemcpyAsync(ctx->d_mesh_of, h_mesh_of, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CKG(cudaMemcpyAsync(ctx->d_mesh_mat, h_mat, (size_t)M * 4, cudaMemcpyHostToDevice, st));
+    CKG(cudaMemcpyAsync(ctx->d_mesh_vel, h_vel, (size_t)M * 12, cudaMemcpyHostToDevice, st));
+    const unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+    CKG(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
+    ctx->num_nodes = 0; ctx->root_ref = 0;
+    if (n > 0) {
+      k_tri_setup<<<nblk(n), 256, 0, st>>>(d_v, d_i, n, d_recs, d_boxes, d_bounds);
+      k_morton<<<nblk(n), 256, 0, st>>>(d_boxes, n, d_bounds, d_keys);
+      CKG(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, (int)n, 0, 64, st));
+      CKG(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+      CKG(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys2, (int)n, 0, 64, st));
+      k_gather<<<nblk(n), 256, 0, st>>>(d_keys2, n, d_recs, d_boxes, ctx->d_tris, ctx->d_tri_gid, ctx->d_box);
+      CKG(cudaGetLastError());
+      if ((int)n <= ctx->leaf_max) {
+        ctx->root_ref = hrt_leaf_ref(0u, n);
+      } else {
+        int *d_used = ctx->d_newidx + n;
+        CKG(cudaMemsetAsync(d_arrive, 0, nn * sizeof(unsigned), st));
+        k_karras<<<nblk(n - 1), 256, 0, st>>>(d_keys2, (int)n, ctx->d_kl, ctx->d_kr, ctx->d_kfirst, ctx->d_klast, d_parent);
+        k_refit<<<nblk(n), 256, 0, st>>>((int)n, ctx->d_kl, ctx->d_kr, d_parent, ctx->d_box, d_arrive);
+        k_mark<<<nblk(n - 1), 256, 0, st>>>((int)n, ctx->d_kfirst, ctx->d_klast, ctx->leaf_max, d_used);
+        CKG(cudaGetLastError());
+        void *d_tmp2 = nullptr; size_t tb2 = 0;
+        CKG(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_used, ctx->d_newidx, (int)n, st));
+        CKG(cudaMalloc(&d_tmp2, tb2 ? tb2 : 1));
+        cudaError_t es = cub::DeviceScan::ExclusiveSum(d_tmp2, tb2, d_used, ctx->d_newidx, (int)n, st);
+        int last_idx = 0, last_used = 0;
+        if (es == cudaSuccess) es = cudaMemcpyAsync(&last_idx, ctx->d_newidx + (n - 2), 4, cudaMemcpyDeviceToHost, st);
+        if (es == cudaSuccess) es = cudaMemcpyAsync(&last_used, d_used + (n - 2), 4, cudaMemcpyDeviceToHost, st);
+        if (es == cudaSuccess) es = cudaStreamSynchronize(st);
+        cudaFree(d_tmp2);
+        CKG(es);
+        ctx->num_nodes = (uint32_t)(last_idx + last_used);
+        ctx->root_ref = 0;
+        CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4));
+      }
+    }
+    ctx->pad = hrt_box_pad(max_abs, ctx->pad_ulps);
+    if (ctx->num_nodes) {
+      int erc = emit_nodes(ctx, ctx->pad);
+      if (erc) { rc = erc; goto done; }
+    }
+    if (normals_out && n) {
+      float4 *h_recs = (float4 *)malloc((size_t)n * 48);
+      if (!h_recs) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto done; }
+      cudaError_t e2 = cudaMemcpyAsync(h_recs, d_recs, (size_t)n * 48, cudaMemcpyDeviceToHost, st);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+      if (e2 == cudaSuccess)
+        for (uint32_t g = 0; g < n; ++g) { normals_out[g].x = h_recs[3 * g + 2].y; normals_out[g].y = h_recs[3 * g + 2].z; normals_out[g].z = h_recs[3 * g + 2].w; }
+      free(h_recs);
+      CKG(e2);
+    }
+    CKG(cudaStreamSynchronize(st));
+    ctx->have_scene = true;
+  }
+done:
+#undef CKG
+  cudaFree(d_v); cudaFree(d_i); cudaFree(d_recs); cudaFree(d_boxes); cudaFree(d_bounds);
+  cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_parent); cudaFree(d_arrive); cudaFree(d_tmp);
+  free(h_v); free(h_i); free(h_mesh_of); free(h_mat); free(h_vel);
+  if (rc) free_scene_dev(ctx);
+  return rc;
+}
+
+extern "C" int hrt_materials_set(hrt_ctx *ctx, const HrtMaterialDerived table[NUM_G_MATERIALS])
+{
+  if (!ctx || !table) return HRT_E_ARG;
+  memcpy(&ctx->mats, table, sizeof ctx->mats);
+  ctx->have_mats = true;
+  return HRT_OK;
+}
+
+extern "C" int hrt_get_stats(const hrt_ctx *ctx, HrtRunStats *out)
+{
+  if (!ctx || !out) return HRT_E_ARG;
+  *out = ctx->stats;
+  return HRT_OK;
+}
+
+static SceneDev scene_dev(const hrt_ctx *c)
+{
+  SceneDev s;
+  s.nodes = c->d_nodes; s.tris = c->d_tris; s.tri_gid = c->d_tri_gid; s.mesh_of = c->d_mesh_of;
+  s.mesh_mat = c->d_mesh_mat; s.mesh_vel = c->d_mesh_vel;
+  s.num_tris = c->num_tris; s.num_nodes = c->num_nodes; s.root_ref = c->root_ref;
+  return s;
+}
+
+/* make sure boxes are padded for ray origins as far out as max_abs */
+static int ensure_pad(hrt_ctx *ctx, float max_abs)
+{
+  const float need = hrt_box_pad(fmaxf(max_abs, ctx->scene_max_abs), ctx->pad_ulps);
+  if (need > ctx->pad) return emit_nodes(ctx, need);
+  return HRT_OK;
+}
+
+/* kernel dispatch over the <SMEM, BRUTE> variants */
+#define DISPATCH2(KERNEL, smem, brute, grid, block, shbytes, st, ...)                         \
+  do {                                                                                        \
+    if (smem) { if (brute) KERNEL<true, true><<<grid, block, shbytes, st>>>(__VA_ARGS__);     \
+                else       KERNEL<true, false><<<grid, block, shbytes, st>>>(__VA_ARGS__); }  \
+    else      { if (brute) KERNEL<false, true><<<grid, block, shbytes, st>>>(__VA_ARGS__);    \
+                else       KERNEL<false, false><<<grid, block, shbytes, st>>>(__VA_ARGS__); } \
+  } while (0)
+
+template <class K> static cudaError_t allow_smem(K kernel, size_t bytes)
+{
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int sm_count(int device)
+{
+  int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device); return v;
+}
+
+extern "C" int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_t flags,
+                                uint32_t *tri, float *t, float *theta)
+{
+  if (!ctx || !ctx->have_scene) return fail(ctx, HRT_E_STATE, "no scene uploaded");
+  if (!n) return HRT_OK;
+  CK(cudaSetDevice(ctx->device));
+  float max_abs = 0.f;
+  for (size_t i = 0; i < n; ++i) { max_abs = fmaxf(max_abs, fmaxf(fabsf(rays[i].o.x), fmaxf(fabsf(rays[i].o.y), fabsf(rays[i].o.z)))); }
+  int rc = ensure_pad(ctx, max_abs); if (rc) return rc;
+  Ray *d_r = nullptr; uint32_t *d_tri = nullptr; float *d_t = nullptr, *d_th = nullptr;
+  cudaStream_t st = ctx->stream;
+  CK(dev_alloc(&d_r, n)); CK(dev_alloc(&d_tri, n)); CK(dev_alloc(&d_t, n)); CK(dev_alloc(&d_th, n));
+  CK(cudaMemcpyAsync(d_r, rays, n * sizeof(Ray), cudaMemcpyHostToDevice, st));
+  const size_t sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris);
+  const bool smem = sb <= HRT_SMEM_SCENE_LIMIT, brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
+  const SceneDev sc = scene_dev(ctx);
+  const unsigned grid = (unsigned)min((size_t)sm_count(ctx->device) * 8, (n + HRT_BLOCK - 1) / HRT_BLOCK);
+  if (smem) {
+    CK(allow_smem(k_closest<true, true>, sb)); CK(allow_smem(k_closest<true, false>, sb));
+  }
+  DISPATCH2(k_closest, smem, brute, grid, HRT_BLOCK, smem ? sb : 0, st, sc, d_r, (uint32_t)n, d_tri, d_t, d_th);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(tri, d_tri, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(theta, d_th, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_r); cudaFree(d_tri); cudaFree(d_t); cudaFree(d_th);
+  return HRT_OK;
+}
+
+/* ---- run buffers ---- */
+
+static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t B, uint32_t flags)
+{
+  const uint32_t shape_flags = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_SUMMARY | HRT_FLAG_TRACE);
+  if (ctx->cap_n >= n && ctx->cap_R == R && ctx->cap_T == T && ctx->cap_B == B && ctx->cap_flags == shape_flags)
+    return HRT_OK;
+  free_run_dev(ctx);
+  RunDev &r = ctx->rd;
+  const size_t TN = T * n, rows = (flags & HRT_FLAG_RAYSINFO) ? B + 1 : 1;
+  CK(dev_alloc(&r.dirs, n * 3)); CK(dev_alloc(&r.rays, rows * TN)); CK(dev_alloc(&r.gain, TN));
+  CK(dev_alloc(&r.tau, TN)); CK(dev_alloc(&r.theta, TN)); CK(dev_alloc(&r.hslot, TN));
+  CK(dev_alloc(&r.dead_at, TN)); CK(dev_alloc(&r.queue[0], TN)); CK(dev_alloc(&r.queue[1], TN));
+  CK(dev_alloc(&r.qcount, (B + 1) * T));
+  CK(dev_alloc(&r.amb_list, HRT_AMB_CAP)); CK(dev_alloc(&r.amb_count, 1));
+  CK(dev_alloc(&r.counters, 16));
+  const size_t slots = R * T * B * n;
+  if (flags & HRT_FLAG_DENSE) {
+    for (int k = 0; k < 6; ++k) CK(dev_alloc(&r.out_f[k], slots));
+    CK(dev_alloc(&r.out_dir, slots * 3));
+  }
+  if (flags & HRT_FLAG_TRACE) {
+    CK(dev_alloc(&r.tr_hit, T * B * n)); CK(dev_alloc(&r.tr_t, T * B * n)); CK(dev_alloc(&r.tr_state, slots));
+  }
+  CK(dev_alloc(&r.pair, R * T * B)); CK(dev_alloc(&r.bounce, T * B));
+  ctx->cap_n = n; ctx->cap_R = R; ctx->cap_T = T; ctx->cap_B = B; ctx->cap_flags = shape_flags;
+  return HRT_OK;
+}
+
+/* number of paths of [0, P) owned by this shard */
+static uint64_t shard_count(uint64_t P, uint32_t rank, uint32_t world, uint64_t blk)
+{
+  if (world <= 1) return P;
+  const uint64_t nblocks = (P + blk - 1) / blk;
+  uint64_t mine = nblocks / world + ((nblocks % world) > rank ? 1 : 0);
+  if (mine == 0) return 0;
+  uint64_t cnt = mine * blk;
+  /* the globally last block may be partial */
+  if ((nblocks - 1) % world == rank) cnt -= nblocks * blk - P;
+  return cnt;
+}
+
+/* copy device rows [nrows][n_alloc] (elem bytes) into host rows of pitch P at
+ * the columns of the chunk's paths */
+static cudaError_t d2h_columns(const hrt_ctx *ctx, cudaStream_t st, void *host, const void *dev, size_t elem,
+                               size_t nrows, const RunDev &rd)
+{
+  if (!host) return cudaSuccess;
+  (void)ctx;
+  uint64_t L = 0;
+  while (L < rd.n) {
+    /* contiguous run inside one shard block */
+    uint64_t run = rd.n - L;
+    if (rd.world > 1) { const uint64_t in_blk = (rd.l0 + L) % rd.blk; run = (rd.blk - in_blk < run) ? rd.blk - in_blk : run; }
+    const uint64_t g = hrt_gpath(rd.l0 + L, rd.rank, rd.world, rd.blk);
+    cudaError_t e = cudaMemcpy2DAsync((char *)host + g * elem, rd.P * elem, (const char *)dev + L * elem,
+                                      (size_t)rd.n_alloc * elem, run * elem, nrows, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    L += run;
+  }
+  return cudaSuccess;
+}
+
+extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
+{
+  if (!ctx || !p) return HRT_E_ARG;
+  if (!ctx->have_scene) return fail(ctx, HRT_E_STATE, "hrt_run before hrt_scene_upload");
+  if (!ctx->have_mats) return fail(ctx, HRT_E_STATE, "hrt_run before hrt_materials_set");
+  const size_t R = p->num_rx, T = p->num_tx, B = p->num_bounces;
+  const uint64_t P = p->num_paths;
+  if (!R || !T || !B || !P || !(p->carrier_frequency_GHz > 0.f)) return fail(ctx, HRT_E_ARG, "num_rx, num_tx, num_paths, num_bounces and the carrier frequency must be > 0");
+  if (B > 254 || T > 65535 || R > (1u << 20)) return fail(ctx, HRT_E_ARG, "num_bounces <= 254, num_tx <= 65535, num_rx <= 2^20");
+  if (!p->rx_pos || !p->tx_pos || !p->rx_vel || !p->tx_vel) return fail(ctx, HRT_E_ARG, "NULL position/velocity array");
+  uint32_t flags = p->flags;
+  if ((flags & HRT_FLAG_RAYSINFO) && !(flags & HRT_FLAG_DENSE)) return fail(ctx, HRT_E_ARG, "RAYSINFO needs DENSE");
+  if ((flags & HRT_FLAG_DENSE) && !p->scat) return fail(ctx, HRT_E_ARG, "DENSE needs scat outputs");
+  if ((flags & HRT_FLAG_RAYSINFO) && !p->rays_scat) flags &= ~HRT_FLAG_RAYSINFO;
+  if ((flags & HRT_FLAG_SUMMARY) && (!p->pair_summary || !p->bounce_summary)) return fail(ctx, HRT_E_ARG, "SUMMARY needs both summary arrays");
+  if ((flags & HRT_FLAG_HOST_DIRS) && !p->dirs) return fail(ctx, HRT_E_ARG, "HOST_DIRS needs dirs");
+  const uint32_t world = p->shard_world ? p->shard_world : 1, rank = p->shard_rank;
+  uint64_t blk = p->shard_block ? p->shard_block : (1u << 20);
+  if (world > 1 && (rank >= world || (blk % 32))) return fail(ctx, HRT_E_ARG, "bad shard (rank %u of %u, block %llu must be a multiple of 32)", rank, world, (unsigned long long)blk);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = p->stream ? (cudaStream_t)p->stream : ctx->stream;
+
+  /* positions -> device; padding must cover every ray origin */
+  float max_abs = 0.f;
+  for (size_t i = 0; i < R; ++i) max_abs = fmaxf(max_abs, fmaxf(fabsf(p->rx_pos[i].x), fmaxf(fabsf(p->rx_pos[i].y), fabsf(p->rx_pos[i].z))));
+  for (size_t i = 0; i < T; ++i) max_abs = fmaxf(max_abs, fmaxf(fabsf(p->tx_pos[i].x), fmaxf(fabsf(p->tx_pos[i].y), fabsf(p->tx_pos[i].z))));
+  if (!(max_abs < 1e30f)) return fail(ctx, HRT_E_ARG, "non-finite position");
+  int rc = ensure_pad(ctx, max_abs); if (rc) return rc;
+  const size_t npos = 6 * (R + T);
+  if (ctx->cap_pos < npos) { dev_free(ctx->d_pos); CK(dev_alloc(&ctx->d_pos, npos)); ctx->cap_pos = npos; }
+  float *d_rx = ctx->d_pos, *d_tx = d_rx + 3 * R, *d_rxv = d_tx + 3 * T, *d_txv = d_rxv + 3 * R;
+  CK(cudaMemcpyAsync(d_rx, p->rx_pos, R * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_tx, p->tx_pos, T * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_rxv, p->rx_vel, R * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_txv, p->tx_vel, T * 12, cudaMemcpyHostToDevice, st));
+
+  /* chunking of this shard's paths */
+  const uint64_t n_shard = shard_count(P, rank, world, blk);
+  size_t chunk = 1u << 23;
+  if (const char *s = getenv("HRT_CHUNK")) { long long v = atoll(s); if (v >= 32) chunk = (size_t)v; }
+  if (flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE)) {
+    /* bound the dense staging buffers to ~6 GB */
+    const size_t per_path = R * T * B * 40 + T * (B + 1) * 24 + 64 * T;
+    const size_t lim = (size_t)6e9 / per_path;
+    if (chunk > lim) chunk = lim < 32 ? 32 : lim;
+  }
+  if (world > 1) { chunk = (chunk / blk) * blk; if (chunk == 0) chunk = blk; }
+  else chunk &= ~(size_t)31;
+  if (chunk > n_shard) chunk = n_shard ? n_shard : 32;
+  rc = ensure_run_buffers(ctx, chunk, R, T, B, flags); if (rc) return rc;
+
+  RunDev rd = ctx->rd;
+  rd.R = (uint32_t)R; rd.T = (uint32_t)T; rd.B = (uint32_t)B; rd.P = P;
+  rd.n_alloc = (uint32_t)ctx->cap_n; rd.rank = rank; rd.world = world; rd.blk = blk;
+  rd.rx_pos = d_rx; rd.tx_pos = d_tx; rd.rx_vel = d_rxv; rd.tx_vel = d_txv;
+  rd.flags = flags;
+  const float f_hz = (float)((double)p->carrier_frequency_GHz * 1e9);          /* reference :483 */
+  rd.k.fsl_k = 4.f * HRT_PI * f_hz / HRT_C0;                                   /* reference :484 */
+  rd.k.dop_k = f_hz / HRT_C0;                                                  /* reference :488 */
+
+  HrtRunStats &S = ctx->stats;
+  memset(&S, 0, sizeof S);
+  S.num_tris = ctx->num_tris; S.num_nodes = ctx->num_nodes; S.box_pad = ctx->pad;
+  const SceneDev sc = scene_dev(ctx);
+  const size_t scene_sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris);
+  const bool smem = scene_sb <= HRT_SMEM_SCENE_LIMIT;
+  const bool brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
+  S.scene_in_smem = smem;
+  const int sms = sm_count(ctx->device);
+
+  /* scatter kernel shared memory: scene + receivers + reduction table */
+  const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
+  const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 160 * 1024;
+  const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
+  const bool warp_mode = R >= 8;
+  if (smem) {
+    CK(allow_smem(k_bounce<true, true>, scene_sb)); CK(allow_smem(k_bounce<true, false>, scene_sb));
+    CK(allow_smem(k_los<true, true>, scene_sb)); CK(allow_smem(k_los<true, false>, scene_sb));
+  }
+  CK(allow_smem(k_scatter<true, true, true>, scat_sb)); CK(allow_smem(k_scatter<true, false, true>, scat_sb));
+  CK(allow_smem(k_scatter<true, true, false>, scat_sb)); CK(allow_smem(k_scatter<true, false, false>, scat_sb));
+  CK(allow_smem(k_scatter<false, true, true>, scat_sb)); CK(allow_smem(k_scatter<false, false, true>, scat_sb));
+  CK(allow_smem(k_scatter<false, true, false>, scat_sb)); CK(allow_smem(k_scatter<false, false, false>, scat_sb));
+
+  CK(cudaEventRecord(ctx->ev[0], st));
+
+  /* ---- line of sight (rank 0 of the shard group only) ---- */
+  if (p->los && rank == 0) {
+    const size_t npair = R * T;
+    if (ctx->cap_los < npair) { if (ctx->d_los) cudaFree(ctx->d_los); CK(cudaMalloc(&ctx->d_los, npair * sizeof(HrtLosOut))); ctx->cap_los = npair; }
+    DISPATCH2(k_los, smem, brute, nblk(npair, HRT_BLOCK), HRT_BLOCK, smem ? scene_sb : 0, st, rd, sc, (HrtLosOut *)ctx->d_los);
+    CK(cudaGetLastError());
+    S.kernel_launches++; S.los_queries = npair;
+    HrtLosOut *h = (HrtLosOut *)malloc(npair * sizeof(HrtLosOut));
+    if (!h) return fail(ctx, HRT_E_NOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(h, ctx->d_los, npair * sizeof(HrtLosOut), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { free(h); CK(e); }
+    ChannelInfo *L = p->los;
+    for (size_t k = 0; k < npair; ++k) {
+      const size_t r = k / T, t = k % T;
+      L->a_te_im[k] = L->a_tm_im[k] = 0.f;                                     /* reference :515-516 */
+      if (p->rays_los && p->rays_los->rays) {                                  /* reference :526-528 */
+        Ray *lr = &p->rays_los->rays[k];
+        lr->o = p->tx_pos[t];
+        lr->d = vec3_sub(&p->rx_pos[r], &lr->o);
+      }
+      uint8_t *bits = (p->rays_los && p->rays_los->rays_active) ? p->rays_los->rays_active : nullptr;
+      if (h[k].state == 0) {                                                   /* blocked, reference :548-554 */
+        L->a_te_re[k] = L->a_tm_re[k] = L->tau[k] = 0.f;
+        if (bits) bits[k / 8] &= (uint8_t)~(1u << (k % 8));
+        continue;
+      }
+      L->directions_tx[k].x = h[k].dir_tx.x; L->directions_tx[k].y = h[k].dir_tx.y; L->directions_tx[k].z = h[k].dir_tx.z;
+      L->directions_rx[k].x = h[k].dir_rx.x; L->directions_rx[k].y = h[k].dir_rx.y; L->directions_rx[k].z = h[k].dir_rx.z;
+      L->a_te_re[k] = L->a_tm_re[k] = h[k].a;
+      L->tau[k] = h[k].tau;
+      L->freq_shift[k] = h[k].freq;
+      if (bits) bits[k / 8] |= (uint8_t)(1u << (k % 8));
+    }
+    free(h);
+  }
+  CK(cudaEventRecord(ctx->ev[1], st));
+
+  if (flags & HRT_FLAG_SUMMARY) {
+    CK(cudaMemsetAsync(rd.pair, 0, R * T * B * sizeof(HrtPairSummary), st));
+    CK(cudaMemsetAsync(rd.bounce, 0, T * B * sizeof(HrtBounceSummary), st));
+  }
+
+  uint32_t *h_counts = (uint32_t *)malloc((B + 1) * T * 4);
+  uint8_t *h_dead = nullptr;
+  if (flags & HRT_FLAG_RAYSINFO) h_dead = (uint8_t *)malloc(T * ctx->cap_n);
+  if (!h_counts || ((flags & HRT_FLAG_RAYSINFO) && !h_dead)) { free(h_counts); free(h_dead); return fail(ctx, HRT_E_NOMEM, "out of host memory"); }
+  float ms_bounce = 0.f, ms_scatter = 0.f;
+  const bool time_kernels = getenv("HRT_TIME_KERNELS") != nullptr;
+  rc = HRT_OK;
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto run_done; } } while (0)
+
+  for (uint64_t l0 = 0; l0 < n_shard; l0 += chunk) {
+    rd.l0 = l0;
+    rd.n = (uint32_t)((n_shard - l0 < chunk) ? n_shard - l0 : chunk);
+    const unsigned g1 = (unsigned)min((size_t)sms * 16, ((size_t)rd.n + 255) / 256);
+
+    /* launch directions */
+    if (flags & HRT_FLAG_HOST_DIRS) {
+      uint64_t L = 0;
+      while (L < rd.n) {
+        uint64_t run = rd.n - L;
+        if (world > 1) { const uint64_t in_blk = (l0 + L) % blk; run = (blk - in_blk < run) ? blk - in_blk : run; }
+        const uint64_t g = hrt_gpath(l0 + L, rank, world, blk);
+        CKR(cudaMemcpyAsync(rd.dirs + 3 * L, p->dirs + g, run * 12, cudaMemcpyHostToDevice, st));
+        L += run;
+      }
+    } else {
+      CKR(cudaMemsetAsync(rd.amb_count, 0, 4, st));
+      k_raygen<<<g1, 256, 0, st>>>(rd);
+      CKR(cudaGetLastError());
+      S.kernel_launches++;
+      uint32_t namb = 0;
+      CKR(cudaMemcpyAsync(&namb, rd.amb_count, 4, cudaMemcpyDeviceToHost, st));
+      CKR(cudaStreamSynchronize(st));
+      if (namb) {
+        /* recompute the flagged directions with the host libm (see hrt_launch_dir) */
+        if (namb > HRT_AMB_CAP) { rc = fail(ctx, HRT_E_STATE, "ambiguous-direction list overflow (%u)", namb); goto run_done; }
+        uint32_t *idx = (uint32_t *)malloc(namb * 4);
+        if (!idx) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
+        cudaError_t e = cudaMemcpyAsync(idx, rd.amb_list, namb * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        for (uint32_t k = 0; k < namb && e == cudaSuccess; ++k) {
+          float d[3];
+          hrt_host_launch_dir(hrt_gpath(l0 + idx[k], rank, world, blk), P, d);
+          e = cudaMemcpyAsync(rd.dirs + 3 * (size_t)idx[k], d, 12, cudaMemcpyHostToDevice, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);   /* d is a stack temporary */
+        }
+        free(idx);
+        CKR(e);
+        S.ambiguous_dirs += namb;
+      }
+    }
+
+    CKR(cudaMemsetAsync(rd.qcount, 0, (B + 1) * T * 4, st));
+    k_init<<<g1, 256, 0, st>>>(rd);
+    CKR(cudaGetLastError());
+    S.kernel_launches++;
+
+    for (uint32_t b = 0; b < B; ++b) {
+      if (flags & HRT_FLAG_RAYSINFO)
+        CKR(cudaMemcpyAsync(rd.rays + (size_t)(b + 1) * T * rd.n_alloc, rd.rays + (size_t)b * T * rd.n_alloc,
+                            T * (size_t)rd.n_alloc * sizeof(Ray), cudaMemcpyDeviceToDevice, st));
+      /* persistent grids: enough blocks to fill the machine, grid-stride inside */
+      const dim3 gb((unsigned)min((size_t)((sms * 8 + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      if (time_kernels) CKR(cudaEventRecord(ctx->ev[4], st));
+      DISPATCH2(k_bounce, smem, brute, gb, HRT_BLOCK, smem ? scene_sb : 0, st, rd, sc, ctx->mats, b);
+      CKR(cudaGetLastError());
+      if (time_kernels) CKR(cudaEventRecord(ctx->ev[5], st));
+      const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
+      const dim3 gs((unsigned)min((size_t)((sms * 8 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      if (warp_mode) {
+        if (smem) { if (brute) k_scatter<true, true, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+                    else       k_scatter<true, false, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
+        else      { if (brute) k_scatter<false, true, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+                    else       k_scatter<false, false, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
+      } else {
+        if (smem) { if (brute) k_scatter<true, true, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+                    else       k_scatter<true, false, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
+        else      { if (brute) k_scatter<false, true, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+                    else       k_scatter<false, false, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
+      }
+      CKR(cudaGetLastError());
+      S.kernel_launches += 2;
+      if (time_kernels) {
+        CKR(cudaEventRecord(ctx->ev[6], st));
+        CKR(cudaEventSynchronize(ctx->ev[6]));
+        float a = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]); cudaEventElapsedTime(&c, ctx->ev[5], ctx->ev[6]);
+        ms_bounce += a; ms_scatter += c;
+      }
+    }
+
+    if (flags & HRT_FLAG_SUMMARY) {
+      k_fold_counts<<<nblk(T * B, 128), 128, 0, st>>>(rd);
+      CKR(cudaGetLastError());
+      S.kernel_launches++;
+    }
+    CKR(cudaMemcpyAsync(h_counts, rd.qcount, (B + 1) * T * 4, cudaMemcpyDeviceToHost, st));
+
+    /* dense outputs -> the caller's arrays (columns of this chunk) */
+    if (flags & HRT_FLAG_DENSE) {
+      ChannelInfo *O = p->scat;
+      float *dst[6] = { O->a_te_re, O->a_te_im, O->a_tm_re, O->a_tm_im, O->tau, O->freq_shift };
+      for (int k = 0; k < 6; ++k) CKR(d2h_columns(ctx, st, dst[k], rd.out_f[k], 4, R * T * B, rd));
+      CKR(d2h_columns(ctx, st, O->directions_rx, rd.out_dir, 12, R * T * B, rd));
+    }
+    if (flags & HRT_FLAG_TRACE) {
+      CKR(d2h_columns(ctx, st, p->trace_hit_tri, rd.tr_hit, 4, T * B, rd));
+      CKR(d2h_columns(ctx, st, p->trace_hit_t, rd.tr_t, 4, T * B, rd));
+      CKR(d2h_columns(ctx, st, p->trace_slot_state, rd.tr_state, 1, R * T * B, rd));
+    }
+    if (flags & HRT_FLAG_RAYSINFO) {
+      /* reference row order (:589, :732-743): row 0 = initial rays of TX 0,
+       * row t*B+b+1 = rays of TX t after bounce b */
+      RaysInfo *RI = p->rays_scat;
+      if (RI->rays) {
+        CKR(d2h_columns(ctx, st, RI->rays, rd.rays, sizeof(Ray), 1, rd));
+        for (size_t t = 0; t < T; ++t)
+          for (size_t b = 0; b < B; ++b)
+            CKR(d2h_columns(ctx, st, RI->rays + (t * B + b + 1) * P, rd.rays + ((b + 1) * T + t) * (size_t)rd.n_alloc,
+                            sizeof(Ray), 1, rd));
+      }
+      CKR(cudaMemcpyAsync(h_dead, rd.dead_at, T * (size_t)rd.n_alloc, cudaMemcpyDeviceToHost, st));
+    }
+    CKR(cudaStreamSynchronize(st));
+
+    for (size_t b = 0; b < B; ++b)
+      for (size_t t = 0; t < T; ++t) { S.ray_bounces += h_counts[b * T + t]; S.primary_hits += h_counts[(b + 1) * T + t]; }
+
+    if ((flags & HRT_FLAG_RAYSINFO) && p->rays_scat->rays_active) {
+      /* activity masks.  The reference copies the first P/8+1 bytes of its
+       * global bitmask (bit index tx*P+path) into every row: TX 0's bits, plus
+       * for T > 1 the first bits of TX 1 in the last byte (appendix A-9). */
+      uint8_t *A = p->rays_scat->rays_active;
+      const size_t rowb = P / 8 + 1;
+      for (uint64_t L = 0; L < rd.n; ++L) {
+        const uint64_t g = hrt_gpath(l0 + L, rank, world, blk);
+        const uint8_t dead0 = h_dead[L];
+        for (size_t t = 0; t < T; ++t)
+          for (size_t b = 0; b < B; ++b) {
+            uint8_t *row = A + (t * B + b + 1) * rowb;
+            const uint8_t bit = (uint8_t)(1u << (g & 7));
+            if (dead0 > b) row[g >> 3] |= bit; else row[g >> 3] &= (uint8_t)~bit;
+          }
+      }
+    }
+  }
+  S.shadow_queries = S.primary_hits * R;
+
+  if ((flags & HRT_FLAG_RAYSINFO) && p->rays_scat->rays_active && rank == 0) {
+    /* bits outside TX 0's path range: row 0 is all ones (:470); in later rows
+     * the tail bits of the last byte stay set for T == 1 */
+    uint8_t *A = p->rays_scat->rays_active;
+    const size_t rowb = P / 8 + 1;
+    memset(A, 0xff, rowb);
+    for (size_t row = 1; row <= T * B; ++row)
+      for (uint64_t bit = P; bit < rowb * 8; ++bit) A[row * rowb + (bit >> 3)] |= (uint8_t)(1u << (bit & 7));
+  }
+
+  if (flags & HRT_FLAG_SUMMARY) {
+    const size_t np = R * T * B, nb = T * B;
+    if (flags & HRT_FLAG_SUMMARY_DEV) {
+      /* pair: fields 4,5 of each 6-word record are doubles */
+      unsigned char *d_isd = nullptr;
+      unsigned char *h_isd = (unsigned char *)calloc(np * 6, 1);
+      if (!h_isd) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
+      for (size_t i = 0; i < np; ++i) h_isd[6 * i + 4] = h_isd[6 * i + 5] = 1;
+      cudaError_t e = cudaMalloc((void **)&d_isd, np * 6);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_isd, h_isd, np * 6, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        k_add_u64<<<nblk(np * 6), 256, 0, st>>>((unsigned long long *)p->pair_summary, (const unsigned long long *)rd.pair, np * 6, d_isd);
+        k_add_u64<<<nblk(nb * 4), 256, 0, st>>>((unsigned long long *)p->bounce_summary, (const unsigned long long *)rd.bounce, nb * 4, nullptr);
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      cudaFree(d_isd); free(h_isd);
+      CKR(e);
+      S.kernel_launches += 2;
+    } else {
+      HrtPairSummary *hp = (HrtPairSummary *)malloc(np * sizeof(HrtPairSummary));
+      HrtBounceSummary *hb = (HrtBounceSummary *)malloc(nb * sizeof(HrtBounceSummary));
+      if (!hp || !hb) { free(hp); free(hb); rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
+      cudaError_t e = cudaMemcpyAsync(hp, rd.pair, np * sizeof(HrtPairSummary), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(hb, rd.bounce, nb * sizeof(HrtBounceSummary), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) {
+        for (size_t i = 0; i < np; ++i) {
+          p->pair_summary[i].n_valid += hp[i].n_valid; p->pair_summary[i].n_occluded += hp[i].n_occluded;
+          p->pair_summary[i].hit_hash += hp[i].hit_hash; p->pair_summary[i].tau_bits += hp[i].tau_bits;
+          p->pair_summary[i].power_te += hp[i].power_te; p->pair_summary[i].power_tm += hp[i].power_tm;
+        }
+        for (size_t i = 0; i < nb; ++i) {
+          p->bounce_summary[i].n_traced += hb[i].n_traced; p->bounce_summary[i].n_hit += hb[i].n_hit;
+          p->bounce_summary[i].hit_hash += hb[i].hit_hash; p->bounce_summary[i].t_bits += hb[i].t_bits;
+        }
+      }
+      free(hp); free(hb);
+      CKR(e);
+    }
+  }
+
+  CKR(cudaEventRecord(ctx->ev[2], st));
+  CKR(cudaEventSynchronize(ctx->ev[2]));
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&b, ctx->ev[0], ctx->ev[1]);
+    S.ms_total = a; S.ms_bounce = ms_bounce; S.ms_scatter = ms_scatter;
+    S.ms_other = time_kernels ? a - ms_bounce - ms_scatter : b;
+  }
+run_done:
+#undef CKR
+  free(h_counts); free(h_dead);
+  return rc;
+}

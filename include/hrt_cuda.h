@@ -1,0 +1,167 @@
+/* hrt_cuda.h -- thin C-ABI over the CUDA (sm_100a) implementation.
+ *
+ * Plain C: opaque context, pointers, sizes and int status codes only.  The
+ * host-side compute_paths() (hermespy-rt_b200/csrc/compute_paths.c) is written
+ * against this interface; so are bench.py, the tests (through ctypes) and any
+ * FFI binding.
+ *
+ * Which reference code each entry point stands in for:
+ *   hrt_scene_upload ...... the scene walk of moeller_trumbore + precompute_normals
+ *                           (src/compute_paths.c:208-224, :253-258), now a
+ *                           flattened SoA triangle buffer + GPU-built BVH
+ *   hrt_materials_set ..... g_materials_precomputed (src/compute_paths.c:169-206)
+ *   hrt_run ............... compute_paths() proper (src/compute_paths.c:419-757)
+ *                           for one shard of the (tx, path) space
+ *   hrt_closest_hits ...... moeller_trumbore() (src/compute_paths.c:237-287)
+ *                           for a batch of rays (unit-test / validation entry)
+ *
+ * Every function returns HRT_OK (0) or a negative HRT_E_* code;
+ * hrt_last_error() gives the message.  There is no CPU fallback anywhere:
+ * without a CUDA device hrt_ctx_create() fails with HRT_E_NO_DEVICE.
+ */
+#ifndef HRT_CUDA_H
+#define HRT_CUDA_H
+
+#include "hermespy_rt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRT_OK            0
+#define HRT_E_NO_DEVICE  -1   /* no usable CUDA device / driver            */
+#define HRT_E_CUDA       -2   /* a CUDA call failed (see hrt_last_error)   */
+#define HRT_E_ARG        -3   /* invalid argument / scene                  */
+#define HRT_E_NOMEM      -4   /* host or device allocation failed          */
+#define HRT_E_STATE      -5   /* call order (e.g. run before scene upload) */
+
+typedef struct hrt_ctx hrt_ctx;
+
+/* Derived per-material constants (reference MaterialPrecomputed,
+ * src/compute_paths.c:125-132) in the layout the kernels consume.  Filled on
+ * the host by hrt_materials_derive() with the host libm, like the reference. */
+typedef struct {
+  float eta_abs2, eta_abs_inv_sqrt;
+  float sqrt_re, sqrt_im;
+  float inv_re, inv_im;
+  float r, s, s1_alpha;
+  float pad_[3];
+} HrtMaterialDerived;
+
+/* hrt_run flags */
+#define HRT_FLAG_DENSE        0x01u  /* fill dense ChannelInfo arrays (reference layout) */
+#define HRT_FLAG_RAYSINFO     0x02u  /* also export RaysInfo rows (needs DENSE)          */
+#define HRT_FLAG_SUMMARY      0x04u  /* accumulate HrtPairSummary / HrtBounceSummary     */
+#define HRT_FLAG_TRACE        0x08u  /* export hit triangle ids / slot states (tests)    */
+#define HRT_FLAG_BRUTE_FORCE  0x10u  /* skip the BVH: test every triangle (validation)   */
+#define HRT_FLAG_HOST_DIRS    0x20u  /* launch directions supplied by caller (dirs)      */
+#define HRT_FLAG_SUMMARY_DEV  0x40u  /* summary pointers are DEVICE memory               */
+
+/* Order-independent per-(rx, tx, bounce) reduction of the scatter paths.
+ * Integer fields are exact and comparable bit for bit with a CPU run. */
+typedef struct {
+  uint64_t n_valid;      /* paths written with a gain (reference :692-722)        */
+  uint64_t n_occluded;   /* slots zeroed by the 1 m occlusion rule (:683-691)     */
+  uint64_t hit_hash;     /* sum of mix64(path << 32 | primary triangle id), valid */
+  uint64_t tau_bits;     /* sum of the fp32 bit patterns of tau, valid paths      */
+  double   power_te;     /* sum |a_te|^2, valid paths                             */
+  double   power_tm;     /* sum |a_tm|^2                                          */
+} HrtPairSummary;
+
+/* Per-(tx, bounce) counters of the primary rays. */
+typedef struct {
+  uint64_t n_traced;     /* rays alive at bounce start = primary queries (:615)  */
+  uint64_t n_hit;        /* of which hit something                                */
+  uint64_t hit_hash;     /* sum of mix64(path << 32 | triangle id) over hits      */
+  uint64_t t_bits;       /* sum of the fp32 bit patterns of the hit distances     */
+} HrtBounceSummary;
+
+typedef struct {
+  /* problem (reference compute_paths arguments, inc/compute_paths.h:59-74) */
+  size_t num_rx, num_tx, num_paths, num_bounces;
+  float  carrier_frequency_GHz;
+  const Vec3 *rx_pos, *tx_pos, *rx_vel, *tx_vel;      /* host memory */
+
+  /* shard: paths are dealt in blocks of shard_block to shard_world ranks;
+   * this call processes the blocks b with b % shard_world == shard_rank.
+   * shard_world = 1 (or 0) means the whole path range. */
+  uint32_t shard_rank, shard_world;
+  size_t   shard_block;
+
+  uint32_t flags;
+
+  /* HRT_FLAG_DENSE: caller-owned host arrays in the reference's layout.
+   * Only the columns of this shard's paths are written. */
+  ChannelInfo *los;        /* may be NULL: LoS skipped                      */
+  RaysInfo    *rays_los;   /* may be NULL                                   */
+  ChannelInfo *scat;
+  RaysInfo    *rays_scat;  /* used with HRT_FLAG_RAYSINFO                   */
+
+  /* HRT_FLAG_SUMMARY: [num_rx][num_tx][num_bounces] and [num_tx][num_bounces];
+   * ADDED to (caller zeroes them).  Host memory unless HRT_FLAG_SUMMARY_DEV. */
+  HrtPairSummary   *pair_summary;
+  HrtBounceSummary *bounce_summary;
+
+  /* HRT_FLAG_TRACE (host, full-size arrays, shard columns written):
+   * hit_tri [T][B][P] u32 (HRT id / 0xFFFFFFFF miss / 0xFFFFFFFE idle),
+   * hit_t [T][B][P] f32, slot_state [R][T][B][P] u8 (0/1 path/2 occluded) */
+  uint32_t *trace_hit_tri;
+  float    *trace_hit_t;
+  uint8_t  *trace_slot_state;
+
+  /* HRT_FLAG_HOST_DIRS: [num_paths] launch directions (host) */
+  const Vec3 *dirs;
+
+  /* CUDA stream to run on (cudaStream_t), NULL = the context's own stream */
+  void *stream;
+} HrtRunParams;
+
+/* Counters and timings of the last hrt_run on a context. */
+typedef struct {
+  uint64_t ray_bounces;        /* primary closest-hit queries                     */
+  uint64_t primary_hits;
+  uint64_t shadow_queries;     /* per-(hit, rx) closest-hit queries               */
+  uint64_t los_queries;
+  uint64_t ambiguous_dirs;     /* launch directions recomputed on the host        */
+  uint64_t kernel_launches;    /* kernels of this library launched by the run     */
+  float    ms_total;           /* CUDA-event time of the whole run on its stream  */
+  float    ms_bounce;          /* sum over k_bounce launches                      */
+  float    ms_scatter;         /* sum over k_scatter launches (dominant kernel)   */
+  float    ms_other;
+  uint32_t num_tris, num_nodes, scene_in_smem;
+  float    box_pad;
+} HrtRunStats;
+
+int  hrt_device_count(void);
+int  hrt_ctx_create(int device, hrt_ctx **out);
+void hrt_ctx_destroy(hrt_ctx *ctx);
+const char *hrt_last_error(const hrt_ctx *ctx);   /* ctx may be NULL: creation errors */
+
+/* Flatten + upload the scene and build the BVH on the GPU.  If normals_out is
+ * not NULL it receives one Vec3 per triangle in (mesh, face) order -- the
+ * values the reference stores in Mesh.ns (src/compute_paths.c:208-224). */
+int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_out);
+
+/* Host-side: derive the constants of material `index` at f GHz (reference
+ * precompute_materials, src/compute_paths.c:171-206). */
+void hrt_materials_derive(uint32_t index, float carrier_frequency_GHz, HrtMaterialDerived *out);
+int  hrt_materials_set(hrt_ctx *ctx, const HrtMaterialDerived table[NUM_G_MATERIALS]);
+
+int hrt_run(hrt_ctx *ctx, const HrtRunParams *p);
+int hrt_get_stats(const hrt_ctx *ctx, HrtRunStats *out);
+
+/* Batch closest hit (host arrays): tri = id in (mesh, face) order or
+ * 0xFFFFFFFF, t = distance or -1, theta = folded incidence angle or 0. */
+int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_t flags,
+                     uint32_t *tri, float *t, float *theta);
+
+/* Timing loop for the roofline: runs the closest-hit kernel `reps` times over
+ * n device-resident rays generated from (tx, launch directions); returns the
+ * average kernel time in ms and the number of box/triangle tests performed. */
+int hrt_bench_closest_hit(hrt_ctx *ctx, const Vec3 *origin, size_t n, int reps, uint32_t flags,
+                          float *ms_avg, uint64_t *node_tests, uint64_t *tri_tests);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRT_CUDA_H */

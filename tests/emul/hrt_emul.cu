@@ -1,0 +1,217 @@
+/* hrt_emul.cu -- TEST-ONLY serial CPU instantiation of the kernel logic.
+ *
+ * The authoring container has no GPU.  hrt_core.cuh / hrt_bvh.cuh are written
+ * as __host__ __device__ code, so this driver runs the very same functions the
+ * kernels call (BVH build steps, traversal, Moeller-Trumbore with the
+ * division-free shortcuts, bounce, scatter, LoS) one ray at a time on the CPU,
+ * and tests/test_emul_vs_oracle.py compares the result with the oracle.  It
+ * mirrors the launch logic of hrt_cuda.cu; it is NOT linked into, loaded by or
+ * reachable from libhermespy_rt.so.
+ */
+#include <algorithm>
+#include <vector>
+#include <string.h>
+
+#include "../../include/hrt_cuda.h"
+#include "../../hermespy-rt_b200/csrc/hrt_bvh.cuh"
+
+struct EmulScene {
+  std::vector<float4> tris, nodes;
+  std::vector<uint32_t> gid, mesh_of, mesh_mat;
+  std::vector<V3> mesh_vel;
+  uint32_t n = 0; int root = 0; uint32_t num_nodes = 0;
+};
+
+static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, float extra_abs)
+{
+  std::vector<V3> A, B, C;
+  float max_abs = extra_abs;
+  for (uint32_t m = 0; m < sc->num_meshes; ++m) {
+    const Mesh *me = &sc->meshes[m];
+    for (uint32_t f = 0; f < me->num_triangles; ++f) {
+      const Vec3 a = me->vs[me->is[3 * f]], b = me->vs[me->is[3 * f + 1]], c = me->vs[me->is[3 * f + 2]];
+      A.push_back(v3(a.x, a.y, a.z)); B.push_back(v3(b.x, b.y, b.z)); C.push_back(v3(c.x, c.y, c.z));
+      E.mesh_of.push_back(m);
+    }
+    for (uint32_t v = 0; v < me->num_vertices; ++v)
+      max_abs = fmaxf(max_abs, fmaxf(fabsf(me->vs[v].x), fmaxf(fabsf(me->vs[v].y), fabsf(me->vs[v].z))));
+    E.mesh_mat.push_back(me->material_index);
+    E.mesh_vel.push_back(v3(me->velocity.x, me->velocity.y, me->velocity.z));
+  }
+  const int n = (int)A.size();
+  E.n = n;
+  if (n == 0) return;
+  std::vector<HrtTriSetup> S(n);
+  V3 slo = v3(1e30f, 1e30f, 1e30f), shi = v3(-1e30f, -1e30f, -1e30f);
+  for (int g = 0; g < n; ++g) {
+    S[g] = hrt_tri_setup(A[g], B[g], C[g]);
+    slo = v3(fminf(slo.x, S[g].lo.x), fminf(slo.y, S[g].lo.y), fminf(slo.z, S[g].lo.z));
+    shi = v3(fmaxf(shi.x, S[g].hi.x), fmaxf(shi.y, S[g].hi.y), fmaxf(shi.z, S[g].hi.z));
+  }
+  const V3 inv = v3(1.f / fmaxf(shi.x - slo.x, 1e-30f), 1.f / fmaxf(shi.y - slo.y, 1e-30f), 1.f / fmaxf(shi.z - slo.z, 1e-30f));
+  std::vector<uint64_t> keys(n);
+  for (int g = 0; g < n; ++g) keys[g] = hrt_morton_key(S[g].lo, S[g].hi, slo, inv, g);
+  std::sort(keys.begin(), keys.end());
+  E.tris.resize(3 * (size_t)n); E.gid.resize(n);
+  std::vector<V3> blo(2 * (size_t)n), bhi(2 * (size_t)n);
+  for (int s = 0; s < n; ++s) {
+    const uint32_t g = (uint32_t)(keys[s] & 0xFFFFFFFFull);
+    E.tris[3 * s] = S[g].q0; E.tris[3 * s + 1] = S[g].q1; E.tris[3 * s + 2] = S[g].q2;
+    E.gid[s] = g;
+    blo[n - 1 + s] = S[g].lo; bhi[n - 1 + s] = S[g].hi;
+  }
+  if (n <= leaf_max) { E.root = hrt_leaf_ref(0u, (uint32_t)n); return; }
+  std::vector<int> kl(n - 1), kr(n - 1), kf(n - 1), kla(n - 1), parent(2 * (size_t)n, -1), arrive(n - 1, 0);
+  for (int i = 0; i < n - 1; ++i) {
+    hrt_karras_node(keys.data(), n, i, &kl[i], &kr[i], &kf[i], &kla[i]);
+    parent[kl[i]] = i; parent[kr[i]] = i;
+  }
+  parent[0] = -1;
+  for (int s = 0; s < n; ++s) {           /* same arrival protocol as k_refit */
+    int cur = parent[n - 1 + s];
+    while (cur >= 0) {
+      if (arrive[cur]++ == 0) break;
+      const int a = kl[cur], b = kr[cur];
+      blo[cur] = v3(fminf(blo[a].x, blo[b].x), fminf(blo[a].y, blo[b].y), fminf(blo[a].z, blo[b].z));
+      bhi[cur] = v3(fmaxf(bhi[a].x, bhi[b].x), fmaxf(bhi[a].y, bhi[b].y), fmaxf(bhi[a].z, bhi[b].z));
+      cur = parent[cur];
+    }
+  }
+  std::vector<int> used(n - 1), newidx(n - 1);
+  int count = 0;
+  for (int i = 0; i < n - 1; ++i) { used[i] = (kla[i] - kf[i] + 1) > leaf_max; newidx[i] = count; count += used[i]; }
+  E.num_nodes = count; E.nodes.resize(4 * (size_t)count); E.root = 0;
+  const float pad = hrt_box_pad(max_abs, pad_ulps);
+  for (int i = 0; i < n - 1; ++i) {
+    if (!used[i]) continue;
+    hrt_emit_node(&E.nodes[4 * (size_t)newidx[i]],
+                  hrt_child_ref(kl[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
+                  hrt_child_ref(kr[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
+                  blo[kl[i]], bhi[kl[i]], blo[kr[i]], bhi[kr[i]], pad);
+  }
+}
+
+static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
+{
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
+  if (brute) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d);
+  return hrt_closest_hit(m, E.gid.data(), E.root, E.n, o, d);
+}
+
+static V3 nrm(const EmulScene &E, uint32_t slot) { const float4 q = E.tris[3 * slot + 2]; return v3(q.y, q.z, q.w); }
+static V3 tov(Vec3 a) { return v3(a.x, a.y, a.z); }
+
+extern "C" int emul_closest_hits(const Scene *sc, const Ray *rays, size_t n, int leaf_max, float pad_ulps,
+                                 int brute, uint32_t *tri, float *t, float *theta)
+{
+  EmulScene E;
+  float ma = 0.f;
+  for (size_t i = 0; i < n; ++i) ma = fmaxf(ma, fmaxf(fabsf(rays[i].o.x), fmaxf(fabsf(rays[i].o.y), fabsf(rays[i].o.z))));
+  build(sc, E, leaf_max, pad_ulps, ma);
+  for (size_t i = 0; i < n; ++i) {
+    const HrtHit h = query(E, tov(rays[i].o), tov(rays[i].d), brute);
+    const bool hit = h.gid != HRT_NONE;
+    tri[i] = h.gid; t[i] = hit ? h.t : -1.f;
+    theta[i] = hit ? hrt_theta_fold(nrm(E, h.slot), tov(rays[i].d)) : 0.f;
+  }
+  return 0;
+}
+
+/* Dense compute_paths with the product's output conventions: gains/tau/dir of
+ * untouched slots are 0, freq_shift carries the Doppler base everywhere.
+ * RaysInfo is not emulated (pure host bookkeeping in hrt_cuda.cu). */
+extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec3 *tx_pos,
+                                  const Vec3 *rx_vel, const Vec3 *tx_vel, float f_ghz,
+                                  size_t R, size_t T, size_t P, size_t B,
+                                  ChannelInfo *los, ChannelInfo *scat,
+                                  uint32_t *tr_hit, uint8_t *tr_state,
+                                  int leaf_max, float pad_ulps, int brute)
+{
+  EmulScene E;
+  float ma = 0.f;
+  for (size_t i = 0; i < R; ++i) ma = fmaxf(ma, fmaxf(fabsf(rx_pos[i].x), fmaxf(fabsf(rx_pos[i].y), fabsf(rx_pos[i].z))));
+  for (size_t i = 0; i < T; ++i) ma = fmaxf(ma, fmaxf(fabsf(tx_pos[i].x), fmaxf(fabsf(tx_pos[i].y), fabsf(tx_pos[i].z))));
+  build(sc, E, leaf_max, pad_ulps, ma);
+  HrtMaterialTable mats; memset(&mats, 0, sizeof mats);
+  for (uint32_t m = 0; m < sc->num_meshes; ++m)
+    hrt_materials_derive(sc->meshes[m].material_index, f_ghz, (HrtMaterialDerived *)&mats.m[sc->meshes[m].material_index]);
+  HrtRunConst k;
+  const float f_hz = (float)((double)f_ghz * 1e9);
+  k.fsl_k = 4.f * HRT_PI * f_hz / HRT_C0; k.dop_k = f_hz / HRT_C0;
+
+  for (size_t r = 0, q = 0; r < R; ++r)
+    for (size_t t = 0; t < T; ++t, ++q) {
+      los->a_te_im[q] = los->a_tm_im[q] = 0.f;
+      const V3 o = tov(tx_pos[t]);
+      const V3 d = v3_sub(tov(rx_pos[r]), o);
+      HrtLosOut res;
+      if (v3_dot(d, d) < HRT_EPS) { res.dir_rx = v3(1, 0, 0); res.dir_tx = v3(-1, 0, 0); res.a = 1.f; res.tau = 0.f; res.freq = 0.f; res.state = 2; }
+      else { const HrtHit h = query(E, o, d, brute); res = hrt_los_finish(d, h.gid != HRT_NONE, h.t, tov(tx_vel[0]), tov(rx_vel[0]), k, k.dop_k); }
+      if (res.state == 0) { los->a_te_re[q] = los->a_tm_re[q] = los->tau[q] = 0.f; continue; }
+      los->directions_tx[q] = {res.dir_tx.x, res.dir_tx.y, res.dir_tx.z};
+      los->directions_rx[q] = {res.dir_rx.x, res.dir_rx.y, res.dir_rx.z};
+      los->a_te_re[q] = los->a_tm_re[q] = res.a; los->tau[q] = res.tau; los->freq_shift[q] = res.freq;
+    }
+
+  std::vector<HrtRayState> st(T * P);
+  std::vector<uint8_t> alive(T * P, 1);
+  for (size_t p = 0; p < P; ++p) {
+    bool amb = false;
+    const V3 d = hrt_launch_dir(p, P, &amb);
+    for (size_t t = 0; t < T; ++t) {
+      HrtRayState &s = st[t * P + p];
+      s.o = tov(tx_pos[t]); s.d = d; s.te_r = 1.f; s.te_i = 0.f; s.tm_r = 1.f; s.tm_i = 0.f; s.tau = 0.f;
+      for (size_t b = 0; b < B; ++b) {
+        tr_hit[(t * B + b) * P + p] = HRT_IDLE;
+        const size_t j = (t * B + b) % T;
+        const size_t src = (j % B == 0) ? j / B : t;
+        float base = v3_dot(tov(tx_vel[src]), d); base = HRT_MUL(base, k.dop_k);
+        for (size_t r = 0; r < R; ++r) {
+          const size_t so = ((r * T + t) * B + b) * P + p;
+          scat->a_te_re[so] = scat->a_te_im[so] = scat->a_tm_re[so] = scat->a_tm_im[so] = scat->tau[so] = 0.f;
+          scat->freq_shift[so] = base;
+          scat->directions_rx[so] = {0.f, 0.f, 0.f};
+          tr_state[so] = 0;
+        }
+      }
+    }
+  }
+  for (size_t b = 0; b < B; ++b)
+    for (size_t t = 0; t < T; ++t)
+      for (size_t p = 0; p < P; ++p) {
+        const size_t i = t * P + p;
+        if (!alive[i]) continue;
+        HrtRayState &s = st[i];
+        const HrtHit h = query(E, s.o, s.d, brute);
+        tr_hit[(t * B + b) * P + p] = h.gid;
+        if (h.gid == HRT_NONE) { alive[i] = 0; continue; }
+        const V3 n = nrm(E, h.slot);
+        const float theta = hrt_theta_fold(n, s.d);
+        const uint32_t mesh = E.mesh_of[h.gid];
+        const HrtMaterial &mat = mats.m[E.mesh_mat[mesh]];
+        hrt_bounce_update(s, mat, k, h.t, n, theta);
+        float carry = theta;
+        for (size_t r = 0; r < R; ++r) {
+          const size_t so = ((r * T + t) * B + b) * P + p;
+          float dist;
+          const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
+          const HrtHit sh = query(E, s.o, sd, brute);
+          if (sh.gid != HRT_NONE) carry = hrt_theta_fold(nrm(E, sh.slot), sd);
+          if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
+          const HrtScatterOut o = hrt_scatter_path(s, mat, k, n, E.mesh_vel[mesh], sd, dist, carry);
+          scat->a_te_re[so] = o.te_r; scat->a_te_im[so] = o.te_i; scat->a_tm_re[so] = o.tm_r; scat->a_tm_im[so] = o.tm_i;
+          scat->tau[so] = o.tau;
+          scat->freq_shift[so] = HRT_SUB(scat->freq_shift[so], o.dfreq);
+          scat->directions_rx[so] = {o.dir_rx.x, o.dir_rx.y, o.dir_rx.z};
+          tr_state[so] = 1;
+        }
+      }
+  return 0;
+}
+
+extern "C" int emul_bvh_stats(const Scene *sc, int leaf_max, uint32_t *num_nodes, uint32_t *num_tris)
+{
+  EmulScene E; build(sc, E, leaf_max, 64.f, 0.f);
+  *num_nodes = E.num_nodes; *num_tris = E.n;
+  return 0;
+}

@@ -216,3 +216,102 @@ def assert_gains_close(ref_words, mask, test_words, rtol=GAIN_RTOL):
         bad = err > rtol * mag + 1e-38
         assert not bad.any(), f"a_{pol}: {int(bad.sum())} of {ar.size} gains off, " \
                               f"worst rel {float((err / np.maximum(mag, 1e-300)).max()):.3e}"
+
+
+# ------------------------------------------- serial CPU run of the kernel logic
+
+_emul = None
+
+
+def emul_lib() -> C.CDLL:
+    """tests/emul/libhrt_emul.so: hrt_core.cuh / hrt_bvh.cuh compiled for the
+    host (test-only, see tests/emul/hrt_emul.cu)."""
+    global _emul
+    if _emul is None:
+        so = os.path.join(ROOT, "tests", "emul", "libhrt_emul.so")
+        if not os.path.exists(so):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "hermespy-rt_b200"), "emul"],
+                           check=True, capture_output=True)
+        lib = C.CDLL(so)
+        lib.scene_load.restype = abi.Scene
+        lib.scene_load.argtypes = [C.c_char_p]
+        lib.emul_closest_hits.argtypes = [C.POINTER(abi.Scene), C.c_void_p, C.c_size_t, C.c_int,
+                                          C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.emul_compute_paths.argtypes = [
+            C.POINTER(abi.Scene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+            C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+            C.POINTER(abi.ChannelInfo), C.POINTER(abi.ChannelInfo), C.c_void_p, C.c_void_p,
+            C.c_int, C.c_float, C.c_int]
+        lib.emul_bvh_stats.argtypes = [C.POINTER(abi.Scene), C.c_int, C.c_void_p, C.c_void_p]
+        _emul = lib
+    return _emul
+
+
+def run_emul(scene, rx, tx, rxv, txv, f_ghz, P, B, leaf_max=4, pad_ulps=64.0, brute=False):
+    lib = emul_lib()
+    sc = lib.scene_load(scene_path(scene).encode())
+    rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
+    R, T = rx.shape[0], tx.shape[0]
+    rxv = abi.vec3_array(rxv, R); txv = abi.vec3_array(txv, T)
+    o = abi.alloc_outputs(R, T, P, B, 0)
+    tr = {"hit_tri": np.zeros((T, B, P), np.uint32), "slot_state": np.zeros((R, T, B, P), np.uint8)}
+    los = abi.chan_struct(o.los, 1)
+    scs = abi.chan_struct(o.scat, B * P)
+    try:
+        rc = lib.emul_compute_paths(C.byref(sc), rx.ctypes.data, tx.ctypes.data, rxv.ctypes.data,
+                                    txv.ctypes.data, C.c_float(f_ghz), R, T, P, B,
+                                    C.byref(los), C.byref(scs), tr["hit_tri"].ctypes.data,
+                                    tr["slot_state"].ctypes.data, leaf_max, C.c_float(pad_ulps),
+                                    int(brute))
+        assert rc == 0
+    finally:
+        abi.free_scene(sc)
+    return o, tr
+
+
+def random_rays(scene_name, n, seed=0):
+    """Rays with origins inside the scene's bounding box (slightly inflated) and
+    isotropic directions, plus a share of axis-aligned and grazing directions."""
+    lib = oracle_lib()
+    sc = lib.scene_load(scene_path(scene_name).encode())
+    tris, *_ = abi.scene_to_numpy(sc)
+    abi.free_scene(sc)
+    lo = tris.reshape(-1, 3).min(0); hi = tris.reshape(-1, 3).max(0)
+    ext = np.maximum(hi - lo, 1.0)
+    rng = np.random.default_rng(seed)
+    o = (lo - 0.1 * ext + rng.random((n, 3)) * 1.2 * ext).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = n // 8
+    d[:k, 2] *= 1e-3                                   # grazing w.r.t. horizontal planes
+    d[k:2 * k] = np.eye(3)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], (k, 1))  # axis aligned
+    # a share aimed exactly at triangle corners / edge midpoints (ties, edges)
+    tgt = tris[rng.integers(0, len(tris), k)]
+    w = rng.random((k, 3)); w[: k // 2, 2] = 0.0; w[: k // 4, 1] = 0.0
+    w /= w.sum(1, keepdims=True)
+    pts = (tgt * w[:, :, None]).sum(1)
+    d[2 * k:3 * k] = pts - o[2 * k:3 * k]
+    rays = np.concatenate([o, d.astype(np.float32)], axis=1).astype(np.float32)
+    return np.ascontiguousarray(rays)
+
+
+def oracle_closest(scene_name, rays):
+    lib = oracle_lib()
+    sc = lib.scene_load(scene_path(scene_name).encode())
+    n = rays.shape[0]
+    tri = np.zeros(n, np.uint32); t = np.zeros(n, np.float32); th = np.zeros(n, np.float32)
+    lib.oracle_closest_hits(C.byref(sc), rays.ctypes.data, n, tri.ctypes.data, t.ctypes.data,
+                            th.ctypes.data)
+    abi.free_scene(sc)
+    return tri, t, th
+
+
+def emul_closest(scene_name, rays, leaf_max=4, pad_ulps=64.0, brute=False):
+    lib = emul_lib()
+    sc = lib.scene_load(scene_path(scene_name).encode())
+    n = rays.shape[0]
+    tri = np.zeros(n, np.uint32); t = np.zeros(n, np.float32); th = np.zeros(n, np.float32)
+    lib.emul_closest_hits(C.byref(sc), rays.ctypes.data, n, leaf_max, C.c_float(pad_ulps),
+                          int(brute), tri.ctypes.data, t.ctypes.data, th.ctypes.data)
+    abi.free_scene(sc)
+    return tri, t, th

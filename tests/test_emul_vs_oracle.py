@@ -1,0 +1,52 @@
+"""Kernel logic (hrt_core.cuh, hrt_bvh.cuh) instantiated for the host and run
+serially (tests/emul) against the oracle.  On the CPU both sides use the same
+libm, so EVERY reference-written word -- gains included -- must be bit-equal;
+this isolates logic errors from CUDA libm differences before any GPU time is
+spent."""
+import numpy as np
+import pytest
+
+import hrt_testlib as tl
+
+SCENES = ["simple_reflector", "box", "2cars", "simple_street_canyon_with_cars"]
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("leaf_max,brute", [(4, False), (1, False), (8, False), (4, True)])
+def test_closest_hit_matches_oracle(scene, leaf_max, brute):
+    rays = tl.random_rays(scene, 20000, seed=7)
+    tri_o, t_o, th_o = tl.oracle_closest(scene, rays)
+    tri_e, t_e, th_e = tl.emul_closest(scene, rays, leaf_max=leaf_max, brute=brute)
+    assert (tri_o != tl.NONE).sum() > 1000
+    assert np.array_equal(tri_o, tri_e)
+    assert np.array_equal(t_o.view(np.uint32), t_e.view(np.uint32))
+    assert np.array_equal(th_o.view(np.uint32), th_e.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", tl.GOLDEN_NAMES)
+def test_compute_paths_matches_golden(name):
+    g = tl.load_golden(name)
+    o, tr = tl.run_emul(g["scene"], g["rx"], g["tx"], g["rxv"], g["txv"], g["f"], g["P"], g["B"])
+    w = tl.outputs_words(o)
+    ref = {k[4:]: v for k, v in g.items() if k.startswith("out.")}
+    mask = {k[5:]: v for k, v in g.items() if k.startswith("mask.")}
+    keys = [k for k in tl.EXACT_KEYS if not k.startswith(("scat_rays", "scat_active", "los_rays", "los_active"))]
+    tl.assert_exact(ref, mask, w, keys=keys + list(tl.GAIN_KEYS))
+    assert np.array_equal(tr["hit_tri"], g["trace.hit_tri"])
+    assert np.array_equal(tr["slot_state"], g["trace.slot_state"])
+
+
+def test_two_tx_doppler_layout():
+    """T = 2 with moving TX: the freq_shift index algebra of the reference
+    (SURVEY A-8) on the determinate words."""
+    scene, rx, tx, f = tl.CONFIGS["box_generic"]
+    tx = list(tx) + [[-2.0, 3.0, 1.0]]
+    rx = list(rx) + [[3.0, 3.0, 3.0]]
+    rxv = [[0, 0, 0]] * 2
+    txv = [[1.0, 2.0, 3.0], [-2.0, 0.5, 0.0]]
+    a, _ = tl.run_oracle(scene, rx, tx, rxv, txv, f, 2000, 3, fill=0x00, trace=False)
+    b, _ = tl.run_oracle(scene, rx, tx, rxv, txv, f, 2000, 3, fill=0x5A, trace=False)
+    mask = tl.written_mask(a, b)
+    o, _ = tl.run_emul(scene, rx, tx, rxv, txv, f, 2000, 3)
+    keys = ["scat.tau", "scat.freq_shift", "scat.directions_rx"] + list(tl.GAIN_KEYS)
+    tl.assert_exact(tl.outputs_words(a), mask, tl.outputs_words(o), keys=keys)
