@@ -111,6 +111,20 @@ HRT_HD int hrt_float_as_int(float f)
 #endif
 }
 
+/* Work counters for the roofline accounting: box tests and
+ * Moeller-Trumbore tests by the stage they reach (A: det, B: u, C: v, D: t).
+ * HrtNoCount compiles to nothing; HrtCount is used by the instrumented kernel
+ * variants only. */
+struct HrtNoCount {
+  HRT_HD void box(uint32_t) {}
+  HRT_HD void tri(int) {}
+};
+struct HrtCount {
+  uint32_t c[5];
+  HRT_HD void box(uint32_t n) { c[0] += n; }
+  HRT_HD void tri(int stage) { c[1 + stage] += 1u; }
+};
+
 struct HrtHit {
   float    t;      /* distance, reference *t                           */
   uint32_t gid;    /* triangle id in (mesh, face) order; HRT_NONE: miss */
@@ -125,15 +139,18 @@ struct HrtHit {
  * thresholds that sit 1e-5 away from the reference's, while IEEE division is
  * monotonic and off by at most 2^-24 relative -- so the shortcut never changes
  * a decision, it only skips divisions. */
+template <class Cnt>
 HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
-                        float best, uint32_t best_gid, uint32_t gid, float *t_out)
+                        float best, uint32_t best_gid, uint32_t gid, float *t_out, Cnt &cnt)
 {
+  cnt.tri(0);
   const V3 a  = v3(q0.x, q0.y, q0.z);
   const V3 ab = v3(q0.w, q1.x, q1.y);
   const V3 ac = v3(q1.z, q1.w, q2.x);
   const V3 pv = v3_cross(d, ac);                         /* :261 */
   const float det = v3_dot(ab, pv);                      /* :262 */
   if (det > -HRT_EPS && det < HRT_EPS) return false;     /* :263 (NaN passes, as there) */
+  cnt.tri(1);
   const float ad  = fabsf(det);
   const float sgn = det < 0.f ? -1.f : 1.f;
   const float lo  = HRT_MUL(ad, -1e-5f), hi = HRT_MUL(ad, 1.00001f);
@@ -143,6 +160,7 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   if (snu < lo || snu > hi) return false;                /* u clearly outside */
   const float u = HRT_DIV(nu, det);                      /* :265 */
   if ((u < 0.f && -u > HRT_EPS) || (u > 1.f && HRT_SUB(u, 1.f) > HRT_EPS)) return false; /* :266 */
+  cnt.tri(2);
   const V3 qv = v3_cross(sv, ab);                        /* :269 */
   const float nv = v3_dot(d, qv);
   const float snv = nv * sgn;
@@ -150,6 +168,7 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   const float v = HRT_DIV(nv, det);                      /* :270 */
   const float uv = HRT_ADD(u, v);
   if ((v < 0.f && -v > HRT_EPS) || (uv > 1.f && HRT_SUB(uv, 1.f) > HRT_EPS)) return false; /* :271 */
+  cnt.tri(3);
   const float nt = v3_dot(ac, qv);
   if (!(nt * sgn > 0.f) && nt == nt) return false;       /* t <= 0 */
   const float t = HRT_DIV(nt, det);                      /* :274 */
@@ -223,9 +242,9 @@ struct HrtGlobalMem {
 /* Closest hit over the BVH == the reference's loop over every triangle
  * (moeller_trumbore, :237-287): minimum t, ties to the lowest (mesh, face).
  * root_ref: inner node index, a leaf ref, or 0 with num_tris == 0. */
-template <class Mem>
+template <class Mem, class Cnt>
 HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_ref,
-                              uint32_t num_tris, V3 o, V3 d)
+                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
@@ -242,6 +261,7 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
       const bool hl = hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl);
       const bool hr = hrt_slab(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr);
       const int rl = hrt_float_as_int(n3.x), rr = hrt_float_as_int(n3.y);
+      cnt.box(2u);
       if (hl && hr) {
         const bool left_first = tl <= tr;
         stack_ref[sp] = left_first ? rr : rl;
@@ -254,12 +274,12 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
       if (hr) { cur = rr; continue; }
     } else {
       const uint32_t code = (uint32_t)~cur;
-      const uint32_t first = code >> 3, cnt = (code & 7u) + 1u;
-      for (uint32_t k = 0; k < cnt; ++k) {
+      const uint32_t first = code >> 3, ntri = (code & 7u) + 1u;
+      for (uint32_t k = 0; k < ntri; ++k) {
         const uint32_t s = first + k;
         float t;
         const uint32_t gid = tri_gid[s];
-        if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t)) {
+        if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) {
           h.t = t; h.gid = gid; h.slot = s;
           tmax = HRT_FMA(t, 1.0001f, 1e-30f);
         }
@@ -276,15 +296,15 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
 
 /* Brute force over every triangle in leaf order -- debug/validation path of
  * the kernels (HRT_FLAG_BRUTE_FORCE), same decisions by construction. */
-template <class Mem>
+template <class Mem, class Cnt>
 HRT_HD HrtHit hrt_closest_hit_brute(const Mem &mem, const uint32_t *tri_gid,
-                                    uint32_t num_tris, V3 o, V3 d)
+                                    uint32_t num_tris, V3 o, V3 d, Cnt &cnt)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   for (uint32_t s = 0; s < num_tris; ++s) {
     float t;
     const uint32_t gid = tri_gid[s];
-    if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t)) {
+    if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) {
       h.t = t; h.gid = gid; h.slot = s;
     }
   }

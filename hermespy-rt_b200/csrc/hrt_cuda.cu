@@ -95,6 +95,7 @@ struct hrt_ctx {
   int device;
   cudaStream_t stream;
   cudaEvent_t ev[8];
+  cudaEvent_t *evpool; size_t evpool_n;   /* per-launch timing events, grown on demand */
   char err[512];
   int leaf_max;
   float pad_ulps;
@@ -254,8 +255,8 @@ __global__ void k_emit(int n, const int *kl, const int *kr, const int *kfirst, c
 struct HrtSharedMem {
   const float4 *nodes;
   const float4 *tris;
-  __device__ __forceinline__ float4 node(int i, int k) const { return nodes[4 * i + k]; }
-  __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return tris[3 * s + k]; }
+  HRT_HD float4 node(int i, int k) const { return nodes[4 * i + k]; }
+  HRT_HD float4 tri(uint32_t s, int k) const { return tris[3 * s + k]; }
 };
 
 extern __shared__ float4 hrt_smem4[];
@@ -275,22 +276,30 @@ __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
 static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris)
 { return (size_t)num_nodes * 64 + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
 
-template <bool SMEM, bool BRUTE>
-__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d)
+template <bool SMEM, bool BRUTE, class Cnt>
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt)
 {
   if (SMEM) {
     HrtSharedMem m;
     m.nodes = hrt_smem4;
     m.tris = hrt_smem4 + sc.num_nodes * 4u;
     const uint32_t *gid = (const uint32_t *)(hrt_smem4 + sc.num_nodes * 4u + sc.num_tris * 3u);
-    if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d);
-    return hrt_closest_hit(m, gid, sc.root_ref, sc.num_tris, o, d);
+    if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
+    return hrt_closest_hit(m, gid, sc.root_ref, sc.num_tris, o, d, cnt);
   } else {
     HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
-    if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d);
-    return hrt_closest_hit(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d);
+    if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
+    return hrt_closest_hit(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt);
   }
 }
+
+template <bool COUNT> struct CntSel { typedef HrtNoCount type; };
+template <> struct CntSel<true> { typedef HrtCount type; };
+__device__ __forceinline__ void cnt_init(HrtNoCount &) {}
+__device__ __forceinline__ void cnt_init(HrtCount &c) { for (int k = 0; k < 5; ++k) c.c[k] = 0; }
+__device__ __forceinline__ void cnt_flush(const HrtNoCount &, unsigned long long *) {}
+__device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long *dst)
+{ for (int k = 0; k < 5; ++k) if (c.c[k]) atomicAdd(&dst[k], (unsigned long long)c.c[k]); }
 
 template <bool SMEM>
 __device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
@@ -372,7 +381,8 @@ __global__ void k_init(RunDev rd)
           for (uint32_t r = 0; r < R; ++r) rd.tr_state[((size_t)(r * T + t) * B + b) * np + l] = 0;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < T) rd.qcount[threadIdx.x] = rd.n;
+  if (blockIdx.x == 0)
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) rd.qcount[t] = rd.n;
 }
 
 /* line of sight (reference :520-577), one thread per (rx, tx) pair */
@@ -390,7 +400,8 @@ __global__ void k_los(RunDev rd, SceneDev sc, HrtLosOut *out)
     res.dir_rx = v3(1.f, 0.f, 0.f); res.dir_tx = v3(-1.f, 0.f, 0.f);
     res.a = 1.f; res.tau = 0.f; res.freq = 0.f; res.state = 2;
   } else {
-    const HrtHit h = query<SMEM, BRUTE>(sc, o, d);
+    HrtNoCount nc;
+    const HrtHit h = query<SMEM, BRUTE>(sc, o, d, nc);
     res = hrt_los_finish(d, h.gid != HRT_NONE, h.t, ld3(rd.tx_vel, 0), ld3(rd.rx_vel, 0),
                          rd.k, rd.k.dop_k);
   }
@@ -400,11 +411,12 @@ __global__ void k_los(RunDev rd, SceneDev sc, HrtLosOut *out)
 /* One bounce depth of the wavefront (reference :599-664): a thread per active
  * ray of TX blockIdx.y.  Survivors are appended to the next queue with one
  * atomicAdd per warp (ballot + prefix popcount). */
-template <bool SMEM, bool BRUTE>
+template <bool SMEM, bool BRUTE, bool COUNT>
 __global__ void __launch_bounds__(HRT_BLOCK)
 k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
 {
   if (SMEM) { stage_scene(sc); __syncthreads(); }
+  typename CntSel<COUNT>::type wc; cnt_init(wc);
   const uint32_t t = blockIdx.y, T = rd.T, B = rd.B;
   const size_t np = rd.n_alloc;
   const uint32_t cnt = rd.qcount[depth * T + t];
@@ -428,7 +440,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
       const float2 a = rp[0], b = rp[1], c = rp[2];
       HrtRayState s;
       s.o = v3(a.x, a.y, b.x); s.d = v3(b.y, c.x, c.y);
-      const HrtHit h = query<SMEM, BRUTE>(sc, s.o, s.d);                       /* :615 */
+      const HrtHit h = query<SMEM, BRUTE>(sc, s.o, s.d, wc);                  /* :615 */
       hit = h.gid != HRT_NONE;
       const size_t si = t * np + l;
       if (rd.flags & HRT_FLAG_TRACE) {
@@ -467,6 +479,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
       if (hit) qout[base + __popc(m & ((1u << lane) - 1u))] = l;
     }
   }
+  cnt_flush(wc, rd.counters);
   if (rd.flags & HRT_FLAG_SUMMARY) {
     for (int o = 16; o; o >>= 1) {
       hash_acc += __shfl_xor_sync(0xFFFFFFFFu, hash_acc, o);
@@ -493,10 +506,11 @@ struct PairAcc {
  *                 inclusive "last lane that hit" scan over ballot bits, carried
  *                 from tile to tile.
  *   WARP = false: one thread per hit, receivers in sequence (small num_rx). */
-template <bool SMEM, bool BRUTE, bool WARP>
+template <bool SMEM, bool BRUTE, bool WARP, bool COUNT>
 __global__ void __launch_bounds__(HRT_BLOCK)
 k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
 {
+  typename CntSel<COUNT>::type wc; cnt_init(wc);
   uint32_t used4 = 0;
   if (SMEM) used4 = stage_scene(sc);
   const uint32_t R = rd.R, T = rd.T, B = rd.B, t = blockIdx.y;
@@ -555,7 +569,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = query<SMEM, BRUTE>(sc, s.o, sd);                                   /* :682 */
+        h = query<SMEM, BRUTE>(sc, s.o, sd, wc);                              /* :682 */
         if (h.gid != HRT_NONE) th_sh = hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), sd);
       }
       const bool shit = act && h.gid != HRT_NONE;
@@ -618,6 +632,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       }
     }
   }
+  cnt_flush(wc, rd.counters + 5);
   if (summary && smem_rx_ok) {
     __syncthreads();
     for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
@@ -662,11 +677,32 @@ __global__ void k_closest(SceneDev sc, const Ray *rays, uint32_t n, uint32_t *tr
     const float2 *rp = (const float2 *)(rays + i);
     const float2 a = rp[0], b = rp[1], c = rp[2];
     const V3 o = v3(a.x, a.y, b.x), d = v3(b.y, c.x, c.y);
-    const HrtHit h = query<SMEM, BRUTE>(sc, o, d);
+    HrtNoCount nc;
+    const HrtHit h = query<SMEM, BRUTE>(sc, o, d, nc);
     const bool hit = h.gid != HRT_NONE;
     tri[i] = h.gid; t[i] = hit ? h.t : -1.f;
     theta[i] = hit ? hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), d) : 0.f;
   }
+}
+
+/* fp32 issue-rate probe: 8 independent dependency chains per thread, either
+ * FMUL+FADD pairs (separately rounded, like the exact intersection code) or
+ * FFMA.  2 flops per chain step in both cases. */
+template <bool FMA>
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b)
+{
+  float x[8];
+  for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (FMA) x[k] = __fmaf_rn(x[k], a, b);
+      else     x[k] = __fadd_rn(__fmul_rn(x[k], a), b);
+    }
+  }
+  float s = 0.f;
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == 123.456f) out[0] = s;   /* keep the chains alive */
 }
 
 /* ------------------------------------------------------------------- API */
@@ -741,6 +777,8 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   dev_free(c->d_pos);
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
+  for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
+  free(c->evpool);
   cudaStreamDestroy(c->stream);
   free(c);
 }
@@ -843,9 +881,9 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         k_mark<<<nblk(n - 1), 256, 0, st>>>((int)n, ctx->d_kfirst, ctx->d_klast, ctx->leaf_max, d_used);
         CKG(cudaGetLastError());
         void *d_tmp2 = nullptr; size_t tb2 = 0;
-        CKG(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_used, ctx->d_newidx, (int)n, st));
+        CKG(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_used, ctx->d_newidx, (int)n - 1, st));
         CKG(cudaMalloc(&d_tmp2, tb2 ? tb2 : 1));
-        cudaError_t es = cub::DeviceScan::ExclusiveSum(d_tmp2, tb2, d_used, ctx->d_newidx, (int)n, st);
+        cudaError_t es = cub::DeviceScan::ExclusiveSum(d_tmp2, tb2, d_used, ctx->d_newidx, (int)n - 1, st);
         int last_idx = 0, last_used = 0;
         if (es == cudaSuccess) es = cudaMemcpyAsync(&last_idx, ctx->d_newidx + (n - 2), 4, cudaMemcpyDeviceToHost, st);
         if (es == cudaSuccess) es = cudaMemcpyAsync(&last_used, d_used + (n - 2), 4, cudaMemcpyDeviceToHost, st);
@@ -899,6 +937,34 @@ extern "C" int hrt_get_stats(const hrt_ctx *ctx, HrtRunStats *out)
   return HRT_OK;
 }
 
+extern "C" int hrt_fp32_peak(hrt_ctx *ctx, float *tflops_unfused, float *tflops_fma)
+{
+  if (!ctx) return HRT_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  float *d = nullptr;
+  CK(dev_alloc(&d, 1));
+  const int sms = [&] { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ctx->device); return v; }();
+  const int blocks = sms * 8, iters = 1 << 15;
+  const double flops = (double)blocks * 256 * 8 * 2.0 * iters;
+  float best[2] = {0.f, 0.f};
+  for (int rep = 0; rep < 4; ++rep)
+    for (int v = 0; v < 2; ++v) {
+      CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+      if (v) k_fp32_peak<true><<<blocks, 256, 0, ctx->stream>>>(d, iters, 0.999f, 1e-3f);
+      else   k_fp32_peak<false><<<blocks, 256, 0, ctx->stream>>>(d, iters, 0.999f, 1e-3f);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+      CK(cudaEventSynchronize(ctx->ev[7]));
+      float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+      const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+      if (rep && tf > best[v]) best[v] = tf;
+    }
+  cudaFree(d);
+  if (tflops_unfused) *tflops_unfused = best[0];
+  if (tflops_fma) *tflops_fma = best[1];
+  return HRT_OK;
+}
+
 static SceneDev scene_dev(const hrt_ctx *c)
 {
   SceneDev s;
@@ -929,6 +995,34 @@ template <class K> static cudaError_t allow_smem(K kernel, size_t bytes)
 {
   if (bytes <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+typedef void (*BounceFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t);
+typedef void (*ScatterFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t, uint32_t);
+
+/* [smem][brute][count]; the instrumented build exists for BVH traversal only */
+static BounceFn bounce_fn(bool smem, bool brute, bool count)
+{
+  static const BounceFn tab[2][2][2] = {
+    { { k_bounce<false, false, false>, k_bounce<false, false, true> },
+      { k_bounce<false, true, false>,  k_bounce<false, true, false> } },
+    { { k_bounce<true, false, false>,  k_bounce<true, false, true> },
+      { k_bounce<true, true, false>,   k_bounce<true, true, false> } } };
+  return tab[smem][brute][count];
+}
+/* [smem][brute][warp][count] */
+static ScatterFn scatter_fn(bool smem, bool brute, bool warp, bool count)
+{
+  static const ScatterFn tab[2][2][2][2] = {
+    { { { k_scatter<false, false, false, false>, k_scatter<false, false, false, true> },
+        { k_scatter<false, false, true, false>,  k_scatter<false, false, true, true> } },
+      { { k_scatter<false, true, false, false>,  k_scatter<false, true, false, false> },
+        { k_scatter<false, true, true, false>,   k_scatter<false, true, true, false> } } },
+    { { { k_scatter<true, false, false, false>,  k_scatter<true, false, false, true> },
+        { k_scatter<true, false, true, false>,   k_scatter<true, false, true, true> } },
+      { { k_scatter<true, true, false, false>,   k_scatter<true, true, false, false> },
+        { k_scatter<true, true, true, false>,    k_scatter<true, true, true, false> } } } };
+  return tab[smem][brute][warp][count];
 }
 
 static int sm_count(int device)
@@ -1104,14 +1198,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 160 * 1024;
   const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
   const bool warp_mode = R >= 8;
+  const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
+  const BounceFn f_bounce = bounce_fn(smem, brute, count);
+  const ScatterFn f_scatter = scatter_fn(smem, brute, warp_mode, count);
   if (smem) {
-    CK(allow_smem(k_bounce<true, true>, scene_sb)); CK(allow_smem(k_bounce<true, false>, scene_sb));
+    CK(allow_smem(f_bounce, scene_sb));
     CK(allow_smem(k_los<true, true>, scene_sb)); CK(allow_smem(k_los<true, false>, scene_sb));
   }
-  CK(allow_smem(k_scatter<true, true, true>, scat_sb)); CK(allow_smem(k_scatter<true, false, true>, scat_sb));
-  CK(allow_smem(k_scatter<true, true, false>, scat_sb)); CK(allow_smem(k_scatter<true, false, false>, scat_sb));
-  CK(allow_smem(k_scatter<false, true, true>, scat_sb)); CK(allow_smem(k_scatter<false, false, true>, scat_sb));
-  CK(allow_smem(k_scatter<false, true, false>, scat_sb)); CK(allow_smem(k_scatter<false, false, false>, scat_sb));
+  CK(allow_smem(f_scatter, scat_sb));
+  if (count) CK(cudaMemsetAsync(rd.counters, 0, 16 * sizeof(unsigned long long), st));
 
   CK(cudaEventRecord(ctx->ev[0], st));
 
@@ -1163,7 +1258,11 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   if (flags & HRT_FLAG_RAYSINFO) h_dead = (uint8_t *)malloc(T * ctx->cap_n);
   if (!h_counts || ((flags & HRT_FLAG_RAYSINFO) && !h_dead)) { free(h_counts); free(h_dead); return fail(ctx, HRT_E_NOMEM, "out of host memory"); }
   float ms_bounce = 0.f, ms_scatter = 0.f;
-  const bool time_kernels = getenv("HRT_TIME_KERNELS") != nullptr;
+  /* per-launch timing: three events per (chunk, bounce), resolved after the
+   * run -- no synchronisation inside the loop */
+  const size_t EV_CAP = 3 * 512;
+  size_t ev_used = 0;
+  uint8_t tail_dead[8] = {255, 255, 255, 255, 255, 255, 255, 255};  /* TX 1, paths 0..7 */
   rc = HRT_OK;
 #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto run_done; } } while (0)
 
@@ -1220,32 +1319,25 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
                             T * (size_t)rd.n_alloc * sizeof(Ray), cudaMemcpyDeviceToDevice, st));
       /* persistent grids: enough blocks to fill the machine, grid-stride inside */
       const dim3 gb((unsigned)min((size_t)((sms * 8 + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      if (time_kernels) CKR(cudaEventRecord(ctx->ev[4], st));
-      DISPATCH2(k_bounce, smem, brute, gb, HRT_BLOCK, smem ? scene_sb : 0, st, rd, sc, ctx->mats, b);
+      const bool timed = ev_used + 3 <= EV_CAP;
+      if (timed) {
+        if (ctx->evpool_n < ev_used + 3) {
+          cudaEvent_t *np_ = (cudaEvent_t *)realloc(ctx->evpool, (ev_used + 3) * sizeof(cudaEvent_t));
+          if (!np_) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
+          ctx->evpool = np_;
+          while (ctx->evpool_n < ev_used + 3) CKR(cudaEventCreate(&ctx->evpool[ctx->evpool_n++]));
+        }
+        CKR(cudaEventRecord(ctx->evpool[ev_used], st));
+      }
+      f_bounce<<<gb, HRT_BLOCK, smem ? scene_sb : 0, st>>>(rd, sc, ctx->mats, b);
       CKR(cudaGetLastError());
-      if (time_kernels) CKR(cudaEventRecord(ctx->ev[5], st));
+      if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 1], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * 8 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      if (warp_mode) {
-        if (smem) { if (brute) k_scatter<true, true, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
-                    else       k_scatter<true, false, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
-        else      { if (brute) k_scatter<false, true, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
-                    else       k_scatter<false, false, true><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
-      } else {
-        if (smem) { if (brute) k_scatter<true, true, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
-                    else       k_scatter<true, false, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
-        else      { if (brute) k_scatter<false, true, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
-                    else       k_scatter<false, false, false><<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok); }
-      }
+      f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
-      if (time_kernels) {
-        CKR(cudaEventRecord(ctx->ev[6], st));
-        CKR(cudaEventSynchronize(ctx->ev[6]));
-        float a = 0.f, c = 0.f;
-        cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]); cudaEventElapsedTime(&c, ctx->ev[5], ctx->ev[6]);
-        ms_bounce += a; ms_scatter += c;
-      }
+      if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st)); ev_used += 3; }
     }
 
     if (flags & HRT_FLAG_SUMMARY) {
@@ -1281,6 +1373,8 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       CKR(cudaMemcpyAsync(h_dead, rd.dead_at, T * (size_t)rd.n_alloc, cudaMemcpyDeviceToHost, st));
     }
     CKR(cudaStreamSynchronize(st));
+    if ((flags & HRT_FLAG_RAYSINFO) && T > 1 && l0 == 0 && rank == 0)
+      for (uint32_t j = 0; j < 8 && j < rd.n; ++j) tail_dead[j] = h_dead[rd.n_alloc + j];
 
     for (size_t b = 0; b < B; ++b)
       for (size_t t = 0; t < T; ++t) { S.ray_bounces += h_counts[b * T + t]; S.primary_hits += h_counts[(b + 1) * T + t]; }
@@ -1311,8 +1405,22 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     uint8_t *A = p->rays_scat->rays_active;
     const size_t rowb = P / 8 + 1;
     memset(A, 0xff, rowb);
-    for (size_t row = 1; row <= T * B; ++row)
-      for (uint64_t bit = P; bit < rowb * 8; ++bit) A[row * rowb + (bit >> 3)] |= (uint8_t)(1u << (bit & 7));
+    for (size_t t = 0; t < T; ++t)
+      for (size_t b = 0; b < B; ++b) {
+        uint8_t *row = A + (t * B + b + 1) * rowb;
+        for (uint64_t bit = P; bit < rowb * 8; ++bit) {
+          /* global bit index `bit` = TX 1, path bit-P (if it exists): its state
+           * when the reference copies the row, i.e. after bounce b for t >= 1,
+           * after bounce b-1 for t == 0 */
+          bool on = true;
+          const uint64_t j = bit - P;
+          if (T > 1 && j < P && j < 8) {
+            const int done = (int)b - (t == 0 ? 1 : 0);     /* last bounce TX 1 has finished */
+            on = done < 0 || (int)tail_dead[j] > done;
+          }
+          if (on) row[bit >> 3] |= (uint8_t)(1u << (bit & 7)); else row[bit >> 3] &= (uint8_t)~(1u << (bit & 7));
+        }
+      }
   }
 
   if (flags & HRT_FLAG_SUMMARY) {
@@ -1357,14 +1465,27 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     }
   }
 
+  if (count) {
+    unsigned long long hc[16];
+    CKR(cudaMemcpyAsync(hc, rd.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    for (int k = 0; k < 5; ++k) { S.work_bounce[k] = hc[k]; S.work_scatter[k] = hc[5 + k]; }
+  }
   CKR(cudaEventRecord(ctx->ev[2], st));
   CKR(cudaEventSynchronize(ctx->ev[2]));
   {
     float a = 0.f, b = 0.f;
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[2]);
     cudaEventElapsedTime(&b, ctx->ev[0], ctx->ev[1]);
+    for (size_t e = 0; e + 3 <= ev_used; e += 3) {
+      float x = 0.f, y = 0.f;
+      cudaEventElapsedTime(&x, ctx->evpool[e], ctx->evpool[e + 1]);
+      cudaEventElapsedTime(&y, ctx->evpool[e + 1], ctx->evpool[e + 2]);
+      ms_bounce += x; ms_scatter += y;
+    }
+    S.n_bounce_launches = S.n_scatter_launches = (uint32_t)(ev_used / 3);
     S.ms_total = a; S.ms_bounce = ms_bounce; S.ms_scatter = ms_scatter;
-    S.ms_other = time_kernels ? a - ms_bounce - ms_scatter : b;
+    S.ms_other = b;
   }
 run_done:
 #undef CKR

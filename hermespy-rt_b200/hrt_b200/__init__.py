@@ -1,0 +1,308 @@
+"""Python host-side mirror of the reference interface for the compute_paths()
+hot path, over the C-ABI library libhermespy_rt.so (ctypes; no torch types).
+
+Two levels:
+
+* ``compute_paths(mesh_filepath, rx_positions, ...) -> (los, scatter)`` -- same
+  name, argument order/meaning and result attributes as the reference's
+  pybind11 module (compute_paths_pybind11.cpp:99-210, test/test.py:20-87); it
+  goes through the drop-in C entry ``compute_paths`` (include/hermespy_rt.h).
+* ``Context`` -- the thin C-ABI of include/hrt_cuda.h (scene upload once, many
+  runs, summary/streaming mode, sharding), used by bench.py and the tests.
+
+There is no CPU fallback: if the CUDA library is missing or no device is
+usable, importing works but any call raises ``HrtError`` immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "..", "libhermespy_rt.so")
+
+FLAG_DENSE, FLAG_RAYSINFO, FLAG_SUMMARY, FLAG_TRACE = 0x01, 0x02, 0x04, 0x08
+FLAG_BRUTE_FORCE, FLAG_HOST_DIRS, FLAG_SUMMARY_DEV, FLAG_COUNT = 0x10, 0x20, 0x40, 0x80
+
+PAIR_DTYPE = np.dtype([("n_valid", "<u8"), ("n_occluded", "<u8"), ("hit_hash", "<u8"),
+                       ("tau_bits", "<u8"), ("power_te", "<f8"), ("power_tm", "<f8")])
+BOUNCE_DTYPE = np.dtype([("n_traced", "<u8"), ("n_hit", "<u8"), ("hit_hash", "<u8"),
+                         ("t_bits", "<u8")])
+
+
+class HrtError(RuntimeError):
+    pass
+
+
+class MaterialDerived(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("eta_abs2", "eta_abs_inv_sqrt", "sqrt_re", "sqrt_im",
+                                         "inv_re", "inv_im", "r", "s", "s1_alpha",
+                                         "pad0", "pad1", "pad2")]
+
+
+class RunParams(C.Structure):
+    _fields_ = [
+        ("num_rx", C.c_size_t), ("num_tx", C.c_size_t), ("num_paths", C.c_size_t),
+        ("num_bounces", C.c_size_t), ("carrier_frequency_GHz", C.c_float),
+        ("rx_pos", C.c_void_p), ("tx_pos", C.c_void_p), ("rx_vel", C.c_void_p), ("tx_vel", C.c_void_p),
+        ("shard_rank", C.c_uint32), ("shard_world", C.c_uint32), ("shard_block", C.c_size_t),
+        ("flags", C.c_uint32),
+        ("los", C.POINTER(abi.ChannelInfo)), ("rays_los", C.POINTER(abi.RaysInfo)),
+        ("scat", C.POINTER(abi.ChannelInfo)), ("rays_scat", C.POINTER(abi.RaysInfo)),
+        ("pair_summary", C.c_void_p), ("bounce_summary", C.c_void_p),
+        ("trace_hit_tri", C.c_void_p), ("trace_hit_t", C.c_void_p), ("trace_slot_state", C.c_void_p),
+        ("dirs", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class RunStats(C.Structure):
+    _fields_ = [
+        ("ray_bounces", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_queries", C.c_uint64),
+        ("los_queries", C.c_uint64), ("ambiguous_dirs", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("ms_total", C.c_float), ("ms_bounce", C.c_float), ("ms_scatter", C.c_float),
+        ("ms_other", C.c_float), ("n_bounce_launches", C.c_uint32), ("n_scatter_launches", C.c_uint32),
+        ("num_tris", C.c_uint32), ("num_nodes", C.c_uint32), ("scene_in_smem", C.c_uint32),
+        ("box_pad", C.c_float),
+        ("work_bounce", C.c_uint64 * 5), ("work_scatter", C.c_uint64 * 5),
+    ]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["work_bounce"] = list(self.work_bounce)
+        d["work_scatter"] = list(self.work_scatter)
+        return d
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The product library.  Raises HrtError when it has not been built."""
+    global _lib
+    if _lib is None:
+        path = os.path.abspath(LIB_PATH)
+        if not os.path.exists(path):
+            raise HrtError(f"{path} not found: build it with __graft_entry__.build() "
+                           "(make -C hermespy-rt_b200); there is no CPU fallback")
+        L = C.CDLL(path)
+        abi.bind_compute_paths(L)
+        L.hrt_device_count.restype = C.c_int
+        L.hrt_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.hrt_ctx_destroy.argtypes = [C.c_void_p]
+        L.hrt_last_error.restype = C.c_char_p
+        L.hrt_last_error.argtypes = [C.c_void_p]
+        L.hrt_scene_upload.argtypes = [C.c_void_p, C.POINTER(abi.Scene), C.c_void_p]
+        L.hrt_materials_derive.argtypes = [C.c_uint32, C.c_float, C.POINTER(MaterialDerived)]
+        L.hrt_materials_derive.restype = None
+        L.hrt_materials_set.argtypes = [C.c_void_p, C.POINTER(MaterialDerived)]
+        L.hrt_run.argtypes = [C.c_void_p, C.POINTER(RunParams)]
+        L.hrt_get_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
+        L.hrt_closest_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hrt_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def device_count() -> int:
+    return lib().hrt_device_count()
+
+
+class Context:
+    """One GPU: a scene (BVH resident in HBM) and any number of runs on it."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        L = lib()
+        rc = L.hrt_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            raise HrtError(f"hrt_ctx_create({device}) failed ({rc}): "
+                           f"{L.hrt_last_error(None).decode()}")
+        self._scene = None
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().hrt_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+        if self._scene is not None:
+            abi.free_scene(self._scene)
+            self._scene = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise HrtError(f"{what} failed ({rc}): {lib().hrt_last_error(self._h).decode()}")
+
+    # -- scene ---------------------------------------------------------------
+    def load_scene(self, path: str, want_normals: bool = False):
+        """scene_load() + hrt_scene_upload(): flatten, normals, BVH on the GPU."""
+        L = lib()
+        if self._scene is not None:
+            abi.free_scene(self._scene)
+        if not os.path.exists(path):
+            raise HrtError(f"scene file not found: {path}")
+        self._scene = L.scene_load(path.encode())
+        ntri = sum(self._scene.meshes[m].num_triangles for m in range(self._scene.num_meshes))
+        normals = np.zeros((max(ntri, 1), 3), np.float32) if want_normals else None
+        self._check(L.hrt_scene_upload(self._h, C.byref(self._scene),
+                                       normals.ctypes.data if want_normals else None),
+                    "hrt_scene_upload")
+        self.num_tris = ntri
+        return normals[:ntri] if want_normals else None
+
+    def set_frequency(self, f_ghz: float):
+        """Material constants at f_ghz for the materials the scene uses
+        (reference precompute_materials, src/compute_paths.c:171-206)."""
+        L = lib()
+        tab = (MaterialDerived * 17)()
+        for m in range(self._scene.num_meshes):
+            mi = self._scene.meshes[m].material_index
+            L.hrt_materials_derive(mi, C.c_float(f_ghz), C.byref(tab[mi]))
+        self._check(L.hrt_materials_set(self._h, tab), "hrt_materials_set")
+
+    # -- runs ----------------------------------------------------------------
+    def run(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, *, dense=False, raysinfo=False,
+            summary=False, trace=False, brute_force=False, count_work=False, los=True, dirs=None,
+            shard=(0, 1), shard_block=1 << 20, out: abi.Outputs | None = None,
+            summary_dev_ptrs=None, stream=None):
+        """hrt_run().  Returns a dict with whatever was requested:
+        'out' (abi.Outputs, dense), 'pair'/'bounce' (structured arrays, summary),
+        'trace' (dict), 'stats'."""
+        rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
+        R, T = rx.shape[0], tx.shape[0]
+        rxv = abi.vec3_array(rx_vel, R); txv = abi.vec3_array(tx_vel, T)
+        self.set_frequency(f_ghz)
+        p = RunParams()
+        p.num_rx, p.num_tx, p.num_paths, p.num_bounces = R, T, P, B
+        p.carrier_frequency_GHz = f_ghz
+        p.rx_pos, p.tx_pos, p.rx_vel, p.tx_vel = (a.ctypes.data for a in (rx, tx, rxv, txv))
+        p.shard_rank, p.shard_world = shard
+        p.shard_block = shard_block
+        flags = 0
+        res = {}
+        keep = [rx, tx, rxv, txv]
+        if dense:
+            flags |= FLAG_DENSE
+            o = out if out is not None else abi.alloc_outputs(R, T, P, B, 0)
+            res["out"] = o
+            los_s = abi.chan_struct(o.los, 1); sc_s = abi.chan_struct(o.scat, B * P)
+            rl = abi.RaysInfo(1, 1, o.los_rays.ctypes.data, o.los_active.ctypes.data)
+            rs = abi.RaysInfo(B + 1, P, o.scat_rays.ctypes.data, o.scat_active.ctypes.data)
+            keep += [los_s, sc_s, rl, rs]
+            p.scat = C.pointer(sc_s)
+            if los:
+                p.los = C.pointer(los_s); p.rays_los = C.pointer(rl)
+            if raysinfo:
+                flags |= FLAG_RAYSINFO
+                p.rays_scat = C.pointer(rs)
+        elif los:
+            o = abi.alloc_outputs(R, T, 1, 1, 0)
+            res["out"] = o
+            los_s = abi.chan_struct(o.los, 1)
+            rl = abi.RaysInfo(1, 1, o.los_rays.ctypes.data, o.los_active.ctypes.data)
+            keep += [los_s, rl]
+            p.los = C.pointer(los_s); p.rays_los = C.pointer(rl)
+        if summary:
+            flags |= FLAG_SUMMARY
+            if summary_dev_ptrs is not None:
+                flags |= FLAG_SUMMARY_DEV
+                p.pair_summary, p.bounce_summary = summary_dev_ptrs
+            else:
+                res["pair"] = np.zeros((R, T, B), PAIR_DTYPE)
+                res["bounce"] = np.zeros((T, B), BOUNCE_DTYPE)
+                p.pair_summary = res["pair"].ctypes.data
+                p.bounce_summary = res["bounce"].ctypes.data
+        if trace:
+            flags |= FLAG_TRACE
+            tr = {"hit_tri": np.full((T, B, P), 0xFFFFFFFE, np.uint32),
+                  "hit_t": np.full((T, B, P), -1.0, np.float32),
+                  "slot_state": np.zeros((R, T, B, P), np.uint8)}
+            res["trace"] = tr
+            p.trace_hit_tri = tr["hit_tri"].ctypes.data
+            p.trace_hit_t = tr["hit_t"].ctypes.data
+            p.trace_slot_state = tr["slot_state"].ctypes.data
+        if brute_force:
+            flags |= FLAG_BRUTE_FORCE
+        if count_work:
+            flags |= FLAG_COUNT
+        if dirs is not None:
+            dirs = abi.vec3_array(dirs, P)
+            keep.append(dirs)
+            flags |= FLAG_HOST_DIRS
+            p.dirs = dirs.ctypes.data
+        if stream is not None:
+            p.stream = stream
+        p.flags = flags
+        self._check(lib().hrt_run(self._h, C.byref(p)), "hrt_run")
+        res["stats"] = self.stats()
+        del keep
+        return res
+
+    def stats(self) -> dict:
+        s = RunStats()
+        self._check(lib().hrt_get_stats(self._h, C.byref(s)), "hrt_get_stats")
+        return s.as_dict()
+
+    def fp32_peak(self):
+        """(unfused FMUL+FADD, FFMA) sustained Tflop/s of this GPU, measured."""
+        a, b = C.c_float(), C.c_float()
+        self._check(lib().hrt_fp32_peak(self._h, C.byref(a), C.byref(b)), "hrt_fp32_peak")
+        return a.value, b.value
+
+    def closest_hits(self, rays: np.ndarray, brute_force: bool = False):
+        """Batch moeller_trumbore(): rays (n,6) float32 -> (tri, t, theta)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        tri = np.zeros(n, np.uint32); t = np.zeros(n, np.float32); th = np.zeros(n, np.float32)
+        self._check(lib().hrt_closest_hits(self._h, rays.ctypes.data, n,
+                                           FLAG_BRUTE_FORCE if brute_force else 0,
+                                           tri.ctypes.data, t.ctypes.data, th.ctypes.data),
+                    "hrt_closest_hits")
+        return tri, t, th
+
+
+# ------------------------------------------------- reference-shaped Python API
+
+class ChannelInfo:
+    """Same read-only attributes as the reference's pybind11 ChannelInfo
+    (compute_paths_pybind11.cpp:44-97, :189-196)."""
+
+    def __init__(self, d: dict, num_paths: int):
+        self.num_paths = num_paths
+        R, T = d["tau"].shape[:2]
+        self.directions_rx = d["directions_rx"].reshape(R, T, num_paths, 3)
+        self.directions_tx = d["directions_tx"].reshape(R, T, num_paths, 3)
+        self.a_te = (d["a_te_re"] + 1j * d["a_te_im"]).astype(np.complex64).reshape(R, T, num_paths)
+        self.a_tm = (d["a_tm_re"] + 1j * d["a_tm_im"]).astype(np.complex64).reshape(R, T, num_paths)
+        self.tau = d["tau"].reshape(R, T, num_paths)
+        self.freq_shift = d["freq_shift"].reshape(R, T, num_paths)
+
+
+def compute_paths(mesh_filepath, rx_positions, tx_positions, rx_velocities, tx_velocities,
+                  carrier_frequency, num_rx, num_tx, num_paths, num_bounces):
+    """Drop-in for ``hermespy_rt.compute_paths`` (reference
+    compute_paths_pybind11.cpp:99-186): loads the scene, calls the C entry
+    ``compute_paths`` and returns ``(los, scatter)`` ChannelInfo objects."""
+    L = lib()
+    if L.hrt_device_count() <= 0:
+        raise HrtError("no CUDA device available; hermespy-rt_b200 has no CPU path")
+    if not os.path.exists(mesh_filepath):
+        raise HrtError(f"scene file not found: {mesh_filepath}")
+    rx = abi.vec3_array(rx_positions, num_rx); tx = abi.vec3_array(tx_positions, num_tx)
+    sc = L.scene_load(str(mesh_filepath).encode())
+    try:
+        o = abi.call_compute_paths(L, sc, rx, tx, rx_velocities, tx_velocities,
+                                   float(carrier_frequency), int(num_paths), int(num_bounces))
+    finally:
+        abi.free_scene(sc)
+    return ChannelInfo(o.los, 1), ChannelInfo(o.scat, int(num_bounces) * int(num_paths))

@@ -56,6 +56,7 @@ typedef struct {
 #define HRT_FLAG_BRUTE_FORCE  0x10u  /* skip the BVH: test every triangle (validation)   */
 #define HRT_FLAG_HOST_DIRS    0x20u  /* launch directions supplied by caller (dirs)      */
 #define HRT_FLAG_SUMMARY_DEV  0x40u  /* summary pointers are DEVICE memory               */
+#define HRT_FLAG_COUNT        0x80u  /* instrumented kernels: count box/triangle tests   */
 
 /* Order-independent per-(rx, tx, bounce) reduction of the scatter paths.
  * Integer fields are exact and comparable bit for bit with a CPU run. */
@@ -128,8 +129,14 @@ typedef struct {
   float    ms_bounce;          /* sum over k_bounce launches                      */
   float    ms_scatter;         /* sum over k_scatter launches (dominant kernel)   */
   float    ms_other;
+  uint32_t n_bounce_launches;  /* launches behind ms_bounce / ms_scatter           */
+  uint32_t n_scatter_launches;
   uint32_t num_tris, num_nodes, scene_in_smem;
   float    box_pad;
+  /* HRT_FLAG_COUNT runs only: tests performed by k_bounce / k_scatter:
+   * [0] ray-box tests, [1..4] Moeller-Trumbore tests reaching stage A (det),
+   * B (u), C (v), D (t) -- SURVEY section 8d's unit of algorithmic work */
+  uint64_t work_bounce[5], work_scatter[5];
 } HrtRunStats;
 
 int  hrt_device_count(void);
@@ -150,16 +157,16 @@ int  hrt_materials_set(hrt_ctx *ctx, const HrtMaterialDerived table[NUM_G_MATERI
 int hrt_run(hrt_ctx *ctx, const HrtRunParams *p);
 int hrt_get_stats(const hrt_ctx *ctx, HrtRunStats *out);
 
+/* Measures this GPU's sustained fp32 rate with separately rounded FMUL/FADD
+ * (the arithmetic of the exact intersection code) and with FFMA, in Tflop/s.
+ * Denominator of the intersection roofline (no fp32 figure exists in
+ * MEASURED_PEAKS.json). */
+int hrt_fp32_peak(hrt_ctx *ctx, float *tflops_unfused, float *tflops_fma);
+
 /* Batch closest hit (host arrays): tri = id in (mesh, face) order or
  * 0xFFFFFFFF, t = distance or -1, theta = folded incidence angle or 0. */
 int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_t flags,
                      uint32_t *tri, float *t, float *theta);
-
-/* Timing loop for the roofline: runs the closest-hit kernel `reps` times over
- * n device-resident rays generated from (tx, launch directions); returns the
- * average kernel time in ms and the number of box/triangle tests performed. */
-int hrt_bench_closest_hit(hrt_ctx *ctx, const Vec3 *origin, size_t n, int reps, uint32_t flags,
-                          float *ms_avg, uint64_t *node_tests, uint64_t *tri_tests);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,42 @@
+#!/bin/bash
+# One GPU session: parity tests, small + full bench, ncu launch list and one
+# full capture of the dominant kernel.  Everything is logged to gpurun_out/.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
+
+echo "== pytest -m gpu"; 
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+tail -15 $OUT/pytest_gpu.log
+
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
+tail -3 $OUT/smoke.log
+
+echo "== bench small (4e6 rays)"
+HRT_BENCH_RAYS=4e6 HRT_REF_PATHS=200 timeout 600 python bench.py --steps 2 --warmup 1 > $OUT/bench_small.json 2> $OUT/bench_small.err; echo "rc=$?"
+cat $OUT/bench_small.json | cut -c1-1500; tail -5 $OUT/bench_small.err
+
+if [ "${FULL:-1}" = "1" ]; then
+echo "== bench full (1e8 rays)"
+timeout 1200 python bench.py --steps ${STEPS:-3} --warmup 3 > $OUT/bench_full.json 2> $OUT/bench_full.err; echo "rc=$?"
+cat $OUT/bench_full.json | cut -c1-3000; tail -5 $OUT/bench_full.err
+echo "== reference arm"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "rc=$?"
+cat $OUT/bench_ref.json | cut -c1-400
+fi
+
+if [ "${NCU:-1}" = "1" ]; then
+echo "== ncu launch list"
+export HRT_BENCH_RAYS=2e6 HRT_REF_PATHS=100
+python bench.py --steps 1 --warmup 0 > $OUT/ncu_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 1 --warmup 0 > $OUT/ncu_launches.log 2>&1
+echo "ncu launches rc=$?"
+python bench.py --steps 1 --warmup 0 > $OUT/ncu_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_scatter -s 1 -c 2 -f -o $OUT/prof_scatter \
+    python bench.py --steps 1 --warmup 0 > $OUT/ncu_full.log 2>&1
+echo "ncu full rc=$?"
+ls -la $OUT
+fi

@@ -94,8 +94,9 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
 static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
 {
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
-  if (brute) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d);
-  return hrt_closest_hit(m, E.gid.data(), E.root, E.n, o, d);
+  HrtNoCount nc;
+  if (brute) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
+  return hrt_closest_hit(m, E.gid.data(), E.root, E.n, o, d, nc);
 }
 
 static V3 nrm(const EmulScene &E, uint32_t slot) { const float4 q = E.tris[3 * slot + 2]; return v3(q.y, q.z, q.w); }

@@ -315,3 +315,56 @@ def emul_closest(scene_name, rays, leaf_max=4, pad_ulps=64.0, brute=False):
                           int(brute), tri.ctypes.data, t.ctypes.data, th.ctypes.data)
     abi.free_scene(sc)
     return tri, t, th
+
+
+# ------------------------------------------------ summaries from an oracle run
+
+def mix64(x: np.ndarray) -> np.ndarray:
+    """numpy twin of hrt_mix64 (hrt_core.cuh)."""
+    x = x.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def oracle_summaries(o: abi.Outputs, tr: dict, path_ids: np.ndarray | None = None):
+    """HrtPairSummary / HrtBounceSummary (include/hrt_cuda.h) computed from an
+    oracle run's outputs and trace.  Returns dicts of arrays."""
+    R, T, B, P = o.R, o.T, o.B, o.P
+    paths = (np.arange(P, dtype=np.uint64) if path_ids is None else path_ids.astype(np.uint64))
+    hit = tr["hit_tri"]                                   # (T,B,P)
+    is_hit = hit < IDLE
+    key = mix64((paths[None, None, :] << np.uint64(32)) | hit.astype(np.uint64))
+    with np.errstate(over="ignore"):
+        bounce = {
+            "n_traced": (hit != IDLE).sum(-1).astype(np.uint64),
+            "n_hit": is_hit.sum(-1).astype(np.uint64),
+            "hit_hash": np.where(is_hit, key, np.uint64(0)).sum(-1, dtype=np.uint64),
+            "t_bits": np.where(is_hit, tr["hit_t"].view(np.uint32).astype(np.uint64),
+                               np.uint64(0)).sum(-1, dtype=np.uint64),
+        }
+        st = tr["slot_state"]                             # (R,T,B,P)
+        valid = st == 1
+        tau_bits = o.scat["tau"].view(np.uint32).astype(np.uint64)
+        pair = {
+            "n_valid": valid.sum(-1).astype(np.uint64),
+            "n_occluded": (st == 2).sum(-1).astype(np.uint64),
+            "hit_hash": np.where(valid, key[None], np.uint64(0)).sum(-1, dtype=np.uint64),
+            "tau_bits": np.where(valid, tau_bits, np.uint64(0)).sum(-1, dtype=np.uint64),
+            "power_te": np.where(valid, o.scat["a_te_re"].astype(np.float64) ** 2
+                                 + o.scat["a_te_im"].astype(np.float64) ** 2, 0.0).sum(-1),
+            "power_tm": np.where(valid, o.scat["a_tm_re"].astype(np.float64) ** 2
+                                 + o.scat["a_tm_im"].astype(np.float64) ** 2, 0.0).sum(-1),
+        }
+    return pair, bounce
+
+
+def assert_summaries_equal(pair_ref, bounce_ref, pair, bounce, rtol=GAIN_RTOL * 2):
+    for k in ("n_traced", "n_hit", "hit_hash", "t_bits"):
+        assert np.array_equal(bounce_ref[k], bounce[k]), f"bounce.{k}"
+    for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+        assert np.array_equal(pair_ref[k], pair[k]), f"pair.{k}"
+    for k in ("power_te", "power_tm"):
+        np.testing.assert_allclose(pair[k], pair_ref[k], rtol=rtol, atol=1e-300, err_msg=k)

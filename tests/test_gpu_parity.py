@@ -1,0 +1,222 @@
+"""Parity of the CUDA path with the oracle, through the C ABI, on a real GPU.
+
+Bit-exact: hit triangle ids, hit distances, tau, directions, Doppler, LoS,
+RaysInfo.  fp32 relative tolerance 1e-4 (north star): complex gains, which pass
+through sinf/cosf/expf/acosf.  Reference quirks reproduced: SURVEY appendix A."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import hrt_testlib as tl
+from hrt_b200 import abi
+import hrt_b200 as hrt
+
+pytestmark = pytest.mark.gpu
+
+SCENES = ["simple_reflector", "box", "2cars", "simple_street_canyon_with_cars"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = hrt.Context(0)
+    yield c
+    c.close()
+
+
+def _ulps(a, b):
+    ai = a.view(np.int32).astype(np.int64); bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("brute", [False, True])
+def test_closest_hit_bit_exact(ctx, scene, brute):
+    """moeller_trumbore(): triangle id and t bit-exact, BVH and brute force."""
+    ctx.load_scene(tl.scene_path(scene))
+    rays = tl.random_rays(scene, 200000, seed=11)
+    tri_o, t_o, th_o = tl.oracle_closest(scene, rays)
+    tri, t, th = ctx.closest_hits(rays, brute_force=brute)
+    assert np.array_equal(tri_o, tri)
+    assert np.array_equal(t_o.view(np.uint32), t.view(np.uint32))
+    # incidence angle: double acos on the GPU is within 2 ulp of glibc's, so the
+    # fp32-rounded value may differ in the last place for ~1e-8 of the rays
+    assert _ulps(th_o, th).max() <= 1
+    assert (_ulps(th_o, th) > 0).mean() < 1e-4
+
+
+def _compare_dense(o_ref, mask, o, trace_ref=None, trace=None, raysinfo=True):
+    wr, wt = tl.outputs_words(o_ref), tl.outputs_words(o)
+    keys = [k for k in tl.EXACT_KEYS if raysinfo or not k.startswith(("scat_rays", "scat_active"))]
+    tl.assert_exact(wr, mask, wt, keys=keys)
+    tl.assert_gains_close(wr, mask, wt)
+    if trace_ref is not None:
+        assert np.array_equal(trace_ref["hit_tri"], trace["hit_tri"])
+        assert np.array_equal(trace_ref["slot_state"], trace["slot_state"])
+
+
+@pytest.mark.parametrize("name", tl.GOLDEN_NAMES)
+def test_drop_in_entry_vs_golden(name):
+    """The C symbol compute_paths() itself (host buffers in, host buffers out)
+    against the vectors produced by the unmodified reference."""
+    g = tl.load_golden(name)
+    L = hrt.lib()
+    sc = L.scene_load(tl.scene_path(g["scene"]).encode())
+    try:
+        o = abi.call_compute_paths(L, sc, g["rx"], g["tx"], g["rxv"], g["txv"], g["f"],
+                                   g["P"], g["B"], fill=0x5A)
+        # Mesh.ns must have been filled like the reference does
+        assert bool(sc.meshes[0].ns)
+    finally:
+        abi.free_scene(sc)
+    w = tl.outputs_words(o)
+    ref = {k[4:]: v for k, v in g.items() if k.startswith("out.")}
+    mask = {k[5:]: v for k, v in g.items() if k.startswith("mask.")}
+    tl.assert_exact(ref, mask, w)
+    tl.assert_gains_close(ref, mask, w)
+
+
+CASES = [
+    # scene cfg, P, B, n_rx (grid), moving, T
+    ("box_generic", 40000, 3, 1, True, 1),
+    ("2cars_raised", 30000, 5, 3, True, 1),
+    ("canyon_1x1", 12000, 5, 40, True, 1),     # warp-per-hit scatter + theta carry over 2 tiles
+    ("canyon_1x1", 6000, 4, 9, False, 2),      # two TX
+    ("reflector_testc", 30000, 3, 33, False, 1),
+]
+
+
+def _case_inputs(cfg, n_rx, moving, T):
+    scene, rx, tx, f = tl.CONFIGS[cfg]
+    rng = np.random.default_rng(5)
+    rx = list(rx)
+    if cfg.startswith("canyon"):
+        grid, _ = tl.canyon_c4_positions()
+        rx += grid[: n_rx - 1].tolist()
+    else:
+        rx += (np.asarray(rx[0]) + rng.uniform(-1.5, 1.5, (n_rx - 1, 3)) * [1, 1, 0.3]).tolist()
+    tx = list(tx) + [[tx[0][0] + 7.0 * i, tx[0][1] - 1.0, tx[0][2]] for i in range(1, T)]
+    rxv = rng.uniform(-3, 3, (len(rx), 3)) if moving else np.zeros((len(rx), 3))
+    txv = rng.uniform(-10, 10, (len(tx), 3)) if moving else np.zeros((len(tx), 3))
+    return scene, rx, tx, rxv, txv, f
+
+
+@pytest.mark.parametrize("cfg,P,B,n_rx,moving,T", CASES)
+def test_run_dense_vs_oracle(ctx, cfg, P, B, n_rx, moving, T):
+    scene, rx, tx, rxv, txv, f = _case_inputs(cfg, n_rx, moving, T)
+    a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B, fill=0x00)
+    b, _ = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B, fill=0x5A, trace=False)
+    mask = tl.written_mask(a, b)
+    ctx.load_scene(tl.scene_path(scene))
+    res = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, trace=True, summary=True)
+    _compare_dense(a, mask, res["out"], tr, res["trace"])
+    assert np.array_equal(tr["hit_t"].view(np.uint32)[tr["hit_tri"] < tl.IDLE],
+                          res["trace"]["hit_t"].view(np.uint32)[tr["hit_tri"] < tl.IDLE])
+    pair, bounce = tl.oracle_summaries(a, tr)
+    tl.assert_summaries_equal(pair, bounce, res["pair"], res["bounce"])
+    st = res["stats"]
+    assert st["ray_bounces"] == int(bounce["n_traced"].sum())
+    assert st["kernel_launches"] > 0
+    # brute-force kernels (no BVH) give the very same bits
+    res2 = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, trace=True, brute_force=True)
+    for k in ("tau", "a_te_re", "a_tm_im", "freq_shift", "directions_rx"):
+        assert np.array_equal(res["out"].scat[k].view(np.uint32), res2["out"].scat[k].view(np.uint32)), k
+    assert np.array_equal(res["trace"]["hit_tri"], res2["trace"]["hit_tri"])
+
+
+def test_launch_directions_bit_exact(ctx):
+    """Fibonacci launch directions incl. the host-recomputed ambiguous ones
+    (hrt_core.cuh, hrt_launch_dir) == glibc results of the oracle, every ray."""
+    P = 3_000_000
+    ctx.load_scene(tl.scene_path("simple_reflector"))
+    res = ctx.run([[0, 0, .5]], [[0, 0, .5]], [[0, 0, 0]], [[0, 0, 0]], 3.0, P, 1,
+                  dense=True, raysinfo=True)
+    d = res["out"].scat_rays[0, :, 3:6]
+    ref = np.zeros((P, 3), np.float32)
+    tl.oracle_lib().oracle_launch_dirs(0, P, P, ref.ctypes.data)
+    assert np.array_equal(d.view(np.uint32), ref.view(np.uint32))
+    # above 2^23 rays the fp32 index collapses (SURVEY A-11): same duplicates
+    P2 = 20_000_000
+    first = P2 - 1_000_000
+    res = ctx.run([[0, 0, .5]], [[0, 0, .5]], [[0, 0, 0]], [[0, 0, 0]], 3.0, P2, 1,
+                  dense=True, raysinfo=True, los=False)
+    d = res["out"].scat_rays[0, first:, 3:6]
+    ref = np.zeros((1_000_000, 3), np.float32)
+    tl.oracle_lib().oracle_launch_dirs(first, 1_000_000, P2, ref.ctypes.data)
+    assert np.array_equal(d.view(np.uint32), ref.view(np.uint32))
+
+
+def test_summary_mode_and_shards(ctx):
+    """Summary (streaming) mode == dense mode; shards of the path range add up
+    to the unsharded run; chunked runs (HRT_CHUNK) are identical."""
+    import os
+    scene, rx, tx, rxv, txv, f = _case_inputs("canyon_1x1", 20, True, 2)
+    P, B = 50000, 4
+    ctx.load_scene(tl.scene_path(scene))
+    full = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, summary=True, trace=True)
+    a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B)
+    pair, bounce = tl.oracle_summaries(a, tr)
+    tl.assert_summaries_equal(pair, bounce, full["pair"], full["bounce"])
+    only = ctx.run(rx, tx, rxv, txv, f, P, B, summary=True, los=False)
+    for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+        assert np.array_equal(only["pair"][k], full["pair"][k])
+    # 3 shards, block 4096, dense outputs written into ONE set of host arrays
+    o = abi.alloc_outputs(len(rx), len(tx), P, B, 0)
+    acc_pair = np.zeros_like(full["pair"]); acc_bounce = np.zeros_like(full["bounce"])
+    for r in range(3):
+        part = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, summary=True, out=o,
+                       shard=(r, 3), shard_block=4096, los=(r == 0))
+        for k in acc_pair.dtype.names:
+            acc_pair[k] += part["pair"][k]
+        for k in acc_bounce.dtype.names:
+            acc_bounce[k] += part["bounce"][k]
+    for k in ("tau", "a_te_re", "a_tm_im", "freq_shift", "directions_rx"):
+        assert np.array_equal(o.scat[k].view(np.uint32), full["out"].scat[k].view(np.uint32)), k
+    for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+        assert np.array_equal(acc_pair[k], full["pair"][k]), k
+    for k in ("n_traced", "n_hit", "hit_hash", "t_bits"):
+        assert np.array_equal(acc_bounce[k], full["bounce"][k]), k
+    np.testing.assert_allclose(acc_pair["power_te"], full["pair"]["power_te"], rtol=1e-9)
+    os.environ["HRT_CHUNK"] = "8192"
+    try:
+        ch = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, summary=True)
+    finally:
+        del os.environ["HRT_CHUNK"]
+    for k in ("tau", "a_te_re", "freq_shift"):
+        assert np.array_equal(ch["out"].scat[k].view(np.uint32), full["out"].scat[k].view(np.uint32)), k
+    assert np.array_equal(ch["pair"]["hit_hash"], full["pair"]["hit_hash"])
+
+
+def test_full_size_anchor_counts(ctx):
+    """BASELINE configs at full size through size-independent properties:
+    per-bounce active-ray counts measured on the reference during the survey
+     and BVH == brute force checksums."""
+    ctx.load_scene(tl.scene_path("box"))
+    r = ctx.run([[0, 0, 1]], [[0, 0, 2.5]], [[0, 0, 0]], [[0, 0, 0]], 3.0, 1_000_000, 3, summary=True)
+    assert r["bounce"]["n_traced"][0].tolist() == [1_000_000, 1_000_000, 999_983]
+    ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
+    r = ctx.run([[0, 0, 1.5]], [[0, 0, 10]], [[0, 0, 0]], [[0, 0, 0]], 3.5, 1_000_000, 5, summary=True)
+    assert r["bounce"]["n_traced"][0].tolist() == [1_000_000, 860_405, 619_961, 406_583, 214_445]
+    assert r["pair"]["n_valid"][0, 0].tolist() == [855_563, 565_555, 339_241, 175_663, 89_761]
+    rb = ctx.run([[0, 0, 1.5]], [[0, 0, 10]], [[0, 0, 0]], [[0, 0, 0]], 3.5, 1_000_000, 5,
+                 summary=True, brute_force=True)
+    for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+        assert np.array_equal(r["pair"][k], rb["pair"][k])
+    assert np.array_equal(r["bounce"]["hit_hash"], rb["bounce"]["hit_hash"])
+
+
+def test_python_api_shapes():
+    """The reference's own smoke test (test/test.py:8-87), value checks added."""
+    num_paths, num_bounces = 10000, 3
+    los, sc = hrt.compute_paths(tl.scene_path("simple_reflector"),
+                                np.array([[0., 0., .15]]), np.array([[0., 0., .151]]),
+                                np.zeros((1, 3)), np.zeros((1, 3)), 3.0, 1, 1, num_paths, num_bounces)
+    assert los.num_paths == 1
+    assert los.directions_rx.shape == los.directions_tx.shape == (1, 1, 1, 3)
+    assert los.a_te.shape == los.a_tm.shape == los.tau.shape == los.freq_shift.shape == (1, 1, 1)
+    assert sc.num_paths == num_bounces * num_paths
+    assert sc.directions_rx.shape == (1, 1, sc.num_paths, 3)
+    assert sc.a_te.shape == sc.a_tm.shape == sc.tau.shape == sc.freq_shift.shape == (1, 1, sc.num_paths)
+    assert sc.a_te.dtype == np.complex64
+    assert int((sc.tau[0, 0, :num_paths] > 0).sum()) > 3000     # reference: 3690 hits
+    assert np.isfinite(sc.a_te).all()
