@@ -253,8 +253,12 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
   int   stack_ref[HRT_STACK];
   float stack_tn[HRT_STACK];
   int sp = 0, cur = root_ref;
-  for (;;) {
-    if (cur >= 0) {
+  bool done = false;
+  /* "while-while" traversal: every lane first walks inner nodes until it holds
+   * a leaf (or has nothing left), then the leaves are tested -- lanes of a warp
+   * meet in the triangle loop instead of interleaving box and triangle code. */
+  while (!done) {
+    while (cur >= 0) {
       const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1);
       const float4 n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
       float tl, tr;
@@ -268,11 +272,22 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
         stack_tn[sp]  = left_first ? tr : tl;
         ++sp;
         cur = left_first ? rl : rr;
-        continue;
+      } else if (hl) {
+        cur = rl;
+      } else if (hr) {
+        cur = rr;
+      } else {
+        /* pop, skipping subtrees that start beyond the current best */
+        bool got = false;
+        while (sp > 0) {
+          --sp;
+          if (stack_tn[sp] <= tmax) { cur = stack_ref[sp]; got = true; break; }
+        }
+        if (!got) { done = true; break; }
       }
-      if (hl) { cur = rl; continue; }
-      if (hr) { cur = rr; continue; }
-    } else {
+    }
+    if (done) break;
+    {
       const uint32_t code = (uint32_t)~cur;
       const uint32_t first = code >> 3, ntri = (code & 7u) + 1u;
       for (uint32_t k = 0; k < ntri; ++k) {
@@ -285,13 +300,14 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
         }
       }
     }
-    /* pop, skipping subtrees that start beyond the current best */
-    for (;;) {
-      if (sp == 0) return h;
+    bool got = false;
+    while (sp > 0) {
       --sp;
-      if (stack_tn[sp] <= tmax) { cur = stack_ref[sp]; break; }
+      if (stack_tn[sp] <= tmax) { cur = stack_ref[sp]; got = true; break; }
     }
+    if (!got) done = true;
   }
+  return h;
 }
 
 /* Brute force over every triangle in leaf order -- debug/validation path of

@@ -1102,6 +1102,11 @@ static uint64_t shard_count(uint64_t P, uint32_t rank, uint32_t world, uint64_t 
   return cnt;
 }
 
+extern "C" uint64_t hrt_shard_count(uint64_t num_paths, uint32_t rank, uint32_t world, uint64_t block)
+{ return shard_count(num_paths, rank, world, block ? block : 1); }
+extern "C" uint64_t hrt_shard_path(uint64_t local_index, uint32_t rank, uint32_t world, uint64_t block)
+{ return hrt_gpath(local_index, rank, world, block ? block : 1); }
+
 /* copy device rows [nrows][n_alloc] (elem bytes) into host rows of pitch P at
  * the columns of the chunk's paths */
 static cudaError_t d2h_columns(const hrt_ctx *ctx, cudaStream_t st, void *host, const void *dev, size_t elem,

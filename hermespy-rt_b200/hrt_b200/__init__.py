@@ -104,8 +104,28 @@ def lib() -> C.CDLL:
         L.hrt_closest_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.hrt_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.hrt_shard_count.restype = C.c_uint64
+        L.hrt_shard_count.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.hrt_shard_path.restype = C.c_uint64
+        L.hrt_shard_path.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
         _lib = L
     return _lib
+
+
+def shard_paths(num_paths: int, rank: int, world: int, block: int) -> np.ndarray:
+    """Global path indices owned by `rank` (host arithmetic of the C library)."""
+    L = lib()
+    n = L.hrt_shard_count(num_paths, rank, world, block)
+    if world <= 1:
+        return np.arange(num_paths, dtype=np.uint64)
+    loc = np.arange(n, dtype=np.uint64)
+    q, r = loc // np.uint64(block), loc % np.uint64(block)
+    g = (q * np.uint64(world) + np.uint64(rank)) * np.uint64(block) + r
+    # spot-check the closed form against the C function
+    for i in (0, n // 2, n - 1):
+        if n:
+            assert L.hrt_shard_path(int(i), rank, world, block) == int(g[int(i)])
+    return g
 
 
 def device_count() -> int:

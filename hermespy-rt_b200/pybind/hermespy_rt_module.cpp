@@ -1,0 +1,130 @@
+// hermespy_rt_module.cpp -- Python module `hermespy_rt`, the consumer-facing
+// surface of the reference (compute_paths_pybind11.cpp:99-210), rebuilt over
+// the B200 library.  Same module name, function signature, keyword names and
+// ChannelInfo attributes (num_paths, directions_rx, directions_tx, a_te, a_tm,
+// tau, freq_shift; shapes as asserted by the reference's test/test.py:61-87).
+//
+// Differences from the reference binding, all of them fixes it needs anyway
+// (SURVEY section 8 row f1): the C headers are wrapped in extern "C" (the
+// reference module does not import on Linux), inputs are converted to
+// C-contiguous float32 and their shapes checked, outputs are zero-initialised
+// numpy arrays owned by Python (no leaks, no uninitialised slots), complex
+// gains are assembled once, RaysInfo is not materialised (the reference
+// computes and discards it, :172-176) and the GIL is released while the GPU
+// works.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+
+#include <complex>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/hrt_cuda.h"   // extern "C" inside
+
+namespace py = pybind11;
+using farr = py::array_t<float, py::array::c_style | py::array::forcecast>;
+
+namespace {
+
+struct Channel {
+  size_t num_paths;
+  py::array_t<float> directions_rx, directions_tx, tau, freq_shift;
+  py::array_t<std::complex<float>> a_te, a_tm;
+};
+
+const Vec3 *as_vec3(const farr &a, size_t n, const char *what)
+{
+  if (a.size() != (py::ssize_t)(3 * n))
+    throw std::invalid_argument(std::string(what) + ": expected " + std::to_string(n) + " x 3 values");
+  return reinterpret_cast<const Vec3 *>(a.data());
+}
+
+py::array_t<float> zeros(std::vector<py::ssize_t> shape)
+{
+  py::array_t<float> a(shape);
+  std::fill_n(a.mutable_data(), a.size(), 0.f);
+  return a;
+}
+
+Channel make_channel(size_t R, size_t T, size_t n)
+{
+  Channel c;
+  c.num_paths = n;
+  const auto r = (py::ssize_t)R, t = (py::ssize_t)T, k = (py::ssize_t)n;
+  c.directions_rx = zeros({r, t, k, 3});
+  c.directions_tx = zeros({r, t, k, 3});
+  c.tau = zeros({r, t, k});
+  c.freq_shift = zeros({r, t, k});
+  return c;
+}
+
+py::array_t<std::complex<float>> join(const std::vector<float> &re, const std::vector<float> &im,
+                                      size_t R, size_t T, size_t n)
+{
+  py::array_t<std::complex<float>> a({(py::ssize_t)R, (py::ssize_t)T, (py::ssize_t)n});
+  auto *p = a.mutable_data();
+  for (size_t i = 0; i < re.size(); ++i) p[i] = std::complex<float>(re[i], im[i]);
+  return a;
+}
+
+std::pair<Channel, Channel> compute_paths_py(const std::string &mesh_filepath, farr rx_positions,
+                                             farr tx_positions, farr rx_velocities, farr tx_velocities,
+                                             float carrier_frequency, size_t num_rx, size_t num_tx,
+                                             size_t num_paths, size_t num_bounces)
+{
+  if (!num_rx || !num_tx || !num_paths || !num_bounces || !(carrier_frequency > 0.f))
+    throw std::invalid_argument("num_rx, num_tx, num_paths, num_bounces and carrier_frequency must be > 0");
+  const Vec3 *rx = as_vec3(rx_positions, num_rx, "rx_positions");
+  const Vec3 *tx = as_vec3(tx_positions, num_tx, "tx_positions");
+  const Vec3 *rxv = as_vec3(rx_velocities, num_rx, "rx_velocities");
+  const Vec3 *txv = as_vec3(tx_velocities, num_tx, "tx_velocities");
+  if (hrt_device_count() <= 0)
+    throw std::runtime_error("hermespy_rt: no CUDA device available (this build has no CPU path)");
+  if (FILE *f = fopen(mesh_filepath.c_str(), "rb")) fclose(f);
+  else throw std::runtime_error("hermespy_rt: cannot open scene file " + mesh_filepath);
+
+  const size_t nl = num_rx * num_tx, ns = nl * num_bounces * num_paths;
+  Channel los = make_channel(num_rx, num_tx, 1), sc = make_channel(num_rx, num_tx, num_bounces * num_paths);
+  std::vector<float> l_re[2], l_im[2], s_re[2], s_im[2];
+  for (int k = 0; k < 2; ++k) { l_re[k].assign(nl, 0.f); l_im[k].assign(nl, 0.f); s_re[k].assign(ns, 0.f); s_im[k].assign(ns, 0.f); }
+
+  ChannelInfo ci_los = { 1, (Vec3 *)los.directions_rx.mutable_data(), (Vec3 *)los.directions_tx.mutable_data(),
+                         l_re[0].data(), l_im[0].data(), l_re[1].data(), l_im[1].data(),
+                         los.tau.mutable_data(), los.freq_shift.mutable_data() };
+  ChannelInfo ci_sc = { (uint32_t)(num_bounces * num_paths), (Vec3 *)sc.directions_rx.mutable_data(),
+                        (Vec3 *)sc.directions_tx.mutable_data(),
+                        s_re[0].data(), s_im[0].data(), s_re[1].data(), s_im[1].data(),
+                        sc.tau.mutable_data(), sc.freq_shift.mutable_data() };
+  {
+    py::gil_scoped_release nogil;
+    Scene scene = scene_load(mesh_filepath.c_str());
+    compute_paths(&scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency,
+                  num_rx, num_tx, num_paths, num_bounces, &ci_los, nullptr, &ci_sc, nullptr);
+    free_scene(&scene);
+  }
+  los.a_te = join(l_re[0], l_im[0], num_rx, num_tx, 1);
+  los.a_tm = join(l_re[1], l_im[1], num_rx, num_tx, 1);
+  sc.a_te = join(s_re[0], s_im[0], num_rx, num_tx, num_bounces * num_paths);
+  sc.a_tm = join(s_re[1], s_im[1], num_rx, num_tx, num_bounces * num_paths);
+  return {std::move(los), std::move(sc)};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(hermespy_rt, m)
+{
+  m.doc() = "hermespy-rt compute_paths() on NVIDIA B200 (drop-in for the reference module)";
+  py::class_<Channel>(m, "ChannelInfo")
+      .def_readonly("num_paths", &Channel::num_paths)
+      .def_readonly("directions_rx", &Channel::directions_rx)
+      .def_readonly("directions_tx", &Channel::directions_tx)
+      .def_readonly("a_te", &Channel::a_te)
+      .def_readonly("a_tm", &Channel::a_tm)
+      .def_readonly("tau", &Channel::tau)
+      .def_readonly("freq_shift", &Channel::freq_shift);
+  m.def("compute_paths", &compute_paths_py,
+        "Gains, delays, angles and Doppler shifts of LoS and scatter paths; returns (los, scatter)",
+        py::arg("mesh_filepath"), py::arg("rx_positions"), py::arg("tx_positions"),
+        py::arg("rx_velocities"), py::arg("tx_velocities"), py::arg("carrier_frequency"),
+        py::arg("num_rx"), py::arg("num_tx"), py::arg("num_paths"), py::arg("num_bounces"));
+}

@@ -155,6 +155,12 @@ void hrt_materials_derive(uint32_t index, float carrier_frequency_GHz, HrtMateri
 int  hrt_materials_set(hrt_ctx *ctx, const HrtMaterialDerived table[NUM_G_MATERIALS]);
 
 int hrt_run(hrt_ctx *ctx, const HrtRunParams *p);
+
+/* The shard partition as pure host arithmetic (no GPU): how many of the
+ * num_paths paths rank `rank` of `world` owns, and the global path index of its
+ * local index L.  Every path belongs to exactly one rank. */
+uint64_t hrt_shard_count(uint64_t num_paths, uint32_t rank, uint32_t world, uint64_t block);
+uint64_t hrt_shard_path(uint64_t local_index, uint32_t rank, uint32_t world, uint64_t block);
 int hrt_get_stats(const hrt_ctx *ctx, HrtRunStats *out);
 
 /* Measures this GPU's sustained fp32 rate with separately rounded FMUL/FADD

@@ -108,3 +108,21 @@ def test_material_derivation_matches_oracle():
             for k in ("eta_abs2", "eta_abs_inv_sqrt", "sqrt_re", "sqrt_im", "inv_re", "inv_im", "r"):
                 a, b = getattr(d, k), getattr(o, k)
                 assert (a == b) or (np.isnan(a) and np.isnan(b)), (f, i, k, a, b)
+
+
+def test_python_module_imports_and_refuses_without_gpu():
+    """`import hermespy_rt` -- the module name the reference's test/test.py:5
+    imports -- works (the reference's own build does not import on Linux)."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "hermespy-rt_b200"))
+    m = importlib.import_module("hermespy_rt")
+    assert hasattr(m, "compute_paths") and hasattr(m, "ChannelInfo")
+    if hrt.lib().hrt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        m.compute_paths(tl.scene_path("box"), np.zeros((1, 3)), np.ones((1, 3)), np.zeros((1, 3)),
+                        np.zeros((1, 3)), 3.0, 1, 1, 10, 1)
+    with pytest.raises(ValueError):
+        m.compute_paths(tl.scene_path("box"), np.zeros((2, 3)), np.ones((1, 3)), np.zeros((1, 3)),
+                        np.zeros((1, 3)), 3.0, 1, 1, 10, 1)
