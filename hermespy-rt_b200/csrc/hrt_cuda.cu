@@ -77,6 +77,7 @@ struct RunDev {
   HrtPairSummary *pair;  /* [R][T][B] */
   HrtBounceSummary *bounce; /* [T][B] */
   uint32_t *amb_list, *amb_count;
+  uint32_t *dkey, *dkey2, *perm, *perm2;  /* direction sort of the chunk's paths */
   unsigned long long *counters;  /* [16] instrumented build */
   uint32_t flags;
 };
@@ -119,6 +120,7 @@ struct hrt_ctx {
   RunDev rd;
   float *d_pos;            /* rx_pos, tx_pos, rx_vel, tx_vel */
   size_t cap_pos;
+  void *sort_tmp; size_t sort_tmp_bytes;
   void *d_los;             /* HrtLosOut[R*T] */
   size_t cap_los;
   HrtRunStats stats;
@@ -319,6 +321,36 @@ __device__ __forceinline__ V3 ld3(const float *p, uint32_t i) { return v3(p[3 * 
 
 /* ------------------------------------------------------------ run kernels */
 
+/* Sort key that puts similar launch directions next to each other: 16+16 bit
+ * Morton code of the octahedral map of the direction.  Used only to ORDER the
+ * work (coherent warps); it has no influence on any result. */
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+  v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+__device__ __forceinline__ uint32_t dir_key(V3 d)
+{
+  const float inv = 1.f / fmaxf(fabsf(d.x) + fabsf(d.y) + fabsf(d.z), 1e-30f);
+  float u = d.x * inv, v = d.y * inv;
+  if (d.z < 0.f) {
+    const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f);
+    const float vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
+    u = uu; v = vv;
+  }
+  const uint32_t iu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 65535.f, 0.f), 65535.f);
+  const uint32_t iv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 65535.f, 0.f), 65535.f);
+  return (spread16(iu) << 1) | spread16(iv);
+}
+
+__global__ void k_dirkeys(RunDev rd)
+{
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
+    rd.dkey[l] = dir_key(ld3(rd.dirs, l)); rd.perm[l] = l;
+  }
+}
+
 /* launch directions of the chunk (reference :443-451) + list of the ones the
  * host must recompute (see hrt_launch_dir) */
 __global__ void k_raygen(RunDev rd)
@@ -328,6 +360,7 @@ __global__ void k_raygen(RunDev rd)
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const V3 d = hrt_launch_dir(path, rd.P, &amb);
     rd.dirs[3 * l] = d.x; rd.dirs[3 * l + 1] = d.y; rd.dirs[3 * l + 2] = d.z;
+    rd.dkey[l] = dir_key(d); rd.perm[l] = l;
     if (amb) {
       const uint32_t k = atomicAdd(rd.amb_count, 1u);
       if (k < HRT_AMB_CAP) rd.amb_list[k] = l;
@@ -352,7 +385,7 @@ __global__ void k_init(RunDev rd)
       rd.gain[i] = make_float4(1.f, 0.f, 1.f, 0.f);
       rd.tau[i] = 0.f;
       rd.dead_at[i] = 255;
-      rd.queue[0][i] = l;
+      rd.queue[0][i] = rd.perm2[l];   /* work order: direction-sorted */
       if (rd.flags & HRT_FLAG_TRACE)
         for (uint32_t b = 0; b < B; ++b) {
           rd.tr_hit[(t * B + b) * np + l] = HRT_IDLE;
@@ -540,8 +573,11 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   const uint32_t unit = WARP ? (blockIdx.x * blockDim.x + threadIdx.x) >> 5 : blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nunits = WARP ? (gridDim.x * blockDim.x) >> 5 : gridDim.x * blockDim.x;
 
-  for (uint32_t hi = unit; hi < cnt; hi += nunits) {
-    const uint32_t l = q[hi];
+  /* thread-per-hit mode keeps whole warps in the loop (invalid lanes idle) so
+   * that the per-receiver reductions below can use warp shuffles */
+  for (uint32_t hi = unit; (WARP ? hi : hi - lane) < cnt; hi += nunits) {
+    const bool valid = WARP || hi < cnt;
+    const uint32_t l = valid ? q[hi] : q[0];
     const size_t si = t * np + l;
     const float2 *rp = (const float2 *)(rays + l);
     const float2 a = rp[0], b = rp[1], c = rp[2];
@@ -563,7 +599,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const uint32_t step = WARP ? 32u : 1u;
     for (uint32_t r0 = 0; r0 < R; r0 += step) {
       const uint32_t r = WARP ? r0 + lane : r0;
-      const bool act = r < R;
+      const bool act = WARP ? r < R : valid;
       float dist = 0.f, th_sh = 0.f;
       V3 sd = v3(0.f, 0.f, 1.f);
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
@@ -588,46 +624,84 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         if (shit) theta_carry = th_sh;
         theta_i = theta_carry;
       }
-      if (!act) continue;
-      const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;            /* :674 */
-      if (shit && h.t <= 1.f) {                                                /* :683-691 */
+      const bool occ = shit && h.t <= 1.f;                                     /* :683 */
+      const bool ok = act && !occ;
+      HrtScatterOut p;
+      p.te_r = p.te_i = p.tm_r = p.tm_i = p.tau = p.dfreq = 0.f; p.dir_rx = v3(0.f, 0.f, 0.f);
+      if (ok) p = hrt_scatter_path(s, mat, rd.k, n, mv, sd, dist, theta_i);    /* :694-721 */
+      if (act && (dense || trace)) {
+        const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;          /* :674 */
         if (dense) {
-          rd.out_f[0][so] = 0.f; rd.out_f[1][so] = 0.f; rd.out_f[2][so] = 0.f;
-          rd.out_f[3][so] = 0.f; rd.out_f[4][so] = 0.f;
+          rd.out_f[0][so] = p.te_r; rd.out_f[1][so] = p.te_i;                  /* zeros when occluded, :685-689 */
+          rd.out_f[2][so] = p.tm_r; rd.out_f[3][so] = p.tm_i;
+          rd.out_f[4][so] = p.tau;
+          if (ok) {
+            rd.out_f[5][so] = HRT_SUB(rd.out_f[5][so], p.dfreq);               /* :722 */
+            rd.out_dir[3 * so] = p.dir_rx.x; rd.out_dir[3 * so + 1] = p.dir_rx.y;
+            rd.out_dir[3 * so + 2] = p.dir_rx.z;
+          }
         }
-        if (trace) rd.tr_state[so] = 2;
-        if (summary) {
-          if (smem_rx_ok) atomicAdd(&s_acc[r].n_occl, 1u);
-          else atomicAdd((unsigned long long *)&rd.pair[(r * T + t) * B + depth].n_occluded, 1ull);
-        }
-        continue;
+        if (trace) rd.tr_state[so] = occ ? 2 : 1;
       }
-      const HrtScatterOut p = hrt_scatter_path(s, mat, rd.k, n, mv, sd, dist, theta_i); /* :694-721 */
-      if (dense) {
-        rd.out_f[0][so] = p.te_r; rd.out_f[1][so] = p.te_i;
-        rd.out_f[2][so] = p.tm_r; rd.out_f[3][so] = p.tm_i;
-        rd.out_f[4][so] = p.tau;
-        rd.out_f[5][so] = HRT_SUB(rd.out_f[5][so], p.dfreq);                   /* :722 */
-        rd.out_dir[3 * so] = p.dir_rx.x; rd.out_dir[3 * so + 1] = p.dir_rx.y;
-        rd.out_dir[3 * so + 2] = p.dir_rx.z;
-      }
-      if (trace) rd.tr_state[so] = 1;
       if (summary) {
         const double pte = (double)p.te_r * p.te_r + (double)p.te_i * p.te_i;
         const double ptm = (double)p.tm_r * p.tm_r + (double)p.tm_i * p.tm_i;
-        if (smem_rx_ok) {
-          atomicAdd(&s_acc[r].n_valid, 1u);
-          atomicAdd(&s_acc[r].hash, (unsigned long long)hkey);
-          atomicAdd(&s_acc[r].tau_bits, (unsigned long long)__float_as_uint(p.tau));
-          atomicAdd(&s_acc[r].p_te, pte);
-          atomicAdd(&s_acc[r].p_tm, ptm);
+        if (WARP) {
+          if (occ) {
+            if (smem_rx_ok) atomicAdd(&s_acc[r].n_occl, 1u);
+            else atomicAdd((unsigned long long *)&rd.pair[(r * T + t) * B + depth].n_occluded, 1ull);
+          } else if (ok) {
+            if (smem_rx_ok) {
+              atomicAdd(&s_acc[r].n_valid, 1u);
+              atomicAdd(&s_acc[r].hash, (unsigned long long)hkey);
+              atomicAdd(&s_acc[r].tau_bits, (unsigned long long)__float_as_uint(p.tau));
+              atomicAdd(&s_acc[r].p_te, pte);
+              atomicAdd(&s_acc[r].p_tm, ptm);
+            } else {
+              HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+              atomicAdd((unsigned long long *)&ps->n_valid, 1ull);
+              atomicAdd((unsigned long long *)&ps->hit_hash, (unsigned long long)hkey);
+              atomicAdd((unsigned long long *)&ps->tau_bits, (unsigned long long)__float_as_uint(p.tau));
+              atomicAdd(&ps->power_te, pte);
+              atomicAdd(&ps->power_tm, ptm);
+            }
+          }
         } else {
-          HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
-          atomicAdd((unsigned long long *)&ps->n_valid, 1ull);
-          atomicAdd((unsigned long long *)&ps->hit_hash, (unsigned long long)hkey);
-          atomicAdd((unsigned long long *)&ps->tau_bits, (unsigned long long)__float_as_uint(p.tau));
-          atomicAdd(&ps->power_te, pte);
-          atomicAdd(&ps->power_tm, ptm);
+          /* all lanes look at the same receiver: reduce over the warp, one
+           * update per warp */
+          const unsigned m_ok = __ballot_sync(0xFFFFFFFFu, ok), m_occ = __ballot_sync(0xFFFFFFFFu, occ);
+          unsigned long long hsum = ok ? hkey : 0ull, tsum = ok ? (unsigned long long)__float_as_uint(p.tau) : 0ull;
+          double e = ok ? pte : 0.0, m2 = ok ? ptm : 0.0;
+          if (m_ok) {
+            for (int o = 16; o; o >>= 1) {
+              hsum += __shfl_xor_sync(0xFFFFFFFFu, hsum, o);
+              tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, o);
+              e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+              m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+            }
+          }
+          if (lane == 0 && (m_ok | m_occ)) {
+            if (smem_rx_ok) {
+              if (m_occ) atomicAdd(&s_acc[r].n_occl, (unsigned)__popc(m_occ));
+              if (m_ok) {
+                atomicAdd(&s_acc[r].n_valid, (unsigned)__popc(m_ok));
+                atomicAdd(&s_acc[r].hash, hsum);
+                atomicAdd(&s_acc[r].tau_bits, tsum);
+                atomicAdd(&s_acc[r].p_te, e);
+                atomicAdd(&s_acc[r].p_tm, m2);
+              }
+            } else {
+              HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+              if (m_occ) atomicAdd((unsigned long long *)&ps->n_occluded, (unsigned long long)__popc(m_occ));
+              if (m_ok) {
+                atomicAdd((unsigned long long *)&ps->n_valid, (unsigned long long)__popc(m_ok));
+                atomicAdd((unsigned long long *)&ps->hit_hash, hsum);
+                atomicAdd((unsigned long long *)&ps->tau_bits, tsum);
+                atomicAdd(&ps->power_te, e);
+                atomicAdd(&ps->power_tm, m2);
+              }
+            }
+          }
         }
       }
     }
@@ -732,7 +806,7 @@ extern "C" int hrt_ctx_create(int device, hrt_ctx **out)
   hrt_ctx *c = (hrt_ctx *)calloc(1, sizeof(hrt_ctx));
   if (!c) return fail(nullptr, HRT_E_NOMEM, "out of host memory");
   c->device = device;
-  c->leaf_max = 4;
+  c->leaf_max = 2;   /* measured best on B200 (profiles/r1_v3_sweeps.txt) */
   c->pad_ulps = 64.f;
   if (const char *s = getenv("HRT_LEAF_MAX")) { int v = atoi(s); if (v >= 1 && v <= HRT_LEAF_MAX_CAP) c->leaf_max = v; }
   if (const char *s = getenv("HRT_BVH_PAD_ULPS")) { float v = strtof(s, nullptr); if (v >= 1.f) c->pad_ulps = v; }
@@ -764,6 +838,7 @@ static void free_run_dev(hrt_ctx *c)
   for (int k = 0; k < 6; ++k) dev_free(r.out_f[k]);
   dev_free(r.out_dir); dev_free(r.tr_hit); dev_free(r.tr_t); dev_free(r.tr_state);
   dev_free(r.pair); dev_free(r.bounce); dev_free(r.amb_list); dev_free(r.amb_count);
+  dev_free(r.dkey); dev_free(r.dkey2); dev_free(r.perm); dev_free(r.perm2);
   dev_free(r.counters);
   c->cap_n = 0;
 }
@@ -776,6 +851,7 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   free_scene_dev(c); free_run_dev(c);
   dev_free(c->d_pos);
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
+  if (c->sort_tmp) { cudaFree(c->sort_tmp); c->sort_tmp = nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
   free(c->evpool);
@@ -1044,7 +1120,7 @@ extern "C" int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_
   CK(dev_alloc(&d_r, n)); CK(dev_alloc(&d_tri, n)); CK(dev_alloc(&d_t, n)); CK(dev_alloc(&d_th, n));
   CK(cudaMemcpyAsync(d_r, rays, n * sizeof(Ray), cudaMemcpyHostToDevice, st));
   const size_t sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris);
-  const bool smem = sb <= HRT_SMEM_SCENE_LIMIT, brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
+  const bool smem = sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM"), brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
   const SceneDev sc = scene_dev(ctx);
   const unsigned grid = (unsigned)min((size_t)sm_count(ctx->device) * 8, (n + HRT_BLOCK - 1) / HRT_BLOCK);
   if (smem) {
@@ -1075,6 +1151,7 @@ static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t
   CK(dev_alloc(&r.dead_at, TN)); CK(dev_alloc(&r.queue[0], TN)); CK(dev_alloc(&r.queue[1], TN));
   CK(dev_alloc(&r.qcount, (B + 1) * T));
   CK(dev_alloc(&r.amb_list, HRT_AMB_CAP)); CK(dev_alloc(&r.amb_count, 1));
+  CK(dev_alloc(&r.dkey, n)); CK(dev_alloc(&r.dkey2, n)); CK(dev_alloc(&r.perm, n)); CK(dev_alloc(&r.perm2, n));
   CK(dev_alloc(&r.counters, 16));
   const size_t slots = R * T * B * n;
   if (flags & HRT_FLAG_DENSE) {
@@ -1193,7 +1270,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   S.num_tris = ctx->num_tris; S.num_nodes = ctx->num_nodes; S.box_pad = ctx->pad;
   const SceneDev sc = scene_dev(ctx);
   const size_t scene_sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris);
-  const bool smem = scene_sb <= HRT_SMEM_SCENE_LIMIT;
+  const bool smem = scene_sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM");
   const bool brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
   S.scene_in_smem = smem;
   const int sms = sm_count(ctx->device);
@@ -1202,7 +1279,11 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
   const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 160 * 1024;
   const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
-  const bool warp_mode = R >= 8;
+  /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
+   * thanks to the direction sort) whenever there are enough hits to fill the
+   * machine; a warp per hit (lanes over receivers) for few rays x many RX */
+  bool warp_mode = R >= 8 && (uint64_t)T * (P < chunk ? P : chunk) < (uint64_t)sms * 2048;
+  if (const char *m = getenv("HRT_SCATTER_MODE")) warp_mode = (m[0] == 'w') && R >= 2;
   const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
   const ScatterFn f_scatter = scatter_fn(smem, brute, warp_mode, count);
@@ -1313,6 +1394,21 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       }
     }
 
+    /* order the chunk's paths by launch direction */
+    if (flags & HRT_FLAG_HOST_DIRS) { k_dirkeys<<<g1, 256, 0, st>>>(rd); CKR(cudaGetLastError()); S.kernel_launches++; }
+    if (getenv("HRT_NO_SORT")) {
+      CKR(cudaMemcpyAsync(rd.perm2, rd.perm, (size_t)rd.n * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      size_t tb = 0;
+      CKR(cub::DeviceRadixSort::SortPairs(nullptr, tb, rd.dkey, rd.dkey2, rd.perm, rd.perm2, (int)rd.n, 0, 32, st));
+      if (tb > ctx->sort_tmp_bytes) {
+        if (ctx->sort_tmp) cudaFree(ctx->sort_tmp);
+        ctx->sort_tmp = nullptr; ctx->sort_tmp_bytes = 0;
+        CKR(cudaMalloc(&ctx->sort_tmp, tb)); ctx->sort_tmp_bytes = tb;
+      }
+      CKR(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tb, rd.dkey, rd.dkey2, rd.perm, rd.perm2, (int)rd.n, 0, 32, st));
+      S.kernel_launches += 4;
+    }
     CKR(cudaMemsetAsync(rd.qcount, 0, (B + 1) * T * 4, st));
     k_init<<<g1, 256, 0, st>>>(rd);
     CKR(cudaGetLastError());

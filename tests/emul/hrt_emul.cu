@@ -210,6 +210,24 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
   return 0;
 }
 
+/* work counters for BVH-quality experiments on the CPU: average box / triangle
+ * tests per closest-hit query over a batch of rays */
+extern "C" int emul_count_work(const Scene *sc, const Ray *rays, size_t n, int leaf_max, double out[6])
+{
+  EmulScene E; build(sc, E, leaf_max, 64.f, 0.f);
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
+  HrtCount c;
+  unsigned long long tot[5] = {0, 0, 0, 0, 0};
+  for (size_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 5; ++k) c.c[k] = 0;
+    hrt_closest_hit(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c);
+    for (int k = 0; k < 5; ++k) tot[k] += c.c[k];
+  }
+  for (int k = 0; k < 5; ++k) out[k] = (double)tot[k] / (double)n;
+  out[5] = E.num_nodes;
+  return 0;
+}
+
 extern "C" int emul_bvh_stats(const Scene *sc, int leaf_max, uint32_t *num_nodes, uint32_t *num_tris)
 {
   EmulScene E; build(sc, E, leaf_max, 64.f, 0.f);

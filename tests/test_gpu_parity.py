@@ -35,10 +35,18 @@ def _ulps(a, b):
 @pytest.mark.parametrize("scene", SCENES)
 @pytest.mark.parametrize("brute", [False, True])
 def test_closest_hit_bit_exact(ctx, scene, brute):
-    """moeller_trumbore(): triangle id and t bit-exact, BVH and brute force."""
+    """moeller_trumbore(): triangle id and t bit-exact, BVH and brute force,
+    scene in shared memory and (HRT_NO_SMEM) fetched from global memory."""
+    import os
     ctx.load_scene(tl.scene_path(scene))
     rays = tl.random_rays(scene, 200000, seed=11)
     tri_o, t_o, th_o = tl.oracle_closest(scene, rays)
+    os.environ["HRT_NO_SMEM"] = "1"
+    try:
+        tri_g, t_g, _ = ctx.closest_hits(rays, brute_force=brute)
+    finally:
+        del os.environ["HRT_NO_SMEM"]
+    assert np.array_equal(tri_o, tri_g) and np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32))
     tri, t, th = ctx.closest_hits(rays, brute_force=brute)
     assert np.array_equal(tri_o, tri)
     assert np.array_equal(t_o.view(np.uint32), t.view(np.uint32))
@@ -123,6 +131,21 @@ def test_run_dense_vs_oracle(ctx, cfg, P, B, n_rx, moving, T):
     st = res["stats"]
     assert st["ray_bounces"] == int(bounce["n_traced"].sum())
     assert st["kernel_launches"] > 0
+    # the other scatter mapping (thread per hit <-> warp per hit) and the unsorted
+    # work order give the very same bits
+    import os
+    for env in ({"HRT_SCATTER_MODE": "t"}, {"HRT_SCATTER_MODE": "w"}, {"HRT_NO_SORT": "1"},
+                {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "w"}):
+        os.environ.update(env)
+        try:
+            alt = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, trace=True, summary=True)
+        finally:
+            for k in env:
+                del os.environ[k]
+        _compare_dense(a, mask, alt["out"], tr, alt["trace"])
+        tl.assert_summaries_equal(pair, bounce, alt["pair"], alt["bounce"])
+        for k in ("tau", "a_te_re", "a_tm_im", "freq_shift", "directions_rx"):
+            assert np.array_equal(res["out"].scat[k].view(np.uint32), alt["out"].scat[k].view(np.uint32)), (env, k)
     # brute-force kernels (no BVH) give the very same bits
     res2 = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, trace=True, brute_force=True)
     for k in ("tau", "a_te_re", "a_tm_im", "freq_shift", "directions_rx"):
@@ -248,3 +271,39 @@ def test_pybind_module_matches_golden():
     err = np.abs(sc.a_te.reshape(-1)[mm] - te[mm])
     assert (err <= 1e-4 * np.abs(te[mm]) + 1e-38).all()
     assert los.tau[0, 0, 0] == tl.f32(g["out.los.tau"])[0]
+
+
+def test_large_scene_global_memory_bvh(ctx, tmp_path):
+    """A tiled canyon too big for shared memory (12x12 tiles, 33,696 triangles,
+    mixed ITU materials): BVH fetched from global memory/L2.  Closest hits vs the
+    oracle on a ray sample; BVH == brute-force checksums on a full run."""
+    from hrt_b200 import scenes
+    meshes, pitch = scenes.tiled_canyon(tl.scene_path("simple_street_canyon_with_cars"), 12, 12, block=4)
+    path = str(tmp_path / "tiled.hrt")
+    scenes.write_hrt(path, meshes)
+    rx, tx = scenes.c5_positions(pitch, 12, 12, n_tx=4, n_rx=16)
+    ctx.load_scene(path)
+    # closest hits against the oracle (brute force over 33k triangles on the CPU)
+    rng = np.random.default_rng(3)
+    n = 3000
+    o = np.tile(tx[0], (n, 1)) + rng.uniform(-30, 30, (n, 3)) * [1, 1, 0.2]
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.ascontiguousarray(np.concatenate([o, d], 1).astype(np.float32))
+    lib = tl.oracle_lib()
+    sc = lib.scene_load(path.encode())
+    tri_o = np.zeros(n, np.uint32); t_o = np.zeros(n, np.float32); th_o = np.zeros(n, np.float32)
+    lib.oracle_closest_hits(C.byref(sc), rays.ctypes.data, n, tri_o.ctypes.data, t_o.ctypes.data, th_o.ctypes.data)
+    abi.free_scene(sc)
+    tri, t, _ = ctx.closest_hits(rays)
+    assert (tri_o != tl.NONE).sum() > n // 2
+    assert np.array_equal(tri_o, tri) and np.array_equal(t_o.view(np.uint32), t.view(np.uint32))
+    # full run, summary mode: BVH vs brute-force kernels
+    zr, zt = np.zeros_like(rx), np.zeros_like(tx)
+    a = ctx.run(rx, tx, zr, zt, 3.5, 20000, 3, summary=True)
+    assert a["stats"]["scene_in_smem"] == 0 and a["stats"]["num_tris"] == 144 * 234
+    b = ctx.run(rx, tx, zr, zt, 3.5, 20000, 3, summary=True, brute_force=True)
+    for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+        assert np.array_equal(a["pair"][k], b["pair"][k]), k
+    for k in ("n_traced", "n_hit", "hit_hash", "t_bits"):
+        assert np.array_equal(a["bounce"][k], b["bounce"][k]), k
+    assert int(a["pair"]["n_valid"].sum()) > 100000
