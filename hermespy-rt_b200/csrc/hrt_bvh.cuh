@@ -115,8 +115,19 @@ HRT_HD int hrt_child_ref(int child, int n, const int *first, const int *last,
   return new_index[child];
 }
 
-HRT_HD void hrt_emit_node(float4 *out, int ref_l, int ref_r, V3 llo, V3 lhi, V3 rlo, V3 rhi, float pad)
+/* `oct`: direction octant this copy of the node serves (bit k = component k of
+ * the ray direction negative).  On those axes the two planes are stored
+ * swapped, so that the first slot always holds the plane a ray of that octant
+ * reaches first (hrt_slab_sorted).  oct = 0 is the plain (lo, hi) layout. */
+HRT_HD void hrt_emit_node(float4 *out, int ref_l, int ref_r, V3 llo, V3 lhi, V3 rlo, V3 rhi, float pad,
+                          uint32_t oct = 0)
 {
+  llo = v3(llo.x - pad, llo.y - pad, llo.z - pad); lhi = v3(lhi.x + pad, lhi.y + pad, lhi.z + pad);
+  rlo = v3(rlo.x - pad, rlo.y - pad, rlo.z - pad); rhi = v3(rhi.x + pad, rhi.y + pad, rhi.z + pad);
+  if (oct & 1u) { float t = llo.x; llo.x = lhi.x; lhi.x = t; t = rlo.x; rlo.x = rhi.x; rhi.x = t; }
+  if (oct & 2u) { float t = llo.y; llo.y = lhi.y; lhi.y = t; t = rlo.y; rlo.y = rhi.y; rhi.y = t; }
+  if (oct & 4u) { float t = llo.z; llo.z = lhi.z; lhi.z = t; t = rlo.z; rlo.z = rhi.z; rhi.z = t; }
+  pad = 0.f;
   out[0].x = llo.x - pad; out[0].y = lhi.x + pad; out[0].z = llo.y - pad; out[0].w = lhi.y + pad;
   out[1].x = rlo.x - pad; out[1].y = rhi.x + pad; out[1].z = rlo.y - pad; out[1].w = rhi.y + pad;
   out[2].x = llo.z - pad; out[2].y = lhi.z + pad; out[2].z = rlo.z - pad; out[2].w = rhi.z + pad;

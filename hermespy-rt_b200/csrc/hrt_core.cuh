@@ -213,6 +213,28 @@ HRT_HD bool hrt_slab(const HrtRayCull &c, float lox, float hix, float loy, float
   return tn <= tf;
 }
 
+/* Same test when the node copy in use stores, per axis, the plane the ray
+ * reaches first in the "lo" slot (one node copy per direction octant, see
+ * hrt_emit_node): no per-axis min/max is needed. */
+HRT_HD bool hrt_slab_sorted(const HrtRayCull &c, float nx, float fx, float ny, float fy,
+                            float nz, float fz, float tmax, float *t_near)
+{
+  const float x0 = HRT_FMA(nx, c.inv.x, c.ood.x), x1 = HRT_FMA(fx, c.inv.x, c.ood.x);
+  const float y0 = HRT_FMA(ny, c.inv.y, c.ood.y), y1 = HRT_FMA(fy, c.inv.y, c.ood.y);
+  const float z0 = HRT_FMA(nz, c.inv.z, c.ood.z), z1 = HRT_FMA(fz, c.inv.z, c.ood.z);
+  const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, 0.f));
+  const float tf = fminf(fminf(x1, y1), fminf(z1, tmax));
+  *t_near = tn;
+  return tn <= tf;
+}
+
+/* direction octant of a ray: bit k set when component k of 1/d is negative */
+HRT_HD uint32_t hrt_octant(const HrtRayCull &c)
+{
+  return ((uint32_t)hrt_float_as_int(c.inv.x) >> 31) | (((uint32_t)hrt_float_as_int(c.inv.y) >> 31) << 1) |
+         (((uint32_t)hrt_float_as_int(c.inv.z) >> 31) << 2);
+}
+
 /* Scene view handed to the traversal: how to fetch node / triangle words.
  * `Mem` provides node(i,k) and tri(slot,k) returning float4 -- from shared
  * memory when the scene was staged there, else from global memory. */
@@ -242,13 +264,17 @@ struct HrtGlobalMem {
 /* Closest hit over the BVH == the reference's loop over every triangle
  * (moeller_trumbore, :237-287): minimum t, ties to the lowest (mesh, face).
  * root_ref: inner node index, a leaf ref, or 0 with num_tris == 0. */
-template <class Mem, class Cnt>
-HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_ref,
-                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt)
+/* SORTED: `mem_in.nodes` holds 8 consecutive copies of the node array, one per
+ * direction octant (hrt_emit_node), `oct_stride` float4s apart. */
+template <bool SORTED, class Mem, class Cnt>
+HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const uint32_t *tri_gid, int root_ref,
+                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt, uint32_t oct_stride = 0)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
   const HrtRayCull c = hrt_ray_cull(o, d);
+  Mem mem = mem_in;
+  if (SORTED) mem.nodes += (size_t)hrt_octant(c) * oct_stride;
   float tmax = HRT_T_MAX * 1.0001f;          /* far bound with slack */
   int   stack_ref[HRT_STACK];
   float stack_tn[HRT_STACK];
@@ -262,8 +288,10 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const uint32_t *tri_gid, int root_
       const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1);
       const float4 n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
       float tl, tr;
-      const bool hl = hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl);
-      const bool hr = hrt_slab(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr);
+      const bool hl = SORTED ? hrt_slab_sorted(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl)
+                             : hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl);
+      const bool hr = SORTED ? hrt_slab_sorted(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr)
+                             : hrt_slab(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr);
       const int rl = hrt_float_as_int(n3.x), rr = hrt_float_as_int(n3.y);
       cnt.box(2u);
       if (hl && hr) {

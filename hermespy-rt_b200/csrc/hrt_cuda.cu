@@ -34,8 +34,11 @@ static_assert(sizeof(HrtMaterialDerived) == sizeof(HrtMaterial), "material ABI")
 static_assert(sizeof(Ray) == 24 && sizeof(Vec3) == 12, "reference ABI");
 static_assert(sizeof(HrtPairSummary) == 48 && sizeof(HrtBounceSummary) == 32, "summary ABI");
 
-#define HRT_BLOCK 128
-#define HRT_SMEM_SCENE_LIMIT (96 * 1024)   /* stage nodes+triangles in shared memory below this */
+#define HRT_BLOCK 512   /* 2 blocks of 512 threads per SM: 64 registers, ~85 KB shared memory each */
+#ifndef HRT_MIN_BLOCKS
+#define HRT_MIN_BLOCKS 2   /* => 64 registers (1024 threads/SM): best of the sweep in profiles/r1_sweeps.md; __launch_bounds__ min blocks/SM of the two traversal kernels */
+#endif
+#define HRT_SMEM_SCENE_LIMIT (100 * 1024)  /* stage 8 octant node copies + triangles in shared memory below this */
 #define HRT_AMB_CAP 65536
 
 static char g_create_error[256] = "";
@@ -48,6 +51,7 @@ struct SceneDev {
   const uint32_t *mesh_mat;    /* by mesh */
   const float *mesh_vel;       /* 3 per mesh */
   uint32_t num_tris, num_nodes;
+  uint32_t octants;            /* node copies: 8 (one per direction octant) or 1 */
   int root_ref;
 };
 
@@ -68,7 +72,7 @@ struct RunDev {
   uint32_t *hslot;       /* [T][n_alloc] leaf slot of the last primary hit */
   uint8_t *dead_at;      /* [T][n_alloc] bounce at which the ray left the scene, 255 alive */
   uint32_t *queue[2];    /* [T][n_alloc] active path indices */
-  uint32_t *qcount;      /* [B+1][T] */
+  uint32_t *qcount;      /* [B+1][T] queue sizes, then [B][T] k_bounce and [B][T] k_scatter work cursors */
   float *out_f[6];       /* [R][T][B][n_alloc] te_re te_im tm_re tm_im tau freq */
   float *out_dir;        /* [R][T][B][n_alloc][3] */
   uint32_t *tr_hit;      /* [T][B][n_alloc] */
@@ -103,7 +107,7 @@ struct hrt_ctx {
 
   /* scene */
   bool have_scene;
-  uint32_t num_tris, num_meshes, num_nodes;
+  uint32_t num_tris, num_meshes, num_nodes, octants;
   int root_ref;
   float pad, scene_max_abs;
   float4 *d_tris; uint32_t *d_tri_gid; uint32_t *d_mesh_of; uint32_t *d_mesh_mat; float *d_mesh_vel;
@@ -239,17 +243,18 @@ __global__ void k_mark(int n, const int *kfirst, const int *klast, int leaf_max,
 
 __global__ void k_emit(int n, const int *kl, const int *kr, const int *kfirst, const int *klast,
                        const int *used, const int *newidx, const float *node_box, int leaf_max,
-                       float pad, float4 *nodes)
+                       float pad, float4 *nodes, uint32_t octants, uint32_t num_nodes)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || !used[i]) return;
   const int l = kl[i], r = kr[i];
   const float *bl = node_box + 6 * (size_t)l, *br = node_box + 6 * (size_t)r;
-  hrt_emit_node(nodes + 4 * (size_t)newidx[i],
-                hrt_child_ref(l, n, kfirst, klast, newidx, leaf_max),
-                hrt_child_ref(r, n, kfirst, klast, newidx, leaf_max),
-                v3(bl[0], bl[1], bl[2]), v3(bl[3], bl[4], bl[5]),
-                v3(br[0], br[1], br[2]), v3(br[3], br[4], br[5]), pad);
+  for (uint32_t oct = 0; oct < octants; ++oct)
+    hrt_emit_node(nodes + 4 * ((size_t)oct * num_nodes + newidx[i]),
+                  hrt_child_ref(l, n, kfirst, klast, newidx, leaf_max),
+                  hrt_child_ref(r, n, kfirst, klast, newidx, leaf_max),
+                  v3(bl[0], bl[1], bl[2]), v3(bl[3], bl[4], bl[5]),
+                  v3(br[0], br[1], br[2]), v3(br[3], br[4], br[5]), pad, oct);
 }
 
 /* ------------------------------------------------------- scene in shared */
@@ -267,7 +272,7 @@ extern __shared__ float4 hrt_smem4[];
  * first free float4 slot after them */
 __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
 {
-  const uint32_t nn = sc.num_nodes * 4u, nt = sc.num_tris * 3u;
+  const uint32_t nn = sc.num_nodes * 4u * sc.octants, nt = sc.num_tris * 3u;
   for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.nodes[i];
   for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) hrt_smem4[nn + i] = sc.tris[i];
   uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
@@ -275,8 +280,8 @@ __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
   return nn + nt + (sc.num_tris + 3u) / 4u;
 }
 
-static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris)
-{ return (size_t)num_nodes * 64 + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
+static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris, uint32_t octants = 8)
+{ return (size_t)num_nodes * 64 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
 
 template <bool SMEM, bool BRUTE, class Cnt>
 __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt)
@@ -284,14 +289,14 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
   if (SMEM) {
     HrtSharedMem m;
     m.nodes = hrt_smem4;
-    m.tris = hrt_smem4 + sc.num_nodes * 4u;
-    const uint32_t *gid = (const uint32_t *)(hrt_smem4 + sc.num_nodes * 4u + sc.num_tris * 3u);
+    m.tris = hrt_smem4 + sc.num_nodes * 32u;                /* 8 octant copies of the nodes first */
+    const uint32_t *gid = (const uint32_t *)(hrt_smem4 + sc.num_nodes * 32u + sc.num_tris * 3u);
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
-    return hrt_closest_hit(m, gid, sc.root_ref, sc.num_tris, o, d, cnt);
+    return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u);
   } else {
     HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
     if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
-    return hrt_closest_hit(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt);
+    return hrt_closest_hit<false>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt);
   }
 }
 
@@ -306,14 +311,14 @@ __device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long 
 template <bool SMEM>
 __device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
 {
-  const float4 q2 = SMEM ? hrt_smem4[sc.num_nodes * 4u + 3u * slot + 2u] : __ldg(&sc.tris[3 * slot + 2]);
+  const float4 q2 = SMEM ? hrt_smem4[sc.num_nodes * 32u + 3u * slot + 2u] : __ldg(&sc.tris[3 * slot + 2]);
   return v3(q2.y, q2.z, q2.w);
 }
 
 template <bool SMEM>
 __device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
 {
-  if (SMEM) return ((const uint32_t *)(hrt_smem4 + sc.num_nodes * 4u + sc.num_tris * 3u))[slot];
+  if (SMEM) return ((const uint32_t *)(hrt_smem4 + sc.num_nodes * 32u + sc.num_tris * 3u))[slot];
   return sc.tri_gid[slot];
 }
 
@@ -445,7 +450,7 @@ __global__ void k_los(RunDev rd, SceneDev sc, HrtLosOut *out)
  * ray of TX blockIdx.y.  Survivors are appended to the next queue with one
  * atomicAdd per warp (ballot + prefix popcount). */
 template <bool SMEM, bool BRUTE, bool COUNT>
-__global__ void __launch_bounds__(HRT_BLOCK)
+__global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
 k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
 {
   if (SMEM) { stage_scene(sc); __syncthreads(); }
@@ -461,9 +466,15 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long hash_acc = 0, tbits_acc = 0;
 
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t end = (cnt + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+  /* warps pull batches of 128 queue entries from a shared cursor (dynamic load
+   * balance: ray cost varies a lot with direction) */
+  uint32_t *cursor = rd.qcount + (B + 1) * T + depth * T + t;
+  for (;;) {
+    uint32_t batch = 0;
+    if (lane == 0) batch = atomicAdd(cursor, 128u);
+    batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+    if (batch >= cnt) break;
+  for (uint32_t i = batch + lane; i < batch + 128u && (i - lane) < cnt; i += 32u) {
     const bool valid = i < cnt;
     bool hit = false;
     uint32_t l = 0;
@@ -512,6 +523,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
       if (hit) qout[base + __popc(m & ((1u << lane) - 1u))] = l;
     }
   }
+  }
   cnt_flush(wc, rd.counters);
   if (rd.flags & HRT_FLAG_SUMMARY) {
     for (int o = 16; o; o >>= 1) {
@@ -540,7 +552,7 @@ struct PairAcc {
  *                 from tile to tile.
  *   WARP = false: one thread per hit, receivers in sequence (small num_rx). */
 template <bool SMEM, bool BRUTE, bool WARP, bool COUNT>
-__global__ void __launch_bounds__(HRT_BLOCK)
+__global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
 k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
 {
   typename CntSel<COUNT>::type wc; cnt_init(wc);
@@ -570,12 +582,16 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   const uint32_t lane = threadIdx.x & 31u;
   const bool dense = (rd.flags & HRT_FLAG_DENSE) != 0, trace = (rd.flags & HRT_FLAG_TRACE) != 0;
 
-  const uint32_t unit = WARP ? (blockIdx.x * blockDim.x + threadIdx.x) >> 5 : blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nunits = WARP ? (gridDim.x * blockDim.x) >> 5 : gridDim.x * blockDim.x;
-
-  /* thread-per-hit mode keeps whole warps in the loop (invalid lanes idle) so
-   * that the per-receiver reductions below can use warp shuffles */
-  for (uint32_t hi = unit; (WARP ? hi : hi - lane) < cnt; hi += nunits) {
+  /* work distribution: warps pull batches from a shared cursor -- 32 hits (one
+   * per lane) in thread-per-hit mode, 8 hits in warp-per-hit mode */
+  uint32_t *cursor = rd.qcount + (2 * B + 1) * T + depth * T + t;
+  const uint32_t grab = WARP ? 8u : 32u;
+  for (;;) {
+    uint32_t batch = 0;
+    if (lane == 0) batch = atomicAdd(cursor, grab);
+    batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+    if (batch >= cnt) break;
+  for (uint32_t hi = WARP ? batch : batch + lane; WARP ? (hi < batch + grab && hi < cnt) : hi == batch + lane; hi += WARP ? 1u : 64u) {
     const bool valid = WARP || hi < cnt;
     const uint32_t l = valid ? q[hi] : q[0];
     const size_t si = t * np + l;
@@ -705,6 +721,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         }
       }
     }
+  }
   }
   cnt_flush(wc, rd.counters + 5);
   if (summary && smem_rx_ok) {
@@ -869,7 +886,7 @@ static int emit_nodes(hrt_ctx *ctx, float pad)
   if (ctx->num_nodes == 0) return HRT_OK;
   k_emit<<<nblk(n - 1), 256, 0, ctx->stream>>>(n, ctx->d_kl, ctx->d_kr, ctx->d_kfirst, ctx->d_klast,
                                                ctx->d_newidx + n /* used flags live behind newidx */,
-                                               ctx->d_newidx, ctx->d_box, ctx->leaf_max, pad, ctx->d_nodes);
+                                               ctx->d_newidx, ctx->d_box, ctx->leaf_max, pad, ctx->d_nodes, ctx->octants, ctx->num_nodes);
   CK(cudaGetLastError());
   return HRT_OK;
 }
@@ -938,7 +955,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
     CKG(cudaMemcpyAsync(ctx->d_mesh_vel, h_vel, (size_t)M * 12, cudaMemcpyHostToDevice, st));
     const unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
     CKG(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
-    ctx->num_nodes = 0; ctx->root_ref = 0;
+    ctx->num_nodes = 0; ctx->root_ref = 0; ctx->octants = 8;
     if (n > 0) {
       k_tri_setup<<<nblk(n), 256, 0, st>>>(d_v, d_i, n, d_recs, d_boxes, d_bounds);
       k_morton<<<nblk(n), 256, 0, st>>>(d_boxes, n, d_bounds, d_keys);
@@ -968,7 +985,10 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         CKG(es);
         ctx->num_nodes = (uint32_t)(last_idx + last_used);
         ctx->root_ref = 0;
-        CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4));
+        /* small scenes get one node copy per ray-direction octant (shared-memory
+         * traversal without per-axis min/max, hrt_slab_sorted) */
+        ctx->octants = scene_smem_bytes(ctx->num_nodes, n, 8) <= HRT_SMEM_SCENE_LIMIT ? 8u : 1u;
+        CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
       }
     }
     ctx->pad = hrt_box_pad(max_abs, ctx->pad_ulps);
@@ -1046,7 +1066,7 @@ static SceneDev scene_dev(const hrt_ctx *c)
   SceneDev s;
   s.nodes = c->d_nodes; s.tris = c->d_tris; s.tri_gid = c->d_tri_gid; s.mesh_of = c->d_mesh_of;
   s.mesh_mat = c->d_mesh_mat; s.mesh_vel = c->d_mesh_vel;
-  s.num_tris = c->num_tris; s.num_nodes = c->num_nodes; s.root_ref = c->root_ref;
+  s.num_tris = c->num_tris; s.num_nodes = c->num_nodes; s.root_ref = c->root_ref; s.octants = c->octants;
   return s;
 }
 
@@ -1119,10 +1139,10 @@ extern "C" int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_
   cudaStream_t st = ctx->stream;
   CK(dev_alloc(&d_r, n)); CK(dev_alloc(&d_tri, n)); CK(dev_alloc(&d_t, n)); CK(dev_alloc(&d_th, n));
   CK(cudaMemcpyAsync(d_r, rays, n * sizeof(Ray), cudaMemcpyHostToDevice, st));
-  const size_t sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris);
-  const bool smem = sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM"), brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
+  const size_t sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris, ctx->octants);
+  const bool smem = ctx->octants == 8 && sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM"), brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
   const SceneDev sc = scene_dev(ctx);
-  const unsigned grid = (unsigned)min((size_t)sm_count(ctx->device) * 8, (n + HRT_BLOCK - 1) / HRT_BLOCK);
+  const unsigned grid = (unsigned)min((size_t)sm_count(ctx->device) * 2, (n + HRT_BLOCK - 1) / HRT_BLOCK);
   if (smem) {
     CK(allow_smem(k_closest<true, true>, sb)); CK(allow_smem(k_closest<true, false>, sb));
   }
@@ -1149,7 +1169,7 @@ static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t
   CK(dev_alloc(&r.dirs, n * 3)); CK(dev_alloc(&r.rays, rows * TN)); CK(dev_alloc(&r.gain, TN));
   CK(dev_alloc(&r.tau, TN)); CK(dev_alloc(&r.theta, TN)); CK(dev_alloc(&r.hslot, TN));
   CK(dev_alloc(&r.dead_at, TN)); CK(dev_alloc(&r.queue[0], TN)); CK(dev_alloc(&r.queue[1], TN));
-  CK(dev_alloc(&r.qcount, (B + 1) * T));
+  CK(dev_alloc(&r.qcount, (3 * B + 1) * T));   /* queue sizes + work cursors of k_bounce / k_scatter */
   CK(dev_alloc(&r.amb_list, HRT_AMB_CAP)); CK(dev_alloc(&r.amb_count, 1));
   CK(dev_alloc(&r.dkey, n)); CK(dev_alloc(&r.dkey2, n)); CK(dev_alloc(&r.perm, n)); CK(dev_alloc(&r.perm2, n));
   CK(dev_alloc(&r.counters, 16));
@@ -1269,15 +1289,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   memset(&S, 0, sizeof S);
   S.num_tris = ctx->num_tris; S.num_nodes = ctx->num_nodes; S.box_pad = ctx->pad;
   const SceneDev sc = scene_dev(ctx);
-  const size_t scene_sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris);
-  const bool smem = scene_sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM");
+  const size_t scene_sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris, ctx->octants);
+  const bool smem = ctx->octants == 8 && scene_sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM");
   const bool brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
   S.scene_in_smem = smem;
   const int sms = sm_count(ctx->device);
 
   /* scatter kernel shared memory: scene + receivers + reduction table */
   const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
-  const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 160 * 1024;
+  const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 110 * 1024;
   const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
   /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
    * thanks to the direction sort) whenever there are enough hits to fill the
@@ -1409,7 +1429,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       CKR(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tb, rd.dkey, rd.dkey2, rd.perm, rd.perm2, (int)rd.n, 0, 32, st));
       S.kernel_launches += 4;
     }
-    CKR(cudaMemsetAsync(rd.qcount, 0, (B + 1) * T * 4, st));
+    CKR(cudaMemsetAsync(rd.qcount, 0, (3 * B + 1) * T * 4, st));
     k_init<<<g1, 256, 0, st>>>(rd);
     CKR(cudaGetLastError());
     S.kernel_launches++;
@@ -1419,7 +1439,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
         CKR(cudaMemcpyAsync(rd.rays + (size_t)(b + 1) * T * rd.n_alloc, rd.rays + (size_t)b * T * rd.n_alloc,
                             T * (size_t)rd.n_alloc * sizeof(Ray), cudaMemcpyDeviceToDevice, st));
       /* persistent grids: enough blocks to fill the machine, grid-stride inside */
-      const dim3 gb((unsigned)min((size_t)((sms * 8 + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      const dim3 gb((unsigned)min((size_t)((sms * 2 + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
       const bool timed = ev_used + 3 <= EV_CAP;
       if (timed) {
         if (ctx->evpool_n < ev_used + 3) {
@@ -1434,7 +1454,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       CKR(cudaGetLastError());
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 1], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
-      const dim3 gs((unsigned)min((size_t)((sms * 8 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      const dim3 gs((unsigned)min((size_t)((sms * 2 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
       f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;

@@ -84,7 +84,7 @@ def lib() -> C.CDLL:
     """The product library.  Raises HrtError when it has not been built."""
     global _lib
     if _lib is None:
-        path = os.path.abspath(LIB_PATH)
+        path = os.path.abspath(os.environ.get("HRT_LIB", LIB_PATH))   # HRT_LIB: tuning builds
         if not os.path.exists(path):
             raise HrtError(f"{path} not found: build it with __graft_entry__.build() "
                            "(make -C hermespy-rt_b200); there is no CPU fallback")

@@ -80,14 +80,15 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   std::vector<int> used(n - 1), newidx(n - 1);
   int count = 0;
   for (int i = 0; i < n - 1; ++i) { used[i] = (kla[i] - kf[i] + 1) > leaf_max; newidx[i] = count; count += used[i]; }
-  E.num_nodes = count; E.nodes.resize(4 * (size_t)count); E.root = 0;
+  E.num_nodes = count; E.nodes.resize(4 * (size_t)count * 8); E.root = 0;   /* 8 octant copies */
   const float pad = hrt_box_pad(max_abs, pad_ulps);
   for (int i = 0; i < n - 1; ++i) {
     if (!used[i]) continue;
-    hrt_emit_node(&E.nodes[4 * (size_t)newidx[i]],
-                  hrt_child_ref(kl[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
-                  hrt_child_ref(kr[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
-                  blo[kl[i]], bhi[kl[i]], blo[kr[i]], bhi[kr[i]], pad);
+    for (uint32_t oct = 0; oct < 8; ++oct)
+      hrt_emit_node(&E.nodes[4 * ((size_t)oct * count + newidx[i])],
+                    hrt_child_ref(kl[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
+                    hrt_child_ref(kr[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
+                    blo[kl[i]], bhi[kl[i]], blo[kr[i]], bhi[kr[i]], pad, oct);
   }
 }
 
@@ -95,8 +96,9 @@ static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
 {
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
   HrtNoCount nc;
-  if (brute) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
-  return hrt_closest_hit(m, E.gid.data(), E.root, E.n, o, d, nc);
+  if (brute == 1) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
+  if (brute == 2) return hrt_closest_hit<false>(m, E.gid.data(), E.root, E.n, o, d, nc);   /* plain node copy */
+  return hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, o, d, nc, E.num_nodes * 4u);  /* octant copies */
 }
 
 static V3 nrm(const EmulScene &E, uint32_t slot) { const float4 q = E.tris[3 * slot + 2]; return v3(q.y, q.z, q.w); }
@@ -220,7 +222,7 @@ extern "C" int emul_count_work(const Scene *sc, const Ray *rays, size_t n, int l
   unsigned long long tot[5] = {0, 0, 0, 0, 0};
   for (size_t i = 0; i < n; ++i) {
     for (int k = 0; k < 5; ++k) c.c[k] = 0;
-    hrt_closest_hit(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c);
+    hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c, E.num_nodes * 4u);
     for (int k = 0; k < 5; ++k) tot[k] += c.c[k];
   }
   for (int k = 0; k < 5; ++k) out[k] = (double)tot[k] / (double)n;

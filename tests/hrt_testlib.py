@@ -247,7 +247,7 @@ def emul_lib() -> C.CDLL:
     return _emul
 
 
-def run_emul(scene, rx, tx, rxv, txv, f_ghz, P, B, leaf_max=4, pad_ulps=64.0, brute=False):
+def run_emul(scene, rx, tx, rxv, txv, f_ghz, P, B, leaf_max=2, pad_ulps=64.0, brute=0):
     lib = emul_lib()
     sc = lib.scene_load(scene_path(scene).encode())
     rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
@@ -306,7 +306,7 @@ def oracle_closest(scene_name, rays):
     return tri, t, th
 
 
-def emul_closest(scene_name, rays, leaf_max=4, pad_ulps=64.0, brute=False):
+def emul_closest(scene_name, rays, leaf_max=2, pad_ulps=64.0, brute=0):
     lib = emul_lib()
     sc = lib.scene_load(scene_path(scene_name).encode())
     n = rays.shape[0]
