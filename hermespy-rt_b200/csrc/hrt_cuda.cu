@@ -455,7 +455,10 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
 {
   if (SMEM) { stage_scene(sc); __syncthreads(); }
   typename CntSel<COUNT>::type wc; cnt_init(wc);
-  const uint32_t t = blockIdx.y, T = rd.T, B = rd.B;
+  const uint32_t T = rd.T, B = rd.B;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t tt = 0; tt < T; ++tt) {          /* all transmitters, own one first */
+  const uint32_t t = (blockIdx.y + tt) % T;
   const size_t np = rd.n_alloc;
   const uint32_t cnt = rd.qcount[depth * T + t];
   const uint32_t *qin = rd.queue[depth & 1] + t * np;
@@ -463,7 +466,6 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
   const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
   const Ray *rin = rd.rays + (rows ? (size_t)depth * T * np : 0) + t * np;
   Ray *rout = rd.rays + (rows ? (size_t)(depth + 1) * T * np : 0) + t * np;
-  const uint32_t lane = threadIdx.x & 31u;
   unsigned long long hash_acc = 0, tbits_acc = 0;
 
   /* warps pull batches of 128 queue entries from a shared cursor (dynamic load
@@ -524,7 +526,6 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
     }
   }
   }
-  cnt_flush(wc, rd.counters);
   if (rd.flags & HRT_FLAG_SUMMARY) {
     for (int o = 16; o; o >>= 1) {
       hash_acc += __shfl_xor_sync(0xFFFFFFFFu, hash_acc, o);
@@ -535,6 +536,8 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
       atomicAdd((unsigned long long *)&rd.bounce[t * B + depth].t_bits, tbits_acc);
     }
   }
+  }   /* transmitters */
+  cnt_flush(wc, rd.counters);
 }
 
 /* Shared-memory reduction table of k_scatter: one record per receiver. */
@@ -558,7 +561,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   typename CntSel<COUNT>::type wc; cnt_init(wc);
   uint32_t used4 = 0;
   if (SMEM) used4 = stage_scene(sc);
-  const uint32_t R = rd.R, T = rd.T, B = rd.B, t = blockIdx.y;
+  const uint32_t R = rd.R, T = rd.T, B = rd.B;
   /* receivers (and, in summary mode, the reduction table) in shared memory */
   float *s_rx = (float *)(hrt_smem4 + used4);
   PairAcc *s_acc = (PairAcc *)(hrt_smem4 + used4 + (smem_rx_ok ? (3u * R + 3u) / 4u : 0u));
@@ -574,6 +577,10 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   if (SMEM || smem_rx_ok) __syncthreads();
   const float *rxp = smem_rx_ok ? s_rx : rd.rx_pos;
 
+  /* every block works through all transmitters, starting with "its own"
+   * (blockIdx.y): when one TX runs out of hits its blocks help with the others */
+  for (uint32_t tt = 0; tt < T; ++tt) {
+  const uint32_t t = (blockIdx.y + tt) % T;
   const size_t np = rd.n_alloc;
   const uint32_t cnt = rd.qcount[(depth + 1) * T + t];
   const uint32_t *q = rd.queue[(depth + 1) & 1] + t * np;
@@ -723,7 +730,6 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     }
   }
   }
-  cnt_flush(wc, rd.counters + 5);
   if (summary && smem_rx_ok) {
     __syncthreads();
     for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
@@ -736,9 +742,14 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         atomicAdd((unsigned long long *)&ps->tau_bits, a.tau_bits);
         atomicAdd(&ps->power_te, a.p_te);
         atomicAdd(&ps->power_tm, a.p_tm);
+        PairAcc z; z.hash = 0; z.tau_bits = 0; z.p_te = 0.0; z.p_tm = 0.0; z.n_valid = 0; z.n_occl = 0;
+        s_acc[r] = z;
       }
     }
+    __syncthreads();
   }
+  }   /* transmitters */
+  cnt_flush(wc, rd.counters + 5);
 }
 
 /* adds the per-depth queue sizes of a chunk into the bounce summary */
