@@ -257,6 +257,7 @@ struct HrtGlobalMem {
     return tris[3 * s + k];
 #endif
   }
+  HRT_HD void select_octant(uint32_t oct, uint32_t stride) { nodes += (size_t)oct * stride; }
 };
 
 #define HRT_STACK 64
@@ -274,7 +275,7 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const uint32_t *tri_gid, int ro
   if (num_tris == 0) return h;
   const HrtRayCull c = hrt_ray_cull(o, d);
   Mem mem = mem_in;
-  if (SORTED) mem.nodes += (size_t)hrt_octant(c) * oct_stride;
+  if (SORTED) mem.select_octant(hrt_octant(c), oct_stride);
   float tmax = HRT_T_MAX * 1.0001f;          /* far bound with slack */
   int   stack_ref[HRT_STACK];
   float stack_tn[HRT_STACK];

@@ -259,14 +259,19 @@ __global__ void k_emit(int n, const int *kl, const int *kr, const int *kfirst, c
 
 /* ------------------------------------------------------- scene in shared */
 
-struct HrtSharedMem {
-  const float4 *nodes;
-  const float4 *tris;
-  HRT_HD float4 node(int i, int k) const { return nodes[4 * i + k]; }
-  HRT_HD float4 tri(uint32_t s, int k) const { return tris[3 * s + k]; }
-};
-
 extern __shared__ float4 hrt_smem4[];
+
+/* scene words in shared memory, addressed with 32-bit indices into hrt_smem4 */
+struct HrtSharedMem {
+  uint32_t node_base, tri_base;
+  __device__ __forceinline__ float4 node(int i, int k) const { return hrt_smem4[node_base + 4u * (uint32_t)i + (uint32_t)k]; }
+  __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return hrt_smem4[tri_base + 3u * s + (uint32_t)k]; }
+  __device__ __forceinline__ void select_octant(uint32_t oct, uint32_t stride)
+  {
+    node_base += oct * stride;
+    asm volatile("" : "+r"(node_base));   /* keep it in a register: do not recompute per node */
+  }
+};
 
 /* copies nodes, triangle records and ids into shared memory; returns the
  * first free float4 slot after them */
@@ -288,8 +293,8 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
 {
   if (SMEM) {
     HrtSharedMem m;
-    m.nodes = hrt_smem4;
-    m.tris = hrt_smem4 + sc.num_nodes * 32u;                /* 8 octant copies of the nodes first */
+    m.node_base = 0u;
+    m.tri_base = sc.num_nodes * 32u;                        /* 8 octant copies of the nodes first */
     const uint32_t *gid = (const uint32_t *)(hrt_smem4 + sc.num_nodes * 32u + sc.num_tris * 3u);
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
     return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u);
