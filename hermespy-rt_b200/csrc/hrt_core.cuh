@@ -267,8 +267,8 @@ struct HrtGlobalMem {
  * root_ref: inner node index, a leaf ref, or 0 with num_tris == 0. */
 /* SORTED: `mem_in.nodes` holds 8 consecutive copies of the node array, one per
  * direction octant (hrt_emit_node), `oct_stride` float4s apart. */
-template <bool SORTED, class Mem, class Cnt>
-HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const uint32_t *tri_gid, int root_ref,
+template <bool SORTED, class Mem, class Gid, class Cnt>
+HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref,
                               uint32_t num_tris, V3 o, V3 d, Cnt &cnt, uint32_t oct_stride = 0)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
@@ -341,8 +341,8 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const uint32_t *tri_gid, int ro
 
 /* Brute force over every triangle in leaf order -- debug/validation path of
  * the kernels (HRT_FLAG_BRUTE_FORCE), same decisions by construction. */
-template <class Mem, class Cnt>
-HRT_HD HrtHit hrt_closest_hit_brute(const Mem &mem, const uint32_t *tri_gid,
+template <class Mem, class Gid, class Cnt>
+HRT_HD HrtHit hrt_closest_hit_brute(const Mem &mem, const Gid tri_gid,
                                     uint32_t num_tris, V3 o, V3 d, Cnt &cnt)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;

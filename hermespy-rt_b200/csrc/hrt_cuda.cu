@@ -261,16 +261,38 @@ __global__ void k_emit(int n, const int *kl, const int *kr, const int *kfirst, c
 
 extern __shared__ float4 hrt_smem4[];
 
-/* scene words in shared memory, addressed with 32-bit indices into hrt_smem4 */
+/* Scene words in shared memory, read with explicit ld.shared through 32-bit
+ * byte addresses held in registers (the compiler otherwise recomputes the
+ * shared-window base with S2UR/ULEA on every node visit). */
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t smem_base_addr() { return (uint32_t)__cvta_generic_to_shared(hrt_smem4); }
+
 struct HrtSharedMem {
-  uint32_t node_base, tri_base;
-  __device__ __forceinline__ float4 node(int i, int k) const { return hrt_smem4[node_base + 4u * (uint32_t)i + (uint32_t)k]; }
-  __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return hrt_smem4[tri_base + 3u * s + (uint32_t)k]; }
+  uint32_t node_addr, tri_addr;     /* byte addresses in the shared window */
+  __device__ __forceinline__ float4 node(int i, int k) const { return lds128(node_addr + ((uint32_t)i << 6) + ((uint32_t)k << 4)); }
+  __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return lds128(tri_addr + s * 48u + ((uint32_t)k << 4)); }
   __device__ __forceinline__ void select_octant(uint32_t oct, uint32_t stride)
   {
-    node_base += oct * stride;
-    asm volatile("" : "+r"(node_base));   /* keep it in a register: do not recompute per node */
+    node_addr += oct * stride * 16u;
+    asm volatile("" : "+r"(node_addr));   /* keep it in a register: do not recompute per node */
   }
+};
+
+/* leaf slot -> triangle id, from shared memory */
+struct HrtSharedGid {
+  uint32_t addr;
+  __device__ __forceinline__ uint32_t operator[](uint32_t s) const { return lds32(addr + 4u * s); }
 };
 
 /* copies nodes, triangle records and ids into shared memory; returns the
@@ -293,9 +315,9 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
 {
   if (SMEM) {
     HrtSharedMem m;
-    m.node_base = 0u;
-    m.tri_base = sc.num_nodes * 32u;                        /* 8 octant copies of the nodes first */
-    const uint32_t *gid = (const uint32_t *)(hrt_smem4 + sc.num_nodes * 32u + sc.num_tris * 3u);
+    m.node_addr = smem_base_addr();
+    m.tri_addr = m.node_addr + sc.num_nodes * 512u;         /* 8 octant copies of the nodes first */
+    HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
     return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u);
   } else {
