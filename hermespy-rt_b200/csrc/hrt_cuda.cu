@@ -53,6 +53,7 @@ struct SceneDev {
   uint32_t num_tris, num_nodes;
   uint32_t octants;            /* node copies: 8 (one per direction octant) or 1 */
   int root_ref;
+  float key_lo[3], key_scale[3];   /* vertex bounds -> 10-bit grid of the hit-order keys */
 };
 
 struct RunDev {
@@ -72,6 +73,8 @@ struct RunDev {
   uint32_t *hslot;       /* [T][n_alloc] leaf slot of the last primary hit */
   uint8_t *dead_at;      /* [T][n_alloc] bounce at which the ray left the scene, 255 alive */
   uint32_t *queue[2];    /* [T][n_alloc] active path indices */
+  uint32_t *queue_alt;   /* [T][n_alloc] sort output, swapped with queue[k] on the host */
+  uint32_t *qkey, *qkey_alt; /* [T][n_alloc] Morton code of the hit point, order of the next queue */
   uint32_t *qcount;      /* [B+1][T] queue sizes, then [B][T] k_bounce and [B][T] k_scatter work cursors */
   float *out_f[6];       /* [R][T][B][n_alloc] te_re te_im tm_re tm_im tau freq */
   float *out_dir;        /* [R][T][B][n_alloc][3] */
@@ -110,6 +113,7 @@ struct hrt_ctx {
   uint32_t num_tris, num_meshes, num_nodes, octants;
   int root_ref;
   float pad, scene_max_abs;
+  float scene_lo[3], scene_hi[3];
   float4 *d_tris; uint32_t *d_tri_gid; uint32_t *d_mesh_of; uint32_t *d_mesh_mat; float *d_mesh_vel;
   float4 *d_nodes;
   /* builder arrays kept for re-padding */
@@ -376,6 +380,18 @@ __device__ __forceinline__ uint32_t dir_key(V3 d)
   return (spread16(iu) << 1) | spread16(iv);
 }
 
+/* Order key of a hit: 30-bit Morton code of the reflected ray's origin on a
+ * 1024^3 grid over the vertex bounds.  The next queue is sorted by it, so the
+ * 32 hits a warp of k_scatter works on are neighbours in space -- their shadow
+ * rays to one receiver are nearly the same ray.  Order only, never results. */
+__device__ __forceinline__ uint32_t hit_key(const SceneDev &sc, V3 o)
+{
+  const uint32_t x = (uint32_t)fminf(fmaxf((o.x - sc.key_lo[0]) * sc.key_scale[0], 0.f), 1023.f);
+  const uint32_t y = (uint32_t)fminf(fmaxf((o.y - sc.key_lo[1]) * sc.key_scale[1], 0.f), 1023.f);
+  const uint32_t z = (uint32_t)fminf(fmaxf((o.z - sc.key_lo[2]) * sc.key_scale[2], 0.f), 1023.f);
+  return (hrt_expand10(x) << 2) | (hrt_expand10(y) << 1) | hrt_expand10(z);
+}
+
 __global__ void k_dirkeys(RunDev rd)
 {
   for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
@@ -506,7 +522,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
   for (uint32_t i = batch + lane; i < batch + 128u && (i - lane) < cnt; i += 32u) {
     const bool valid = i < cnt;
     bool hit = false;
-    uint32_t l = 0;
+    uint32_t l = 0, okey = 0;
     if (valid) {
       l = qin[i];
       const float2 *rp = (const float2 *)(rin + l);
@@ -537,6 +553,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
         rd.tau[si] = s.tau;
         rd.theta[si] = theta;
         rd.hslot[si] = h.slot;
+        okey = hit_key(sc, s.o);
         if (rd.flags & HRT_FLAG_SUMMARY) {
           const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
           hash_acc += hrt_mix64((path << 32) | h.gid);
@@ -549,7 +566,11 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&rd.qcount[(depth + 1) * T + t], (uint32_t)__popc(m));
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (hit) qout[base + __popc(m & ((1u << lane) - 1u))] = l;
+      if (hit) {
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+        qout[pos] = l;
+        rd.qkey[t * np + pos] = okey;
+      }
     }
   }
   }
@@ -889,6 +910,7 @@ static void free_run_dev(hrt_ctx *c)
   RunDev &r = c->rd;
   dev_free(r.dirs); dev_free(r.rays); dev_free(r.gain); dev_free(r.tau); dev_free(r.theta);
   dev_free(r.hslot); dev_free(r.dead_at); dev_free(r.queue[0]); dev_free(r.queue[1]);
+  dev_free(r.queue_alt); dev_free(r.qkey); dev_free(r.qkey_alt);
   dev_free(r.qcount);
   for (int k = 0; k < 6; ++k) dev_free(r.out_f[k]);
   dev_free(r.out_dir); dev_free(r.tr_hit); dev_free(r.tr_t); dev_free(r.tr_state);
@@ -947,11 +969,18 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
   float *h_vel = (float *)malloc(M * 12);
   if (!h_v || !h_i || !h_mesh_of || !h_mat || !h_vel) { free(h_v); free(h_i); free(h_mesh_of); free(h_mat); free(h_vel); return fail(ctx, HRT_E_NOMEM, "out of host memory"); }
   size_t vo = 0, to = 0; float max_abs = 0.f; int bad = 0;
+  float blo[3] = { 3e38f, 3e38f, 3e38f }, bhi[3] = { -3e38f, -3e38f, -3e38f };
   for (uint32_t m = 0; m < M && !bad; ++m) {
     const Mesh *me = &scene->meshes[m];
     if (me->material_index >= NUM_G_MATERIALS) { bad = 1; break; }
     memcpy(h_v + 3 * vo, me->vs, (size_t)me->num_vertices * 12);
-    for (size_t k = 0; k < (size_t)3 * me->num_vertices; ++k) { const float a = fabsf(h_v[3 * vo + k]); if (a > max_abs) max_abs = a; if (!(a == a)) bad = 2; }
+    for (size_t k = 0; k < (size_t)3 * me->num_vertices; ++k) {
+      const float v = h_v[3 * vo + k], a = fabsf(v);
+      if (a > max_abs) max_abs = a;
+      if (!(a == a)) bad = 2;
+      if (v < blo[k % 3]) blo[k % 3] = v;
+      if (v > bhi[k % 3]) bhi[k % 3] = v;
+    }
     for (size_t k = 0; k < (size_t)3 * me->num_triangles; ++k) {
       const uint32_t ix = me->is[k];
       if (ix >= me->num_vertices) { bad = 3; break; }
@@ -969,6 +998,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
 
   const uint32_t n = (uint32_t)nt;
   ctx->num_tris = n; ctx->num_meshes = M; ctx->scene_max_abs = max_abs;
+  for (int k = 0; k < 3; ++k) { ctx->scene_lo[k] = nv ? blo[k] : 0.f; ctx->scene_hi[k] = nv ? bhi[k] : 1.f; }
   float *d_v = nullptr; uint32_t *d_i = nullptr; float4 *d_recs = nullptr; float *d_boxes = nullptr;
   unsigned *d_bounds = nullptr; uint64_t *d_keys = nullptr, *d_keys2 = nullptr; int *d_parent = nullptr;
   unsigned *d_arrive = nullptr; void *d_tmp = nullptr; size_t tmp_bytes = 0;
@@ -1105,6 +1135,10 @@ static SceneDev scene_dev(const hrt_ctx *c)
   s.nodes = c->d_nodes; s.tris = c->d_tris; s.tri_gid = c->d_tri_gid; s.mesh_of = c->d_mesh_of;
   s.mesh_mat = c->d_mesh_mat; s.mesh_vel = c->d_mesh_vel;
   s.num_tris = c->num_tris; s.num_nodes = c->num_nodes; s.root_ref = c->root_ref; s.octants = c->octants;
+  for (int k = 0; k < 3; ++k) {
+    s.key_lo[k] = c->scene_lo[k];
+    s.key_scale[k] = 1024.f / fmaxf(c->scene_hi[k] - c->scene_lo[k], 1e-20f);
+  }
   return s;
 }
 
@@ -1207,6 +1241,7 @@ static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t
   CK(dev_alloc(&r.dirs, n * 3)); CK(dev_alloc(&r.rays, rows * TN)); CK(dev_alloc(&r.gain, TN));
   CK(dev_alloc(&r.tau, TN)); CK(dev_alloc(&r.theta, TN)); CK(dev_alloc(&r.hslot, TN));
   CK(dev_alloc(&r.dead_at, TN)); CK(dev_alloc(&r.queue[0], TN)); CK(dev_alloc(&r.queue[1], TN));
+  CK(dev_alloc(&r.queue_alt, TN)); CK(dev_alloc(&r.qkey, TN)); CK(dev_alloc(&r.qkey_alt, TN));
   CK(dev_alloc(&r.qcount, (3 * B + 1) * T));   /* queue sizes + work cursors of k_bounce / k_scatter */
   CK(dev_alloc(&r.amb_list, HRT_AMB_CAP)); CK(dev_alloc(&r.amb_count, 1));
   CK(dev_alloc(&r.dkey, n)); CK(dev_alloc(&r.dkey2, n)); CK(dev_alloc(&r.perm, n)); CK(dev_alloc(&r.perm2, n));
@@ -1351,6 +1386,17 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   }
   CK(allow_smem(f_scatter, scat_sb));
   if (count) CK(cudaMemsetAsync(rd.counters, 0, 16 * sizeof(unsigned long long), st));
+  const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT");
+  if (sort_hits) {
+    /* the chunk's direction sort below needs less: same pair types, 32 key bits */
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, rd.qkey, rd.qkey_alt, rd.queue[0], rd.queue_alt, (int)ctx->cap_n, 0, 32, st));
+    if (tb > ctx->sort_tmp_bytes) {
+      if (ctx->sort_tmp) cudaFree(ctx->sort_tmp);
+      ctx->sort_tmp = nullptr; ctx->sort_tmp_bytes = 0;
+      CK(cudaMalloc(&ctx->sort_tmp, tb)); ctx->sort_tmp_bytes = tb;
+    }
+  }
 
   CK(cudaEventRecord(ctx->ev[0], st));
 
@@ -1490,6 +1536,21 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       }
       f_bounce<<<gb, HRT_BLOCK, smem ? scene_sb : 0, st>>>(rd, sc, ctx->mats, b);
       CKR(cudaGetLastError());
+      if (sort_hits) {
+        /* order the hits of this depth by position (see hit_key) */
+        CKR(cudaMemcpyAsync(h_counts, rd.qcount + (size_t)(b + 1) * T, T * 4, cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        uint32_t *&qcur = rd.queue[(b + 1) & 1];
+        for (size_t t = 0; t < T; ++t) {
+          const size_t off = t * (size_t)rd.n_alloc;
+          if (h_counts[t] == 0) continue;
+          size_t tb = ctx->sort_tmp_bytes;
+          CKR(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tb, rd.qkey + off, rd.qkey_alt + off, qcur + off,
+                                              rd.queue_alt + off, (int)h_counts[t], 0, 30, st));
+          S.kernel_launches += 4;
+        }
+        uint32_t *tmpq = qcur; qcur = rd.queue_alt; rd.queue_alt = tmpq;
+      }
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 1], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * 2 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
