@@ -213,15 +213,32 @@ HRT_HD bool hrt_slab(const HrtRayCull &c, float lox, float hix, float loy, float
   return tn <= tf;
 }
 
+/* (a0, a1) * b + c in one issue slot: Blackwell's packed fp32 FMA (FFMA2, PTX
+ * fma.rn.f32x2) with the scalars b, c broadcast; each half rounds like fmaf. */
+HRT_HD void hrt_fma_pair(float a0, float a1, float b, float c, float *r0, float *r1)
+{
+#if defined(__CUDA_ARCH__)
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c), "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(*r0), "=f"(*r1) : "l"(rd));
+#else
+  *r0 = fmaf(a0, b, c); *r1 = fmaf(a1, b, c);
+#endif
+}
+
 /* Same test when the node copy in use stores, per axis, the plane the ray
  * reaches first in the "lo" slot (one node copy per direction octant, see
  * hrt_emit_node): no per-axis min/max is needed. */
 HRT_HD bool hrt_slab_sorted(const HrtRayCull &c, float nx, float fx, float ny, float fy,
                             float nz, float fz, float tmax, float *t_near)
 {
-  const float x0 = HRT_FMA(nx, c.inv.x, c.ood.x), x1 = HRT_FMA(fx, c.inv.x, c.ood.x);
-  const float y0 = HRT_FMA(ny, c.inv.y, c.ood.y), y1 = HRT_FMA(fy, c.inv.y, c.ood.y);
-  const float z0 = HRT_FMA(nz, c.inv.z, c.ood.z), z1 = HRT_FMA(fz, c.inv.z, c.ood.z);
+  float x0, x1, y0, y1, z0, z1;
+  hrt_fma_pair(nx, fx, c.inv.x, c.ood.x, &x0, &x1);
+  hrt_fma_pair(ny, fy, c.inv.y, c.ood.y, &y0, &y1);
+  hrt_fma_pair(nz, fz, c.inv.z, c.ood.z, &z0, &z1);
   const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, 0.f));
   const float tf = fminf(fminf(x1, y1), fminf(z1, tmax));
   *t_near = tn;
@@ -261,6 +278,11 @@ struct HrtGlobalMem {
 };
 
 #define HRT_STACK 64
+#if defined(__CUDACC__)
+struct __align__(8) HrtStackEntry { int ref; float tn; };
+#else
+struct HrtStackEntry { int ref; float tn; };
+#endif
 
 /* Closest hit over the BVH == the reference's loop over every triangle
  * (moeller_trumbore, :237-287): minimum t, ties to the lowest (mesh, face).
@@ -277,8 +299,7 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
   Mem mem = mem_in;
   if (SORTED) mem.select_octant(hrt_octant(c), oct_stride);
   float tmax = HRT_T_MAX * 1.0001f;          /* far bound with slack */
-  int   stack_ref[HRT_STACK];
-  float stack_tn[HRT_STACK];
+  HrtStackEntry stack[HRT_STACK];    /* (subtree ref, entry distance): one 8-byte store / load each */
   int sp = 0, cur = root_ref;
   bool done = false;
   /* "while-while" traversal: every lane first walks inner nodes until it holds
@@ -297,9 +318,10 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
       cnt.box(2u);
       if (hl && hr) {
         const bool left_first = tl <= tr;
-        stack_ref[sp] = left_first ? rr : rl;
-        stack_tn[sp]  = left_first ? tr : tl;
-        ++sp;
+        HrtStackEntry e;
+        e.ref = left_first ? rr : rl;
+        e.tn  = left_first ? tr : tl;
+        stack[sp++] = e;
         cur = left_first ? rl : rr;
       } else if (hl) {
         cur = rl;
@@ -310,7 +332,8 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
         bool got = false;
         while (sp > 0) {
           --sp;
-          if (stack_tn[sp] <= tmax) { cur = stack_ref[sp]; got = true; break; }
+          const HrtStackEntry e = stack[sp];
+          if (e.tn <= tmax) { cur = e.ref; got = true; break; }
         }
         if (!got) { done = true; break; }
       }
@@ -332,7 +355,8 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
     bool got = false;
     while (sp > 0) {
       --sp;
-      if (stack_tn[sp] <= tmax) { cur = stack_ref[sp]; got = true; break; }
+      const HrtStackEntry e = stack[sp];
+      if (e.tn <= tmax) { cur = e.ref; got = true; break; }
     }
     if (!got) done = true;
   }

@@ -119,6 +119,10 @@ struct hrt_ctx {
   /* builder arrays kept for re-padding */
   int *d_kl, *d_kr, *d_kfirst, *d_klast, *d_newidx;
   float *d_box;            /* [(2n-1)][6] lo.xyz hi.xyz; inner nodes then leaves */
+  bool sah;                /* tree built by the binned-SAH builder (raw arrays below) */
+  int2 *d_raw_ref;         /* [num_nodes] child refs */
+  float *d_raw_box;        /* [num_nodes][12] both children's boxes, unpadded */
+  float build_ms; int build_levels;
 
   bool have_mats;
   HrtMaterialTable mats;
@@ -259,6 +263,211 @@ __global__ void k_emit(int n, const int *kl, const int *kr, const int *kfirst, c
                   hrt_child_ref(r, n, kfirst, klast, newidx, leaf_max),
                   v3(bl[0], bl[1], bl[2]), v3(bl[3], bl[4], bl[5]),
                   v3(br[0], br[1], br[2]), v3(br[3], br[4], br[5]), pad, oct);
+}
+
+/* ---------------------------------------------- binned-SAH builder (default)
+ * Top-down, level-synchronous: every level bins the triangles of each open node
+ * (16 bins x 3 axes over the node's centroid bounds), picks the plane with the
+ * lowest surface-area cost, and partitions the node's slice of the index array.
+ * Ranges of <= leaf_max triangles become leaves; the final index array IS the
+ * leaf order.  Compared with the Morton/Karras tree this roughly halves the
+ * box tests of a shadow query on street scenes (scripts/bvh_lab.py).
+ * Tree shape never influences results: the traversal returns the minimum over
+ * (t, triangle id) whatever the tree. */
+#define SAH_BINS 16
+#define SAH_FORCE_MEDIAN_LEVEL 32   /* depth <= 32 + log2(n) < HRT_STACK */
+
+struct SahWork {
+  uint32_t start, end;
+  int inner;                 /* index of this node in the raw node arrays */
+  unsigned cb[6];            /* centroid bounds, order-encoded (enc_f): lo xyz, hi xyz */
+  float box[6];              /* the node's own box */
+  float cmin[3], cscale[3];
+  int axis, bin;             /* split: axis < 0 = halve by position */
+  uint32_t nl;
+  int child[2];              /* work index on the next level, -1 = leaf */
+  unsigned fill[2];
+};
+struct SahBin { unsigned count, lo[3], hi[3]; };
+
+__device__ __forceinline__ int sah_bin_of(const SahWork &w, int ax, float c)
+{
+  const int b = (int)((c - w.cmin[ax]) * w.cscale[ax]);
+  return b < 0 ? 0 : (b > SAH_BINS - 1 ? SAH_BINS - 1 : b);
+}
+
+/* level 0: identity order, everything belongs to the root (work[0], set up by
+ * the host), whose centroid bounds are accumulated here */
+__global__ void k_sah_init(uint32_t n, const float *boxes, uint32_t *idx, int *work_of, SahWork *work)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  idx[p] = p; work_of[p] = 0;
+  const float *b = boxes + 6 * (size_t)p;
+  for (int k = 0; k < 3; ++k) {
+    const unsigned e = enc_f(0.5f * (b[k] + b[3 + k]));
+    atomicMin(&work[0].cb[k], e); atomicMax(&work[0].cb[3 + k], e);
+  }
+}
+
+/* per open node: bin grid from the centroid bounds, empty bins */
+__global__ void k_sah_prep(int count, SahWork *work, SahBin *bins)
+{
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= count) return;
+  SahWork &W = work[w];
+  for (int k = 0; k < 3; ++k) {
+    const float lo = dec_f(W.cb[k]), hi = dec_f(W.cb[3 + k]);
+    W.cmin[k] = lo;
+    W.cscale[k] = hi > lo ? (float)SAH_BINS * (1.f - 1e-6f) / (hi - lo) : 0.f;
+  }
+  W.fill[0] = W.fill[1] = 0;
+  SahBin z; z.count = 0;
+  for (int k = 0; k < 3; ++k) { z.lo[k] = 0xFFFFFFFFu; z.hi[k] = 0u; }
+  for (int k = 0; k < 3 * SAH_BINS; ++k) bins[(size_t)w * 3 * SAH_BINS + k] = z;
+}
+
+__global__ void k_sah_bin(uint32_t n, const uint32_t *idx, const int *work_of, const SahWork *work,
+                          const float *boxes, SahBin *bins)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int w = work_of[p];
+  if (w < 0) return;
+  const SahWork &W = work[w];
+  const float *b = boxes + 6 * (size_t)idx[p];
+  unsigned lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) { lo[k] = enc_f(b[k]); hi[k] = enc_f(b[3 + k]); }
+  for (int ax = 0; ax < 3; ++ax) {
+    SahBin *bin = &bins[((size_t)w * 3 + ax) * SAH_BINS + sah_bin_of(W, ax, 0.5f * (b[ax] + b[3 + ax]))];
+    atomicAdd(&bin->count, 1u);
+    for (int k = 0; k < 3; ++k) { atomicMin(&bin->lo[k], lo[k]); atomicMax(&bin->hi[k], hi[k]); }
+  }
+}
+
+__device__ __forceinline__ float sah_area(const float lo[3], const float hi[3])
+{
+  const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+  return x * y + y * z + z * x;
+}
+
+/* per open node: best plane, children, raw node record */
+__global__ void k_sah_split(int count, int level, int leaf_max, SahWork *work, const SahBin *bins, SahWork *next,
+                            int *counters, int2 *raw_ref, float *raw_box)
+{
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= count) return;
+  SahWork &W = work[w];
+  const uint32_t cnt = W.end - W.start;
+  float best = 3.0e38f; int best_ax = -1, best_k = 0; uint32_t best_nl = 0;
+  if (level < SAH_FORCE_MEDIAN_LEVEL) {
+    for (int ax = 0; ax < 3; ++ax) {
+      const SahBin *B = bins + ((size_t)w * 3 + ax) * SAH_BINS;
+      float r_area[SAH_BINS];
+      float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+      for (int k = SAH_BINS - 1; k >= 1; --k) {
+        if (B[k].count)
+          for (int j = 0; j < 3; ++j) { lo[j] = fminf(lo[j], dec_f(B[k].lo[j])); hi[j] = fmaxf(hi[j], dec_f(B[k].hi[j])); }
+        r_area[k] = sah_area(lo, hi);
+      }
+      for (int j = 0; j < 3; ++j) { lo[j] = 3e38f; hi[j] = -3e38f; }
+      uint32_t nl = 0;
+      for (int k = 1; k < SAH_BINS; ++k) {
+        if (B[k - 1].count)
+          for (int j = 0; j < 3; ++j) { lo[j] = fminf(lo[j], dec_f(B[k - 1].lo[j])); hi[j] = fmaxf(hi[j], dec_f(B[k - 1].hi[j])); }
+        nl += B[k - 1].count;
+        if (nl == 0 || nl == cnt) continue;
+        const float c = sah_area(lo, hi) * (float)nl + r_area[k] * (float)(cnt - nl);
+        if (c < best) { best = c; best_ax = ax; best_k = k; best_nl = nl; }
+      }
+    }
+  }
+  float cbox[2][6];
+  if (best_ax >= 0) {
+    const SahBin *B = bins + ((size_t)w * 3 + best_ax) * SAH_BINS;
+    for (int s = 0; s < 2; ++s) {
+      float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+      for (int k = s ? best_k : 0; k < (s ? SAH_BINS : best_k); ++k)
+        if (B[k].count)
+          for (int j = 0; j < 3; ++j) { lo[j] = fminf(lo[j], dec_f(B[k].lo[j])); hi[j] = fmaxf(hi[j], dec_f(B[k].hi[j])); }
+      for (int j = 0; j < 3; ++j) { cbox[s][j] = lo[j]; cbox[s][3 + j] = hi[j]; }
+    }
+  } else {
+    best_nl = cnt / 2;
+    for (int s = 0; s < 2; ++s) for (int j = 0; j < 6; ++j) cbox[s][j] = W.box[j];
+  }
+  W.axis = best_ax; W.bin = best_k; W.nl = best_nl;
+  int2 ref;
+  for (int s = 0; s < 2; ++s) {
+    const uint32_t cs = s ? W.start + best_nl : W.start, ce = s ? W.end : W.start + best_nl;
+    int r;
+    if (ce - cs <= (uint32_t)leaf_max) {
+      r = hrt_leaf_ref(cs, ce - cs);
+      W.child[s] = -1;
+    } else {
+      r = atomicAdd(&counters[0], 1);
+      const int nw = atomicAdd(&counters[1], 1);
+      SahWork &C = next[nw];
+      C.start = cs; C.end = ce; C.inner = r;
+      for (int j = 0; j < 3; ++j) { C.cb[j] = 0xFFFFFFFFu; C.cb[3 + j] = 0u; }
+      for (int j = 0; j < 6; ++j) C.box[j] = cbox[s][j];
+      W.child[s] = nw;
+    }
+    if (s) ref.y = r; else ref.x = r;
+  }
+  raw_ref[W.inner] = ref;
+  float *rb = raw_box + 12 * (size_t)W.inner;
+  for (int j = 0; j < 6; ++j) { rb[j] = cbox[0][j]; rb[6 + j] = cbox[1][j]; }
+}
+
+/* per triangle: move to its side of the split; children's centroid bounds */
+__global__ void k_sah_part(uint32_t n, const uint32_t *idx, const int *work_of, SahWork *work, SahWork *next,
+                           const float *boxes, uint32_t *idx_out, int *work_out)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int w = work_of[p];
+  const uint32_t prim = idx[p];
+  if (w < 0) { idx_out[p] = prim; work_out[p] = -1; return; }
+  SahWork &W = work[w];
+  const float *b = boxes + 6 * (size_t)prim;
+  int side; uint32_t dest;
+  if (W.axis < 0) {
+    side = (p - W.start) >= W.nl; dest = p;
+  } else {
+    side = sah_bin_of(W, W.axis, 0.5f * (b[W.axis] + b[3 + W.axis])) >= W.bin;
+    dest = side ? W.start + W.nl + atomicAdd(&W.fill[1], 1u) : W.start + atomicAdd(&W.fill[0], 1u);
+  }
+  idx_out[dest] = prim;
+  const int cw = W.child[side];
+  work_out[dest] = cw;
+  if (cw >= 0)
+    for (int k = 0; k < 3; ++k) {
+      const unsigned e = enc_f(0.5f * (b[k] + b[3 + k]));
+      atomicMin(&next[cw].cb[k], e); atomicMax(&next[cw].cb[3 + k], e);
+    }
+}
+
+/* leaf order from the final index array */
+__global__ void k_gather_idx(const uint32_t *idx, uint32_t n, const float4 *recs, float4 *tris, uint32_t *tri_gid)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t g = idx[s];
+  tris[3 * s] = recs[3 * g]; tris[3 * s + 1] = recs[3 * g + 1]; tris[3 * s + 2] = recs[3 * g + 2];
+  tri_gid[s] = g;
+}
+
+__global__ void k_emit_raw(int num_inner, const int2 *raw_ref, const float *raw_box, float pad, float4 *nodes,
+                           uint32_t octants, uint32_t num_nodes)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_inner) return;
+  const int2 r = raw_ref[i];
+  const float *b = raw_box + 12 * (size_t)i;
+  for (uint32_t oct = 0; oct < octants; ++oct)
+    hrt_emit_node(nodes + 4 * ((size_t)oct * num_nodes + i), r.x, r.y, v3(b[0], b[1], b[2]), v3(b[3], b[4], b[5]),
+                  v3(b[6], b[7], b[8]), v3(b[9], b[10], b[11]), pad, oct);
 }
 
 /* ------------------------------------------------------- scene in shared */
@@ -902,6 +1111,7 @@ static void free_scene_dev(hrt_ctx *c)
   dev_free(c->d_tris); dev_free(c->d_tri_gid); dev_free(c->d_mesh_of); dev_free(c->d_mesh_mat);
   dev_free(c->d_mesh_vel); dev_free(c->d_nodes); dev_free(c->d_kl); dev_free(c->d_kr);
   dev_free(c->d_kfirst); dev_free(c->d_klast); dev_free(c->d_newidx); dev_free(c->d_box);
+  dev_free(c->d_raw_ref); dev_free(c->d_raw_box);
   c->have_scene = false;
 }
 
@@ -944,11 +1154,78 @@ static int emit_nodes(hrt_ctx *ctx, float pad)
   const int n = (int)ctx->num_tris;
   ctx->pad = pad;
   if (ctx->num_nodes == 0) return HRT_OK;
+  if (ctx->sah) {
+    k_emit_raw<<<nblk(ctx->num_nodes), 256, 0, ctx->stream>>>((int)ctx->num_nodes, ctx->d_raw_ref, ctx->d_raw_box, pad,
+                                                             ctx->d_nodes, ctx->octants, ctx->num_nodes);
+    CK(cudaGetLastError());
+    return HRT_OK;
+  }
   k_emit<<<nblk(n - 1), 256, 0, ctx->stream>>>(n, ctx->d_kl, ctx->d_kr, ctx->d_kfirst, ctx->d_klast,
                                                ctx->d_newidx + n /* used flags live behind newidx */,
                                                ctx->d_newidx, ctx->d_box, ctx->leaf_max, pad, ctx->d_nodes, ctx->octants, ctx->num_nodes);
   CK(cudaGetLastError());
   return HRT_OK;
+}
+
+/* binned-SAH build over the triangle boxes; fills d_tris / d_tri_gid in leaf
+ * order and the raw node arrays.  See the kernels above. */
+static int build_sah(hrt_ctx *ctx, uint32_t n, const float *d_boxes, const float4 *d_recs)
+{
+  cudaStream_t st = ctx->stream;
+  const size_t max_work = (size_t)n / (size_t)(ctx->leaf_max + 1) + 2;
+  uint32_t *d_idx[2] = { nullptr, nullptr }; int *d_wof[2] = { nullptr, nullptr };
+  SahWork *d_work[2] = { nullptr, nullptr }; SahBin *d_bins = nullptr; int *d_cnt = nullptr;
+  int rc = HRT_OK, level = 0, count = 1, cur = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto out; } } while (0)
+  CKB(cudaEventCreate(&e0)); CKB(cudaEventCreate(&e1));
+  CKB(cudaEventRecord(e0, st));
+  for (int k = 0; k < 2; ++k) {
+    CKB(dev_alloc(&d_idx[k], n)); CKB(dev_alloc(&d_wof[k], n)); CKB(dev_alloc(&d_work[k], max_work));
+  }
+  CKB(dev_alloc(&d_bins, max_work * 3 * SAH_BINS)); CKB(dev_alloc(&d_cnt, 2));
+  CKB(dev_alloc(&ctx->d_raw_ref, n)); CKB(dev_alloc(&ctx->d_raw_box, (size_t)n * 12));
+  {
+    SahWork root; memset(&root, 0, sizeof root);
+    root.start = 0; root.end = n; root.inner = 0;
+    for (int k = 0; k < 3; ++k) { root.cb[k] = 0xFFFFFFFFu; root.cb[3 + k] = 0u; root.box[k] = ctx->scene_lo[k]; root.box[3 + k] = ctx->scene_hi[k]; }
+    const int c0[2] = { 1, 0 };   /* inner nodes allocated, work items of the next level */
+    CKB(cudaMemcpyAsync(d_work[0], &root, sizeof root, cudaMemcpyHostToDevice, st));
+    CKB(cudaMemcpyAsync(d_cnt, c0, sizeof c0, cudaMemcpyHostToDevice, st));
+    CKB(cudaStreamSynchronize(st));   /* root and c0 are stack temporaries */
+  }
+  k_sah_init<<<nblk(n), 256, 0, st>>>(n, d_boxes, d_idx[0], d_wof[0], d_work[0]);
+  CKB(cudaGetLastError());
+  while (count > 0) {
+    if ((size_t)count > max_work) { rc = fail(ctx, HRT_E_STATE, "SAH builder: work list overflow"); goto out; }
+    k_sah_prep<<<nblk(count), 256, 0, st>>>(count, d_work[cur], d_bins);
+    k_sah_bin<<<nblk(n), 256, 0, st>>>(n, d_idx[cur], d_wof[cur], d_work[cur], d_boxes, d_bins);
+    k_sah_split<<<nblk(count, 64), 64, 0, st>>>(count, level, ctx->leaf_max, d_work[cur], d_bins, d_work[cur ^ 1], d_cnt,
+                                               ctx->d_raw_ref, ctx->d_raw_box);
+    k_sah_part<<<nblk(n), 256, 0, st>>>(n, d_idx[cur], d_wof[cur], d_work[cur], d_work[cur ^ 1], d_boxes,
+                                        d_idx[cur ^ 1], d_wof[cur ^ 1]);
+    CKB(cudaGetLastError());
+    int hc[2];
+    CKB(cudaMemcpyAsync(hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CKB(cudaMemsetAsync(d_cnt + 1, 0, 4, st));
+    CKB(cudaStreamSynchronize(st));
+    ctx->num_nodes = (uint32_t)hc[0];
+    count = hc[1]; cur ^= 1; ++level;
+    if (level > 200) { rc = fail(ctx, HRT_E_STATE, "SAH builder did not terminate"); goto out; }
+  }
+  k_gather_idx<<<nblk(n), 256, 0, st>>>(d_idx[cur], n, d_recs, ctx->d_tris, ctx->d_tri_gid);
+  CKB(cudaGetLastError());
+  CKB(cudaEventRecord(e1, st));
+  CKB(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&ctx->build_ms, e0, e1);
+  ctx->build_levels = level;
+out:
+#undef CKB
+  for (int k = 0; k < 2; ++k) { cudaFree(d_idx[k]); cudaFree(d_wof[k]); cudaFree(d_work[k]); }
+  cudaFree(d_bins); cudaFree(d_cnt);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return rc;
 }
 
 extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_out)
@@ -1026,6 +1303,16 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
     ctx->num_nodes = 0; ctx->root_ref = 0; ctx->octants = 8;
     if (n > 0) {
       k_tri_setup<<<nblk(n), 256, 0, st>>>(d_v, d_i, n, d_recs, d_boxes, d_bounds);
+      ctx->sah = !getenv("HRT_BVH_LBVH");
+      if (ctx->sah && (int)n > ctx->leaf_max) {
+        CKG(cudaGetLastError());
+        const int brc = build_sah(ctx, n, d_boxes, d_recs);
+        if (brc) { rc = brc; goto done; }
+        ctx->octants = scene_smem_bytes(ctx->num_nodes, n, 8) <= HRT_SMEM_SCENE_LIMIT ? 8u : 1u;
+        CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
+        goto built;
+      }
+      ctx->sah = false;
       k_morton<<<nblk(n), 256, 0, st>>>(d_boxes, n, d_bounds, d_keys);
       CKG(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, (int)n, 0, 64, st));
       CKG(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
@@ -1059,6 +1346,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
       }
     }
+built:
     ctx->pad = hrt_box_pad(max_abs, ctx->pad_ulps);
     if (ctx->num_nodes) {
       int erc = emit_nodes(ctx, ctx->pad);
@@ -1361,6 +1649,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   HrtRunStats &S = ctx->stats;
   memset(&S, 0, sizeof S);
   S.num_tris = ctx->num_tris; S.num_nodes = ctx->num_nodes; S.box_pad = ctx->pad;
+  S.bvh_sah = ctx->sah; S.bvh_levels = (uint32_t)ctx->build_levels; S.bvh_build_ms = ctx->build_ms;
   const SceneDev sc = scene_dev(ctx);
   const size_t scene_sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris, ctx->octants);
   const bool smem = ctx->octants == 8 && scene_sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM");
@@ -1450,7 +1739,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   float ms_bounce = 0.f, ms_scatter = 0.f;
   /* per-launch timing: three events per (chunk, bounce), resolved after the
    * run -- no synchronisation inside the loop */
-  const size_t EV_CAP = 3 * 512;
+  const size_t EV_CAP = 4 * 512;
   size_t ev_used = 0;
   uint8_t tail_dead[8] = {255, 255, 255, 255, 255, 255, 255, 255};  /* TX 1, paths 0..7 */
   rc = HRT_OK;
@@ -1524,18 +1813,19 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
                             T * (size_t)rd.n_alloc * sizeof(Ray), cudaMemcpyDeviceToDevice, st));
       /* persistent grids: enough blocks to fill the machine, grid-stride inside */
       const dim3 gb((unsigned)min((size_t)((sms * 2 + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      const bool timed = ev_used + 3 <= EV_CAP;
+      const bool timed = ev_used + 4 <= EV_CAP;
       if (timed) {
-        if (ctx->evpool_n < ev_used + 3) {
-          cudaEvent_t *np_ = (cudaEvent_t *)realloc(ctx->evpool, (ev_used + 3) * sizeof(cudaEvent_t));
+        if (ctx->evpool_n < ev_used + 4) {
+          cudaEvent_t *np_ = (cudaEvent_t *)realloc(ctx->evpool, (ev_used + 4) * sizeof(cudaEvent_t));
           if (!np_) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
           ctx->evpool = np_;
-          while (ctx->evpool_n < ev_used + 3) CKR(cudaEventCreate(&ctx->evpool[ctx->evpool_n++]));
+          while (ctx->evpool_n < ev_used + 4) CKR(cudaEventCreate(&ctx->evpool[ctx->evpool_n++]));
         }
         CKR(cudaEventRecord(ctx->evpool[ev_used], st));
       }
       f_bounce<<<gb, HRT_BLOCK, smem ? scene_sb : 0, st>>>(rd, sc, ctx->mats, b);
       CKR(cudaGetLastError());
+      if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 1], st));
       if (sort_hits) {
         /* order the hits of this depth by position (see hit_key) */
         CKR(cudaMemcpyAsync(h_counts, rd.qcount + (size_t)(b + 1) * T, T * 4, cudaMemcpyDeviceToHost, st));
@@ -1551,13 +1841,13 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
         }
         uint32_t *tmpq = qcur; qcur = rd.queue_alt; rd.queue_alt = tmpq;
       }
-      if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 1], st));
+      if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * 2 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
       f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
-      if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st)); ev_used += 3; }
+      if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 3], st)); ev_used += 4; }
     }
 
     if (flags & HRT_FLAG_SUMMARY) {
@@ -1697,13 +1987,16 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     float a = 0.f, b = 0.f;
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[2]);
     cudaEventElapsedTime(&b, ctx->ev[0], ctx->ev[1]);
-    for (size_t e = 0; e + 3 <= ev_used; e += 3) {
-      float x = 0.f, y = 0.f;
+    float ms_sort = 0.f;
+    for (size_t e = 0; e + 4 <= ev_used; e += 4) {
+      float x = 0.f, y = 0.f, z = 0.f;
       cudaEventElapsedTime(&x, ctx->evpool[e], ctx->evpool[e + 1]);
-      cudaEventElapsedTime(&y, ctx->evpool[e + 1], ctx->evpool[e + 2]);
-      ms_bounce += x; ms_scatter += y;
+      cudaEventElapsedTime(&z, ctx->evpool[e + 1], ctx->evpool[e + 2]);
+      cudaEventElapsedTime(&y, ctx->evpool[e + 2], ctx->evpool[e + 3]);
+      ms_bounce += x; ms_scatter += y; ms_sort += z;
     }
-    S.n_bounce_launches = S.n_scatter_launches = (uint32_t)(ev_used / 3);
+    S.ms_sort = ms_sort;
+    S.n_bounce_launches = S.n_scatter_launches = (uint32_t)(ev_used / 4);
     S.ms_total = a; S.ms_bounce = ms_bounce; S.ms_scatter = ms_scatter;
     S.ms_other = b;
   }

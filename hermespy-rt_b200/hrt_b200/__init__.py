@@ -68,6 +68,7 @@ class RunStats(C.Structure):
         ("num_tris", C.c_uint32), ("num_nodes", C.c_uint32), ("scene_in_smem", C.c_uint32),
         ("box_pad", C.c_float),
         ("work_bounce", C.c_uint64 * 5), ("work_scatter", C.c_uint64 * 5),
+        ("bvh_sah", C.c_uint32), ("bvh_levels", C.c_uint32), ("bvh_build_ms", C.c_float), ("ms_sort", C.c_float),
     ]
 
     def as_dict(self):

@@ -137,6 +137,10 @@ typedef struct {
    * [0] ray-box tests, [1..4] Moeller-Trumbore tests reaching stage A (det),
    * B (u), C (v), D (t) -- SURVEY section 8d's unit of algorithmic work */
   uint64_t work_bounce[5], work_scatter[5];
+  /* the scene's BVH: 1 = binned-SAH builder, 0 = Morton/Karras (HRT_BVH_LBVH=1) */
+  uint32_t bvh_sah, bvh_levels;
+  float    bvh_build_ms;       /* GPU time of the last build */
+  float    ms_sort;            /* hit-queue ordering, part of ms_total */
 } HrtRunStats;
 
 int  hrt_device_count(void);

@@ -123,6 +123,56 @@ def build_sah(tlo, thi, leaf_max=2, bins=0):
     return T
 
 
+def build_binned(tlo, thi, leaf_max=2, nbins=16, axes="all", bounds="centroid"):
+    """top-down binned SAH as the GPU builder does it: nbins bins per axis over the
+    node's centroid bounds (or its box), best plane over the tested axes; nodes
+    whose centroids do not separate are halved by position"""
+    T = Tree(); cen = 0.5 * (tlo + thi)
+
+    def rec(ids):
+        lo = tlo[ids].min(0); hi = thi[ids].max(0)
+        if len(ids) <= leaf_max:
+            f = len(T.order); T.order.extend(ids.tolist())
+            return T.add(lo, hi, first=f, count=len(ids))
+        if bounds == "centroid":
+            blo = cen[ids].min(0); bhi = cen[ids].max(0)
+        else:
+            blo, bhi = lo, hi
+        ext = bhi - blo
+        ax_list = range(3) if axes == "all" else [int(np.argmax(ext))]
+        best = (np.inf, None)
+        for ax in ax_list:
+            if ext[ax] <= 0:
+                continue
+            b = np.minimum(((cen[ids, ax] - blo[ax]) / ext[ax] * nbins).astype(int), nbins - 1)
+            b = np.maximum(b, 0)
+            cnt = np.bincount(b, minlength=nbins)
+            blo_b = np.full((nbins, 3), np.inf); bhi_b = np.full((nbins, 3), -np.inf)
+            np.minimum.at(blo_b, b, tlo[ids]); np.maximum.at(bhi_b, b, thi[ids])
+            l_lo = np.minimum.accumulate(blo_b, 0); l_hi = np.maximum.accumulate(bhi_b, 0)
+            r_lo = np.minimum.accumulate(blo_b[::-1], 0)[::-1]; r_hi = np.maximum.accumulate(bhi_b[::-1], 0)[::-1]
+            cl = np.cumsum(cnt)
+            for k in range(1, nbins):
+                nl = cl[k - 1]; nr = len(ids) - nl
+                if nl == 0 or nr == 0:
+                    continue
+                c = area(l_lo[k - 1], l_hi[k - 1]) * nl + area(r_lo[k], r_hi[k]) * nr
+                if c < best[0]:
+                    best = (c, b < k)
+        if best[1] is None:
+            m = np.zeros(len(ids), bool); m[:len(ids) // 2] = True
+        else:
+            m = best[1]
+        me = T.add(lo, hi)
+        l = rec(ids[m]); r = rec(ids[~m])
+        T.left[me] = l; T.right[me] = r
+        return me
+
+    sys.setrecursionlimit(100000)
+    rec(np.arange(len(tlo)))
+    return T
+
+
 def expand_bits(v, nbits):
     out = np.zeros_like(v, dtype=np.uint64)
     for b in range(nbits):
@@ -318,6 +368,13 @@ if __name__ == "__main__":
                 ("ploc r=8", lambda: build_ploc(tlo, thi, 8)),
                 ("ploc r=16", lambda: build_ploc(tlo, thi, 16)),
                 ("ploc r=32", lambda: build_ploc(tlo, thi, 32))]
+    builders += [("binned16 all cen", lambda: build_binned(tlo, thi, 2, 16, "all", "centroid")),
+                 ("binned16 all aabb", lambda: build_binned(tlo, thi, 2, 16, "all", "aabb")),
+                 ("binned16 longest cen", lambda: build_binned(tlo, thi, 2, 16, "longest", "centroid")),
+                 ("binned8 all cen", lambda: build_binned(tlo, thi, 2, 8, "all", "centroid")),
+                 ("binned32 all cen", lambda: build_binned(tlo, thi, 2, 32, "all", "centroid")),
+                 ("binned16 all cen leaf1", lambda: build_binned(tlo, thi, 1, 16, "all", "centroid")),
+                 ("binned16 all cen leaf4", lambda: build_binned(tlo, thi, 4, 16, "all", "centroid"))]
     if len(tris) <= 20000:
         builders.append(("sah sweep", lambda: build_sah(tlo, thi, 2)))
     sel = sys.argv[3].split(",") if len(sys.argv) > 3 else None
