@@ -158,19 +158,31 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   const float nu = v3_dot(sv, pv);
   const float snu = nu * sgn;                            /* exact sign flip */
   if (snu < lo || snu > hi) return false;                /* u clearly outside */
-  const float u = HRT_DIV(nu, det);                      /* :265 */
-  if ((u < 0.f && -u > HRT_EPS) || (u > 1.f && HRT_SUB(u, 1.f) > HRT_EPS)) return false; /* :266 */
+  /* clearly inside (1e-5 away from both ends, the quotient being off by 2^-24
+   * at most): the reference's u test passes, no need to form u yet */
+  const float in_lo = HRT_MUL(ad, 1e-5f), in_hi = HRT_MUL(ad, 0.99999f);
+  const bool u_sure = snu > in_lo && snu < in_hi;
+  float u = 0.f;
+  if (!u_sure) {
+    u = HRT_DIV(nu, det);                                /* :265 */
+    if ((u < 0.f && -u > HRT_EPS) || (u > 1.f && HRT_SUB(u, 1.f) > HRT_EPS)) return false; /* :266 */
+  }
   cnt.tri(2);
   const V3 qv = v3_cross(sv, ab);                        /* :269 */
   const float nv = v3_dot(d, qv);
   const float snv = nv * sgn;
   if (snv < lo || snv > hi) return false;                /* v clearly outside */
-  const float v = HRT_DIV(nv, det);                      /* :270 */
-  const float uv = HRT_ADD(u, v);
-  if ((v < 0.f && -v > HRT_EPS) || (uv > 1.f && HRT_SUB(uv, 1.f) > HRT_EPS)) return false; /* :271 */
+  if (!(u_sure && snv > in_lo && HRT_ADD(snu, snv) < in_hi)) {
+    if (u_sure) u = HRT_DIV(nu, det);
+    const float v = HRT_DIV(nv, det);                    /* :270 */
+    const float uv = HRT_ADD(u, v);
+    if ((v < 0.f && -v > HRT_EPS) || (uv > 1.f && HRT_SUB(uv, 1.f) > HRT_EPS)) return false; /* :271 */
+  }
   cnt.tri(3);
   const float nt = v3_dot(ac, qv);
-  if (!(nt * sgn > 0.f) && nt == nt) return false;       /* t <= 0 */
+  const float snt = nt * sgn;
+  if (!(snt > 0.f) && nt == nt) return false;            /* t <= 0 */
+  if (snt > HRT_MUL(HRT_MUL(best, ad), 1.00001f)) return false;   /* clearly behind the best hit so far */
   const float t = HRT_DIV(nt, det);                      /* :274 */
   if (!(t > HRT_EPS)) return false;                      /* :275 */
   if (t < best || (t == best && gid < best_gid)) { *t_out = t; return true; }
@@ -188,7 +200,13 @@ HRT_HD float hrt_safe_inv(float d)
 {
   const float tiny = 1e-20f;
   if (fabsf(d) < tiny) d = (hrt_float_as_int(d) < 0) ? -tiny : tiny;
+#if defined(__CUDA_ARCH__)
+  float r;                                   /* MUFU.RCP, 1 ulp: culling only, covered by the box padding */
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+#else
   return 1.0f / d;
+#endif
 }
 
 HRT_HD HrtRayCull hrt_ray_cull(V3 o, V3 d)
@@ -455,6 +473,18 @@ HRT_HD void hrt_scat_coefs(const HrtMaterial &m, float th_s, float th_i, float o
   out[0] = te_r; out[1] = te_i; out[2] = tm_r; out[3] = tm_i;
 }
 
+/* Per-hit constants of the scattering model (material only): hoisted out of
+ * the receiver loop by the kernels. */
+struct HrtScatConst { float rough, one_minus_rough, neg_alpha, alpha, s; };
+HRT_HD HrtScatConst hrt_scat_const(const HrtMaterial &m)
+{
+  HrtScatConst c;
+  c.rough = HRT_DIV(1.0f, HRT_ADD(1.0f, m.s1_alpha));                          /* :382 */
+  c.one_minus_rough = HRT_SUB(1.0f, c.rough);
+  c.neg_alpha = -m.s1_alpha; c.alpha = m.s1_alpha; c.s = m.s;
+  return c;
+}
+
 /* ----------------------------------------------------- launch directions
  * Fibonacci sphere, reference :444-451.  fp32 index math, double trig rounded
  * to fp32.  CUDA's double acos/sin/cos are within 2 ulp, glibc's within 1, so
@@ -561,6 +591,49 @@ HRT_HD HrtScatterOut hrt_scatter_path(const HrtRayState &s, const HrtMaterial &m
     r.te_r = HRT_DIV(r.te_r, l2); r.te_i = HRT_DIV(r.te_i, l2);
     r.tm_r = HRT_DIV(r.tm_r, l2); r.tm_i = HRT_DIV(r.tm_i, l2);
   }
+  const V3 dd = v3_sub(sd, s.d);                                               /* :720 */
+  r.dfreq = HRT_MUL(v3_dot(dd, mesh_vel), k.dop_k);                            /* :721 */
+  return r;
+}
+
+/* The same path for the kernels' receiver loop: identical formulas for the
+ * delay, direction and Doppler terms (bit-exact); the gains apply the two
+ * normalisations (|scat| and the free-space loss, :401-405 and :713-718) as one
+ * reciprocal-multiply instead of eight divisions -- a few ulp, inside the
+ * 1e-4 gain tolerance that libm differences impose anyway. */
+HRT_HD HrtScatterOut hrt_scatter_path_fast(const HrtRayState &s, const HrtScatConst &m,
+                                           const HrtRunConst &k, V3 n, V3 mesh_vel,
+                                           V3 sd, float dist, float theta_i)
+{
+  HrtScatterOut r;
+  const float th_s = acosf(v3_dot(sd, n));                                     /* :694 */
+  float si, ci;
+#if defined(__CUDA_ARCH__)
+  sincosf(theta_i, &si, &ci);
+#else
+  si = sinf(theta_i); ci = cosf(theta_i);
+#endif
+  const float cs = cosf(th_s);                                                 /* :372 */
+  const float lobe = HRT_MUL(m.s, expf(HRT_MUL(m.neg_alpha, fabsf(HRT_SUB(th_s, theta_i))))); /* :378 */
+  const float spec = HRT_MUL(m.rough, cs);                                     /* :383 */
+  const float diff = HRT_MUL(m.one_minus_rough, cs);                           /* :384 */
+  const float te_r = HRT_MUL(lobe, HRT_ADD(spec, diff));                       /* :388 */
+  const float tm_r = HRT_MUL(lobe, HRT_ADD(HRT_MUL(spec, ci), diff));          /* :390 */
+  const float sp = sinf(HRT_MUL(HRT_MUL(m.alpha, si), 0.1f));                  /* :394 */
+  const float te_i = HRT_MUL(te_r, sp), tm_i = HRT_MUL(tm_r, sp);              /* :395 */
+  const float nrm = HRT_SQRT(HRT_ADD(HRT_ADD(HRT_ADD(HRT_MUL(te_r, te_r), HRT_MUL(te_i, te_i)),
+                                             HRT_MUL(tm_r, tm_r)), HRT_MUL(tm_i, tm_i))); /* :399 */
+  float l2 = HRT_MUL(k.fsl_k, dist);                                           /* :711 */
+  l2 = HRT_MUL(l2, l2);
+  float den = nrm > 1e-6f ? nrm : 1.f;                                         /* :401 */
+  if (l2 > 1.f) den = HRT_MUL(den, l2);                                        /* :713 */
+  const float sc = HRT_DIV(1.f, den);
+  r.te_r = HRT_MUL(HRT_SUB(HRT_MUL(s.te_r, te_r), HRT_MUL(s.te_i, te_i)), sc); /* :698 */
+  r.te_i = HRT_MUL(HRT_ADD(HRT_MUL(s.te_r, te_i), HRT_MUL(s.te_i, te_r)), sc);
+  r.tm_r = HRT_MUL(HRT_SUB(HRT_MUL(s.tm_r, tm_r), HRT_MUL(s.tm_i, tm_i)), sc);
+  r.tm_i = HRT_MUL(HRT_ADD(HRT_MUL(s.tm_r, tm_i), HRT_MUL(s.tm_i, tm_r)), sc);
+  r.dir_rx = v3(-sd.x, -sd.y, -sd.z);                                          /* :707 */
+  r.tau = HRT_ADD(s.tau, HRT_DIV(dist, HRT_C0));                               /* :709 */
   const V3 dd = v3_sub(sd, s.d);                                               /* :720 */
   r.dfreq = HRT_MUL(v3_dot(dd, mesh_vel), k.dop_k);                            /* :721 */
   return r;

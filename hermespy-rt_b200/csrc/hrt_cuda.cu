@@ -870,7 +870,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const V3 n = tri_normal<SMEM>(sc, slot);
     const uint32_t gid = tri_gid_of<SMEM>(sc, slot);
     const uint32_t mesh = sc.mesh_of[gid];
-    const HrtMaterial &mat = mats.m[sc.mesh_mat[mesh]];
+    const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
     const V3 mv = ld3(sc.mesh_vel, mesh);
     float theta_carry = rd.theta[si];
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
@@ -908,7 +908,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       const bool ok = act && !occ;
       HrtScatterOut p;
       p.te_r = p.te_i = p.tm_r = p.tm_i = p.tau = p.dfreq = 0.f; p.dir_rx = v3(0.f, 0.f, 0.f);
-      if (ok) p = hrt_scatter_path(s, mat, rd.k, n, mv, sd, dist, theta_i);    /* :694-721 */
+      if (ok) p = hrt_scatter_path_fast(s, mat, rd.k, n, mv, sd, dist, theta_i); /* :694-721 */
       if (act && (dense || trace)) {
         const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;          /* :674 */
         if (dense) {
@@ -950,12 +950,19 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
           /* all lanes look at the same receiver: reduce over the warp, one
            * update per warp */
           const unsigned m_ok = __ballot_sync(0xFFFFFFFFu, ok), m_occ = __ballot_sync(0xFFFFFFFFu, occ);
-          unsigned long long hsum = ok ? hkey : 0ull, tsum = ok ? (unsigned long long)__float_as_uint(p.tau) : 0ull;
+          unsigned long long hsum = 0ull, tsum = 0ull;
           double e = ok ? pte : 0.0, m2 = ok ? ptm : 0.0;
           if (m_ok) {
+            /* integer sums: one REDUX per 16-bit digit (32 x 65535 fits 32 bits) */
+            const unsigned long long hk = ok ? hkey : 0ull;
+            const unsigned tb = ok ? __float_as_uint(p.tau) : 0u;
+            hsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk & 0xFFFFu))
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 16) & 0xFFFFu)) << 16)
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 32) & 0xFFFFu)) << 32)
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk >> 48)) << 48);
+            tsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb & 0xFFFFu)
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb >> 16) << 16);
             for (int o = 16; o; o >>= 1) {
-              hsum += __shfl_xor_sync(0xFFFFFFFFu, hsum, o);
-              tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, o);
               e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
               m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, o);
             }
