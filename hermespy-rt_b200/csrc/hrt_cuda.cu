@@ -520,6 +520,16 @@ __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
   return nn + nt + (sc.num_tris + 3u) / 4u;
 }
 
+/* Eight node copies (one per ray-direction octant, planes pre-ordered: no
+ * per-axis min/max in the slab test) whenever they fit the budget -- shared
+ * memory for small scenes, HBM (HRT_OCTANT_BYTES_MAX, default 4 GB) otherwise. */
+static uint32_t octant_copies(uint32_t num_nodes)
+{
+  size_t lim = (size_t)4 << 30;
+  if (const char *e = getenv("HRT_OCTANT_BYTES_MAX")) lim = (size_t)atoll(e);
+  return (size_t)num_nodes * 64 * 8 <= lim ? 8u : 1u;
+}
+
 static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris, uint32_t octants = 8)
 { return (size_t)num_nodes * 64 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
 
@@ -536,6 +546,7 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
   } else {
     HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
     if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
+    if (sc.octants == 8) return hrt_closest_hit<true>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u);
     return hrt_closest_hit<false>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt);
   }
 }
@@ -1315,7 +1326,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         CKG(cudaGetLastError());
         const int brc = build_sah(ctx, n, d_boxes, d_recs);
         if (brc) { rc = brc; goto done; }
-        ctx->octants = scene_smem_bytes(ctx->num_nodes, n, 8) <= HRT_SMEM_SCENE_LIMIT ? 8u : 1u;
+        ctx->octants = octant_copies(ctx->num_nodes);
         CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
         goto built;
       }
@@ -1349,7 +1360,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         ctx->root_ref = 0;
         /* small scenes get one node copy per ray-direction octant (shared-memory
          * traversal without per-axis min/max, hrt_slab_sorted) */
-        ctx->octants = scene_smem_bytes(ctx->num_nodes, n, 8) <= HRT_SMEM_SCENE_LIMIT ? 8u : 1u;
+        ctx->octants = octant_copies(ctx->num_nodes);
         CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
       }
     }

@@ -13,5 +13,5 @@ for B in range(1, 6):
     for _ in range(2):
         s = ctx.run(rx, tx, zr, zt, 3.5, P, B, summary=True, los=False)["stats"]
     dq, dms = s["shadow_queries"] - prev_q, s["ms_scatter"] - prev_ms
-    print(f"B={B}: total ms {s['ms_total']:.1f} scatter {s['ms_scatter']:.1f} bounce {s['ms_bounce']:.1f} | depth {B-1}: {dq:.3e} shadow queries in {dms:.1f} ms = {dq/dms/1e6:.1f} Gq/s")
+    print(f"B={B}: total ms {s['ms_total']:.1f} scatter {s['ms_scatter']:.1f} bounce {s['ms_bounce']:.1f} sort {s['ms_sort']:.1f} | depth {B-1}: {dq:.3e} shadow queries in {dms:.1f} ms = {dq/dms/1e6:.1f} Gq/s")
     prev_q, prev_ms = s["shadow_queries"], s["ms_scatter"]

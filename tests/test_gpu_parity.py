@@ -47,6 +47,19 @@ def test_closest_hit_bit_exact(ctx, scene, brute):
     finally:
         del os.environ["HRT_NO_SMEM"]
     assert np.array_equal(tri_o, tri_g) and np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32))
+    if not brute:
+        # the other tree shapes / node layouts give the very same bits: single node
+        # copy in global memory (large-scene layout) and the Morton/Karras builder
+        for env in ({"HRT_OCTANT_BYTES_MAX": "0"}, {"HRT_BVH_LBVH": "1"}, {"HRT_BVH_LBVH": "1", "HRT_OCTANT_BYTES_MAX": "0"}):
+            os.environ.update(env)
+            try:
+                ctx.load_scene(tl.scene_path(scene))
+                tri_g, t_g, _ = ctx.closest_hits(rays)
+            finally:
+                for k in env:
+                    del os.environ[k]
+            assert np.array_equal(tri_o, tri_g) and np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32)), env
+        ctx.load_scene(tl.scene_path(scene))
     tri, t, th = ctx.closest_hits(rays, brute_force=brute)
     assert np.array_equal(tri_o, tri)
     assert np.array_equal(t_o.view(np.uint32), t.view(np.uint32))
