@@ -289,10 +289,19 @@ def main_gpu(args):
         peak_unfused, peak_fma = ctx.fp32_peak()
         achieved = flops_per_shadow * shadow_rank0 / (ms_scatter * 1e-3) / 1e12 if ms_scatter else None
         nominal = 148 * 128 * 1.965e9 / 1e12
+        traffic, traffic_note = None, "no ncu capture committed under profiles/"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k_scatter_traffic.json")))
+            l0 = tj["launches"][0]
+            traffic = l0["dram_bytes_read"] + l0["dram_bytes_write"]
+            traffic_note = ("DRAM bytes of ONE k_scatter launch under ncu (%s, %.1f ms launch): the kernel is fp32-issue "
+                            "bound; its DRAM traffic is the gather of per-hit state" % (tj["source"], l0["duration_ms"]))
+        except Exception:
+            pass
         roofline = {
             "bound": "fp32", "kernel": "k_scatter", "achieved": achieved, "peak": peak_unfused,
             "unit": "TFLOP/s", "frac": (achieved / peak_unfused) if achieved and peak_unfused else None,
-            "traffic": None,
+            "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": "measured in this run with separately rounded FMUL+FADD chains "
                            "(hrt_fp32_peak); MEASURED_PEAKS.json has no fp32 figure. nominal "
                            f"unfused {nominal:.1f}, measured FFMA {peak_fma:.1f} TFLOP/s",
@@ -326,8 +335,10 @@ def main_gpu(args):
             "ray_bounces_per_step": rb_total / args.steps,
             "valid_paths_last_step": n_valid,
             "ambiguous_dirs_per_step": s0["ambiguous_dirs"],
-            "bvh": {"triangles": s0["num_tris"], "nodes": s0["num_nodes"],
-                    "scene_in_smem": bool(s0["scene_in_smem"]), "box_pad_m": s0["box_pad"]},
+            "bvh": {"triangles": s0["num_tris"], "nodes": s0["num_nodes"], "builder": "binned SAH" if s0["bvh_sah"] else "LBVH",
+                    "build_ms": s0["bvh_build_ms"], "scene_in_smem": bool(s0["scene_in_smem"]), "box_pad_m": s0["box_pad"]},
+            "ms_breakdown_rank0_last_step": {"scatter": stats[-1]["ms_scatter"], "bounce": stats[-1]["ms_bounce"],
+                                             "hit_sort": stats[-1]["ms_sort"], "total": stats[-1]["ms_total"]},
         }
         print(json.dumps(out))
     ctx.close()

@@ -292,7 +292,13 @@ struct HrtGlobalMem {
     return tris[3 * s + k];
 #endif
   }
-  HRT_HD void select_octant(uint32_t oct, uint32_t stride) { nodes += (size_t)oct * stride; }
+  HRT_HD void select_octant(uint32_t oct, uint32_t stride)
+  {
+    nodes += (size_t)oct * stride;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(nodes));   /* keep the octant's base in registers: do not recompute per node */
+#endif
+  }
 };
 
 #define HRT_STACK 64
@@ -313,7 +319,10 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
-  const HrtRayCull c = hrt_ray_cull(o, d);
+  HrtRayCull c = hrt_ray_cull(o, d);
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+f"(c.ood.x), "+f"(c.ood.y), "+f"(c.ood.z));   /* likewise -o/d */
+#endif
   Mem mem = mem_in;
   if (SORTED) mem.select_octant(hrt_octant(c), oct_stride);
   float tmax = HRT_T_MAX * 1.0001f;          /* far bound with slack */

@@ -27,6 +27,10 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 cat $OUT/bench_ref.json | cut -c1-400
 fi
 
+echo "== dense configs + C5 shard"
+python scripts/run_dense.py > $OUT/dense.json 2> $OUT/dense.err; echo "rc=$?"
+python scripts/run_c5.py 6.25e7 1024 256 65536 > $OUT/c5_shard.json 2> $OUT/c5.err; echo "rc=$?"; cut -c1-600 $OUT/c5_shard.json
+
 if [ "${NCU:-1}" = "1" ]; then
 echo "== ncu launch list"
 export HRT_BENCH_RAYS=2e6 HRT_REF_PATHS=100
@@ -38,5 +42,9 @@ python bench.py --steps 1 --warmup 0 > $OUT/ncu_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_scatter -s 1 -c 2 -f -o $OUT/prof_scatter \
     python bench.py --steps 1 --warmup 0 > $OUT/ncu_full.log 2>&1
 echo "ncu full rc=$?"
+python scripts/run_c5.py 6.25e7 1024 256 65536 > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_scatter -s 1 -c 1 -f -o $OUT/prof_c5 \
+    python scripts/run_c5.py 6.25e7 1024 256 65536 > $OUT/ncu_c5.log 2>&1
+echo "ncu c5 rc=$?"
 ls -la $OUT
 fi
