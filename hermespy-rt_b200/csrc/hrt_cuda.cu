@@ -34,7 +34,9 @@ static_assert(sizeof(HrtMaterialDerived) == sizeof(HrtMaterial), "material ABI")
 static_assert(sizeof(Ray) == 24 && sizeof(Vec3) == 12, "reference ABI");
 static_assert(sizeof(HrtPairSummary) == 48 && sizeof(HrtBounceSummary) == 32, "summary ABI");
 
+#ifndef HRT_BLOCK
 #define HRT_BLOCK 512   /* 2 blocks of 512 threads per SM: 64 registers, ~85 KB shared memory each */
+#endif
 #ifndef HRT_MIN_BLOCKS
 #define HRT_MIN_BLOCKS 2   /* => 64 registers (1024 threads/SM): best of the sweep in profiles/r1_sweeps.md; __launch_bounds__ min blocks/SM of the two traversal kernels */
 #endif
@@ -85,7 +87,10 @@ struct RunDev {
   HrtBounceSummary *bounce; /* [T][B] */
   uint32_t *amb_list, *amb_count;
   uint32_t *dkey, *dkey2, *perm, *perm2;  /* direction sort of the chunk's paths */
-  unsigned long long *counters;  /* [16] instrumented build */
+  unsigned long long *counters;  /* [16] instrumented build; [15] = CIR paths outside the window */
+  float *cir;            /* [R][T][cir_bins][4] HRT_FLAG_CIR */
+  float cir_tau0, cir_inv_dt;
+  uint32_t cir_bins;
   uint32_t flags;
 };
 
@@ -135,6 +140,7 @@ struct hrt_ctx {
   void *sort_tmp; size_t sort_tmp_bytes;
   void *d_los;             /* HrtLosOut[R*T] */
   size_t cap_los;
+  float *d_cir; size_t cap_cir;
   HrtRunStats stats;
 };
 
@@ -934,6 +940,18 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         }
         if (trace) rd.tr_state[so] = occ ? 2 : 1;
       }
+      if (ok && rd.cir) {
+        /* impulse response: a * delta(t - tau) into its delay bin, one 16-byte
+         * reduction per path (red.global.add.v4.f32) */
+        const float fb = HRT_MUL(HRT_SUB(p.tau, rd.cir_tau0), rd.cir_inv_dt);
+        if (fb >= 0.f && fb < (float)rd.cir_bins) {
+          float *dst = rd.cir + ((size_t)(r * T + t) * rd.cir_bins + (uint32_t)fb) * 4u;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                       :: "l"(dst), "f"(p.te_r), "f"(p.te_i), "f"(p.tm_r), "f"(p.tm_i) : "memory");
+        } else {
+          atomicAdd(&rd.counters[15], 1ull);
+        }
+      }
       if (summary) {
         const double pte = (double)p.te_r * p.te_r + (double)p.te_i * p.te_i;
         const double ptm = (double)p.tm_r * p.tm_r + (double)p.tm_i * p.tm_i;
@@ -1156,6 +1174,7 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   free_scene_dev(c); free_run_dev(c);
   dev_free(c->d_pos);
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
+  if (c->d_cir) { cudaFree(c->d_cir); c->d_cir = nullptr; }
   if (c->sort_tmp) { cudaFree(c->sort_tmp); c->sort_tmp = nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
@@ -1620,6 +1639,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   if ((flags & HRT_FLAG_RAYSINFO) && !p->rays_scat) flags &= ~HRT_FLAG_RAYSINFO;
   if ((flags & HRT_FLAG_SUMMARY) && (!p->pair_summary || !p->bounce_summary)) return fail(ctx, HRT_E_ARG, "SUMMARY needs both summary arrays");
   if ((flags & HRT_FLAG_HOST_DIRS) && !p->dirs) return fail(ctx, HRT_E_ARG, "HOST_DIRS needs dirs");
+  if ((flags & HRT_FLAG_CIR) && (!p->cir || !p->cir_bins || !(p->cir_dt_s > 0.f))) return fail(ctx, HRT_E_ARG, "CIR needs cir, cir_bins > 0 and cir_dt_s > 0");
   const uint32_t world = p->shard_world ? p->shard_world : 1, rank = p->shard_rank;
   uint64_t blk = p->shard_block ? p->shard_block : (1u << 20);
   if (world > 1 && (rank >= world || (blk % 32))) return fail(ctx, HRT_E_ARG, "bad shard (rank %u of %u, block %llu must be a multiple of 32)", rank, world, (unsigned long long)blk);
@@ -1692,7 +1712,18 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     CK(allow_smem(k_los<true, true>, scene_sb)); CK(allow_smem(k_los<true, false>, scene_sb));
   }
   CK(allow_smem(f_scatter, scat_sb));
-  if (count) CK(cudaMemsetAsync(rd.counters, 0, 16 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(rd.counters, 0, 16 * sizeof(unsigned long long), st));
+  rd.cir = nullptr; rd.cir_bins = 0; rd.cir_tau0 = 0.f; rd.cir_inv_dt = 0.f;
+  if (flags & HRT_FLAG_CIR) {
+    const size_t ncir = R * T * (size_t)p->cir_bins * 4;
+    if (ctx->cap_cir < ncir) {
+      if (ctx->d_cir) cudaFree(ctx->d_cir);
+      ctx->d_cir = nullptr; ctx->cap_cir = 0;
+      CK(dev_alloc(&ctx->d_cir, ncir)); ctx->cap_cir = ncir;
+    }
+    CK(cudaMemsetAsync(ctx->d_cir, 0, ncir * sizeof(float), st));
+    rd.cir = ctx->d_cir; rd.cir_bins = p->cir_bins; rd.cir_tau0 = p->cir_tau0_s; rd.cir_inv_dt = 1.f / p->cir_dt_s;
+  }
   const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT");
   if (sort_hits) {
     /* the chunk's direction sort below needs less: same pair types, 32 key bits */
@@ -1830,7 +1861,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
         CKR(cudaMemcpyAsync(rd.rays + (size_t)(b + 1) * T * rd.n_alloc, rd.rays + (size_t)b * T * rd.n_alloc,
                             T * (size_t)rd.n_alloc * sizeof(Ray), cudaMemcpyDeviceToDevice, st));
       /* persistent grids: enough blocks to fill the machine, grid-stride inside */
-      const dim3 gb((unsigned)min((size_t)((sms * 2 + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      const dim3 gb((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
       const bool timed = ev_used + 4 <= EV_CAP;
       if (timed) {
         if (ctx->evpool_n < ev_used + 4) {
@@ -1861,7 +1892,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       }
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
-      const dim3 gs((unsigned)min((size_t)((sms * 2 + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      const dim3 gs((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
       f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
@@ -1991,6 +2022,33 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       free(hp); free(hb);
       CKR(e);
     }
+  }
+
+  if (flags & HRT_FLAG_CIR) {
+    const size_t ncir = R * T * (size_t)p->cir_bins * 4;
+    float *h = (float *)malloc(ncir * sizeof(float));
+    if (!h) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
+    unsigned long long dropped = 0;
+    cudaError_t e = cudaMemcpyAsync(h, ctx->d_cir, ncir * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&dropped, rd.counters + 15, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+      for (size_t i = 0; i < ncir; ++i) p->cir[i] += h[i];
+      S.cir_dropped = dropped;
+      /* the LoS paths (reference :556-577), written to p->los above */
+      if (p->los && rank == 0)
+        for (size_t k = 0; k < R * T; ++k) {
+          if (p->los->a_te_re[k] == 0.f && p->los->tau[k] == 0.f) continue;   /* blocked */
+          const float fb = (p->los->tau[k] - p->cir_tau0_s) * rd.cir_inv_dt;
+          if (fb >= 0.f && fb < (float)p->cir_bins) {
+            float *dst = p->cir + (k * p->cir_bins + (size_t)fb) * 4;
+            dst[0] += p->los->a_te_re[k]; dst[1] += p->los->a_te_im[k];
+            dst[2] += p->los->a_tm_re[k]; dst[3] += p->los->a_tm_im[k];
+          } else S.cir_dropped++;
+        }
+    }
+    free(h);
+    CKR(e);
   }
 
   if (count) {

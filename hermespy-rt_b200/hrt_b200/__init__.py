@@ -27,6 +27,7 @@ LIB_PATH = os.path.join(_HERE, "..", "libhermespy_rt.so")
 
 FLAG_DENSE, FLAG_RAYSINFO, FLAG_SUMMARY, FLAG_TRACE = 0x01, 0x02, 0x04, 0x08
 FLAG_BRUTE_FORCE, FLAG_HOST_DIRS, FLAG_SUMMARY_DEV, FLAG_COUNT = 0x10, 0x20, 0x40, 0x80
+FLAG_CIR = 0x100
 
 PAIR_DTYPE = np.dtype([("n_valid", "<u8"), ("n_occluded", "<u8"), ("hit_hash", "<u8"),
                        ("tau_bits", "<u8"), ("power_te", "<f8"), ("power_tm", "<f8")])
@@ -56,6 +57,7 @@ class RunParams(C.Structure):
         ("pair_summary", C.c_void_p), ("bounce_summary", C.c_void_p),
         ("trace_hit_tri", C.c_void_p), ("trace_hit_t", C.c_void_p), ("trace_slot_state", C.c_void_p),
         ("dirs", C.c_void_p), ("stream", C.c_void_p),
+        ("cir", C.c_void_p), ("cir_tau0_s", C.c_float), ("cir_dt_s", C.c_float), ("cir_bins", C.c_uint32),
     ]
 
 
@@ -69,6 +71,7 @@ class RunStats(C.Structure):
         ("box_pad", C.c_float),
         ("work_bounce", C.c_uint64 * 5), ("work_scatter", C.c_uint64 * 5),
         ("bvh_sah", C.c_uint32), ("bvh_levels", C.c_uint32), ("bvh_build_ms", C.c_float), ("ms_sort", C.c_float),
+        ("cir_dropped", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -195,7 +198,7 @@ class Context:
     def run(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, *, dense=False, raysinfo=False,
             summary=False, trace=False, brute_force=False, count_work=False, los=True, dirs=None,
             shard=(0, 1), shard_block=1 << 20, out: abi.Outputs | None = None,
-            summary_dev_ptrs=None, stream=None):
+            summary_dev_ptrs=None, stream=None, cir=None):
         """hrt_run().  Returns a dict with whatever was requested:
         'out' (abi.Outputs, dense), 'pair'/'bounce' (structured arrays, summary),
         'trace' (dict), 'stats'."""
@@ -263,6 +266,13 @@ class Context:
             p.dirs = dirs.ctypes.data
         if stream is not None:
             p.stream = stream
+        if cir is not None:
+            # cir = (tau0_s, dt_s, bins): res["cir"] is (R, T, bins, 4) float32
+            tau0, dt, bins = cir
+            res["cir"] = np.zeros((R, T, int(bins), 4), np.float32)
+            flags |= FLAG_CIR
+            p.cir = res["cir"].ctypes.data
+            p.cir_tau0_s, p.cir_dt_s, p.cir_bins = float(tau0), float(dt), int(bins)
         p.flags = flags
         self._check(lib().hrt_run(self._h, C.byref(p)), "hrt_run")
         res["stats"] = self.stats()

@@ -57,6 +57,7 @@ typedef struct {
 #define HRT_FLAG_HOST_DIRS    0x20u  /* launch directions supplied by caller (dirs)      */
 #define HRT_FLAG_SUMMARY_DEV  0x40u  /* summary pointers are DEVICE memory               */
 #define HRT_FLAG_COUNT        0x80u  /* instrumented kernels: count box/triangle tests   */
+#define HRT_FLAG_CIR         0x100u  /* accumulate the delay-binned impulse response    */
 
 /* Order-independent per-(rx, tx, bounce) reduction of the scatter paths.
  * Integer fields are exact and comparable bit for bit with a CPU run. */
@@ -115,6 +116,18 @@ typedef struct {
 
   /* CUDA stream to run on (cudaStream_t), NULL = the context's own stream */
   void *stream;
+
+  /* HRT_FLAG_CIR: channel impulse response per (rx, tx), the reduction a
+   * consumer of ChannelInfo performs next (sum of a * delta(t - tau) over all
+   * paths and bounces), formed on the GPU so that C4/C5-sized runs need no
+   * per-path output: cir[((rx * num_tx + tx) * cir_bins + bin) * 4 + k],
+   * k = a_te_re, a_te_im, a_tm_re, a_tm_im summed over the valid scatter paths
+   * (and the LoS path when `los` is given) with
+   * bin = floor((tau - cir_tau0_s) / cir_dt_s) in [0, cir_bins).  Host memory,
+   * ADDED to (caller zeroes).  fp32 accumulation in arbitrary order. */
+  float   *cir;
+  float    cir_tau0_s, cir_dt_s;
+  uint32_t cir_bins;
 } HrtRunParams;
 
 /* Counters and timings of the last hrt_run on a context. */
@@ -141,6 +154,7 @@ typedef struct {
   uint32_t bvh_sah, bvh_levels;
   float    bvh_build_ms;       /* GPU time of the last build */
   float    ms_sort;            /* hit-queue ordering, part of ms_total */
+  uint64_t cir_dropped;        /* HRT_FLAG_CIR: valid paths whose delay fell outside the window */
 } HrtRunStats;
 
 int  hrt_device_count(void);

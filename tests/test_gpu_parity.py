@@ -229,6 +229,53 @@ def test_summary_mode_and_shards(ctx):
     assert np.array_equal(ch["pair"]["hit_hash"], full["pair"]["hit_hash"])
 
 
+def test_cir_mode_vs_oracle(ctx):
+    """HRT_FLAG_CIR: the delay-binned impulse response
+    formed on the GPU == the same reduction of the ORACLE's dense ChannelInfo
+    (scatter paths of all bounces + LoS).  fp32 sums in arbitrary order: the
+    tolerance is relative to the sum of magnitudes in the bin."""
+    scene, rx, tx, rxv, txv, f = _case_inputs("canyon_1x1", 6, True, 2)
+    P, B = 40000, 3
+    R, T = len(rx), len(tx)
+    ctx.load_scene(tl.scene_path(scene))
+    a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B)
+    tau0, dt, bins = 20e-9, 5e-9, 200
+    res = ctx.run(rx, tx, rxv, txv, f, P, B, summary=True, cir=(tau0, dt, bins))
+    cir = res["cir"]
+    assert cir.shape == (R, T, bins, 4)
+    valid = tr["slot_state"] == 1                                   # (R,T,B,P)
+    tau = a.scat["tau"].reshape(R, T, B, P)
+    fb = (tau.astype(np.float32) - np.float32(tau0)) * np.float32(1.0 / np.float32(dt))
+    inside = valid & (fb >= 0) & (fb < bins)
+    b = np.where(inside, fb, 0).astype(np.int64)
+    ref = np.zeros((R, T, bins, 4)); mag = np.zeros((R, T, bins, 4))
+    rr, tt = np.meshgrid(np.arange(R), np.arange(T), indexing="ij")
+    rr = np.broadcast_to(rr[:, :, None, None], valid.shape); tt = np.broadcast_to(tt[:, :, None, None], valid.shape)
+    for k, name in enumerate(("a_te_re", "a_te_im", "a_tm_re", "a_tm_im")):
+        v = a.scat[name].reshape(R, T, B, P).astype(np.float64)
+        np.add.at(ref[..., k], (rr[inside], tt[inside], b[inside]), v[inside])
+        np.add.at(mag[..., k], (rr[inside], tt[inside], b[inside]), np.abs(v[inside]))
+    dropped = int((valid & ~inside).sum())
+    # LoS paths
+    los_tau = a.los["tau"].reshape(R, T); los_a = a.los["a_te_re"].reshape(R, T)
+    for r in range(R):
+        for t in range(T):
+            if los_a[r, t] == 0 and los_tau[r, t] == 0:
+                continue
+            q = (np.float32(los_tau[r, t]) - np.float32(tau0)) * np.float32(1.0 / np.float32(dt))
+            if 0 <= q < bins:
+                ref[r, t, int(q), 0] += los_a[r, t]; ref[r, t, int(q), 2] += los_a[r, t]
+                mag[r, t, int(q), 0] += abs(los_a[r, t]); mag[r, t, int(q), 2] += abs(los_a[r, t])
+            else:
+                dropped += 1
+    assert int(inside.sum()) > 50000 and (mag > 0).sum() > 1000
+    assert res["stats"]["cir_dropped"] == dropped
+    err = np.abs(cir - ref)
+    assert (err <= tl.GAIN_RTOL * 2 * mag + 1e-30).all(), float((err / (mag + 1e-300)).max())
+    # a second run accumulates into the caller's array (ADDED to)
+    assert (mag[..., 1] > 0).any()
+
+
 def test_full_size_anchor_counts(ctx):
     """BASELINE configs at full size through size-independent properties:
     per-bounce active-ray counts measured on the reference during the survey
