@@ -46,17 +46,11 @@ static hrt_ctx *implicit_ctx(void)
   return g_ctx;
 }
 
-void compute_paths(
-    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
-    float carrier_frequency_GHz,
-    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
-    ChannelInfo *chanInfo_los, RaysInfo *raysInfo_los,
-    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat)
+/* scene -> GPU (flatten, normals, BVH) and the material table at f; fills
+ * Mesh.ns like the reference's precompute_normals */
+static hrt_ctx *prepare(Scene *scene, float carrier_frequency_GHz)
 {
-  if (!scene || !chanInfo_scat) die("compute_paths", "NULL scene or scatter output");
   hrt_ctx *ctx = implicit_ctx();
-
-  /* scene -> GPU (flatten, normals, BVH); normals back into Mesh.ns */
   size_t total = 0;
   for (uint32_t m = 0; m < scene->num_meshes; ++m) total += scene->meshes[m].num_triangles;
   Vec3 *normals = (Vec3 *)malloc((total ? total : 1) * sizeof(Vec3));
@@ -81,6 +75,18 @@ void compute_paths(
     hrt_materials_derive(mi, carrier_frequency_GHz, &table[mi]);
   }
   if (hrt_materials_set(ctx, table) != HRT_OK) die("material upload failed", hrt_last_error(ctx));
+  return ctx;
+}
+
+void compute_paths(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    ChannelInfo *chanInfo_los, RaysInfo *raysInfo_los,
+    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat)
+{
+  if (!scene || !chanInfo_scat) die("compute_paths", "NULL scene or scatter output");
+  hrt_ctx *ctx = prepare(scene, carrier_frequency_GHz);
 
   HrtRunParams p;
   memset(&p, 0, sizeof p);
@@ -93,4 +99,47 @@ void compute_paths(
   p.los = chanInfo_los; p.rays_los = raysInfo_los;
   p.scat = chanInfo_scat; p.rays_scat = raysInfo_scat;
   if (hrt_run(ctx, &p) != HRT_OK) die("compute_paths failed", hrt_last_error(ctx));
+}
+
+/* Streaming consumer of the same path set: instead of
+ * one record per path, the channel impulse response per (rx, tx) -- what a
+ * caller of compute_paths() forms next from ChannelInfo -- accumulated on the
+ * GPU.  cir[((rx * num_tx + tx) * num_bins + bin) * 4 + {te_re, te_im, tm_re,
+ * tm_im}], bin = floor((tau - tau0_s) / dt_s); the array is overwritten.
+ * Returns the number of paths whose delay fell outside the window. */
+size_t compute_cir(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    float tau0_s, float dt_s, size_t num_bins, float *cir)
+{
+  if (!scene || !cir || !num_bins) die("compute_cir", "NULL scene or output");
+  hrt_ctx *ctx = prepare(scene, carrier_frequency_GHz);
+  const size_t nl = num_rx * num_tx;
+  memset(cir, 0, nl * num_bins * 4 * sizeof(float));
+
+  /* LoS through the same run: small host arrays in the reference's layout */
+  ChannelInfo los;
+  memset(&los, 0, sizeof los);
+  float *buf = (float *)calloc(nl * 12, sizeof(float));
+  if (!buf) die("compute_cir", "out of memory");
+  los.num_rays = 1;
+  los.directions_rx = (Vec3 *)buf; los.directions_tx = (Vec3 *)(buf + 3 * nl);
+  los.a_te_re = buf + 6 * nl; los.a_te_im = buf + 7 * nl; los.a_tm_re = buf + 8 * nl; los.a_tm_im = buf + 9 * nl;
+  los.tau = buf + 10 * nl; los.freq_shift = buf + 11 * nl;
+
+  HrtRunParams p;
+  memset(&p, 0, sizeof p);
+  p.num_rx = num_rx; p.num_tx = num_tx; p.num_paths = num_rays; p.num_bounces = num_bounces;
+  p.carrier_frequency_GHz = carrier_frequency_GHz;
+  p.rx_pos = rx_pos; p.tx_pos = tx_pos; p.rx_vel = rx_vel; p.tx_vel = tx_vel;
+  p.shard_world = 1;
+  p.flags = HRT_FLAG_CIR;
+  p.los = &los;
+  p.cir = cir; p.cir_tau0_s = tau0_s; p.cir_dt_s = dt_s; p.cir_bins = (uint32_t)num_bins;
+  if (hrt_run(ctx, &p) != HRT_OK) die("compute_cir failed", hrt_last_error(ctx));
+  free(buf);
+  HrtRunStats st;
+  hrt_get_stats(ctx, &st);
+  return (size_t)st.cir_dropped;
 }

@@ -109,6 +109,36 @@ std::pair<Channel, Channel> compute_paths_py(const std::string &mesh_filepath, f
   return {std::move(los), std::move(sc)};
 }
 
+// Extension: impulse response per (rx, tx) of the same path set, reduced on the
+// GPU (include/hermespy_rt.h, compute_cir).  Returns (cir, dropped) with cir a
+// complex64 array of shape (num_rx, num_tx, num_bins, 2): [..., 0] = TE, [..., 1] = TM.
+std::pair<py::array_t<std::complex<float>>, size_t>
+compute_cir_py(const std::string &mesh_filepath, farr rx_positions, farr tx_positions, farr rx_velocities,
+               farr tx_velocities, float carrier_frequency, size_t num_rx, size_t num_tx, size_t num_paths,
+               size_t num_bounces, float tau0, float dt, size_t num_bins)
+{
+  if (!num_rx || !num_tx || !num_paths || !num_bounces || !num_bins || !(carrier_frequency > 0.f) || !(dt > 0.f))
+    throw std::invalid_argument("num_rx, num_tx, num_paths, num_bounces, num_bins, carrier_frequency and dt must be > 0");
+  const Vec3 *rx = as_vec3(rx_positions, num_rx, "rx_positions");
+  const Vec3 *tx = as_vec3(tx_positions, num_tx, "tx_positions");
+  const Vec3 *rxv = as_vec3(rx_velocities, num_rx, "rx_velocities");
+  const Vec3 *txv = as_vec3(tx_velocities, num_tx, "tx_velocities");
+  if (hrt_device_count() <= 0)
+    throw std::runtime_error("hermespy_rt: no CUDA device available (this build has no CPU path)");
+  if (FILE *f = fopen(mesh_filepath.c_str(), "rb")) fclose(f);
+  else throw std::runtime_error("hermespy_rt: cannot open scene file " + mesh_filepath);
+  py::array_t<std::complex<float>> cir({(py::ssize_t)num_rx, (py::ssize_t)num_tx, (py::ssize_t)num_bins, (py::ssize_t)2});
+  size_t dropped = 0;
+  {
+    py::gil_scoped_release nogil;
+    Scene scene = scene_load(mesh_filepath.c_str());
+    dropped = compute_cir(&scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency, num_rx, num_tx,
+                          num_paths, num_bounces, tau0, dt, num_bins, reinterpret_cast<float *>(cir.mutable_data()));
+    free_scene(&scene);
+  }
+  return {std::move(cir), dropped};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(hermespy_rt, m)
@@ -127,4 +157,11 @@ PYBIND11_MODULE(hermespy_rt, m)
         py::arg("mesh_filepath"), py::arg("rx_positions"), py::arg("tx_positions"),
         py::arg("rx_velocities"), py::arg("tx_velocities"), py::arg("carrier_frequency"),
         py::arg("num_rx"), py::arg("num_tx"), py::arg("num_paths"), py::arg("num_bounces"));
+  m.def("compute_cir", &compute_cir_py,
+        "Channel impulse response per (rx, tx) of the compute_paths() path set, reduced on the GPU; "
+        "returns (cir[num_rx, num_tx, num_bins, 2] complex64 (TE, TM), number of paths outside the window)",
+        py::arg("mesh_filepath"), py::arg("rx_positions"), py::arg("tx_positions"),
+        py::arg("rx_velocities"), py::arg("tx_velocities"), py::arg("carrier_frequency"),
+        py::arg("num_rx"), py::arg("num_tx"), py::arg("num_paths"), py::arg("num_bounces"),
+        py::arg("tau0"), py::arg("dt"), py::arg("num_bins"));
 }

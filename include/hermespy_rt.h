@@ -156,6 +156,23 @@ void compute_paths(
     OUT ChannelInfo *chanInfo_los,  OUT RaysInfo *raysInfo_los,
     OUT ChannelInfo *chanInfo_scat, OUT RaysInfo *raysInfo_scat);
 
+/* Extension (no reference counterpart; it is the reduction a caller of
+ * compute_paths() performs next, and the reference's own TODO for large runs,
+ * SURVEY section 8 row f2): the channel impulse response per (rx, tx) of the
+ * SAME path set -- LoS + scatter paths of all bounces -- accumulated on the GPU
+ * without materialising per-path records:
+ *   cir[((rx * num_tx + tx) * num_bins + bin) * 4 + k],
+ *   k = 0..3: sum of a_te_re, a_te_im, a_tm_re, a_tm_im over the paths with
+ *   bin = floor((tau - tau0_s) / dt_s) in [0, num_bins).
+ * `cir` is caller-allocated (num_rx * num_tx * num_bins * 4 floats) and
+ * overwritten.  Returns the number of paths outside the delay window. */
+size_t compute_cir(
+    IN Scene *scene,
+    IN Vec3 *rx_pos, IN Vec3 *tx_pos, IN Vec3 *rx_vel, IN Vec3 *tx_vel,
+    IN float carrier_frequency_GHz,
+    IN size_t num_rx, IN size_t num_tx, IN size_t num_rays, IN size_t num_bounces,
+    IN float tau0_s, IN float dt_s, IN size_t num_bins, OUT float *cir);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,6 +331,29 @@ def test_pybind_module_matches_golden():
     err = np.abs(sc.a_te.reshape(-1)[mm] - te[mm])
     assert (err <= 1e-4 * np.abs(te[mm]) + 1e-38).all()
     assert los.tau[0, 0, 0] == tl.f32(g["out.los.tau"])[0]
+    # compute_cir(): the same path set reduced to delay bins == the reduction of
+    # the module's own per-path output
+    tau0, dt, bins = 0.0, 0.5e-9, 64
+    cir, dropped = rt.compute_cir(tl.scene_path(g["scene"]), g["rx"], g["tx"], g["rxv"], g["txv"], g["f"],
+                                  1, 1, P, B, tau0, dt, bins)
+    assert cir.shape == (1, 1, bins, 2) and cir.dtype == np.complex64
+    tau = sc.tau.reshape(-1); a_te = sc.a_te.reshape(-1); a_tm = sc.a_tm.reshape(-1)
+    valid = tau != 0
+    fb = (tau - np.float32(tau0)) * np.float32(1.0 / np.float32(dt))
+    ins = valid & (fb >= 0) & (fb < bins)
+    ref = np.zeros((bins, 2), np.complex128); mag = np.zeros((bins, 2))
+    np.add.at(ref[:, 0], fb[ins].astype(np.int64), a_te[ins]); np.add.at(ref[:, 1], fb[ins].astype(np.int64), a_tm[ins])
+    np.add.at(mag[:, 0], fb[ins].astype(np.int64), np.abs(a_te[ins])); np.add.at(mag[:, 1], fb[ins].astype(np.int64), np.abs(a_tm[ins]))
+    lb = (los.tau[0, 0, 0] - np.float32(tau0)) * np.float32(1.0 / np.float32(dt))
+    n_out = int((valid & ~ins).sum())
+    if los.a_te[0, 0, 0] != 0 or los.tau[0, 0, 0] != 0:
+        if 0 <= lb < bins:
+            ref[int(lb), 0] += los.a_te[0, 0, 0]; ref[int(lb), 1] += los.a_tm[0, 0, 0]
+            mag[int(lb), 0] += abs(los.a_te[0, 0, 0]); mag[int(lb), 1] += abs(los.a_tm[0, 0, 0])
+        else:
+            n_out += 1
+    assert dropped == n_out and ins.sum() > 100
+    assert (np.abs(cir[0, 0] - ref) <= 1e-5 * mag + 1e-30).all()
 
 
 def test_large_scene_global_memory_bvh(ctx, tmp_path):
