@@ -39,7 +39,7 @@ import numpy as np  # noqa: E402
 SCENE = os.path.join(ROOT, "scenes", "simple_street_canyon_with_cars.hrt")
 F_GHZ, NUM_TX, NUM_RX, BOUNCES = 3.5, 4, 64, 5
 TOTAL_RAYS = int(float(os.environ.get("HRT_BENCH_RAYS", "1e8")))
-SHARD_BLOCK = 1 << 20
+SHARD_BLOCK = int(os.environ.get("HRT_SHARD_BLOCK", 1 << 16))   # paths per block dealt round-robin to the ranks
 METRIC = "ray-bounces/s on street_canyon_with_cars at 1/2/4/8 B200 vs host-CPU C path"
 
 # algorithmic flops per unit of work (edges are stored, so
@@ -187,6 +187,11 @@ def main_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON); anything libraries print (NCCL's
+    # version banner ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -340,7 +345,7 @@ def main_gpu(args):
             "ms_breakdown_rank0_last_step": {"scatter": stats[-1]["ms_scatter"], "bounce": stats[-1]["ms_bounce"],
                                              "hit_sort": stats[-1]["ms_sort"], "total": stats[-1]["ms_total"]},
         }
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
