@@ -128,6 +128,13 @@ struct hrt_ctx {
   int2 *d_raw_ref;         /* [num_nodes] child refs */
   float *d_raw_box;        /* [num_nodes][12] both children's boxes, unpadded */
   float build_ms; int build_levels;
+  /* geometry kept for hrt_scene_advance: vertices, rebased indices, vertex ->
+   * mesh, triangle records and boxes in (mesh, face) order, first node of
+   * every build level (children always live on the next level) */
+  float *d_verts; uint32_t *d_idx3; uint32_t *d_vmesh; float4 *d_recs; float *d_tboxes; unsigned *d_bounds;
+  size_t num_verts;
+  int level_first[256];
+  float max_speed;
 
   bool have_mats;
   HrtMaterialTable mats;
@@ -474,6 +481,42 @@ __global__ void k_emit_raw(int num_inner, const int2 *raw_ref, const float *raw_
   for (uint32_t oct = 0; oct < octants; ++oct)
     hrt_emit_node(nodes + 4 * ((size_t)oct * num_nodes + i), r.x, r.y, v3(b[0], b[1], b[2]), v3(b[3], b[4], b[5]),
                   v3(b[6], b[7], b[8]), v3(b[9], b[10], b[11]), pad, oct);
+}
+
+/* ---- moving meshes (Mesh.velocity, reference inc/scene.h:21-22) ---- */
+
+__global__ void k_move_verts(float *verts, const uint32_t *vmesh, const float *mesh_vel, size_t nv, float dt)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const uint32_t m = vmesh[i];
+  for (int k = 0; k < 3; ++k) verts[3 * i + k] = HRT_ADD(verts[3 * i + k], HRT_MUL(mesh_vel[3 * m + k], dt));
+}
+
+/* boxes of one build level from the level below (children always have larger
+ * node indices and live on the next level) and from the leaf triangles */
+__global__ void k_sah_refit(int first, int last, const int2 *raw_ref, float *raw_box, const uint32_t *tri_gid,
+                            const float *boxes)
+{
+  const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= last) return;
+  const int2 r = raw_ref[i];
+  for (int s = 0; s < 2; ++s) {
+    const int ref = s ? r.y : r.x;
+    float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+    if (ref < 0) {
+      const uint32_t code = (uint32_t)~ref, f = code >> 3, cnt = (code & 7u) + 1u;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const float *b = boxes + 6 * (size_t)tri_gid[f + k];
+        for (int j = 0; j < 3; ++j) { lo[j] = fminf(lo[j], b[j]); hi[j] = fmaxf(hi[j], b[3 + j]); }
+      }
+    } else {
+      const float *c = raw_box + 12 * (size_t)ref;
+      for (int j = 0; j < 3; ++j) { lo[j] = fminf(c[j], c[6 + j]); hi[j] = fmaxf(c[3 + j], c[9 + j]); }
+    }
+    float *o = raw_box + 12 * (size_t)i + 6 * s;
+    for (int j = 0; j < 3; ++j) { o[j] = lo[j]; o[3 + j] = hi[j]; }
+  }
 }
 
 /* ------------------------------------------------------- scene in shared */
@@ -1148,6 +1191,7 @@ static void free_scene_dev(hrt_ctx *c)
   dev_free(c->d_mesh_vel); dev_free(c->d_nodes); dev_free(c->d_kl); dev_free(c->d_kr);
   dev_free(c->d_kfirst); dev_free(c->d_klast); dev_free(c->d_newidx); dev_free(c->d_box);
   dev_free(c->d_raw_ref); dev_free(c->d_raw_box);
+  dev_free(c->d_verts); dev_free(c->d_idx3); dev_free(c->d_vmesh); dev_free(c->d_recs); dev_free(c->d_tboxes); dev_free(c->d_bounds);
   c->have_scene = false;
 }
 
@@ -1233,6 +1277,7 @@ static int build_sah(hrt_ctx *ctx, uint32_t n, const float *d_boxes, const float
   }
   k_sah_init<<<nblk(n), 256, 0, st>>>(n, d_boxes, d_idx[0], d_wof[0], d_work[0]);
   CKB(cudaGetLastError());
+  ctx->level_first[0] = 0;
   while (count > 0) {
     if ((size_t)count > max_work) { rc = fail(ctx, HRT_E_STATE, "SAH builder: work list overflow"); goto out; }
     k_sah_prep<<<nblk(count), 256, 0, st>>>(count, d_work[cur], d_bins);
@@ -1248,6 +1293,7 @@ static int build_sah(hrt_ctx *ctx, uint32_t n, const float *d_boxes, const float
     CKB(cudaStreamSynchronize(st));
     ctx->num_nodes = (uint32_t)hc[0];
     count = hc[1]; cur ^= 1; ++level;
+    ctx->level_first[level] = hc[0] - count;      /* the nodes just allocated are the next level */
     if (level > 200) { rc = fail(ctx, HRT_E_STATE, "SAH builder did not terminate"); goto out; }
   }
   k_gather_idx<<<nblk(n), 256, 0, st>>>(d_idx[cur], n, d_recs, ctx->d_tris, ctx->d_tri_gid);
@@ -1313,14 +1359,29 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
   const uint32_t n = (uint32_t)nt;
   ctx->num_tris = n; ctx->num_meshes = M; ctx->scene_max_abs = max_abs;
   for (int k = 0; k < 3; ++k) { ctx->scene_lo[k] = nv ? blo[k] : 0.f; ctx->scene_hi[k] = nv ? bhi[k] : 1.f; }
-  float *d_v = nullptr; uint32_t *d_i = nullptr; float4 *d_recs = nullptr; float *d_boxes = nullptr;
-  unsigned *d_bounds = nullptr; uint64_t *d_keys = nullptr, *d_keys2 = nullptr; int *d_parent = nullptr;
+  float *&d_v = ctx->d_verts; uint32_t *&d_i = ctx->d_idx3; float4 *&d_recs = ctx->d_recs; float *&d_boxes = ctx->d_tboxes;
+  unsigned *&d_bounds = ctx->d_bounds; uint64_t *d_keys = nullptr, *d_keys2 = nullptr; int *d_parent = nullptr;
+  uint32_t *h_vmesh = nullptr;
   unsigned *d_arrive = nullptr; void *d_tmp = nullptr; size_t tmp_bytes = 0;
   int rc = HRT_OK;
 #define CKG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
   {
     cudaStream_t st = ctx->stream;
     CKG(dev_alloc(&d_v, nv * 3)); CKG(dev_alloc(&d_i, (size_t)n * 3));
+    CKG(dev_alloc(&ctx->d_vmesh, nv));
+    ctx->num_verts = nv;
+    h_vmesh = (uint32_t *)malloc((nv ? nv : 1) * 4);
+    if (!h_vmesh) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto done; }
+    {
+      size_t o = 0; float ms = 0.f;
+      for (uint32_t m = 0; m < M; ++m) {
+        for (uint32_t k = 0; k < scene->meshes[m].num_vertices; ++k) h_vmesh[o++] = m;
+        const Vec3 v = scene->meshes[m].velocity;
+        ms = fmaxf(ms, fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))));
+      }
+      ctx->max_speed = ms;
+    }
+    CKG(cudaMemcpyAsync(ctx->d_vmesh, h_vmesh, nv * 4, cudaMemcpyHostToDevice, st));
     CKG(dev_alloc(&d_recs, (size_t)n * 3)); CKG(dev_alloc(&d_boxes, (size_t)n * 6));
     CKG(dev_alloc(&d_bounds, 6)); CKG(dev_alloc(&d_keys, n)); CKG(dev_alloc(&d_keys2, n));
     CKG(dev_alloc(&ctx->d_tris, (size_t)n * 3)); CKG(dev_alloc(&ctx->d_tri_gid, n));
@@ -1404,11 +1465,62 @@ built:
   }
 done:
 #undef CKG
-  cudaFree(d_v); cudaFree(d_i); cudaFree(d_recs); cudaFree(d_boxes); cudaFree(d_bounds);
+  free(h_vmesh);
   cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_parent); cudaFree(d_arrive); cudaFree(d_tmp);
   free(h_v); free(h_i); free(h_mesh_of); free(h_mat); free(h_vel);
   if (rc) free_scene_dev(ctx);
   return rc;
+}
+
+/* Advance every mesh by velocity * dt_s on the GPU and bring the BVH up to
+ * date: in place (same topology, boxes recomputed level by level, bottom-up)
+ * or, with rebuild != 0, by building a fresh SAH tree from the moved triangles. */
+extern "C" int hrt_scene_advance(hrt_ctx *ctx, float dt_s, int rebuild)
+{
+  if (!ctx) return HRT_E_ARG;
+  if (!ctx->have_scene) return fail(ctx, HRT_E_STATE, "hrt_scene_advance before hrt_scene_upload");
+  if (!(dt_s == dt_s) || fabsf(dt_s) > 1e30f) return fail(ctx, HRT_E_ARG, "bad time step");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = ctx->num_tris;
+  if (n == 0 || ctx->max_speed == 0.f) return HRT_OK;
+  if (!ctx->sah && !rebuild && ctx->num_nodes) return fail(ctx, HRT_E_STATE, "in-place refit needs the SAH tree (unset HRT_BVH_LBVH) or rebuild = 1");
+  k_move_verts<<<nblk(ctx->num_verts), 256, 0, st>>>(ctx->d_verts, ctx->d_vmesh, ctx->d_mesh_vel, ctx->num_verts, dt_s);
+  const unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+  CK(cudaMemcpyAsync(ctx->d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
+  k_tri_setup<<<nblk(n), 256, 0, st>>>(ctx->d_verts, ctx->d_idx3, n, ctx->d_recs, ctx->d_tboxes, ctx->d_bounds);
+  CK(cudaGetLastError());
+  unsigned hb[6];
+  CK(cudaMemcpyAsync(hb, ctx->d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float max_abs = 0.f;
+  for (int k = 0; k < 3; ++k) {
+    ctx->scene_lo[k] = dec_f(hb[k]); ctx->scene_hi[k] = dec_f(hb[3 + k]);
+    max_abs = fmaxf(max_abs, fmaxf(fabsf(ctx->scene_lo[k]), fabsf(ctx->scene_hi[k])));
+  }
+  ctx->scene_max_abs = max_abs;
+  const float pad = fmaxf(ctx->pad, hrt_box_pad(max_abs, ctx->pad_ulps));
+  if (rebuild && (int)n > ctx->leaf_max) {
+    dev_free(ctx->d_raw_ref); dev_free(ctx->d_raw_box); dev_free(ctx->d_nodes);
+    ctx->sah = true;
+    const int rc = build_sah(ctx, n, ctx->d_tboxes, ctx->d_recs);
+    if (rc) { ctx->have_scene = false; return rc; }
+    ctx->octants = octant_copies(ctx->num_nodes);
+    CK(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
+    ctx->root_ref = 0;
+  } else {
+    /* same leaf order: refresh the triangle records, then the boxes */
+    k_gather_idx<<<nblk(n), 256, 0, st>>>(ctx->d_tri_gid, n, ctx->d_recs, ctx->d_tris, ctx->d_tri_gid);
+    for (int L = ctx->build_levels - 1; L >= 0 && ctx->num_nodes; --L) {
+      const int f = ctx->level_first[L], l = ctx->level_first[L + 1];
+      if (l > f) k_sah_refit<<<nblk(l - f), 256, 0, st>>>(f, l, ctx->d_raw_ref, ctx->d_raw_box, ctx->d_tri_gid, ctx->d_tboxes);
+    }
+    CK(cudaGetLastError());
+  }
+  const int erc = emit_nodes(ctx, pad);
+  if (erc) return erc;
+  CK(cudaStreamSynchronize(st));
+  return HRT_OK;
 }
 
 extern "C" int hrt_materials_set(hrt_ctx *ctx, const HrtMaterialDerived table[NUM_G_MATERIALS])

@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         L.hrt_materials_set.argtypes = [C.c_void_p, C.POINTER(MaterialDerived)]
         L.hrt_run.argtypes = [C.c_void_p, C.POINTER(RunParams)]
         L.hrt_get_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
+        L.hrt_scene_advance.argtypes = [C.c_void_p, C.c_float, C.c_int]
         L.hrt_closest_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.hrt_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -193,6 +194,10 @@ class Context:
             mi = self._scene.meshes[m].material_index
             L.hrt_materials_derive(mi, C.c_float(f_ghz), C.byref(tab[mi]))
         self._check(L.hrt_materials_set(self._h, tab), "hrt_materials_set")
+
+    def advance(self, dt_s: float, rebuild: bool = False):
+        """Move every mesh by velocity * dt_s on the GPU; refit (or rebuild) the BVH."""
+        self._check(lib().hrt_scene_advance(self._h, C.c_float(dt_s), int(rebuild)), "hrt_scene_advance")
 
     # -- runs ----------------------------------------------------------------
     def run(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, *, dense=False, raysinfo=False,

@@ -167,6 +167,14 @@ const char *hrt_last_error(const hrt_ctx *ctx);   /* ctx may be NULL: creation e
  * values the reference stores in Mesh.ns (src/compute_paths.c:208-224). */
 int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_out);
 
+/* Moving scenes (Mesh.velocity, reference inc/scene.h:21-22; SURVEY section 8
+ * row f3): advance every mesh of the uploaded scene by velocity * dt_s on the
+ * GPU (v <- v + vel * dt, each operation rounded to fp32) and bring the BVH up
+ * to date -- in place (same topology, boxes recomputed bottom-up: rebuild = 0)
+ * or with a fresh build from the moved triangles (rebuild = 1).  Results are
+ * those of loading a scene file with the moved vertices. */
+int hrt_scene_advance(hrt_ctx *ctx, float dt_s, int rebuild);
+
 /* Host-side: derive the constants of material `index` at f GHz (reference
  * precompute_materials, src/compute_paths.c:171-206). */
 void hrt_materials_derive(uint32_t index, float carrier_frequency_GHz, HrtMaterialDerived *out);

@@ -166,6 +166,99 @@ def test_run_dense_vs_oracle(ctx, cfg, P, B, n_rx, moving, T):
     assert np.array_equal(res["trace"]["hit_tri"], res2["trace"]["hit_tri"])
 
 
+def test_mixed_materials_tiled_scene_vs_oracle(ctx, tmp_path):
+    """Dense outputs against the oracle on a tiled canyon with the C5 material
+    mix (concrete, brick, glass, marble, metal, dry/wet ground): the Fresnel and
+    scattering coefficients of every ITU material class, two TX, moving ends."""
+    from hrt_b200 import scenes
+    meshes, pitch = scenes.tiled_canyon(tl.scene_path("simple_street_canyon_with_cars"), 3, 3, block=1)
+    assert len({m["material"] for m in meshes}) >= 6
+    path = str(tmp_path / "tiled3.hrt")
+    scenes.write_hrt(path, meshes)
+    rx, tx = scenes.c5_positions(pitch, 3, 3, n_tx=4, n_rx=9)
+    rx, tx = rx[:5], tx[:2]
+    rng = np.random.default_rng(8)
+    rxv, txv = rng.uniform(-3, 3, rx.shape), rng.uniform(-10, 10, tx.shape)
+    P, B, f = 1500, 3, 28.0
+    a, tr = tl.run_oracle(path, rx, tx, rxv, txv, f, P, B, fill=0x00)
+    b, _ = tl.run_oracle(path, rx, tx, rxv, txv, f, P, B, fill=0x5A, trace=False)
+    mask = tl.written_mask(a, b)
+    ctx.load_scene(path)
+    res = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, trace=True, summary=True)
+    _compare_dense(a, mask, res["out"], tr, res["trace"])
+    pair, bounce = tl.oracle_summaries(a, tr)
+    tl.assert_summaries_equal(pair, bounce, res["pair"], res["bounce"])
+    assert int(pair["n_valid"].sum()) > 3000
+    # gains are not trivially zero/one on this scene
+    te = np.abs(res["out"].scat["a_te_re"]); assert (te > 0).sum() > 3000 and np.unique(te[te > 0]).size > 1000
+
+
+def test_many_receivers_global_reduction(ctx):
+    """More receivers than the shared-memory reduction table holds (the per-pair
+    sums then go straight to global atomics), both scatter mappings."""
+    import os
+    scene = "box"
+    rng = np.random.default_rng(2)
+    rx = rng.uniform(-4, 4, (3000, 3)) * [1, 1, 0.5] + [0, 0, 2.5]
+    tx = np.array([[0.5, -1.0, 2.5]])
+    zr, zt = np.zeros_like(rx), np.zeros_like(tx)
+    P, B, f = 1500, 2, 3.0
+    a, tr = tl.run_oracle(scene, rx, tx, zr, zt, f, P, B)
+    pair, bounce = tl.oracle_summaries(a, tr)
+    ctx.load_scene(tl.scene_path(scene))
+    for mode in ("t", "w"):
+        os.environ["HRT_SCATTER_MODE"] = mode
+        try:
+            res = ctx.run(rx, tx, zr, zt, f, P, B, summary=True)
+        finally:
+            del os.environ["HRT_SCATTER_MODE"]
+        tl.assert_summaries_equal(pair, bounce, res["pair"], res["bounce"])
+    assert int(pair["n_valid"].sum()) > 1_000_000
+
+
+def test_scene_advance_refit_and_rebuild(ctx, tmp_path):
+    """hrt_scene_advance: meshes moved on the GPU by
+    velocity * dt + BVH refit in place (or rebuild) == loading a scene file with
+    the same moved vertices; closest hits also against the oracle on that file."""
+    from hrt_b200 import scenes
+    meshes = scenes.read_hrt(tl.scene_path("simple_street_canyon_with_cars"))
+    k = 0
+    for m in meshes:
+        if len(m["tris"]) == 20:            # the cars
+            m["velocity"] = np.array([14.0 if k % 2 == 0 else -9.5, 0.25 * k, 0.0], np.float32); k += 1
+    assert k >= 4
+    pa = str(tmp_path / "moving.hrt"); scenes.write_hrt(pa, meshes)
+    dts = [np.float32(0.37), np.float32(-0.11)]
+    moved = [dict(m, vs=m["vs"].copy()) for m in meshes]
+    for dt in dts:
+        for m in moved:
+            m["vs"] = (m["vs"] + (m["velocity"] * dt).astype(np.float32)).astype(np.float32)
+    pb = str(tmp_path / "moved.hrt"); scenes.write_hrt(pb, moved)
+    rays = tl.random_rays("simple_street_canyon_with_cars", 100000, seed=4)
+    tri_o, t_o, _ = tl.oracle_closest(pb, rays)
+    rx, tx = tl.canyon_c4_positions()
+    rx, tx = np.asarray(rx[:8], np.float32), np.asarray(tx[:2], np.float32)
+    zr, zt = np.zeros_like(rx), np.zeros_like(tx)
+    ctx.load_scene(pb)
+    ref = ctx.run(rx, tx, zr, zt, 3.5, 30000, 3, summary=True)
+    tri_b, t_b, _ = ctx.closest_hits(rays)
+    assert np.array_equal(tri_o, tri_b) and np.array_equal(t_o.view(np.uint32), t_b.view(np.uint32))
+    for rebuild in (False, True):
+        ctx.load_scene(pa)
+        tri_a, _, _ = ctx.closest_hits(rays)
+        assert not np.array_equal(tri_a, tri_b)            # the cars really are somewhere else
+        for dt in dts:
+            ctx.advance(float(dt), rebuild=rebuild)
+        tri_g, t_g, _ = ctx.closest_hits(rays)
+        assert np.array_equal(tri_o, tri_g) and np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32)), rebuild
+        got = ctx.run(rx, tx, zr, zt, 3.5, 30000, 3, summary=True)
+        for key in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+            assert np.array_equal(ref["pair"][key], got["pair"][key]), (rebuild, key)
+        for key in ("n_traced", "n_hit", "hit_hash", "t_bits"):
+            assert np.array_equal(ref["bounce"][key], got["bounce"][key]), (rebuild, key)
+    ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
+
+
 def test_launch_directions_bit_exact(ctx):
     """Fibonacci launch directions incl. the host-recomputed ambiguous ones
     (hrt_core.cuh, hrt_launch_dir) == glibc results of the oracle, every ray."""
