@@ -174,7 +174,7 @@ def workload_config():
                         f"{BOUNCES} bounces, {F_GHZ} GHz, summary (streaming) outputs",
             "rays": TOTAL_RAYS, "num_tx": NUM_TX, "num_rx": NUM_RX, "bounces": BOUNCES,
             "shard_block": SHARD_BLOCK,
-            "l2": "inputs larger than L2: per-ray state of a step is %.1f GB" % (TOTAL_RAYS * 60 / 1e9)}
+            "l2": "inputs larger than L2: per-ray state of a step is %.1f GB" % (TOTAL_RAYS * 148 / 1e9)}
 
 
 # ------------------------------------------------------------------ GPU arm

@@ -69,12 +69,16 @@ struct RunDev {
   HrtRunConst k;
   const float *rx_pos, *tx_pos, *rx_vel, *tx_vel;
   float *dirs;           /* [n_alloc][3] launch directions of the chunk */
-  Ray *rays;             /* [rows][T][n_alloc] */
-  float4 *gain;          /* [T][n_alloc] te_r te_i tm_r tm_i */
-  float *tau, *theta;    /* [T][n_alloc] */
-  uint32_t *hslot;       /* [T][n_alloc] leaf slot of the last primary hit */
-  uint8_t *dead_at;      /* [T][n_alloc] bounce at which the ray left the scene, 255 alive */
-  uint32_t *queue[2];    /* [T][n_alloc] active path indices */
+  /* Ray records, 64 B = 4 x float4 each, [T][n_alloc], double buffered by depth:
+   *   (o.xyz, d.x) (d.yz, te_r, te_i) (tm_r, tm_i, tau, theta) (leaf slot, path, -, -)
+   * k_bounce(depth) reads rec[depth & 1] through the queue and appends the
+   * survivors -- reflected ray, updated gains/delay, incidence angle, hit slot --
+   * to rec[(depth + 1) & 1] in queue order: one coalesced 64-byte write per
+   * survivor, one 64-byte gather per reader. */
+  float4 *rec[2];
+  Ray *rays;             /* [B+1][T][n_alloc] RaysInfo rows (HRT_FLAG_RAYSINFO only) */
+  uint8_t *dead_at;      /* [T][n_alloc] bounce at which the ray left the scene, 255 alive (RAYSINFO only) */
+  uint32_t *queue[2];    /* [T][n_alloc] record indices, in work order */
   uint32_t *queue_alt;   /* [T][n_alloc] sort output, swapped with queue[k] on the host */
   uint32_t *qkey, *qkey_alt; /* [T][n_alloc] Morton code of the hit point, order of the next queue */
   uint32_t *qcount;      /* [B+1][T] queue sizes, then [B][T] k_bounce and [B][T] k_scatter work cursors */
@@ -694,15 +698,23 @@ __global__ void k_init(RunDev rd)
   const size_t np = rd.n_alloc;
   for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
     const V3 d = ld3(rd.dirs, l);
+    /* record number l of every TX: the path that is l-th in direction order */
+    const uint32_t pl = rd.perm2[l];
+    const V3 pd = ld3(rd.dirs, pl);
     for (uint32_t t = 0; t < T; ++t) {
       const size_t i = t * np + l;
       const V3 o = ld3(rd.tx_pos, t);
-      float2 *ry = (float2 *)(rd.rays + i);
-      ry[0] = make_float2(o.x, o.y); ry[1] = make_float2(o.z, d.x); ry[2] = make_float2(d.y, d.z);
-      rd.gain[i] = make_float4(1.f, 0.f, 1.f, 0.f);
-      rd.tau[i] = 0.f;
-      rd.dead_at[i] = 255;
-      rd.queue[0][i] = rd.perm2[l];   /* work order: direction-sorted */
+      float4 *rc = rd.rec[0] + 4 * i;
+      rc[0] = make_float4(o.x, o.y, o.z, pd.x);
+      rc[1] = make_float4(pd.y, pd.z, 1.f, 0.f);
+      rc[2] = make_float4(1.f, 0.f, 0.f, 0.f);
+      rc[3] = make_float4(0.f, __uint_as_float(pl), 0.f, 0.f);
+      rd.queue[0][i] = l;
+      if (rd.flags & HRT_FLAG_RAYSINFO) {
+        float2 *ry = (float2 *)(rd.rays + i);
+        ry[0] = make_float2(o.x, o.y); ry[1] = make_float2(o.z, d.x); ry[2] = make_float2(d.y, d.z);
+        rd.dead_at[i] = 255;
+      }
       if (rd.flags & HRT_FLAG_TRACE)
         for (uint32_t b = 0; b < B; ++b) {
           rd.tr_hit[(t * B + b) * np + l] = HRT_IDLE;
@@ -775,9 +787,10 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
   const uint32_t cnt = rd.qcount[depth * T + t];
   const uint32_t *qin = rd.queue[depth & 1] + t * np;
   uint32_t *qout = rd.queue[(depth + 1) & 1] + t * np;
+  const float4 *rin = rd.rec[depth & 1] + 4 * t * np;
+  float4 *rout = rd.rec[(depth + 1) & 1] + 4 * t * np;
   const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
-  const Ray *rin = rd.rays + (rows ? (size_t)depth * T * np : 0) + t * np;
-  Ray *rout = rd.rays + (rows ? (size_t)(depth + 1) * T * np : 0) + t * np;
+  Ray *rays_out = rows ? rd.rays + (size_t)(depth + 1) * T * np + t * np : nullptr;
   unsigned long long hash_acc = 0, tbits_acc = 0;
 
   /* warps pull batches of 128 queue entries from a shared cursor (dynamic load
@@ -791,13 +804,15 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
   for (uint32_t i = batch + lane; i < batch + 128u && (i - lane) < cnt; i += 32u) {
     const bool valid = i < cnt;
     bool hit = false;
-    uint32_t l = 0, okey = 0;
+    uint32_t l = 0, okey = 0, hslot = 0;
+    float theta = 0.f;
+    HrtRayState s;
     if (valid) {
-      l = qin[i];
-      const float2 *rp = (const float2 *)(rin + l);
-      const float2 a = rp[0], b = rp[1], c = rp[2];
-      HrtRayState s;
-      s.o = v3(a.x, a.y, b.x); s.d = v3(b.y, c.x, c.y);
+      const float4 *rc = rin + 4 * (size_t)qin[i];
+      const float4 r0 = __ldg(rc), r1 = __ldg(rc + 1), r2 = __ldg(rc + 2), r3 = __ldg(rc + 3);
+      l = __float_as_uint(r3.y);
+      s.o = v3(r0.x, r0.y, r0.z); s.d = v3(r0.w, r1.x, r1.y);
+      s.te_r = r1.z; s.te_i = r1.w; s.tm_r = r2.x; s.tm_i = r2.y; s.tau = r2.z;
       const HrtHit h = query<SMEM, BRUTE>(sc, s.o, s.d, wc);                  /* :615 */
       hit = h.gid != HRT_NONE;
       const size_t si = t * np + l;
@@ -806,22 +821,18 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
         rd.tr_t[(t * B + depth) * np + l] = hit ? h.t : -1.f;
       }
       if (!hit) {
-        rd.dead_at[si] = (uint8_t)depth;                                       /* :616-620 */
+        if (rows) rd.dead_at[si] = (uint8_t)depth;                             /* :616-620 */
       } else {
         const V3 n = tri_normal<SMEM>(sc, h.slot);
-        const float theta = hrt_theta_fold(n, s.d);                            /* :281-283 */
+        theta = hrt_theta_fold(n, s.d);                                        /* :281-283 */
         const uint32_t mat = sc.mesh_mat[sc.mesh_of[h.gid]];                   /* :622 */
-        const float4 g = rd.gain[si];
-        s.te_r = g.x; s.te_i = g.y; s.tm_r = g.z; s.tm_i = g.w;
-        s.tau = rd.tau[si];
         hrt_bounce_update(s, mats.m[mat], rd.k, h.t, n, theta);                /* :623-659 */
-        float2 *wp = (float2 *)(rout + l);
-        wp[0] = make_float2(s.o.x, s.o.y); wp[1] = make_float2(s.o.z, s.d.x);
-        wp[2] = make_float2(s.d.y, s.d.z);
-        rd.gain[si] = make_float4(s.te_r, s.te_i, s.tm_r, s.tm_i);
-        rd.tau[si] = s.tau;
-        rd.theta[si] = theta;
-        rd.hslot[si] = h.slot;
+        if (rows) {
+          float2 *wp = (float2 *)(rays_out + l);
+          wp[0] = make_float2(s.o.x, s.o.y); wp[1] = make_float2(s.o.z, s.d.x);
+          wp[2] = make_float2(s.d.y, s.d.z);
+        }
+        hslot = h.slot;
         okey = hit_key(sc, s.o);
         if (rd.flags & HRT_FLAG_SUMMARY) {
           const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
@@ -837,7 +848,12 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
       if (hit) {
         const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-        qout[pos] = l;
+        float4 *wc4 = rout + 4 * (size_t)pos;
+        wc4[0] = make_float4(s.o.x, s.o.y, s.o.z, s.d.x);
+        wc4[1] = make_float4(s.d.y, s.d.z, s.te_r, s.te_i);
+        wc4[2] = make_float4(s.tm_r, s.tm_i, s.tau, theta);
+        wc4[3] = make_float4(__uint_as_float(hslot), __uint_as_float(l), 0.f, 0.f);
+        qout[pos] = pos;
         rd.qkey[t * np + pos] = okey;
       }
     }
@@ -901,8 +917,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   const size_t np = rd.n_alloc;
   const uint32_t cnt = rd.qcount[(depth + 1) * T + t];
   const uint32_t *q = rd.queue[(depth + 1) & 1] + t * np;
-  const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
-  const Ray *rays = rd.rays + (rows ? (size_t)(depth + 1) * T * np : 0) + t * np;
+  const float4 *recs = rd.rec[(depth + 1) & 1] + 4 * t * np;
   const uint32_t lane = threadIdx.x & 31u;
   const bool dense = (rd.flags & HRT_FLAG_DENSE) != 0, trace = (rd.flags & HRT_FLAG_TRACE) != 0;
 
@@ -917,22 +932,18 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     if (batch >= cnt) break;
   for (uint32_t hi = WARP ? batch : batch + lane; WARP ? (hi < batch + grab && hi < cnt) : hi == batch + lane; hi += WARP ? 1u : 64u) {
     const bool valid = WARP || hi < cnt;
-    const uint32_t l = valid ? q[hi] : q[0];
-    const size_t si = t * np + l;
-    const float2 *rp = (const float2 *)(rays + l);
-    const float2 a = rp[0], b = rp[1], c = rp[2];
+    const float4 *rc = recs + 4 * (size_t)(valid ? q[hi] : q[0]);
+    const float4 r0 = __ldg(rc), r1 = __ldg(rc + 1), r2 = __ldg(rc + 2), r3 = __ldg(rc + 3);
     HrtRayState s;
-    s.o = v3(a.x, a.y, b.x); s.d = v3(b.y, c.x, c.y);
-    const float4 g = rd.gain[si];
-    s.te_r = g.x; s.te_i = g.y; s.tm_r = g.z; s.tm_i = g.w;
-    s.tau = rd.tau[si];
-    const uint32_t slot = rd.hslot[si];
+    s.o = v3(r0.x, r0.y, r0.z); s.d = v3(r0.w, r1.x, r1.y);
+    s.te_r = r1.z; s.te_i = r1.w; s.tm_r = r2.x; s.tm_i = r2.y; s.tau = r2.z;
+    const uint32_t slot = __float_as_uint(r3.x), l = __float_as_uint(r3.y);
     const V3 n = tri_normal<SMEM>(sc, slot);
     const uint32_t gid = tri_gid_of<SMEM>(sc, slot);
     const uint32_t mesh = sc.mesh_of[gid];
     const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
     const V3 mv = ld3(sc.mesh_vel, mesh);
-    float theta_carry = rd.theta[si];
+    float theta_carry = r2.w;
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const uint64_t hkey = hrt_mix64((path << 32) | gid);
 
@@ -1198,8 +1209,8 @@ static void free_scene_dev(hrt_ctx *c)
 static void free_run_dev(hrt_ctx *c)
 {
   RunDev &r = c->rd;
-  dev_free(r.dirs); dev_free(r.rays); dev_free(r.gain); dev_free(r.tau); dev_free(r.theta);
-  dev_free(r.hslot); dev_free(r.dead_at); dev_free(r.queue[0]); dev_free(r.queue[1]);
+  dev_free(r.dirs); dev_free(r.rays); dev_free(r.rec[0]); dev_free(r.rec[1]);
+  dev_free(r.dead_at); dev_free(r.queue[0]); dev_free(r.queue[1]);
   dev_free(r.queue_alt); dev_free(r.qkey); dev_free(r.qkey_alt);
   dev_free(r.qcount);
   for (int k = 0; k < 6; ++k) dev_free(r.out_f[k]);
@@ -1674,10 +1685,10 @@ static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t
     return HRT_OK;
   free_run_dev(ctx);
   RunDev &r = ctx->rd;
-  const size_t TN = T * n, rows = (flags & HRT_FLAG_RAYSINFO) ? B + 1 : 1;
-  CK(dev_alloc(&r.dirs, n * 3)); CK(dev_alloc(&r.rays, rows * TN)); CK(dev_alloc(&r.gain, TN));
-  CK(dev_alloc(&r.tau, TN)); CK(dev_alloc(&r.theta, TN)); CK(dev_alloc(&r.hslot, TN));
-  CK(dev_alloc(&r.dead_at, TN)); CK(dev_alloc(&r.queue[0], TN)); CK(dev_alloc(&r.queue[1], TN));
+  const size_t TN = T * n;
+  CK(dev_alloc(&r.dirs, n * 3)); CK(dev_alloc(&r.rec[0], TN * 4)); CK(dev_alloc(&r.rec[1], TN * 4));
+  if (flags & HRT_FLAG_RAYSINFO) { CK(dev_alloc(&r.rays, (B + 1) * TN)); CK(dev_alloc(&r.dead_at, TN)); }
+  CK(dev_alloc(&r.queue[0], TN)); CK(dev_alloc(&r.queue[1], TN));
   CK(dev_alloc(&r.queue_alt, TN)); CK(dev_alloc(&r.qkey, TN)); CK(dev_alloc(&r.qkey_alt, TN));
   CK(dev_alloc(&r.qcount, (3 * B + 1) * T));   /* queue sizes + work cursors of k_bounce / k_scatter */
   CK(dev_alloc(&r.amb_list, HRT_AMB_CAP)); CK(dev_alloc(&r.amb_count, 1));

@@ -19,6 +19,9 @@ BLOCK = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 16
 SH = dict(shard=(0, WORLD), shard_block=BLOCK) if WORLD > 1 else {}
 t0 = time.perf_counter()
 meshes, pitch = scenes.tiled_canyon(os.path.join(ROOT, "scenes", "simple_street_canyon_with_cars.hrt"), 64, 64)
+for m in meshes:                      # cars drive (Doppler + scene-advance timing); geometry at t = 0 unchanged
+    if m["material"] == scenes.MATERIAL["metal"]:
+        m["velocity"] = np.array([10.0, 0.0, 0.0], np.float32)
 path = "/tmp/c5_tiled_canyon.hrt"
 scenes.write_hrt(path, meshes)
 t_gen = time.perf_counter() - t0
@@ -50,4 +53,8 @@ out["flops_per_shadow_query"] = (22 * c["work_scatter"][0] + 14 * c["work_scatte
 out["box_tests_per_shadow_query"] = c["work_scatter"][0] / max(c["shadow_queries"], 1)
 out["tri_tests_per_shadow_query"] = c["work_scatter"][1] / max(c["shadow_queries"], 1)
 out["box_tests_per_primary_query"] = c["work_bounce"][0] / max(c["ray_bounces"], 1)
+# moving scene: advance by +dt and -dt (back to the original vertices up to rounding), refit vs rebuild
+for name, rebuild in (("bvh_refit_ms", False), ("bvh_rebuild_ms", True)):
+    t0 = time.perf_counter(); ctx.advance(1e-3, rebuild=rebuild); out[name] = (time.perf_counter() - t0) * 1e3
+    ctx.advance(-1e-3, rebuild=rebuild)
 print(json.dumps(out))
