@@ -56,6 +56,7 @@ struct SceneDev {
   uint32_t octants;            /* node copies: 8 (one per direction octant) or 1 */
   int root_ref;
   float key_lo[3], key_scale[3];   /* vertex bounds -> 10-bit grid of the hit-order keys */
+  float key_log;                   /* > 0: logarithmic x/y grid around the TX, cells per octave */
 };
 
 struct RunDev {
@@ -653,14 +654,27 @@ __device__ __forceinline__ uint32_t dir_key(V3 d)
   return (spread16(iu) << 1) | spread16(iv);
 }
 
-/* Order key of a hit: 30-bit Morton code of the reflected ray's origin on a
- * 1024^3 grid over the vertex bounds.  The next queue is sorted by it, so the
- * 32 hits a warp of k_scatter works on are neighbours in space -- their shadow
- * rays to one receiver are nearly the same ray.  Order only, never results. */
-__device__ __forceinline__ uint32_t hit_key(const SceneDev &sc, V3 o)
+/* Order key of a hit: 30-bit Morton code of the reflected ray's origin.  The
+ * next queue is sorted by it, so the 32 hits a warp of k_scatter works on are
+ * neighbours in space -- their shadow rays to one receiver are nearly the same
+ * ray.  Small scenes: a 1024^3 grid over the vertex bounds.  Scenes wider than
+ * 256 m (a uniform cell would be metres wide): x and y on a logarithmic scale
+ * around the transmitter, 2.5 cm cells next to it, ~2 m at 100 m -- hit density
+ * falls with the square of that distance, so cells keep similar populations.
+ * Order only, never results. */
+__device__ __forceinline__ uint32_t hit_key(const SceneDev &sc, V3 o, V3 tx)
 {
-  const uint32_t x = (uint32_t)fminf(fmaxf((o.x - sc.key_lo[0]) * sc.key_scale[0], 0.f), 1023.f);
-  const uint32_t y = (uint32_t)fminf(fmaxf((o.y - sc.key_lo[1]) * sc.key_scale[1], 0.f), 1023.f);
+  float fx, fy;
+  if (sc.key_log) {
+    const float dx = o.x - tx.x, dy = o.y - tx.y;
+    fx = 512.f + copysignf(__log2f(1.f + fabsf(dx) * 20.f) * sc.key_log, dx);
+    fy = 512.f + copysignf(__log2f(1.f + fabsf(dy) * 20.f) * sc.key_log, dy);
+  } else {
+    fx = (o.x - sc.key_lo[0]) * sc.key_scale[0];
+    fy = (o.y - sc.key_lo[1]) * sc.key_scale[1];
+  }
+  const uint32_t x = (uint32_t)fminf(fmaxf(fx, 0.f), 1023.f);
+  const uint32_t y = (uint32_t)fminf(fmaxf(fy, 0.f), 1023.f);
   const uint32_t z = (uint32_t)fminf(fmaxf((o.z - sc.key_lo[2]) * sc.key_scale[2], 0.f), 1023.f);
   return (hrt_expand10(x) << 2) | (hrt_expand10(y) << 1) | hrt_expand10(z);
 }
@@ -789,6 +803,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
   uint32_t *qout = rd.queue[(depth + 1) & 1] + t * np;
   const float4 *rin = rd.rec[depth & 1] + 4 * t * np;
   float4 *rout = rd.rec[(depth + 1) & 1] + 4 * t * np;
+  const V3 txp = ld3(rd.tx_pos, t);
   const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
   Ray *rays_out = rows ? rd.rays + (size_t)(depth + 1) * T * np + t * np : nullptr;
   unsigned long long hash_acc = 0, tbits_acc = 0;
@@ -833,7 +848,7 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
           wp[2] = make_float2(s.d.y, s.d.z);
         }
         hslot = h.slot;
-        okey = hit_key(sc, s.o);
+        okey = hit_key(sc, s.o, txp);
         if (rd.flags & HRT_FLAG_SUMMARY) {
           const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
           hash_acc += hrt_mix64((path << 32) | h.gid);
@@ -1586,6 +1601,11 @@ static SceneDev scene_dev(const hrt_ctx *c)
   for (int k = 0; k < 3; ++k) {
     s.key_lo[k] = c->scene_lo[k];
     s.key_scale[k] = 1024.f / fmaxf(c->scene_hi[k] - c->scene_lo[k], 1e-20f);
+  }
+  {
+    const float ext = fmaxf(c->scene_hi[0] - c->scene_lo[0], c->scene_hi[1] - c->scene_lo[1]);
+    /* 511 cells for log2(1 + 2 * ext / 5 cm) octaves: covers a TX anywhere inside the bounds */
+    s.key_log = (ext > 256.f && !getenv("HRT_KEY_UNIFORM")) ? 511.f / log2f(1.f + 2.f * ext * 20.f) : 0.f;
   }
   return s;
 }
