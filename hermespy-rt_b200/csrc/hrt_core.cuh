@@ -292,6 +292,17 @@ struct HrtGlobalMem {
     return tris[3 * s + k];
 #endif
   }
+  /* halves of node words 2 and 3: z planes of child `right`, and the two refs */
+  HRT_HD void node_z(int i, uint32_t right, float *z0, float *z1) const
+  {
+    const float4 n2 = node(i, 2);
+    *z0 = right ? n2.z : n2.x; *z1 = right ? n2.w : n2.y;
+  }
+  HRT_HD void node_refs(int i, int *rl, int *rr) const
+  {
+    const float4 n3 = node(i, 3);
+    *rl = hrt_float_as_int(n3.x); *rr = hrt_float_as_int(n3.y);
+  }
   HRT_HD void select_octant(uint32_t oct, uint32_t stride)
   {
     nodes += (size_t)oct * stride;
@@ -308,6 +319,38 @@ struct __align__(8) HrtStackEntry { int ref; float tn; };
 struct HrtStackEntry { int ref; float tn; };
 #endif
 
+/* Origin chain.  Every shadow ray of one hit point starts inside the same
+ * nested sequence of node boxes -- from the root down to (usually) the leaf of
+ * the surface it starts on.  A ray that starts inside a box needs no test for
+ * it, and which child contains the origin does not depend on the direction: the
+ * walk down that chain is done once per hit point (`path`: bit k set = the
+ * origin is in the RIGHT child at level k), and each of its rays then tests only
+ * the SIBLING at every level -- one box test and no ordering decision instead of
+ * two tests and a three-way branch.  Pure traversal order: results are the
+ * minimum over (t, triangle id) as before. */
+struct HrtChain { uint32_t path, depth; };
+
+/* `mem` must be the plain (octant 0) node copy: (lo, hi) per axis */
+template <class Mem>
+HRT_HD HrtChain hrt_origin_chain(const Mem &mem, int root_ref, uint32_t num_tris, V3 o)
+{
+  HrtChain ch; ch.path = 0u; ch.depth = 0u;
+  if (num_tris == 0) return ch;
+  int cur = root_ref;
+  while (cur >= 0 && ch.depth < 32u) {
+    const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1), n2 = mem.node(cur, 2);
+    int rl, rr;
+    mem.node_refs(cur, &rl, &rr);
+    const bool in_l = o.x >= n0.x && o.x <= n0.y && o.y >= n0.z && o.y <= n0.w && o.z >= n2.x && o.z <= n2.y;
+    const bool in_r = o.x >= n1.x && o.x <= n1.y && o.y >= n1.z && o.y <= n1.w && o.z >= n2.z && o.z <= n2.w;
+    if (in_l) cur = rl;
+    else if (in_r) { ch.path |= 1u << ch.depth; cur = rr; }
+    else break;
+    ++ch.depth;
+  }
+  return ch;
+}
+
 /* Closest hit over the BVH == the reference's loop over every triangle
  * (moeller_trumbore, :237-287): minimum t, ties to the lowest (mesh, face).
  * root_ref: inner node index, a leaf ref, or 0 with num_tris == 0. */
@@ -315,7 +358,8 @@ struct HrtStackEntry { int ref; float tn; };
  * direction octant (hrt_emit_node), `oct_stride` float4s apart. */
 template <bool SORTED, class Mem, class Gid, class Cnt>
 HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref,
-                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt, uint32_t oct_stride = 0)
+                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt, uint32_t oct_stride = 0,
+                              HrtChain chain = HrtChain{0u, 0u})
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
@@ -329,6 +373,24 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
   HrtStackEntry stack[HRT_STACK];    /* (subtree ref, entry distance): one 8-byte store / load each */
   int sp = 0, cur = root_ref;
   bool done = false;
+  /* the origin's chain (hrt_origin_chain): siblings only */
+  for (uint32_t lvl = 0; lvl < chain.depth; ++lvl) {
+    const uint32_t right = (chain.path >> lvl) & 1u;      /* origin in the right child: test the left */
+    const float4 sxy = mem.node(cur, right ? 0 : 1);
+    float z0, z1, ts;
+    mem.node_z(cur, right ^ 1u, &z0, &z1);
+    int rl, rr;
+    mem.node_refs(cur, &rl, &rr);
+    const bool hs = SORTED ? hrt_slab_sorted(c, sxy.x, sxy.y, sxy.z, sxy.w, z0, z1, tmax, &ts)
+                           : hrt_slab(c, sxy.x, sxy.y, sxy.z, sxy.w, z0, z1, tmax, &ts);
+    cnt.box(1u);
+    if (hs) {
+      HrtStackEntry e;
+      e.ref = right ? rl : rr; e.tn = ts;
+      stack[sp++] = e;
+    }
+    cur = right ? rr : rl;
+  }
   /* "while-while" traversal: every lane first walks inner nodes until it holds
    * a leaf (or has nothing left), then the leaves are tested -- lanes of a warp
    * meet in the triangle loop instead of interleaving box and triangle code. */

@@ -57,6 +57,7 @@ struct SceneDev {
   int root_ref;
   float key_lo[3], key_scale[3];   /* vertex bounds -> 10-bit grid of the hit-order keys */
   float key_log;                   /* > 0: logarithmic x/y grid around the TX, cells per octave */
+  uint32_t no_chain;               /* HRT_NO_CHAIN=1: shadow rays start at the root (A/B switch) */
 };
 
 struct RunDev {
@@ -549,6 +550,14 @@ struct HrtSharedMem {
   uint32_t node_addr, tri_addr;     /* byte addresses in the shared window */
   __device__ __forceinline__ float4 node(int i, int k) const { return lds128(node_addr + ((uint32_t)i << 6) + ((uint32_t)k << 4)); }
   __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return lds128(tri_addr + s * 48u + ((uint32_t)k << 4)); }
+  __device__ __forceinline__ void node_z(int i, uint32_t right, float *z0, float *z1) const
+  {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(*z0), "=f"(*z1) : "r"(node_addr + ((uint32_t)i << 6) + 32u + (right << 3)));
+  }
+  __device__ __forceinline__ void node_refs(int i, int *rl, int *rr) const
+  {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(*rl), "=r"(*rr) : "r"(node_addr + ((uint32_t)i << 6) + 48u));
+  }
   __device__ __forceinline__ void select_octant(uint32_t oct, uint32_t stride)
   {
     node_addr += oct * stride * 16u;
@@ -588,7 +597,7 @@ static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris, uint32_t o
 { return (size_t)num_nodes * 64 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
 
 template <bool SMEM, bool BRUTE, class Cnt>
-__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt)
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, HrtChain chain = HrtChain{0u, 0u})
 {
   if (SMEM) {
     HrtSharedMem m;
@@ -596,13 +605,27 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
     m.tri_addr = m.node_addr + sc.num_nodes * 512u;         /* 8 octant copies of the nodes first */
     HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
-    return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u);
+    return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
   } else {
     HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
     if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
-    if (sc.octants == 8) return hrt_closest_hit<true>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u);
-    return hrt_closest_hit<false>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt);
+    if (sc.octants == 8) return hrt_closest_hit<true>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
+    return hrt_closest_hit<false>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, 0u, chain);
   }
+}
+
+/* the chain of node boxes that contain `o` (hrt_origin_chain), on the plain node copy */
+template <bool SMEM>
+__device__ __forceinline__ HrtChain origin_chain(const SceneDev &sc, V3 o)
+{
+  if (sc.no_chain) return HrtChain{0u, 0u};
+  if (SMEM) {
+    HrtSharedMem m;
+    m.node_addr = smem_base_addr(); m.tri_addr = 0;
+    return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
+  }
+  HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
+  return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
 }
 
 template <bool COUNT> struct CntSel { typedef HrtNoCount type; };
@@ -959,6 +982,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
     const V3 mv = ld3(sc.mesh_vel, mesh);
     float theta_carry = r2.w;
+    const HrtChain chain = BRUTE ? HrtChain{0u, 0u} : origin_chain<SMEM>(sc, s.o);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const uint64_t hkey = hrt_mix64((path << 32) | gid);
 
@@ -971,7 +995,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = query<SMEM, BRUTE>(sc, s.o, sd, wc);                              /* :682 */
+        h = query<SMEM, BRUTE>(sc, s.o, sd, wc, chain);                       /* :682 */
         if (h.gid != HRT_NONE) th_sh = hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), sd);
       }
       const bool shit = act && h.gid != HRT_NONE;
@@ -1607,6 +1631,7 @@ static SceneDev scene_dev(const hrt_ctx *c)
     /* 511 cells for log2(1 + 2 * ext / 5 cm) octaves: covers a TX anywhere inside the bounds */
     s.key_log = (ext > 256.f && !getenv("HRT_KEY_UNIFORM")) ? 511.f / log2f(1.f + 2.f * ext * 20.f) : 0.f;
   }
+  s.no_chain = getenv("HRT_NO_CHAIN") ? 1u : 0u;
   return s;
 }
 

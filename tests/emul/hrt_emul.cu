@@ -92,13 +92,20 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   }
 }
 
-static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
+static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute, HrtChain chain = HrtChain{0u, 0u})
 {
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
   HrtNoCount nc;
   if (brute == 1) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
-  if (brute == 2) return hrt_closest_hit<false>(m, E.gid.data(), E.root, E.n, o, d, nc);   /* plain node copy */
-  return hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, o, d, nc, E.num_nodes * 4u);  /* octant copies */
+  if (brute == 2) return hrt_closest_hit<false>(m, E.gid.data(), E.root, E.n, o, d, nc, 0u, chain);   /* plain node copy */
+  return hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, o, d, nc, E.num_nodes * 4u, chain);  /* octant copies */
+}
+
+/* the shadow rays of a hit point start from its origin chain, as in k_scatter */
+static HrtChain chain_of(const EmulScene &E, V3 o)
+{
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
+  return hrt_origin_chain(m, E.root, E.n, o);
 }
 
 static V3 nrm(const EmulScene &E, uint32_t slot) { const float4 q = E.tris[3 * slot + 2]; return v3(q.y, q.z, q.w); }
@@ -194,11 +201,12 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
         const HrtMaterial &mat = mats.m[E.mesh_mat[mesh]];
         hrt_bounce_update(s, mat, k, h.t, n, theta);
         float carry = theta;
+        const HrtChain chain = brute == 1 ? HrtChain{0u, 0u} : chain_of(E, s.o);
         for (size_t r = 0; r < R; ++r) {
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
-          const HrtHit sh = query(E, s.o, sd, brute);
+          const HrtHit sh = query(E, s.o, sd, brute, chain);
           if (sh.gid != HRT_NONE) carry = hrt_theta_fold(nrm(E, sh.slot), sd);
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
           const HrtScatterOut o = hrt_scatter_path(s, mat, k, n, E.mesh_vel[mesh], sd, dist, carry);
