@@ -126,6 +126,6 @@ if os.path.exists(os.path.join(G, "launches.csv")):
     shutil.copy(os.path.join(G, "launches.csv"), os.path.join(OUT, "launches.csv"))
     launch_shares(os.path.join(G, "launches.csv"), os.path.join(OUT, "launch_shares.txt"))
 for f in ("bench_full.json", "bench_ref.json", "bench_small.json", "pytest_gpu.log", "smoke.log", "c5_shard.json", "dense.json",
-          "bench_n2.json", "bench_n4.json", "bench_n8.json", "gpu.txt"):
+          "bench_n2.json", "bench_n4.json", "bench_n8.json", "gpu.txt", "c5_full.json"):
     if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(OUT, f))
 print("wrote", OUT, sorted(os.listdir(OUT)))
