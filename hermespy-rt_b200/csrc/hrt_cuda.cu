@@ -1433,14 +1433,10 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
     }
     CKG(cudaMemcpyAsync(ctx->d_vmesh, h_vmesh, nv * 4, cudaMemcpyHostToDevice, st));
     CKG(dev_alloc(&d_recs, (size_t)n * 3)); CKG(dev_alloc(&d_boxes, (size_t)n * 6));
-    CKG(dev_alloc(&d_bounds, 6)); CKG(dev_alloc(&d_keys, n)); CKG(dev_alloc(&d_keys2, n));
+    CKG(dev_alloc(&d_bounds, 6));
     CKG(dev_alloc(&ctx->d_tris, (size_t)n * 3)); CKG(dev_alloc(&ctx->d_tri_gid, n));
     CKG(dev_alloc(&ctx->d_mesh_of, n)); CKG(dev_alloc(&ctx->d_mesh_mat, M)); CKG(dev_alloc(&ctx->d_mesh_vel, (size_t)M * 3));
     const size_t nn = n > 1 ? n - 1 : 1;
-    CKG(dev_alloc(&ctx->d_kl, nn)); CKG(dev_alloc(&ctx->d_kr, nn)); CKG(dev_alloc(&ctx->d_kfirst, nn));
-    CKG(dev_alloc(&ctx->d_klast, nn)); CKG(dev_alloc(&ctx->d_newidx, 2 * (size_t)n + 2));
-    CKG(dev_alloc(&ctx->d_box, (2 * (size_t)n) * 6)); CKG(dev_alloc(&d_parent, 2 * (size_t)n));
-    CKG(dev_alloc(&d_arrive, nn));
     CKG(cudaMemcpyAsync(d_v, h_v, nv * 12, cudaMemcpyHostToDevice, st));
     CKG(cudaMemcpyAsync(d_i, h_i, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     CKG(cudaMemcpyAsync(ctx->d_mesh_of, h_mesh_of, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -1460,7 +1456,13 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
         goto built;
       }
+      /* Morton/Karras builder (HRT_BVH_LBVH=1, and scenes of <= leaf_max triangles) */
       ctx->sah = false;
+      CKG(dev_alloc(&d_keys, n)); CKG(dev_alloc(&d_keys2, n));
+      CKG(dev_alloc(&ctx->d_kl, nn)); CKG(dev_alloc(&ctx->d_kr, nn)); CKG(dev_alloc(&ctx->d_kfirst, nn));
+      CKG(dev_alloc(&ctx->d_klast, nn)); CKG(dev_alloc(&ctx->d_newidx, 2 * (size_t)n + 2));
+      CKG(dev_alloc(&ctx->d_box, (2 * (size_t)n) * 6)); CKG(dev_alloc(&d_parent, 2 * (size_t)n));
+      CKG(dev_alloc(&d_arrive, nn));
       k_morton<<<nblk(n), 256, 0, st>>>(d_boxes, n, d_bounds, d_keys);
       CKG(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, (int)n, 0, 64, st));
       CKG(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
@@ -1870,7 +1872,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
    * thanks to the direction sort) whenever there are enough hits to fill the
    * machine; a warp per hit (lanes over receivers) for few rays x many RX */
-  bool warp_mode = R >= 8 && (uint64_t)T * (P < chunk ? P : chunk) < (uint64_t)sms * 2048;
+  bool warp_mode = R >= 8 && (uint64_t)T * (P < chunk ? P : chunk) < (uint64_t)sms * 4096;   /* crossover measured with scripts/mode_sweep.py */
   if (const char *m = getenv("HRT_SCATTER_MODE")) warp_mode = (m[0] == 'w') && R >= 2;
   const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
