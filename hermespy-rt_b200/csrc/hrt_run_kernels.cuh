@@ -1,0 +1,675 @@
+/* hrt_run_kernels.cuh -- the kernels of one hrt_run() (included by hrt_cuda.cu):
+ * scene access from shared / global memory, launch directions, state
+ * initialisation, line of sight, the per-depth wavefront pair k_bounce /
+ * k_scatter (reference src/compute_paths.c:599-723), reductions.  The per-ray
+ * arithmetic itself is in hrt_core.cuh. */
+#pragma once
+
+/* ------------------------------------------------------- scene in shared */
+
+extern __shared__ float4 hrt_smem4[];
+
+/* Scene words in shared memory, read with explicit ld.shared through 32-bit
+ * byte addresses held in registers (the compiler otherwise recomputes the
+ * shared-window base with S2UR/ULEA on every node visit). */
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t smem_base_addr() { return (uint32_t)__cvta_generic_to_shared(hrt_smem4); }
+
+struct HrtSharedMem {
+  uint32_t node_addr, tri_addr;     /* byte addresses in the shared window */
+  __device__ __forceinline__ float4 node(int i, int k) const { return lds128(node_addr + ((uint32_t)i << 6) + ((uint32_t)k << 4)); }
+  __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return lds128(tri_addr + s * 48u + ((uint32_t)k << 4)); }
+  __device__ __forceinline__ void node_z(int i, uint32_t right, float *z0, float *z1) const
+  {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(*z0), "=f"(*z1) : "r"(node_addr + ((uint32_t)i << 6) + 32u + (right << 3)));
+  }
+  __device__ __forceinline__ void node_refs(int i, int *rl, int *rr) const
+  {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(*rl), "=r"(*rr) : "r"(node_addr + ((uint32_t)i << 6) + 48u));
+  }
+  __device__ __forceinline__ void select_octant(uint32_t oct, uint32_t stride)
+  {
+    node_addr += oct * stride * 16u;
+    asm volatile("" : "+r"(node_addr));   /* keep it in a register: do not recompute per node */
+  }
+};
+
+/* leaf slot -> triangle id, from shared memory */
+struct HrtSharedGid {
+  uint32_t addr;
+  __device__ __forceinline__ uint32_t operator[](uint32_t s) const { return lds32(addr + 4u * s); }
+};
+
+/* copies nodes, triangle records and ids into shared memory; returns the
+ * first free float4 slot after them */
+__device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
+{
+  const uint32_t nn = sc.num_nodes * 4u * sc.octants, nt = sc.num_tris * 3u;
+  for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.nodes[i];
+  for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) hrt_smem4[nn + i] = sc.tris[i];
+  uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
+  for (uint32_t i = threadIdx.x; i < sc.num_tris; i += blockDim.x) gid[i] = sc.tri_gid[i];
+  return nn + nt + (sc.num_tris + 3u) / 4u;
+}
+
+/* Eight node copies (one per ray-direction octant, planes pre-ordered: no
+ * per-axis min/max in the slab test) whenever they fit the budget -- shared
+ * memory for small scenes, HBM (HRT_OCTANT_BYTES_MAX, default 4 GB) otherwise. */
+static uint32_t octant_copies(uint32_t num_nodes)
+{
+  size_t lim = (size_t)4 << 30;
+  if (const char *e = getenv("HRT_OCTANT_BYTES_MAX")) lim = (size_t)atoll(e);
+  return (size_t)num_nodes * 64 * 8 <= lim ? 8u : 1u;
+}
+
+static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris, uint32_t octants = 8)
+{ return (size_t)num_nodes * 64 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
+
+template <bool SMEM, bool BRUTE, class Cnt>
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, HrtChain chain = HrtChain{0u, 0u})
+{
+  if (SMEM) {
+    HrtSharedMem m;
+    m.node_addr = smem_base_addr();
+    m.tri_addr = m.node_addr + sc.num_nodes * 512u;         /* 8 octant copies of the nodes first */
+    HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
+    if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
+    return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
+  } else {
+    HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
+    if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
+    if (sc.octants == 8) return hrt_closest_hit<true>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
+    return hrt_closest_hit<false>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, 0u, chain);
+  }
+}
+
+/* the chain of node boxes that contain `o` (hrt_origin_chain), on the plain node copy */
+template <bool SMEM>
+__device__ __forceinline__ HrtChain origin_chain(const SceneDev &sc, V3 o)
+{
+  if (sc.no_chain) return HrtChain{0u, 0u};
+  if (SMEM) {
+    HrtSharedMem m;
+    m.node_addr = smem_base_addr(); m.tri_addr = 0;
+    return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
+  }
+  HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
+  return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
+}
+
+template <bool COUNT> struct CntSel { typedef HrtNoCount type; };
+template <> struct CntSel<true> { typedef HrtCount type; };
+__device__ __forceinline__ void cnt_init(HrtNoCount &) {}
+__device__ __forceinline__ void cnt_init(HrtCount &c) { for (int k = 0; k < 5; ++k) c.c[k] = 0; }
+__device__ __forceinline__ void cnt_flush(const HrtNoCount &, unsigned long long *) {}
+__device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long *dst)
+{ for (int k = 0; k < 5; ++k) if (c.c[k]) atomicAdd(&dst[k], (unsigned long long)c.c[k]); }
+
+template <bool SMEM>
+__device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
+{
+  const float4 q2 = SMEM ? hrt_smem4[sc.num_nodes * 32u + 3u * slot + 2u] : __ldg(&sc.tris[3 * slot + 2]);
+  return v3(q2.y, q2.z, q2.w);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
+{
+  if (SMEM) return ((const uint32_t *)(hrt_smem4 + sc.num_nodes * 32u + sc.num_tris * 3u))[slot];
+  return sc.tri_gid[slot];
+}
+
+__device__ __forceinline__ V3 ld3(const float *p, uint32_t i) { return v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+
+/* ------------------------------------------------------------ run kernels */
+
+/* Sort key that puts similar launch directions next to each other: 16+16 bit
+ * Morton code of the octahedral map of the direction.  Used only to ORDER the
+ * work (coherent warps); it has no influence on any result. */
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+  v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+__device__ __forceinline__ uint32_t dir_key(V3 d)
+{
+  const float inv = 1.f / fmaxf(fabsf(d.x) + fabsf(d.y) + fabsf(d.z), 1e-30f);
+  float u = d.x * inv, v = d.y * inv;
+  if (d.z < 0.f) {
+    const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f);
+    const float vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
+    u = uu; v = vv;
+  }
+  const uint32_t iu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 65535.f, 0.f), 65535.f);
+  const uint32_t iv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 65535.f, 0.f), 65535.f);
+  return (spread16(iu) << 1) | spread16(iv);
+}
+
+/* Order key of a hit: 30-bit Morton code of the reflected ray's origin.  The
+ * next queue is sorted by it, so the 32 hits a warp of k_scatter works on are
+ * neighbours in space -- their shadow rays to one receiver are nearly the same
+ * ray.  Small scenes: a 1024^3 grid over the vertex bounds.  Scenes wider than
+ * 256 m (a uniform cell would be metres wide): x and y on a logarithmic scale
+ * around the transmitter, 2.5 cm cells next to it, ~2 m at 100 m -- hit density
+ * falls with the square of that distance, so cells keep similar populations.
+ * Order only, never results. */
+__device__ __forceinline__ uint32_t hit_key(const SceneDev &sc, V3 o, V3 tx)
+{
+  float fx, fy;
+  if (sc.key_log) {
+    const float dx = o.x - tx.x, dy = o.y - tx.y;
+    fx = 512.f + copysignf(__log2f(1.f + fabsf(dx) * 20.f) * sc.key_log, dx);
+    fy = 512.f + copysignf(__log2f(1.f + fabsf(dy) * 20.f) * sc.key_log, dy);
+  } else {
+    fx = (o.x - sc.key_lo[0]) * sc.key_scale[0];
+    fy = (o.y - sc.key_lo[1]) * sc.key_scale[1];
+  }
+  const uint32_t x = (uint32_t)fminf(fmaxf(fx, 0.f), 1023.f);
+  const uint32_t y = (uint32_t)fminf(fmaxf(fy, 0.f), 1023.f);
+  const uint32_t z = (uint32_t)fminf(fmaxf((o.z - sc.key_lo[2]) * sc.key_scale[2], 0.f), 1023.f);
+  return (hrt_expand10(x) << 2) | (hrt_expand10(y) << 1) | hrt_expand10(z);
+}
+
+__global__ void k_dirkeys(RunDev rd)
+{
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
+    rd.dkey[l] = dir_key(ld3(rd.dirs, l)); rd.perm[l] = l;
+  }
+}
+
+/* launch directions of the chunk (reference :443-451) + list of the ones the
+ * host must recompute (see hrt_launch_dir) */
+__global__ void k_raygen(RunDev rd)
+{
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
+    bool amb = false;
+    const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+    const V3 d = hrt_launch_dir(path, rd.P, &amb);
+    rd.dirs[3 * l] = d.x; rd.dirs[3 * l + 1] = d.y; rd.dirs[3 * l + 2] = d.z;
+    rd.dkey[l] = dir_key(d); rd.perm[l] = l;
+    if (amb) {
+      const uint32_t k = atomicAdd(rd.amb_count, 1u);
+      if (k < HRT_AMB_CAP) rd.amb_list[k] = l;
+    }
+  }
+}
+
+/* per-ray state (reference :453-472) and output initialisation: gains/tau
+ * zero, freq_shift = Doppler base value with the reference's index algebra
+ * (:494-508) */
+__global__ void k_init(RunDev rd)
+{
+  const uint32_t T = rd.T, B = rd.B, R = rd.R;
+  const size_t np = rd.n_alloc;
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < rd.n; l += gridDim.x * blockDim.x) {
+    const V3 d = ld3(rd.dirs, l);
+    /* record number l of every TX: the path that is l-th in direction order */
+    const uint32_t pl = rd.perm2[l];
+    const V3 pd = ld3(rd.dirs, pl);
+    for (uint32_t t = 0; t < T; ++t) {
+      const size_t i = t * np + l;
+      const V3 o = ld3(rd.tx_pos, t);
+      float4 *rc = rd.rec[0] + 4 * i;
+      rc[0] = make_float4(o.x, o.y, o.z, pd.x);
+      rc[1] = make_float4(pd.y, pd.z, 1.f, 0.f);
+      rc[2] = make_float4(1.f, 0.f, 0.f, 0.f);
+      rc[3] = make_float4(0.f, __uint_as_float(pl), 0.f, 0.f);
+      rd.queue[0][i] = l;
+      if (rd.flags & HRT_FLAG_RAYSINFO) {
+        float2 *ry = (float2 *)(rd.rays + i);
+        ry[0] = make_float2(o.x, o.y); ry[1] = make_float2(o.z, d.x); ry[2] = make_float2(d.y, d.z);
+        rd.dead_at[i] = 255;
+      }
+      if (rd.flags & HRT_FLAG_TRACE)
+        for (uint32_t b = 0; b < B; ++b) {
+          rd.tr_hit[(t * B + b) * np + l] = HRT_IDLE;
+          rd.tr_t[(t * B + b) * np + l] = -1.f;
+        }
+    }
+    if (rd.flags & HRT_FLAG_DENSE) {
+      for (uint32_t t = 0; t < T; ++t)
+        for (uint32_t b = 0; b < B; ++b) {
+          /* which TX's Doppler base the reference leaves in row (t, b) */
+          const uint32_t j = (t * B + b) % T;
+          const uint32_t src = (j % B == 0) ? j / B : t;
+          float base = v3_dot(ld3(rd.tx_vel, src), d);
+          base = HRT_MUL(base, rd.k.dop_k);
+          for (uint32_t r = 0; r < R; ++r) {
+            const size_t s = ((size_t)(r * T + t) * B + b) * np + l;
+            rd.out_f[0][s] = 0.f; rd.out_f[1][s] = 0.f; rd.out_f[2][s] = 0.f; rd.out_f[3][s] = 0.f;
+            rd.out_f[4][s] = 0.f; rd.out_f[5][s] = base;
+            rd.out_dir[3 * s] = 0.f; rd.out_dir[3 * s + 1] = 0.f; rd.out_dir[3 * s + 2] = 0.f;
+            if (rd.flags & HRT_FLAG_TRACE) rd.tr_state[s] = 0;
+          }
+        }
+    } else if (rd.flags & HRT_FLAG_TRACE) {
+      for (uint32_t t = 0; t < T; ++t)
+        for (uint32_t b = 0; b < B; ++b)
+          for (uint32_t r = 0; r < R; ++r) rd.tr_state[((size_t)(r * T + t) * B + b) * np + l] = 0;
+    }
+  }
+  if (blockIdx.x == 0)
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) rd.qcount[t] = rd.n;
+}
+
+/* line of sight (reference :520-577), one thread per (rx, tx) pair */
+template <bool SMEM, bool BRUTE>
+__global__ void k_los(RunDev rd, SceneDev sc, HrtLosOut *out)
+{
+  if (SMEM) { stage_scene(sc); __syncthreads(); }
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rd.R * rd.T) return;
+  const uint32_t r = k / rd.T, t = k % rd.T;
+  const V3 o = ld3(rd.tx_pos, t);
+  const V3 d = v3_sub(ld3(rd.rx_pos, r), o);                                   /* :528 */
+  HrtLosOut res;
+  if (v3_dot(d, d) < HRT_EPS) {                                                /* :531 */
+    res.dir_rx = v3(1.f, 0.f, 0.f); res.dir_tx = v3(-1.f, 0.f, 0.f);
+    res.a = 1.f; res.tau = 0.f; res.freq = 0.f; res.state = 2;
+  } else {
+    HrtNoCount nc;
+    const HrtHit h = query<SMEM, BRUTE>(sc, o, d, nc);
+    res = hrt_los_finish(d, h.gid != HRT_NONE, h.t, ld3(rd.tx_vel, 0), ld3(rd.rx_vel, 0),
+                         rd.k, rd.k.dop_k);
+  }
+  out[k] = res;
+}
+
+/* One bounce depth of the wavefront (reference :599-664): a thread per active
+ * ray of TX blockIdx.y.  Survivors are appended to the next queue with one
+ * atomicAdd per warp (ballot + prefix popcount). */
+template <bool SMEM, bool BRUTE, bool COUNT>
+__global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
+k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
+{
+  if (SMEM) { stage_scene(sc); __syncthreads(); }
+  typename CntSel<COUNT>::type wc; cnt_init(wc);
+  const uint32_t T = rd.T, B = rd.B;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t tt = 0; tt < T; ++tt) {          /* all transmitters, own one first */
+  const uint32_t t = (blockIdx.y + tt) % T;
+  const size_t np = rd.n_alloc;
+  const uint32_t cnt = rd.qcount[depth * T + t];
+  const uint32_t *qin = rd.queue[depth & 1] + t * np;
+  uint32_t *qout = rd.queue[(depth + 1) & 1] + t * np;
+  const float4 *rin = rd.rec[depth & 1] + 4 * t * np;
+  float4 *rout = rd.rec[(depth + 1) & 1] + 4 * t * np;
+  const V3 txp = ld3(rd.tx_pos, t);
+  const bool rows = (rd.flags & HRT_FLAG_RAYSINFO) != 0;
+  Ray *rays_out = rows ? rd.rays + (size_t)(depth + 1) * T * np + t * np : nullptr;
+  unsigned long long hash_acc = 0, tbits_acc = 0;
+
+  /* warps pull batches of 128 queue entries from a shared cursor (dynamic load
+   * balance: ray cost varies a lot with direction) */
+  uint32_t *cursor = rd.qcount + (B + 1) * T + depth * T + t;
+  for (;;) {
+    uint32_t batch = 0;
+    if (lane == 0) batch = atomicAdd(cursor, 128u);
+    batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+    if (batch >= cnt) break;
+  for (uint32_t i = batch + lane; i < batch + 128u && (i - lane) < cnt; i += 32u) {
+    const bool valid = i < cnt;
+    bool hit = false;
+    uint32_t l = 0, okey = 0, hslot = 0;
+    float theta = 0.f;
+    HrtRayState s;
+    if (valid) {
+      const float4 *rc = rin + 4 * (size_t)qin[i];
+      const float4 r0 = __ldg(rc), r1 = __ldg(rc + 1), r2 = __ldg(rc + 2), r3 = __ldg(rc + 3);
+      l = __float_as_uint(r3.y);
+      s.o = v3(r0.x, r0.y, r0.z); s.d = v3(r0.w, r1.x, r1.y);
+      s.te_r = r1.z; s.te_i = r1.w; s.tm_r = r2.x; s.tm_i = r2.y; s.tau = r2.z;
+      const HrtHit h = query<SMEM, BRUTE>(sc, s.o, s.d, wc);                  /* :615 */
+      hit = h.gid != HRT_NONE;
+      const size_t si = t * np + l;
+      if (rd.flags & HRT_FLAG_TRACE) {
+        rd.tr_hit[(t * B + depth) * np + l] = h.gid;
+        rd.tr_t[(t * B + depth) * np + l] = hit ? h.t : -1.f;
+      }
+      if (!hit) {
+        if (rows) rd.dead_at[si] = (uint8_t)depth;                             /* :616-620 */
+      } else {
+        const V3 n = tri_normal<SMEM>(sc, h.slot);
+        theta = hrt_theta_fold(n, s.d);                                        /* :281-283 */
+        const uint32_t mat = sc.mesh_mat[sc.mesh_of[h.gid]];                   /* :622 */
+        hrt_bounce_update(s, mats.m[mat], rd.k, h.t, n, theta);                /* :623-659 */
+        if (rows) {
+          float2 *wp = (float2 *)(rays_out + l);
+          wp[0] = make_float2(s.o.x, s.o.y); wp[1] = make_float2(s.o.z, s.d.x);
+          wp[2] = make_float2(s.d.y, s.d.z);
+        }
+        hslot = h.slot;
+        okey = hit_key(sc, s.o, txp);
+        if (rd.flags & HRT_FLAG_SUMMARY) {
+          const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+          hash_acc += hrt_mix64((path << 32) | h.gid);
+          tbits_acc += (unsigned long long)__float_as_uint(h.t);
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&rd.qcount[(depth + 1) * T + t], (uint32_t)__popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (hit) {
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+        float4 *wc4 = rout + 4 * (size_t)pos;
+        wc4[0] = make_float4(s.o.x, s.o.y, s.o.z, s.d.x);
+        wc4[1] = make_float4(s.d.y, s.d.z, s.te_r, s.te_i);
+        wc4[2] = make_float4(s.tm_r, s.tm_i, s.tau, theta);
+        wc4[3] = make_float4(__uint_as_float(hslot), __uint_as_float(l), 0.f, 0.f);
+        qout[pos] = pos;
+        rd.qkey[t * np + pos] = okey;
+      }
+    }
+  }
+  }
+  if (rd.flags & HRT_FLAG_SUMMARY) {
+    for (int o = 16; o; o >>= 1) {
+      hash_acc += __shfl_xor_sync(0xFFFFFFFFu, hash_acc, o);
+      tbits_acc += __shfl_xor_sync(0xFFFFFFFFu, tbits_acc, o);
+    }
+    if (lane == 0 && (hash_acc | tbits_acc)) {
+      atomicAdd((unsigned long long *)&rd.bounce[t * B + depth].hit_hash, hash_acc);
+      atomicAdd((unsigned long long *)&rd.bounce[t * B + depth].t_bits, tbits_acc);
+    }
+  }
+  }   /* transmitters */
+  cnt_flush(wc, rd.counters);
+}
+
+/* Shared-memory reduction table of k_scatter: one record per receiver. */
+struct PairAcc {
+  unsigned long long hash, tau_bits;
+  double p_te, p_tm;
+  unsigned n_valid, n_occl;
+};
+
+/* Per-(hit, rx) scatter step (reference :670-723) for the rays that hit at
+ * `depth` (they are exactly the next queue).
+ *   WARP = true : one warp per hit, lanes across receivers in tiles of 32; the
+ *                 incidence-angle carry-over is an
+ *                 inclusive "last lane that hit" scan over ballot bits, carried
+ *                 from tile to tile.
+ *   WARP = false: one thread per hit, receivers in sequence (small num_rx). */
+template <bool SMEM, bool BRUTE, bool WARP, bool COUNT>
+__global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
+k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
+{
+  typename CntSel<COUNT>::type wc; cnt_init(wc);
+  uint32_t used4 = 0;
+  if (SMEM) used4 = stage_scene(sc);
+  const uint32_t R = rd.R, T = rd.T, B = rd.B;
+  /* receivers (and, in summary mode, the reduction table) in shared memory */
+  float *s_rx = (float *)(hrt_smem4 + used4);
+  PairAcc *s_acc = (PairAcc *)(hrt_smem4 + used4 + (smem_rx_ok ? (3u * R + 3u) / 4u : 0u));
+  const bool summary = (rd.flags & HRT_FLAG_SUMMARY) != 0;
+  if (smem_rx_ok) {
+    for (uint32_t i = threadIdx.x; i < 3u * R; i += blockDim.x) s_rx[i] = rd.rx_pos[i];
+    if (summary)
+      for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) {
+        PairAcc z; z.hash = 0; z.tau_bits = 0; z.p_te = 0.0; z.p_tm = 0.0; z.n_valid = 0; z.n_occl = 0;
+        s_acc[i] = z;
+      }
+  }
+  if (SMEM || smem_rx_ok) __syncthreads();
+  const float *rxp = smem_rx_ok ? s_rx : rd.rx_pos;
+
+  /* every block works through all transmitters, starting with "its own"
+   * (blockIdx.y): when one TX runs out of hits its blocks help with the others */
+  for (uint32_t tt = 0; tt < T; ++tt) {
+  const uint32_t t = (blockIdx.y + tt) % T;
+  const size_t np = rd.n_alloc;
+  const uint32_t cnt = rd.qcount[(depth + 1) * T + t];
+  const uint32_t *q = rd.queue[(depth + 1) & 1] + t * np;
+  const float4 *recs = rd.rec[(depth + 1) & 1] + 4 * t * np;
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool dense = (rd.flags & HRT_FLAG_DENSE) != 0, trace = (rd.flags & HRT_FLAG_TRACE) != 0;
+
+  /* work distribution: warps pull batches from a shared cursor -- 32 hits (one
+   * per lane) in thread-per-hit mode, 8 hits in warp-per-hit mode */
+  uint32_t *cursor = rd.qcount + (2 * B + 1) * T + depth * T + t;
+  const uint32_t grab = WARP ? 8u : 32u;
+  for (;;) {
+    uint32_t batch = 0;
+    if (lane == 0) batch = atomicAdd(cursor, grab);
+    batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+    if (batch >= cnt) break;
+  for (uint32_t hi = WARP ? batch : batch + lane; WARP ? (hi < batch + grab && hi < cnt) : hi == batch + lane; hi += WARP ? 1u : 64u) {
+    const bool valid = WARP || hi < cnt;
+    const float4 *rc = recs + 4 * (size_t)(valid ? q[hi] : q[0]);
+    const float4 r0 = __ldg(rc), r1 = __ldg(rc + 1), r2 = __ldg(rc + 2), r3 = __ldg(rc + 3);
+    HrtRayState s;
+    s.o = v3(r0.x, r0.y, r0.z); s.d = v3(r0.w, r1.x, r1.y);
+    s.te_r = r1.z; s.te_i = r1.w; s.tm_r = r2.x; s.tm_i = r2.y; s.tau = r2.z;
+    const uint32_t slot = __float_as_uint(r3.x), l = __float_as_uint(r3.y);
+    const V3 n = tri_normal<SMEM>(sc, slot);
+    const uint32_t gid = tri_gid_of<SMEM>(sc, slot);
+    const uint32_t mesh = sc.mesh_of[gid];
+    const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
+    const V3 mv = ld3(sc.mesh_vel, mesh);
+    float theta_carry = r2.w;
+    const HrtChain chain = BRUTE ? HrtChain{0u, 0u} : origin_chain<SMEM>(sc, s.o);
+    const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+    const uint64_t hkey = hrt_mix64((path << 32) | gid);
+
+    const uint32_t step = WARP ? 32u : 1u;
+    for (uint32_t r0 = 0; r0 < R; r0 += step) {
+      const uint32_t r = WARP ? r0 + lane : r0;
+      const bool act = WARP ? r < R : valid;
+      float dist = 0.f, th_sh = 0.f;
+      V3 sd = v3(0.f, 0.f, 1.f);
+      HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
+      if (act) {
+        sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
+        h = query<SMEM, BRUTE>(sc, s.o, sd, wc, chain);                       /* :682 */
+        if (h.gid != HRT_NONE) th_sh = hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), sd);
+      }
+      const bool shit = act && h.gid != HRT_NONE;
+      float theta_i;
+      if (WARP) {
+        /* theta handed to scat_coefs: the fold angle of the most recent shadow
+         * query (this receiver included) that hit anything, else the primary
+         * incidence angle (appendix A-4) */
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, shit);
+        const unsigned below = m & (0xFFFFFFFFu >> (31u - lane));
+        const int src = below ? 31 - __clz((int)below) : 0;
+        const float from = __shfl_sync(0xFFFFFFFFu, th_sh, src);
+        theta_i = below ? from : theta_carry;
+        if (m) theta_carry = __shfl_sync(0xFFFFFFFFu, th_sh, 31 - __clz((int)m));
+      } else {
+        if (shit) theta_carry = th_sh;
+        theta_i = theta_carry;
+      }
+      const bool occ = shit && h.t <= 1.f;                                     /* :683 */
+      const bool ok = act && !occ;
+      HrtScatterOut p;
+      p.te_r = p.te_i = p.tm_r = p.tm_i = p.tau = p.dfreq = 0.f; p.dir_rx = v3(0.f, 0.f, 0.f);
+      if (ok) p = hrt_scatter_path_fast(s, mat, rd.k, n, mv, sd, dist, theta_i); /* :694-721 */
+      if (act && (dense || trace)) {
+        const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;          /* :674 */
+        if (dense) {
+          rd.out_f[0][so] = p.te_r; rd.out_f[1][so] = p.te_i;                  /* zeros when occluded, :685-689 */
+          rd.out_f[2][so] = p.tm_r; rd.out_f[3][so] = p.tm_i;
+          rd.out_f[4][so] = p.tau;
+          if (ok) {
+            rd.out_f[5][so] = HRT_SUB(rd.out_f[5][so], p.dfreq);               /* :722 */
+            rd.out_dir[3 * so] = p.dir_rx.x; rd.out_dir[3 * so + 1] = p.dir_rx.y;
+            rd.out_dir[3 * so + 2] = p.dir_rx.z;
+          }
+        }
+        if (trace) rd.tr_state[so] = occ ? 2 : 1;
+      }
+      if (ok && rd.cir) {
+        /* impulse response: a * delta(t - tau) into its delay bin, one 16-byte
+         * reduction per path (red.global.add.v4.f32) */
+        const float fb = HRT_MUL(HRT_SUB(p.tau, rd.cir_tau0), rd.cir_inv_dt);
+        if (fb >= 0.f && fb < (float)rd.cir_bins) {
+          float *dst = rd.cir + ((size_t)(r * T + t) * rd.cir_bins + (uint32_t)fb) * 4u;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                       :: "l"(dst), "f"(p.te_r), "f"(p.te_i), "f"(p.tm_r), "f"(p.tm_i) : "memory");
+        } else {
+          atomicAdd(&rd.counters[15], 1ull);
+        }
+      }
+      if (summary) {
+        const double pte = (double)p.te_r * p.te_r + (double)p.te_i * p.te_i;
+        const double ptm = (double)p.tm_r * p.tm_r + (double)p.tm_i * p.tm_i;
+        if (WARP) {
+          if (occ) {
+            if (smem_rx_ok) atomicAdd(&s_acc[r].n_occl, 1u);
+            else atomicAdd((unsigned long long *)&rd.pair[(r * T + t) * B + depth].n_occluded, 1ull);
+          } else if (ok) {
+            if (smem_rx_ok) {
+              atomicAdd(&s_acc[r].n_valid, 1u);
+              atomicAdd(&s_acc[r].hash, (unsigned long long)hkey);
+              atomicAdd(&s_acc[r].tau_bits, (unsigned long long)__float_as_uint(p.tau));
+              atomicAdd(&s_acc[r].p_te, pte);
+              atomicAdd(&s_acc[r].p_tm, ptm);
+            } else {
+              HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+              atomicAdd((unsigned long long *)&ps->n_valid, 1ull);
+              atomicAdd((unsigned long long *)&ps->hit_hash, (unsigned long long)hkey);
+              atomicAdd((unsigned long long *)&ps->tau_bits, (unsigned long long)__float_as_uint(p.tau));
+              atomicAdd(&ps->power_te, pte);
+              atomicAdd(&ps->power_tm, ptm);
+            }
+          }
+        } else {
+          /* all lanes look at the same receiver: reduce over the warp, one
+           * update per warp */
+          const unsigned m_ok = __ballot_sync(0xFFFFFFFFu, ok), m_occ = __ballot_sync(0xFFFFFFFFu, occ);
+          unsigned long long hsum = 0ull, tsum = 0ull;
+          double e = ok ? pte : 0.0, m2 = ok ? ptm : 0.0;
+          if (m_ok) {
+            /* integer sums: one REDUX per 16-bit digit (32 x 65535 fits 32 bits) */
+            const unsigned long long hk = ok ? hkey : 0ull;
+            const unsigned tb = ok ? __float_as_uint(p.tau) : 0u;
+            hsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk & 0xFFFFu))
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 16) & 0xFFFFu)) << 16)
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 32) & 0xFFFFu)) << 32)
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk >> 48)) << 48);
+            tsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb & 0xFFFFu)
+                 + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb >> 16) << 16);
+            for (int o = 16; o; o >>= 1) {
+              e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+              m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+            }
+          }
+          if (lane == 0 && (m_ok | m_occ)) {
+            if (smem_rx_ok) {
+              if (m_occ) atomicAdd(&s_acc[r].n_occl, (unsigned)__popc(m_occ));
+              if (m_ok) {
+                atomicAdd(&s_acc[r].n_valid, (unsigned)__popc(m_ok));
+                atomicAdd(&s_acc[r].hash, hsum);
+                atomicAdd(&s_acc[r].tau_bits, tsum);
+                atomicAdd(&s_acc[r].p_te, e);
+                atomicAdd(&s_acc[r].p_tm, m2);
+              }
+            } else {
+              HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+              if (m_occ) atomicAdd((unsigned long long *)&ps->n_occluded, (unsigned long long)__popc(m_occ));
+              if (m_ok) {
+                atomicAdd((unsigned long long *)&ps->n_valid, (unsigned long long)__popc(m_ok));
+                atomicAdd((unsigned long long *)&ps->hit_hash, hsum);
+                atomicAdd((unsigned long long *)&ps->tau_bits, tsum);
+                atomicAdd(&ps->power_te, e);
+                atomicAdd(&ps->power_tm, m2);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  }
+  if (summary && smem_rx_ok) {
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
+      const PairAcc a = s_acc[r];
+      if (a.n_valid | a.n_occl) {
+        HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+        atomicAdd((unsigned long long *)&ps->n_valid, (unsigned long long)a.n_valid);
+        atomicAdd((unsigned long long *)&ps->n_occluded, (unsigned long long)a.n_occl);
+        atomicAdd((unsigned long long *)&ps->hit_hash, a.hash);
+        atomicAdd((unsigned long long *)&ps->tau_bits, a.tau_bits);
+        atomicAdd(&ps->power_te, a.p_te);
+        atomicAdd(&ps->power_tm, a.p_tm);
+        PairAcc z; z.hash = 0; z.tau_bits = 0; z.p_te = 0.0; z.p_tm = 0.0; z.n_valid = 0; z.n_occl = 0;
+        s_acc[r] = z;
+      }
+    }
+    __syncthreads();
+  }
+  }   /* transmitters */
+  cnt_flush(wc, rd.counters + 5);
+}
+
+/* adds the per-depth queue sizes of a chunk into the bounce summary */
+__global__ void k_fold_counts(RunDev rd)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rd.T * rd.B) return;
+  const uint32_t t = k / rd.B, b = k % rd.B;
+  rd.bounce[k].n_traced += rd.qcount[b * rd.T + t];
+  rd.bounce[k].n_hit += rd.qcount[(b + 1) * rd.T + t];
+}
+
+__global__ void k_add_u64(unsigned long long *dst, const unsigned long long *src, size_t n, const unsigned char *is_double)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is_double && is_double[i]) ((double *)dst)[i] += ((const double *)src)[i];
+  else dst[i] += src[i];
+}
+
+/* batch closest hit for hrt_closest_hits() */
+template <bool SMEM, bool BRUTE>
+__global__ void k_closest(SceneDev sc, const Ray *rays, uint32_t n, uint32_t *tri, float *t, float *theta)
+{
+  if (SMEM) { stage_scene(sc); __syncthreads(); }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float2 *rp = (const float2 *)(rays + i);
+    const float2 a = rp[0], b = rp[1], c = rp[2];
+    const V3 o = v3(a.x, a.y, b.x), d = v3(b.y, c.x, c.y);
+    HrtNoCount nc;
+    const HrtHit h = query<SMEM, BRUTE>(sc, o, d, nc);
+    const bool hit = h.gid != HRT_NONE;
+    tri[i] = h.gid; t[i] = hit ? h.t : -1.f;
+    theta[i] = hit ? hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), d) : 0.f;
+  }
+}
+
+/* fp32 issue-rate probe: 8 independent dependency chains per thread, either
+ * FMUL+FADD pairs (separately rounded, like the exact intersection code) or
+ * FFMA.  2 flops per chain step in both cases. */
+template <bool FMA>
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b)
+{
+  float x[8];
+  for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (FMA) x[k] = __fmaf_rn(x[k], a, b);
+      else     x[k] = __fadd_rn(__fmul_rn(x[k], a), b);
+    }
+  }
+  float s = 0.f;
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == 123.456f) out[0] = s;   /* keep the chains alive */
+}
+
