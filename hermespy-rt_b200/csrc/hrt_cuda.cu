@@ -1101,8 +1101,20 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
        * for T > 1 the first bits of TX 1 in the last byte (appendix A-9). */
       uint8_t *A = p->rays_scat->rays_active;
       const size_t rowb = P / 8 + 1;
-      for (uint64_t L = 0; L < rd.n; ++L) {
+      uint64_t L = 0;
+      while (L < rd.n) {
         const uint64_t g = hrt_gpath(l0 + L, rank, world, blk);
+        /* whole bytes: 8 consecutive paths of one shard block (blocks are multiples of 32) */
+        const bool whole = (g & 7) == 0 && L + 8 <= rd.n && (world <= 1 || (l0 + L) % blk + 8 <= blk);
+        if (whole) {
+          for (size_t b = 0; b < B; ++b) {
+            uint8_t byte = 0;
+            for (int i = 0; i < 8; ++i) byte |= (uint8_t)((h_dead[L + i] > b) << i);
+            for (size_t t = 0; t < T; ++t) A[(t * B + b + 1) * rowb + (g >> 3)] = byte;
+          }
+          L += 8;
+          continue;
+        }
         const uint8_t dead0 = h_dead[L];
         for (size_t t = 0; t < T; ++t)
           for (size_t b = 0; b < B; ++b) {
@@ -1110,6 +1122,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
             const uint8_t bit = (uint8_t)(1u << (g & 7));
             if (dead0 > b) row[g >> 3] |= bit; else row[g >> 3] &= (uint8_t)~bit;
           }
+        ++L;
       }
     }
   }
