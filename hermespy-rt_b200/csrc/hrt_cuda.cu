@@ -859,7 +859,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
    * thanks to the direction sort) whenever there are enough hits to fill the
    * machine; a warp per hit (lanes over receivers) for few rays x many RX */
-  bool warp_mode = R >= 8 && (uint64_t)T * (P < chunk ? P : chunk) < (uint64_t)sms * 4096;   /* crossover measured with scripts/mode_sweep.py */
+  bool warp_mode = R >= 8 && (uint64_t)T * (P < chunk ? P : chunk) < (uint64_t)sms * 8192;   /* crossover measured with scripts/mode_sweep.py */
   if (const char *m = getenv("HRT_SCATTER_MODE")) warp_mode = (m[0] == 'w') && R >= 2;
   const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
@@ -881,7 +881,10 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     CK(cudaMemsetAsync(ctx->d_cir, 0, ncir * sizeof(float), st));
     rd.cir = ctx->d_cir; rd.cir_bins = p->cir_bins; rd.cir_tau0 = p->cir_tau0_s; rd.cir_inv_dt = 1.f / p->cir_dt_s;
   }
-  const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT");
+  /* hit order matters for the thread-per-hit mapping (lanes = neighbouring hits);
+   * with a warp per hit the lanes share their origin anyway, and small runs are
+   * better off without the per-depth count read-back the sort needs */
+  const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT") && (!warp_mode || getenv("HRT_HIT_SORT_ALWAYS"));
   if (sort_hits) {
     /* the chunk's direction sort below needs less: same pair types, 32 key bits */
     size_t tb = 0;
