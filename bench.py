@@ -118,9 +118,15 @@ def run_reference_sample(paths_per_tx, parallel):
     if not os.path.exists(exe):
         return None
     cmds = []
+    # all host cores: every TX's rays go to `split` processes (the reference has no
+    # first-ray argument, so each process traces its own Fibonacci lattice of
+    # paths_per_tx / split rays: same scene, TX, RX and bounce statistics)
+    split = max(1, min((os.cpu_count() or 1) // NUM_TX, 32)) if parallel else 1
+    split = int(os.environ.get("HRT_REF_SPLIT", split))
     for t in range(NUM_TX):
-        cmds.append([exe, SCENE, str(F_GHZ), str(paths_per_tx), str(BOUNCES), str(NUM_RX), "1"]
-                    + [repr(float(v)) for v in rx.reshape(-1)] + [repr(float(v)) for v in tx[t]])
+        for _ in range(split):
+            cmds.append([exe, SCENE, str(F_GHZ), str(max(paths_per_tx // split, 1)), str(BOUNCES), str(NUM_RX), "1"]
+                        + [repr(float(v)) for v in rx.reshape(-1)] + [repr(float(v)) for v in tx[t]])
     t0 = time.perf_counter()
     outs = []
     if parallel:
@@ -133,7 +139,7 @@ def run_reference_sample(paths_per_tx, parallel):
     rb = sum(r["ray_bounces"] for r in recs)
     cpu_s = sum(r["seconds"] for r in recs)
     if parallel:
-        return rb, max(r["seconds"] for r in recs), min(NUM_TX, os.cpu_count() or 1), wall
+        return rb, max(r["seconds"] for r in recs), min(len(cmds), os.cpu_count() or 1), wall
     return rb, cpu_s, 1, wall
 
 
@@ -141,7 +147,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    P = int(os.environ.get("HRT_REF_PATHS", "2500"))
+    P = int(os.environ.get("HRT_REF_PATHS", str(2500 * max(1, min((os.cpu_count() or 1) // NUM_TX, 32)))))
     for _ in range(args.warmup):
         run_reference_sample(max(P // 10, 100), True)
     tot_rb, tot_s = 0, 0.0
@@ -153,8 +159,8 @@ def main_reference(args):
         tot_rb += r[0]; tot_s += r[1]
         cores = r[2]
     v = tot_rb / tot_s
-    sample = (f"canyon 4 TX / 64 RX / 5 bounces, {P} rays per TX per step ({NUM_TX} single-TX "
-              f"processes of the unmodified reference in parallel)")
+    sample = (f"canyon 4 TX / 64 RX / 5 bounces, {P} rays per TX per step, {cores} single-TX processes of the "
+              f"unmodified (single-threaded) reference in parallel, one per host core, each tracing its share of a TX's rays")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "ray-bounces/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
