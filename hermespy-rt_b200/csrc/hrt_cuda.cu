@@ -34,6 +34,7 @@ extern "C" void hrt_host_launch_dir(uint64_t path, uint64_t num_paths, float out
 static_assert(sizeof(HrtMaterialDerived) == sizeof(HrtMaterial), "material ABI");
 static_assert(sizeof(Ray) == 24 && sizeof(Vec3) == 12, "reference ABI");
 static_assert(sizeof(HrtPairSummary) == 48 && sizeof(HrtBounceSummary) == 32, "summary ABI");
+static_assert(sizeof(HrtPathRecord) == 48, "path record ABI");
 
 #ifndef HRT_BLOCK
 #define HRT_BLOCK 512   /* 2 blocks of 512 threads per SM: 64 registers, ~85 KB shared memory each */
@@ -95,6 +96,8 @@ struct RunDev {
   uint32_t *amb_list, *amb_count;
   uint32_t *dkey, *dkey2, *perm, *perm2;  /* direction sort of the chunk's paths */
   unsigned long long *counters;  /* [16] instrumented build; [15] = CIR paths outside the window */
+  float4 *plist;         /* [plist_cap][3] HrtPathRecord, HRT_FLAG_PATHLIST */
+  unsigned long long plist_cap, *plist_count;
   float *cir;            /* [R][T][cir_bins][4] HRT_FLAG_CIR */
   float cir_tau0, cir_inv_dt;
   uint32_t cir_bins;
@@ -155,6 +158,7 @@ struct hrt_ctx {
   void *d_los;             /* HrtLosOut[R*T] */
   size_t cap_los;
   float *d_cir; size_t cap_cir;
+  float4 *d_plist; size_t cap_plist;
   HrtRunStats stats;
 };
 
@@ -256,6 +260,7 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   dev_free(c->d_pos);
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
   if (c->d_cir) { cudaFree(c->d_cir); c->d_cir = nullptr; }
+  if (c->d_plist) { cudaFree(c->d_plist); c->d_plist = nullptr; }
   if (c->sort_tmp) { cudaFree(c->sort_tmp); c->sort_tmp = nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
@@ -674,6 +679,14 @@ static ScatterFn scatter_fn(bool smem, bool brute, bool warp, bool count)
         { k_scatter<true, true, true, false>,    k_scatter<true, true, true, false> } } } };
   return tab[smem][brute][warp][count];
 }
+/* summary-only runs without instrumentation: the lean instantiations */
+static ScatterFn scatter_fn_lean(bool smem, bool warp)
+{
+  static const ScatterFn tab[2][2] = {
+    { k_scatter<false, false, false, false, true>, k_scatter<false, false, true, false, true> },
+    { k_scatter<true, false, false, false, true>,  k_scatter<true, false, true, false, true> } };
+  return tab[smem][warp];
+}
 
 static int sm_count(int device)
 {
@@ -796,6 +809,8 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   if ((flags & HRT_FLAG_RAYSINFO) && !p->rays_scat) flags &= ~HRT_FLAG_RAYSINFO;
   if ((flags & HRT_FLAG_SUMMARY) && (!p->pair_summary || !p->bounce_summary)) return fail(ctx, HRT_E_ARG, "SUMMARY needs both summary arrays");
   if ((flags & HRT_FLAG_HOST_DIRS) && !p->dirs) return fail(ctx, HRT_E_ARG, "HOST_DIRS needs dirs");
+  if ((flags & HRT_FLAG_PATHLIST) && (!p->paths || !p->paths_count || !p->paths_capacity || P >= (1ull << 32)))
+    return fail(ctx, HRT_E_ARG, "PATHLIST needs paths, paths_count, paths_capacity > 0 and num_paths < 2^32");
   if ((flags & HRT_FLAG_CIR) && (!p->cir || !p->cir_bins || !(p->cir_dt_s > 0.f))) return fail(ctx, HRT_E_ARG, "CIR needs cir, cir_bins > 0 and cir_dt_s > 0");
   const uint32_t world = p->shard_world ? p->shard_world : 1, rank = p->shard_rank;
   uint64_t blk = p->shard_block ? p->shard_block : (1u << 20);
@@ -863,7 +878,8 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   if (const char *m = getenv("HRT_SCATTER_MODE")) warp_mode = (m[0] == 'w') && R >= 2;
   const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
-  const ScatterFn f_scatter = scatter_fn(smem, brute, warp_mode, count);
+  const bool lean = !brute && !count && !(flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE | HRT_FLAG_CIR | HRT_FLAG_PATHLIST));
+  const ScatterFn f_scatter = lean ? scatter_fn_lean(smem, warp_mode) : scatter_fn(smem, brute, warp_mode, count);
   if (smem) {
     CK(allow_smem(f_bounce, scene_sb));
     CK(allow_smem(k_los<true, true>, scene_sb)); CK(allow_smem(k_los<true, false>, scene_sb));
@@ -871,6 +887,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   CK(allow_smem(f_scatter, scat_sb));
   CK(cudaMemsetAsync(rd.counters, 0, 16 * sizeof(unsigned long long), st));
   rd.cir = nullptr; rd.cir_bins = 0; rd.cir_tau0 = 0.f; rd.cir_inv_dt = 0.f;
+  rd.plist = nullptr; rd.plist_cap = 0; rd.plist_count = rd.counters + 14;
+  if (flags & HRT_FLAG_PATHLIST) {
+    if (ctx->cap_plist < p->paths_capacity) {
+      if (ctx->d_plist) cudaFree(ctx->d_plist);
+      ctx->d_plist = nullptr; ctx->cap_plist = 0;
+      CK(dev_alloc(&ctx->d_plist, (size_t)p->paths_capacity * 3)); ctx->cap_plist = p->paths_capacity;
+    }
+    rd.plist = ctx->d_plist; rd.plist_cap = p->paths_capacity;
+  }
   if (flags & HRT_FLAG_CIR) {
     const size_t ncir = R * T * (size_t)p->cir_bins * 4;
     if (ctx->cap_cir < ncir) {
@@ -1197,6 +1222,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     }
   }
 
+  if (flags & HRT_FLAG_PATHLIST) {
+    unsigned long long found = 0;
+    CKR(cudaMemcpyAsync(&found, rd.counters + 14, 8, cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    const unsigned long long kept = found < p->paths_capacity ? found : p->paths_capacity;
+    CKR(cudaMemcpyAsync(p->paths, ctx->d_plist, (size_t)kept * sizeof(HrtPathRecord), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    *p->paths_count = found;
+  }
   if (flags & HRT_FLAG_CIR) {
     const size_t ncir = R * T * (size_t)p->cir_bins * 4;
     float *h = (float *)malloc(ncir * sizeof(float));

@@ -405,7 +405,10 @@ struct PairAcc {
  *                 inclusive "last lane that hit" scan over ballot bits, carried
  *                 from tile to tile.
  *   WARP = false: one thread per hit, receivers in sequence (small num_rx). */
-template <bool SMEM, bool BRUTE, bool WARP, bool COUNT>
+/* LEAN: summary tables only (no dense / trace / CIR / path-list outputs) --
+ * the streaming configuration of large runs, compiled without the other
+ * output paths. */
+template <bool SMEM, bool BRUTE, bool WARP, bool COUNT, bool LEAN = false>
 __global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
 k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
 {
@@ -437,7 +440,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   const uint32_t *q = rd.queue[(depth + 1) & 1] + t * np;
   const float4 *recs = rd.rec[(depth + 1) & 1] + 4 * t * np;
   const uint32_t lane = threadIdx.x & 31u;
-  const bool dense = (rd.flags & HRT_FLAG_DENSE) != 0, trace = (rd.flags & HRT_FLAG_TRACE) != 0;
+  const bool dense = !LEAN && (rd.flags & HRT_FLAG_DENSE) != 0, trace = !LEAN && (rd.flags & HRT_FLAG_TRACE) != 0;
 
   /* work distribution: warps pull batches from a shared cursor -- 32 hits (one
    * per lane) in thread-per-hit mode, 8 hits in warp-per-hit mode */
@@ -513,7 +516,28 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         }
         if (trace) rd.tr_state[so] = occ ? 2 : 1;
       }
-      if (ok && rd.cir) {
+      if (!LEAN && rd.plist) {
+        /* compact list of the valid paths: ballot + prefix popcount, one atomic per warp */
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(rd.plist_count, (unsigned long long)__popc(m));
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+          if (ok && pos < rd.plist_cap) {
+            /* freq_shift as the dense path leaves it: Doppler base of row (t, depth), minus this path's term */
+            const uint32_t j = (t * B + depth) % T, src = (j % B == 0) ? j / B : t;
+            const float base_fs = HRT_MUL(v3_dot(ld3(rd.tx_vel, src), ld3(rd.dirs, l)), rd.k.dop_k);
+            const uint64_t gp = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
+            float4 *dst = rd.plist + 3 * pos;
+            dst[0] = make_float4(__uint_as_float((uint32_t)gp), __uint_as_float(r),
+                                 __uint_as_float(t | (depth << 16)), p.te_r);
+            dst[1] = make_float4(p.te_i, p.tm_r, p.tm_i, p.tau);
+            dst[2] = make_float4(HRT_SUB(base_fs, p.dfreq), p.dir_rx.x, p.dir_rx.y, p.dir_rx.z);
+          }
+        }
+      }
+      if (!LEAN && ok && rd.cir) {
         /* impulse response: a * delta(t - tau) into its delay bin, one 16-byte
          * reduction per path (red.global.add.v4.f32) */
         const float fb = HRT_MUL(HRT_SUB(p.tau, rd.cir_tau0), rd.cir_inv_dt);

@@ -27,7 +27,11 @@ LIB_PATH = os.path.join(_HERE, "..", "libhermespy_rt.so")
 
 FLAG_DENSE, FLAG_RAYSINFO, FLAG_SUMMARY, FLAG_TRACE = 0x01, 0x02, 0x04, 0x08
 FLAG_BRUTE_FORCE, FLAG_HOST_DIRS, FLAG_SUMMARY_DEV, FLAG_COUNT = 0x10, 0x20, 0x40, 0x80
-FLAG_CIR = 0x100
+FLAG_CIR, FLAG_PATHLIST = 0x100, 0x200
+PATH_DTYPE = np.dtype([("path", "<u4"), ("rx", "<u4"), ("tx", "<u2"), ("bounce", "<u2"),
+                       ("a_te_re", "<f4"), ("a_te_im", "<f4"), ("a_tm_re", "<f4"), ("a_tm_im", "<f4"),
+                       ("tau", "<f4"), ("freq_shift", "<f4"), ("direction_rx", "<f4", (3,))])
+assert PATH_DTYPE.itemsize == 48
 
 PAIR_DTYPE = np.dtype([("n_valid", "<u8"), ("n_occluded", "<u8"), ("hit_hash", "<u8"),
                        ("tau_bits", "<u8"), ("power_te", "<f8"), ("power_tm", "<f8")])
@@ -58,6 +62,7 @@ class RunParams(C.Structure):
         ("trace_hit_tri", C.c_void_p), ("trace_hit_t", C.c_void_p), ("trace_slot_state", C.c_void_p),
         ("dirs", C.c_void_p), ("stream", C.c_void_p),
         ("cir", C.c_void_p), ("cir_tau0_s", C.c_float), ("cir_dt_s", C.c_float), ("cir_bins", C.c_uint32),
+        ("paths", C.c_void_p), ("paths_capacity", C.c_uint64), ("paths_count", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -203,7 +208,7 @@ class Context:
     def run(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, *, dense=False, raysinfo=False,
             summary=False, trace=False, brute_force=False, count_work=False, los=True, dirs=None,
             shard=(0, 1), shard_block=1 << 20, out: abi.Outputs | None = None,
-            summary_dev_ptrs=None, stream=None, cir=None):
+            summary_dev_ptrs=None, stream=None, cir=None, path_list=None):
         """hrt_run().  Returns a dict with whatever was requested:
         'out' (abi.Outputs, dense), 'pair'/'bounce' (structured arrays, summary),
         'trace' (dict), 'stats'."""
@@ -278,8 +283,18 @@ class Context:
             flags |= FLAG_CIR
             p.cir = res["cir"].ctypes.data
             p.cir_tau0_s, p.cir_dt_s, p.cir_bins = float(tau0), float(dt), int(bins)
+        n_found = C.c_uint64(0)
+        if path_list is not None:
+            # path_list = capacity: res["paths"] is a PATH_DTYPE array of the valid scatter paths
+            buf = np.zeros(int(path_list), PATH_DTYPE)
+            keep.append(buf)
+            flags |= FLAG_PATHLIST
+            p.paths = buf.ctypes.data; p.paths_capacity = int(path_list); p.paths_count = C.pointer(n_found)
         p.flags = flags
         self._check(lib().hrt_run(self._h, C.byref(p)), "hrt_run")
+        if path_list is not None:
+            res["paths_found"] = int(n_found.value)
+            res["paths"] = buf[: min(int(n_found.value), int(path_list))]
         res["stats"] = self.stats()
         del keep
         return res

@@ -58,6 +58,7 @@ typedef struct {
 #define HRT_FLAG_SUMMARY_DEV  0x40u  /* summary pointers are DEVICE memory               */
 #define HRT_FLAG_COUNT        0x80u  /* instrumented kernels: count box/triangle tests   */
 #define HRT_FLAG_CIR         0x100u  /* accumulate the delay-binned impulse response    */
+#define HRT_FLAG_PATHLIST    0x200u  /* emit the valid scatter paths as a compact list  */
 
 /* Order-independent per-(rx, tx, bounce) reduction of the scatter paths.
  * Integer fields are exact and comparable bit for bit with a CPU run. */
@@ -77,6 +78,19 @@ typedef struct {
   uint64_t hit_hash;     /* sum of mix64(path << 32 | triangle id) over hits      */
   uint64_t t_bits;       /* sum of the fp32 bit patterns of the hit distances     */
 } HrtBounceSummary;
+
+/* One valid scatter path (HRT_FLAG_PATHLIST): the words the reference writes
+ * into slot ((rx * num_tx + tx) * num_bounces + bounce) * num_paths + path of
+ * its dense ChannelInfo arrays (src/compute_paths.c:698-722), without the
+ * slots of dead rays and occluded receivers.  48 bytes. */
+typedef struct {
+  uint32_t path;         /* ray index within its transmitter                      */
+  uint32_t rx;
+  uint16_t tx, bounce;
+  float a_te_re, a_te_im, a_tm_re, a_tm_im;
+  float tau, freq_shift;
+  Vec3  direction_rx;
+} HrtPathRecord;
 
 typedef struct {
   /* problem (reference compute_paths arguments, inc/compute_paths.h:59-74) */
@@ -128,6 +142,16 @@ typedef struct {
   float   *cir;
   float    cir_tau0_s, cir_dt_s;
   uint32_t cir_bins;
+
+  /* HRT_FLAG_PATHLIST: the valid scatter paths of this call as records, in no
+   * particular order, compacted on the GPU (warp ballot + prefix sum, one
+   * atomic per warp).  `paths` is host memory for `paths_capacity` records;
+   * *paths_count receives the number of valid paths found -- when it exceeds the
+   * capacity only `paths_capacity` of them (an arbitrary subset) were stored.
+   * Needs num_paths < 2^32. */
+  HrtPathRecord *paths;
+  uint64_t       paths_capacity;
+  uint64_t      *paths_count;
 } HrtRunParams;
 
 /* Counters and timings of the last hrt_run on a context. */

@@ -369,6 +369,47 @@ def test_cir_mode_vs_oracle(ctx):
     assert (mag[..., 1] > 0).any()
 
 
+def test_path_list_mode(ctx):
+    """HRT_FLAG_PATHLIST: the compact list of valid scatter paths (ballot/prefix
+    compaction) holds exactly the reference-written valid slots of the dense
+    arrays -- every word bit-identical to the dense output of the same run,
+    which in turn is checked against the oracle -- in any order; overflowing
+    the capacity reports the true count and keeps a subset."""
+    scene, rx, tx, rxv, txv, f = _case_inputs("canyon_1x1", 9, True, 2)
+    P, B = 6000, 4
+    R, T = len(rx), len(tx)
+    ctx.load_scene(tl.scene_path(scene))
+    a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B)
+    n_valid = int((tr["slot_state"] == 1).sum())
+    res = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, trace=True, path_list=n_valid + 100)
+    assert np.array_equal(tr["slot_state"], res["trace"]["slot_state"])
+    assert res["paths_found"] == n_valid and len(res["paths"]) == n_valid
+    pl = res["paths"]
+    order = np.lexsort((pl["path"], pl["bounce"], pl["tx"], pl["rx"]))
+    pl = pl[order]
+    rr, tt, bb, pp = np.nonzero(tr["slot_state"] == 1)                    # C order == the lexsort order
+    assert np.array_equal(pl["rx"], rr) and np.array_equal(pl["tx"], tt)
+    assert np.array_equal(pl["bounce"], bb) and np.array_equal(pl["path"], pp)
+    d = res["out"].scat
+    for k in ("a_te_re", "a_te_im", "a_tm_re", "a_tm_im", "tau", "freq_shift"):
+        dense = d[k].reshape(R, T, B, P)[rr, tt, bb, pp]
+        assert np.array_equal(pl[k].view(np.uint32), dense.view(np.uint32)), k
+    dense_dir = d["directions_rx"].reshape(R, T, B, P, 3)[rr, tt, bb, pp]
+    assert np.array_equal(pl["direction_rx"].view(np.uint32), dense_dir.view(np.uint32))
+    # and the dense output itself against the oracle (tau bit-exact, gains within tolerance)
+    tau_o = a.scat["tau"].reshape(R, T, B, P)[rr, tt, bb, pp]
+    assert np.array_equal(pl["tau"].view(np.uint32), tau_o.view(np.uint32))
+    te_o = (a.scat["a_te_re"].reshape(R, T, B, P)[rr, tt, bb, pp].astype(np.float64)
+            + 1j * a.scat["a_te_im"].reshape(R, T, B, P)[rr, tt, bb, pp].astype(np.float64))
+    te_g = pl["a_te_re"].astype(np.float64) + 1j * pl["a_te_im"].astype(np.float64)
+    assert (np.abs(te_g - te_o) <= tl.GAIN_RTOL * np.abs(te_o) + 1e-38).all()   # complex, as tl.assert_gains_close
+    # capacity overflow
+    small = ctx.run(rx, tx, rxv, txv, f, P, B, path_list=1000)
+    assert small["paths_found"] == n_valid and len(small["paths"]) == 1000
+    key = lambda q: (q["rx"].astype(np.int64) * T + q["tx"]) * B * P + q["bounce"].astype(np.int64) * P + q["path"]
+    assert np.isin(key(small["paths"]), key(pl)).all() and np.unique(key(small["paths"])).size == 1000
+
+
 def test_full_size_anchor_counts(ctx):
     """BASELINE configs at full size through size-independent properties:
     per-bounce active-ray counts measured on the reference during the survey
