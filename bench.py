@@ -286,6 +286,27 @@ def main_gpu(args):
     h2d = scene_bytes + (R + T) * 24
     d2h = R * T * B * 48 + T * B * 32 + (B + 1) * T * 4
 
+    # ---- per-path results: every rank lists the valid paths of its shard of a
+    # smaller job on the GPU (ballot/prefix compaction), then one NCCL all-gather of
+    # the counts and one of the record buffers over NVLink: every GPU ends up with
+    # every path of the job
+    PL = int(os.environ.get("HRT_BENCH_LIST_PATHS", "40000"))          # rays per TX of the listed job
+    cap = int(PL * T * B * R * 0.6 / world) + 4096                      # records per rank (C4: ~0.42 valid per slot)
+    lbuf = torch.empty(cap * 48, dtype=torch.uint8, device="cuda")
+    g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    sync()
+    g0.record()
+    lr = ctx.run(rx, tx, zr, zt, F_GHZ, PL, B, los=False, shard=(rank, world), shard_block=4096,
+                 path_list_dev=(lbuf.data_ptr(), cap), stream=stream)
+    g1.record()
+    allrec, counts = hrt.gather_path_lists(lbuf, min(lr["paths_found"], cap), cap)
+    g2.record()
+    sync()
+    gather = {"job": f"{PL} rays per TX, same scene/TX/RX/bounces", "records": int(allrec.shape[0]),
+              "record_bytes": 48, "bytes_gathered_per_rank": int(world * cap * 48),
+              "overflow": bool(lr["paths_found"] > cap), "trace_and_list_ms": g0.elapsed_time(g1),
+              "all_gather_ms": g1.elapsed_time(g2), "backend": "nccl" if world > 1 else "single rank"}
+
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel (k_scatter): counted work / live launch time
@@ -341,6 +362,7 @@ def main_gpu(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
+            "path_list_gather": gather,
             "closest_hit_queries_per_s": (rb_total + shadow_total) / (ms_total * 1e-3),
             "shadow_queries_per_step": shadow_total / args.steps,
             "ray_bounces_per_step": rb_total / args.steps,

@@ -879,6 +879,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
   const bool lean = !brute && !count && !(flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE | HRT_FLAG_CIR | HRT_FLAG_PATHLIST));
+  if ((flags & HRT_FLAG_PATHLIST_DEV) && !(flags & HRT_FLAG_PATHLIST)) return fail(ctx, HRT_E_ARG, "PATHLIST_DEV needs PATHLIST");
   const ScatterFn f_scatter = lean ? scatter_fn_lean(smem, warp_mode) : scatter_fn(smem, brute, warp_mode, count);
   if (smem) {
     CK(allow_smem(f_bounce, scene_sb));
@@ -889,12 +890,17 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   rd.cir = nullptr; rd.cir_bins = 0; rd.cir_tau0 = 0.f; rd.cir_inv_dt = 0.f;
   rd.plist = nullptr; rd.plist_cap = 0; rd.plist_count = rd.counters + 14;
   if (flags & HRT_FLAG_PATHLIST) {
-    if (ctx->cap_plist < p->paths_capacity) {
-      if (ctx->d_plist) cudaFree(ctx->d_plist);
-      ctx->d_plist = nullptr; ctx->cap_plist = 0;
-      CK(dev_alloc(&ctx->d_plist, (size_t)p->paths_capacity * 3)); ctx->cap_plist = p->paths_capacity;
+    if (flags & HRT_FLAG_PATHLIST_DEV) {
+      rd.plist = (float4 *)p->paths;
+    } else {
+      if (ctx->cap_plist < p->paths_capacity) {
+        if (ctx->d_plist) cudaFree(ctx->d_plist);
+        ctx->d_plist = nullptr; ctx->cap_plist = 0;
+        CK(dev_alloc(&ctx->d_plist, (size_t)p->paths_capacity * 3)); ctx->cap_plist = p->paths_capacity;
+      }
+      rd.plist = ctx->d_plist;
     }
-    rd.plist = ctx->d_plist; rd.plist_cap = p->paths_capacity;
+    rd.plist_cap = p->paths_capacity;
   }
   if (flags & HRT_FLAG_CIR) {
     const size_t ncir = R * T * (size_t)p->cir_bins * 4;
@@ -1227,8 +1233,10 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     CKR(cudaMemcpyAsync(&found, rd.counters + 14, 8, cudaMemcpyDeviceToHost, st));
     CKR(cudaStreamSynchronize(st));
     const unsigned long long kept = found < p->paths_capacity ? found : p->paths_capacity;
-    CKR(cudaMemcpyAsync(p->paths, ctx->d_plist, (size_t)kept * sizeof(HrtPathRecord), cudaMemcpyDeviceToHost, st));
-    CKR(cudaStreamSynchronize(st));
+    if (!(flags & HRT_FLAG_PATHLIST_DEV)) {
+      CKR(cudaMemcpyAsync(p->paths, ctx->d_plist, (size_t)kept * sizeof(HrtPathRecord), cudaMemcpyDeviceToHost, st));
+      CKR(cudaStreamSynchronize(st));
+    }
     *p->paths_count = found;
   }
   if (flags & HRT_FLAG_CIR) {

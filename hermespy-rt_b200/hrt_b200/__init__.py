@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(_HERE, "..", "libhermespy_rt.so")
 
 FLAG_DENSE, FLAG_RAYSINFO, FLAG_SUMMARY, FLAG_TRACE = 0x01, 0x02, 0x04, 0x08
 FLAG_BRUTE_FORCE, FLAG_HOST_DIRS, FLAG_SUMMARY_DEV, FLAG_COUNT = 0x10, 0x20, 0x40, 0x80
-FLAG_CIR, FLAG_PATHLIST = 0x100, 0x200
+FLAG_CIR, FLAG_PATHLIST, FLAG_PATHLIST_DEV = 0x100, 0x200, 0x400
 PATH_DTYPE = np.dtype([("path", "<u4"), ("rx", "<u4"), ("tx", "<u2"), ("bounce", "<u2"),
                        ("a_te_re", "<f4"), ("a_te_im", "<f4"), ("a_tm_re", "<f4"), ("a_tm_im", "<f4"),
                        ("tau", "<f4"), ("freq_shift", "<f4"), ("direction_rx", "<f4", (3,))])
@@ -122,6 +122,27 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def gather_path_lists(local: "torch.Tensor", count: int, capacity: int):
+    """All-gather of per-rank path lists (torch.distributed, any backend): `local`
+    is this rank's record buffer as a uint8 tensor of capacity * 48 bytes (device
+    memory for NCCL), `count` its number of valid records.  Returns (records of
+    all ranks as one uint8 tensor [total, 48], per-rank counts) -- every rank gets
+    the whole list.  One all_gather of the counts, one of the padded buffers."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return local.view(-1, 48)[:count], [count]
+    cnt = torch.tensor([count], dtype=torch.int64, device=local.device)
+    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(counts, cnt)
+    allbuf = torch.empty(world * capacity * 48, dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(allbuf, local.view(-1)[: capacity * 48].contiguous())
+    counts = [int(c) for c in counts.tolist()]
+    parts = [allbuf.view(world, capacity, 48)[r, : min(counts[r], capacity)] for r in range(world)]
+    return torch.cat(parts, 0), counts
+
+
 def shard_paths(num_paths: int, rank: int, world: int, block: int) -> np.ndarray:
     """Global path indices owned by `rank` (host arithmetic of the C library)."""
     L = lib()
@@ -208,7 +229,7 @@ class Context:
     def run(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, *, dense=False, raysinfo=False,
             summary=False, trace=False, brute_force=False, count_work=False, los=True, dirs=None,
             shard=(0, 1), shard_block=1 << 20, out: abi.Outputs | None = None,
-            summary_dev_ptrs=None, stream=None, cir=None, path_list=None):
+            summary_dev_ptrs=None, stream=None, cir=None, path_list=None, path_list_dev=None):
         """hrt_run().  Returns a dict with whatever was requested:
         'out' (abi.Outputs, dense), 'pair'/'bounce' (structured arrays, summary),
         'trace' (dict), 'stats'."""
@@ -290,8 +311,15 @@ class Context:
             keep.append(buf)
             flags |= FLAG_PATHLIST
             p.paths = buf.ctypes.data; p.paths_capacity = int(path_list); p.paths_count = C.pointer(n_found)
+        if path_list_dev is not None:
+            # path_list_dev = (device pointer, capacity in records): records stay on the GPU
+            flags |= FLAG_PATHLIST | FLAG_PATHLIST_DEV
+            p.paths, p.paths_capacity = int(path_list_dev[0]), int(path_list_dev[1])
+            p.paths_count = C.pointer(n_found)
         p.flags = flags
         self._check(lib().hrt_run(self._h, C.byref(p)), "hrt_run")
+        if path_list_dev is not None:
+            res["paths_found"] = int(n_found.value)
         if path_list is not None:
             res["paths_found"] = int(n_found.value)
             res["paths"] = buf[: min(int(n_found.value), int(path_list))]

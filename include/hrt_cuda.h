@@ -59,6 +59,8 @@ typedef struct {
 #define HRT_FLAG_COUNT        0x80u  /* instrumented kernels: count box/triangle tests   */
 #define HRT_FLAG_CIR         0x100u  /* accumulate the delay-binned impulse response    */
 #define HRT_FLAG_PATHLIST    0x200u  /* emit the valid scatter paths as a compact list  */
+#define HRT_FLAG_PATHLIST_DEV 0x400u /* ... into DEVICE memory (`paths`), e.g. a buffer
+                                        that NCCL gathers next; paths_count stays host */
 
 /* Order-independent per-(rx, tx, bounce) reduction of the scatter paths.
  * Integer fields are exact and comparable bit for bit with a CPU run. */

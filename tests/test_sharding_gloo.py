@@ -76,3 +76,57 @@ def test_gathered_shard_summaries_equal_unsharded(tmp_path):
         assert np.array_equal(total[..., i], pair[k]), k
     np.testing.assert_allclose(np.load(tmp_path / "power.npy").reshape(pair["power_te"].shape),
                                pair["power_te"], rtol=1e-12)
+
+
+def _list_from_oracle(o, tr, path_ids):
+    """HrtPathRecord list (hrt_b200.PATH_DTYPE) of the valid slots of an oracle run
+    restricted to `path_ids` (global path numbers of the columns)."""
+    R, T = o.R, o.T
+    st = tr["slot_state"]
+    rr, tt, bb, pp = np.nonzero(st == 1)
+    rec = np.zeros(rr.size, hrt.PATH_DTYPE)
+    rec["rx"], rec["tx"], rec["bounce"], rec["path"] = rr, tt, bb, path_ids[pp]
+    n = st.shape[-1]
+    for k in ("a_te_re", "a_te_im", "a_tm_re", "a_tm_im", "tau", "freq_shift"):
+        rec[k] = o.scat[k].reshape(R, T, B, n)[rr, tt, bb, pp]
+    rec["direction_rx"] = o.scat["directions_rx"].reshape(R, T, B, n, 3)[rr, tt, bb, pp]
+    return rec
+
+
+def _list_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene, rx, tx, rxv, txv, f = _case()
+    o, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B)
+    mine = hrt.shard_paths(P, rank, world, BLOCK).astype(np.int64)
+    sub = tl.abi.alloc_outputs(o.R, o.T, mine.size, B, 0)
+    for k in ("tau", "a_te_re", "a_te_im", "a_tm_re", "a_tm_im", "freq_shift"):
+        sub.scat[k][...] = o.scat[k][..., mine]
+    sub.scat["directions_rx"][...] = o.scat["directions_rx"].reshape(o.R, o.T, B, P, 3)[:, :, :, mine].reshape(sub.scat["directions_rx"].shape)
+    trs = {k: np.ascontiguousarray(v[..., mine]) for k, v in tr.items()}
+    rec = _list_from_oracle(sub, trs, mine)
+    cap = 2 * P * B
+    buf = torch.zeros(cap * 48, dtype=torch.uint8)
+    buf[: rec.size * 48] = torch.from_numpy(rec.view(np.uint8).copy())
+    allrec, counts = hrt.gather_path_lists(buf, rec.size, cap)
+    assert counts[rank] == rec.size
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), allrec.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gathered_path_lists_equal_unsharded(tmp_path):
+    """All-gather of per-rank compact path lists (hrt_b200.gather_path_lists, the
+    call bench.py makes over NCCL) == the list of the unsharded run, as a set."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_list_worker, args=(WORLD, port, str(tmp_path)), nprocs=WORLD, join=True)
+    scene, rx, tx, rxv, txv, f = _case()
+    o, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B)
+    full = _list_from_oracle(o, tr, np.arange(P, dtype=np.int64))
+    got = np.load(tmp_path / "gathered.npy").reshape(-1).view(hrt.PATH_DTYPE)
+    assert got.size == full.size and full.size > 1000
+    key = lambda q: np.lexsort((q["path"], q["bounce"], q["tx"], q["rx"]))
+    a, b = full[key(full)], got[key(got)]
+    assert a.tobytes() == b.tobytes()
