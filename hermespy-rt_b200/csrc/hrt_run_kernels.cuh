@@ -594,17 +594,22 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
               m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, o);
             }
           }
-          if (lane == 0 && (m_ok | m_occ)) {
-            if (smem_rx_ok) {
-              if (m_occ) atomicAdd(&s_acc[r].n_occl, (unsigned)__popc(m_occ));
-              if (m_ok) {
-                atomicAdd(&s_acc[r].n_valid, (unsigned)__popc(m_ok));
-                atomicAdd(&s_acc[r].hash, hsum);
-                atomicAdd(&s_acc[r].tau_bits, tsum);
-                atomicAdd(&s_acc[r].p_te, e);
-                atomicAdd(&s_acc[r].p_tm, m2);
+          if (smem_rx_ok) {
+            /* the sums are in every lane: lanes 0-2 add the three integer words with ONE
+             * 64-bit atomic instruction (the two counts share a word), lanes 3-4 the powers */
+            if (m_ok | m_occ) {
+              PairAcc *acc = &s_acc[r];
+              if (lane < 3u) {
+                const unsigned long long v = lane == 0u ? ((unsigned long long)__popc(m_ok) | ((unsigned long long)__popc(m_occ) << 32))
+                                           : lane == 1u ? hsum : tsum;
+                unsigned long long *dst = lane == 0u ? (unsigned long long *)&acc->n_valid : lane == 1u ? &acc->hash : &acc->tau_bits;
+                atomicAdd(dst, v);
+              } else if (lane < 5u && m_ok) {
+                atomicAdd(lane == 3u ? &acc->p_te : &acc->p_tm, lane == 3u ? e : m2);
               }
-            } else {
+            }
+          } else if (lane == 0 && (m_ok | m_occ)) {
+            {
               HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
               if (m_occ) atomicAdd((unsigned long long *)&ps->n_occluded, (unsigned long long)__popc(m_occ));
               if (m_ok) {
