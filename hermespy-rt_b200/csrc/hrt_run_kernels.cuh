@@ -589,10 +589,13 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
                  + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk >> 48)) << 48);
             tsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb & 0xFFFFu)
                  + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb >> 16) << 16);
-            for (int o = 16; o; o >>= 1) {
-              e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-              m2 += __shfl_xor_sync(0xFFFFFFFFu, m2, o);
-            }
+            /* both power sums in one butterfly: after the first exchange the lower
+             * half-warp carries the TE sum, the upper half the TM sum */
+            const bool upper = lane >= 16u;
+            double keep = upper ? m2 : e;
+            keep += __shfl_xor_sync(0xFFFFFFFFu, upper ? e : m2, 16);
+            for (int o = 8; o; o >>= 1) keep += __shfl_xor_sync(0xFFFFFFFFu, keep, o);
+            e = keep; m2 = keep;       /* lanes 0-15: e is the total; lanes 16-31: m2 is the total */
           }
           if (smem_rx_ok) {
             /* the sums are in every lane: lanes 0-2 add the three integer words with ONE
@@ -604,21 +607,22 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
                                            : lane == 1u ? hsum : tsum;
                 unsigned long long *dst = lane == 0u ? (unsigned long long *)&acc->n_valid : lane == 1u ? &acc->hash : &acc->tau_bits;
                 atomicAdd(dst, v);
-              } else if (lane < 5u && m_ok) {
+              } else if ((lane == 3u || lane == 16u) && m_ok) {
                 atomicAdd(lane == 3u ? &acc->p_te : &acc->p_tm, lane == 3u ? e : m2);
               }
             }
-          } else if (lane == 0 && (m_ok | m_occ)) {
-            {
-              HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+          } else if (m_ok | m_occ) {
+            HrtPairSummary *ps = &rd.pair[(r * T + t) * B + depth];
+            if (lane == 0u) {
               if (m_occ) atomicAdd((unsigned long long *)&ps->n_occluded, (unsigned long long)__popc(m_occ));
               if (m_ok) {
                 atomicAdd((unsigned long long *)&ps->n_valid, (unsigned long long)__popc(m_ok));
                 atomicAdd((unsigned long long *)&ps->hit_hash, hsum);
                 atomicAdd((unsigned long long *)&ps->tau_bits, tsum);
                 atomicAdd(&ps->power_te, e);
-                atomicAdd(&ps->power_tm, m2);
               }
+            } else if (lane == 16u && m_ok) {
+              atomicAdd(&ps->power_tm, m2);
             }
           }
         }
