@@ -20,6 +20,12 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -114,6 +120,57 @@ __host__ __device__ static inline uint64_t hrt_gpath(uint64_t L, uint32_t rank, 
 
 /* ------------------------------------------------------------------ context */
 
+/* Host side of the dense device -> host path.  cudaMemcpy into pageable memory
+ * runs at 21 GB/s on this box (2.3 GB/s when the destination pages have never
+ * been touched: one thread takes every page fault); PCIe delivers 57 GB/s into
+ * pinned memory and eight host threads copy at 77 GB/s (33 GB/s into fresh
+ * pages) -- scripts/d2h_bandwidth.py.  So large outputs go through two pinned
+ * staging buffers and a small pool of copy threads, double buffered. */
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  std::function<void(int, int)> fn;
+  int gen = 0, pending = 0, n = 0;
+  bool stop = false;
+  void start(int k)
+  {
+    n = k;
+    for (int w = 0; w < k; ++w)
+      th.emplace_back([this, w] {
+        int seen = 0;
+        for (;;) {
+          std::function<void(int, int)> f;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen; f = fn;
+          }
+          f(w, n);
+          { std::lock_guard<std::mutex> lk(mu); if (--pending == 0) cv_done.notify_all(); }
+        }
+      });
+  }
+  void run(const std::function<void(int, int)> &f)
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    fn = f; pending = n; ++gen;
+    cv.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  ~HostPool()
+  {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv.notify_all();
+    for (auto &t : th) t.join();
+  }
+};
+
+struct CopyTile { const char *dev; size_t dpitch; char *host; size_t hpitch, width, rows; };
+#define HRT_STAGE_BYTES ((size_t)128 << 20)
+#define HRT_STAGE_MIN_TOTAL ((size_t)16 << 20)   /* smaller outputs: plain cudaMemcpy2DAsync */
+
 struct hrt_ctx {
   int device;
   cudaStream_t stream;
@@ -159,6 +216,7 @@ struct hrt_ctx {
   size_t cap_los;
   float *d_cir; size_t cap_cir;
   float4 *d_plist; size_t cap_plist;
+  HostPool *pool; char *stage[2]; cudaEvent_t stage_ev[2];
   HrtRunStats stats;
 };
 
@@ -261,6 +319,8 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
   if (c->d_cir) { cudaFree(c->d_cir); c->d_cir = nullptr; }
   if (c->d_plist) { cudaFree(c->d_plist); c->d_plist = nullptr; }
+  delete c->pool; c->pool = nullptr;
+  for (int k = 0; k < 2; ++k) if (c->stage[k]) { cudaFreeHost(c->stage[k]); cudaEventDestroy(c->stage_ev[k]); c->stage[k] = nullptr; }
   if (c->sort_tmp) { cudaFree(c->sort_tmp); c->sort_tmp = nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
@@ -772,9 +832,10 @@ extern "C" uint64_t hrt_shard_count(uint64_t num_paths, uint32_t rank, uint32_t 
 extern "C" uint64_t hrt_shard_path(uint64_t local_index, uint32_t rank, uint32_t world, uint64_t block)
 { return hrt_gpath(local_index, rank, world, block ? block : 1); }
 
-/* copy device rows [nrows][n_alloc] (elem bytes) into host rows of pitch P at
- * the columns of the chunk's paths */
-static cudaError_t d2h_columns(const hrt_ctx *ctx, cudaStream_t st, void *host, const void *dev, size_t elem,
+/* device rows [nrows][n_alloc] (elem bytes) -> host rows of pitch P at the
+ * columns of the chunk's paths: appended to `tiles` as rectangles of at most
+ * HRT_STAGE_BYTES (see run_copy_tiles) */
+static cudaError_t d2h_columns(const hrt_ctx *ctx, std::vector<CopyTile> &tiles, void *host, const void *dev, size_t elem,
                                size_t nrows, const RunDev &rd)
 {
   if (!host) return cudaSuccess;
@@ -785,10 +846,81 @@ static cudaError_t d2h_columns(const hrt_ctx *ctx, cudaStream_t st, void *host, 
     uint64_t run = rd.n - L;
     if (rd.world > 1) { const uint64_t in_blk = (rd.l0 + L) % rd.blk; run = (rd.blk - in_blk < run) ? rd.blk - in_blk : run; }
     const uint64_t g = hrt_gpath(rd.l0 + L, rd.rank, rd.world, rd.blk);
-    cudaError_t e = cudaMemcpy2DAsync((char *)host + g * elem, rd.P * elem, (const char *)dev + L * elem,
-                                      (size_t)rd.n_alloc * elem, run * elem, nrows, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
+    const size_t dpitch = (size_t)rd.n_alloc * elem, hpitch = (size_t)rd.P * elem;
+    /* split: column pieces when one row exceeds the staging buffer, else row bands */
+    const size_t max_cols = HRT_STAGE_BYTES / elem;
+    for (uint64_t c0 = 0; c0 < run; c0 += max_cols) {
+      const size_t cols = (size_t)((run - c0 < max_cols) ? run - c0 : max_cols);
+      const size_t width = cols * elem;
+      const size_t band = HRT_STAGE_BYTES / width ? HRT_STAGE_BYTES / width : 1;
+      for (size_t r0 = 0; r0 < nrows; r0 += band) {
+        CopyTile t;
+        t.rows = (nrows - r0 < band) ? nrows - r0 : band;
+        t.dev = (const char *)dev + r0 * dpitch + (L + c0) * elem; t.dpitch = dpitch;
+        t.host = (char *)host + r0 * hpitch + (g + c0) * elem; t.hpitch = hpitch;
+        t.width = width;
+        tiles.push_back(t);
+      }
+    }
     L += run;
+  }
+  return cudaSuccess;
+}
+
+/* Executes the queued copies on stream `st` (i.e. after the kernels queued
+ * before) and returns when the host arrays are complete. */
+static cudaError_t run_copy_tiles(hrt_ctx *ctx, cudaStream_t st, const std::vector<CopyTile> &tiles)
+{
+  size_t total = 0;
+  for (const CopyTile &t : tiles) total += t.rows * t.width;
+  cudaError_t e = cudaSuccess;
+  if (total < HRT_STAGE_MIN_TOTAL || getenv("HRT_NO_STAGING")) {
+    for (const CopyTile &t : tiles) {
+      e = cudaMemcpy2DAsync(t.host, t.hpitch, t.dev, t.dpitch, t.width, t.rows, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaStreamSynchronize(st);
+  }
+  if (!ctx->pool) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int k = (int)(hw ? hw / 2 : 4);
+    if (const char *s = getenv("HRT_COPY_THREADS")) k = atoi(s);
+    k = k < 1 ? 1 : (k > 16 ? 16 : k);
+    ctx->pool = new HostPool();
+    ctx->pool->start(k);
+  }
+  for (int k = 0; k < 2; ++k)
+    if (!ctx->stage[k]) {
+      e = cudaHostAlloc((void **)&ctx->stage[k], HRT_STAGE_BYTES, cudaHostAllocDefault);
+      if (e != cudaSuccess) { ctx->stage[k] = nullptr; return e; }
+      e = cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+  const size_t nt = tiles.size();
+  for (size_t k = 0; k <= nt; ++k) {
+    if (k < nt) {
+      const CopyTile &t = tiles[k];
+      e = cudaMemcpy2DAsync(ctx->stage[k & 1], t.width, t.dev, t.dpitch, t.width, t.rows, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_ev[k & 1], st);
+      if (e != cudaSuccess) return e;
+    }
+    if (k >= 1) {
+      const CopyTile t = tiles[k - 1];
+      const char *src = ctx->stage[(k - 1) & 1];
+      e = cudaEventSynchronize(ctx->stage_ev[(k - 1) & 1]);
+      if (e != cudaSuccess) return e;
+      const size_t bytes = t.rows * t.width;
+      ctx->pool->run([=](int w, int n) {
+        /* worker w copies bytes [a, b) of the packed tile, row segment by row segment */
+        size_t a = bytes * (size_t)w / (size_t)n, b = bytes * (size_t)(w + 1) / (size_t)n;
+        while (a < b) {
+          const size_t r = a / t.width, off = a % t.width;
+          const size_t len = (t.width - off < b - a) ? t.width - off : b - a;
+          memcpy(t.host + r * t.hpitch + off, src + a, len);
+          a += len;
+        }
+      });
+    }
   }
   return cudaSuccess;
 }
@@ -1098,30 +1230,32 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     CKR(cudaMemcpyAsync(h_counts, rd.qcount, (B + 1) * T * 4, cudaMemcpyDeviceToHost, st));
 
     /* dense outputs -> the caller's arrays (columns of this chunk) */
+    std::vector<CopyTile> tiles;
     if (flags & HRT_FLAG_DENSE) {
       ChannelInfo *O = p->scat;
       float *dst[6] = { O->a_te_re, O->a_te_im, O->a_tm_re, O->a_tm_im, O->tau, O->freq_shift };
-      for (int k = 0; k < 6; ++k) CKR(d2h_columns(ctx, st, dst[k], rd.out_f[k], 4, R * T * B, rd));
-      CKR(d2h_columns(ctx, st, O->directions_rx, rd.out_dir, 12, R * T * B, rd));
+      for (int k = 0; k < 6; ++k) CKR(d2h_columns(ctx, tiles, dst[k], rd.out_f[k], 4, R * T * B, rd));
+      CKR(d2h_columns(ctx, tiles, O->directions_rx, rd.out_dir, 12, R * T * B, rd));
     }
     if (flags & HRT_FLAG_TRACE) {
-      CKR(d2h_columns(ctx, st, p->trace_hit_tri, rd.tr_hit, 4, T * B, rd));
-      CKR(d2h_columns(ctx, st, p->trace_hit_t, rd.tr_t, 4, T * B, rd));
-      CKR(d2h_columns(ctx, st, p->trace_slot_state, rd.tr_state, 1, R * T * B, rd));
+      CKR(d2h_columns(ctx, tiles, p->trace_hit_tri, rd.tr_hit, 4, T * B, rd));
+      CKR(d2h_columns(ctx, tiles, p->trace_hit_t, rd.tr_t, 4, T * B, rd));
+      CKR(d2h_columns(ctx, tiles, p->trace_slot_state, rd.tr_state, 1, R * T * B, rd));
     }
     if (flags & HRT_FLAG_RAYSINFO) {
       /* reference row order (:589, :732-743): row 0 = initial rays of TX 0,
        * row t*B+b+1 = rays of TX t after bounce b */
       RaysInfo *RI = p->rays_scat;
       if (RI->rays) {
-        CKR(d2h_columns(ctx, st, RI->rays, rd.rays, sizeof(Ray), 1, rd));
+        CKR(d2h_columns(ctx, tiles, RI->rays, rd.rays, sizeof(Ray), 1, rd));
         for (size_t t = 0; t < T; ++t)
           for (size_t b = 0; b < B; ++b)
-            CKR(d2h_columns(ctx, st, RI->rays + (t * B + b + 1) * P, rd.rays + ((b + 1) * T + t) * (size_t)rd.n_alloc,
+            CKR(d2h_columns(ctx, tiles, RI->rays + (t * B + b + 1) * P, rd.rays + ((b + 1) * T + t) * (size_t)rd.n_alloc,
                             sizeof(Ray), 1, rd));
       }
       CKR(cudaMemcpyAsync(h_dead, rd.dead_at, T * (size_t)rd.n_alloc, cudaMemcpyDeviceToHost, st));
     }
+    CKR(run_copy_tiles(ctx, st, tiles));
     CKR(cudaStreamSynchronize(st));
     if ((flags & HRT_FLAG_RAYSINFO) && T > 1 && l0 == 0 && rank == 0)
       for (uint32_t j = 0; j < 8 && j < rd.n; ++j) tail_dead[j] = h_dead[rd.n_alloc + j];

@@ -9,6 +9,19 @@ import hrt_b200 as hrt
 from hrt_b200 import abi
 import hrt_testlib as tl
 
+def fresh_outputs(R, T, P, B):
+    """like abi.alloc_outputs but the pages are never touched (what a C caller's malloc returns)"""
+    o = abi.Outputs(R, T, P, B)
+    for k in abi.CHAN_FIELDS:
+        vec = k.startswith("directions")
+        o.los[k] = np.empty((R, T, 3) if vec else (R, T), np.float32)
+        o.scat[k] = np.empty((R, T, B, P, 3) if vec else (R, T, B, P), np.float32)
+    o.los_rays = np.empty((R * T, 6), np.float32); o.los_active = np.empty((R * T // 8 + 1,), np.uint8)
+    rows = T * (B + 1) + 1
+    o.scat_rays = np.empty((rows, P, 6), np.float32); o.scat_active = np.empty((rows, P // 8 + 1), np.uint8)
+    return o
+
+
 L = hrt.lib()
 res = []
 for name, cfg, P, B in (("configs[1] box 1e6 x 3", "box_axis", 1_000_000, 3), ("configs[2] 2cars 1e7 x 5", "2cars_raised", 10_000_000, 5),
@@ -31,7 +44,13 @@ for name, cfg, P, B in (("configs[1] box 1e6 x 3", "box_axis", 1_000_000, 3), ("
         abi.call_compute_paths(L, sc, rx, tx, [[0, 0, 0]], [[0, 0, 0]], f, P, B, out=out)
         best2 = min(best2, time.perf_counter() - t0)
     del os.environ["HRT_NO_RAYSINFO"]
+    fresh = fresh_outputs(1, 1, P, B)
+    t0 = time.perf_counter()
+    abi.call_compute_paths(L, sc, rx, tx, [[0, 0, 0]], [[0, 0, 0]], f, P, B, out=fresh)
+    t_fresh = time.perf_counter() - t0
+    del fresh
     abi.free_scene(sc)
     res.append({"config": name, "seconds": best, "ray_bounces": rb, "ray_bounces_per_s": rb / best,
-                "d2h_bytes": nbytes, "seconds_without_raysinfo": best2, "rb_per_s_without_raysinfo": rb / best2})
+                "d2h_bytes": nbytes, "seconds_without_raysinfo": best2, "rb_per_s_without_raysinfo": rb / best2,
+                "seconds_into_untouched_arrays": t_fresh})
 print(json.dumps(res))
