@@ -127,12 +127,10 @@ HRT_HD void hrt_emit_node(float4 *out, int ref_l, int ref_r, V3 llo, V3 lhi, V3 
   if (oct & 1u) { float t = llo.x; llo.x = lhi.x; lhi.x = t; t = rlo.x; rlo.x = rhi.x; rhi.x = t; }
   if (oct & 2u) { float t = llo.y; llo.y = lhi.y; lhi.y = t; t = rlo.y; rlo.y = rhi.y; rhi.y = t; }
   if (oct & 4u) { float t = llo.z; llo.z = lhi.z; lhi.z = t; t = rlo.z; rlo.z = rhi.z; rhi.z = t; }
-  pad = 0.f;
-  out[0].x = llo.x - pad; out[0].y = lhi.x + pad; out[0].z = llo.y - pad; out[0].w = lhi.y + pad;
-  out[1].x = rlo.x - pad; out[1].y = rhi.x + pad; out[1].z = rlo.y - pad; out[1].w = rhi.y + pad;
-  out[2].x = llo.z - pad; out[2].y = lhi.z + pad; out[2].z = rlo.z - pad; out[2].w = rhi.z + pad;
-  out[3].x = hrt_int_as_float(ref_l); out[3].y = hrt_int_as_float(ref_r);
-  out[3].z = 0.f; out[3].w = 0.f;
+  out[0].x = llo.x; out[0].y = lhi.x; out[0].z = llo.y; out[0].w = lhi.y;
+  out[1].x = llo.z; out[1].y = lhi.z; out[1].z = hrt_int_as_float(ref_l); out[1].w = 0.f;
+  out[2].x = rlo.x; out[2].y = rhi.x; out[2].z = rlo.y; out[2].w = rhi.y;
+  out[3].x = rlo.z; out[3].y = rhi.z; out[3].z = hrt_int_as_float(ref_r); out[3].w = 0.f;
 }
 
 /* Padding rule: `ulps` fp32 epsilons of the largest coordinate magnitude any

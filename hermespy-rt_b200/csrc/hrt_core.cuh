@@ -84,11 +84,10 @@ HRT_HD V3 v3_normalize(V3 a)
  *   q2 = (ac.z, n.x, n.y, n.z)        them per test, :259-260; same rounding)
  * n is the unit normal of reference :208-224.
  *
- * BVH2 node, 64 B = 4 x float4, children's boxes stored in the parent:
- *   n0 = (L.lo.x, L.hi.x, L.lo.y, L.hi.y)
- *   n1 = (R.lo.x, R.hi.x, R.lo.y, R.hi.y)
- *   n2 = (L.lo.z, L.hi.z, R.lo.z, R.hi.z)
- *   n3 = bit patterns (L.ref, R.ref, -, -)
+ * BVH2 node, 64 B = 4 x float4, children's boxes stored in the parent, one
+ * 32-byte record per child (a child's box and ref are fetched with two loads):
+ *   n0 = (L.lo.x, L.hi.x, L.lo.y, L.hi.y)   n1 = (L.lo.z, L.hi.z, L.ref, -)
+ *   n2 = (R.lo.x, R.hi.x, R.lo.y, R.hi.y)   n3 = (R.lo.z, R.hi.z, R.ref, -)
  * ref >= 0: inner node index.  ref < 0: leaf, ~ref = (first_slot << 3) | (count-1).
  * ------------------------------------------------------------------------- */
 #define HRT_LEAF_MAX_CAP 8
@@ -293,16 +292,25 @@ struct HrtGlobalMem {
     return tris[3 * s + k];
 #endif
   }
-  /* halves of node words 2 and 3: z planes of child `right`, and the two refs */
-  HRT_HD void node_z(int i, uint32_t right, float *z0, float *z1) const
+  /* child record at byte offset `off` of the (octant's) node array */
+  HRT_HD void child_at(uint32_t off, float4 *xy, float4 *zr) const
   {
-    const float4 n2 = node(i, 2);
-    *z0 = right ? n2.z : n2.x; *z1 = right ? n2.w : n2.y;
+    const float4 *q = (const float4 *)((const char *)nodes + off);
+#if defined(__CUDA_ARCH__)
+    *xy = __ldg(q); *zr = __ldg(q + 1);
+#else
+    *xy = q[0]; *zr = q[1];
+#endif
   }
-  HRT_HD void node_refs(int i, int *rl, int *rr) const
+  HRT_HD uint32_t cache_word(uint32_t, uint32_t) const { return 0u; }   /* no chain cache for global-memory scenes */
+  HRT_HD int child_ref(int i, uint32_t right) const
   {
-    const float4 n3 = node(i, 3);
-    *rl = hrt_float_as_int(n3.x); *rr = hrt_float_as_int(n3.y);
+    const int *q = (const int *)((const char *)nodes + ((size_t)i << 6) + (right ? 56u : 24u));
+#if defined(__CUDA_ARCH__)
+    return __ldg(q);
+#else
+    return *q;
+#endif
   }
   HRT_HD void select_octant(uint32_t oct, uint32_t stride)
   {
@@ -329,25 +337,38 @@ struct HrtStackEntry { int ref; float tn; };
  * the SIBLING at every level -- one box test and no ordering decision instead of
  * two tests and a three-way branch.  Pure traversal order: results are the
  * minimum over (t, triangle id) as before. */
-struct HrtChain { uint32_t path, depth; };
+struct HrtChain {
+  uint32_t path, depth;
+  uint32_t cached;      /* levels whose sibling record offsets sit in the per-thread cache (shared-memory scenes) */
+  uint32_t cache_addr;  /* shared-window byte address of this thread's entry 0; entries HRT_CHAIN_STRIDE bytes apart */
+};
+#define HRT_CHAIN_CACHE_LEVELS 6u
+HRT_HD HrtChain hrt_no_chain() { HrtChain c; c.path = 0u; c.depth = 0u; c.cached = 0u; c.cache_addr = 0u; return c; }
 
-/* `mem` must be the plain (octant 0) node copy: (lo, hi) per axis */
+/* `mem` must be the plain (octant 0) node copy: (lo, hi) per axis.  With
+ * `cache` != NULL the byte offsets of the sibling records of the first
+ * `max_cached` levels are stored at cache[level * stride_words], followed by the
+ * ref at which that cached part of the chain ends. */
 template <class Mem>
-HRT_HD HrtChain hrt_origin_chain(const Mem &mem, int root_ref, uint32_t num_tris, V3 o)
+HRT_HD HrtChain hrt_origin_chain(const Mem &mem, int root_ref, uint32_t num_tris, V3 o,
+                                 uint32_t *cache = nullptr, uint32_t stride_words = 0, uint32_t max_cached = 0)
 {
-  HrtChain ch; ch.path = 0u; ch.depth = 0u;
+  HrtChain ch = hrt_no_chain();
   if (num_tris == 0) return ch;
   int cur = root_ref;
   while (cur >= 0 && ch.depth < 32u) {
-    const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1), n2 = mem.node(cur, 2);
-    int rl, rr;
-    mem.node_refs(cur, &rl, &rr);
-    const bool in_l = o.x >= n0.x && o.x <= n0.y && o.y >= n0.z && o.y <= n0.w && o.z >= n2.x && o.z <= n2.y;
-    const bool in_r = o.x >= n1.x && o.x <= n1.y && o.y >= n1.z && o.y <= n1.w && o.z >= n2.z && o.z <= n2.w;
-    if (in_l) cur = rl;
-    else if (in_r) { ch.path |= 1u << ch.depth; cur = rr; }
-    else break;
+    const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1), n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
+    const bool in_l = o.x >= n0.x && o.x <= n0.y && o.y >= n0.z && o.y <= n0.w && o.z >= n1.x && o.z <= n1.y;
+    const bool in_r = o.x >= n2.x && o.x <= n2.y && o.y >= n2.z && o.y <= n2.w && o.z >= n3.x && o.z <= n3.y;
+    if (!in_l && !in_r) break;
+    if (cache && ch.depth < max_cached) {
+      cache[ch.depth * stride_words] = ((uint32_t)cur << 6) + (in_l ? 32u : 0u);   /* the sibling's record */
+      ch.cached = ch.depth + 1u;
+    }
+    if (in_l) cur = hrt_float_as_int(n1.z);
+    else { ch.path |= 1u << ch.depth; cur = hrt_float_as_int(n3.z); }
     ++ch.depth;
+    if (cache && ch.depth == ch.cached) cache[ch.depth * stride_words] = (uint32_t)cur;
   }
   return ch;
 }
@@ -360,7 +381,7 @@ HRT_HD HrtChain hrt_origin_chain(const Mem &mem, int root_ref, uint32_t num_tris
 template <bool SORTED, class Mem, class Gid, class Cnt>
 HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref,
                               uint32_t num_tris, V3 o, V3 d, Cnt &cnt, uint32_t oct_stride = 0,
-                              HrtChain chain = HrtChain{0u, 0u})
+                              HrtChain chain = hrt_no_chain())
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
@@ -374,23 +395,36 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
   HrtStackEntry stack[HRT_STACK];    /* (subtree ref, entry distance): one 8-byte store / load each */
   int sp = 0, cur = root_ref;
   bool done = false;
-  /* the origin's chain (hrt_origin_chain): siblings only */
-  for (uint32_t lvl = 0; lvl < chain.depth; ++lvl) {
-    const uint32_t right = (chain.path >> lvl) & 1u;      /* origin in the right child: test the left */
-    const float4 sxy = mem.node(cur, right ? 0 : 1);
-    float z0, z1, ts;
-    mem.node_z(cur, right ^ 1u, &z0, &z1);
-    int rl, rr;
-    mem.node_refs(cur, &rl, &rr);
-    const bool hs = SORTED ? hrt_slab_sorted(c, sxy.x, sxy.y, sxy.z, sxy.w, z0, z1, tmax, &ts)
-                           : hrt_slab(c, sxy.x, sxy.y, sxy.z, sxy.w, z0, z1, tmax, &ts);
+  /* the origin's chain (hrt_origin_chain): siblings only.  First the levels whose
+   * sibling record offsets were cached per thread, then the rest by path bits. */
+  for (uint32_t lvl = 0; lvl < chain.cached; ++lvl) {
+    float4 sxy, szr;
+    mem.child_at(mem.cache_word(chain.cache_addr, lvl), &sxy, &szr);
+    float ts;
+    const bool hs = SORTED ? hrt_slab_sorted(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts)
+                           : hrt_slab(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts);
     cnt.box(1u);
     if (hs) {
       HrtStackEntry e;
-      e.ref = right ? rl : rr; e.tn = ts;
+      e.ref = hrt_float_as_int(szr.z); e.tn = ts;
       stack[sp++] = e;
     }
-    cur = right ? rr : rl;
+  }
+  if (chain.cached) cur = (int)mem.cache_word(chain.cache_addr, chain.cached);
+  for (uint32_t lvl = chain.cached; lvl < chain.depth; ++lvl) {
+    const uint32_t right = (chain.path >> lvl) & 1u;      /* origin in the right child: test the left */
+    float4 sxy, szr;
+    mem.child_at(((uint32_t)cur << 6) + (right ? 0u : 32u), &sxy, &szr);
+    float ts;
+    const bool hs = SORTED ? hrt_slab_sorted(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts)
+                           : hrt_slab(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts);
+    cnt.box(1u);
+    if (hs) {
+      HrtStackEntry e;
+      e.ref = hrt_float_as_int(szr.z); e.tn = ts;
+      stack[sp++] = e;
+    }
+    cur = mem.child_ref(cur, right);
   }
   /* "while-while" traversal: every lane first walks inner nodes until it holds
    * a leaf (or has nothing left), then the leaves are tested -- lanes of a warp
@@ -400,11 +434,11 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
       const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1);
       const float4 n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
       float tl, tr;
-      const bool hl = SORTED ? hrt_slab_sorted(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl)
-                             : hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmax, &tl);
-      const bool hr = SORTED ? hrt_slab_sorted(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr)
-                             : hrt_slab(c, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmax, &tr);
-      const int rl = hrt_float_as_int(n3.x), rr = hrt_float_as_int(n3.y);
+      const bool hl = SORTED ? hrt_slab_sorted(c, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tmax, &tl)
+                             : hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tmax, &tl);
+      const bool hr = SORTED ? hrt_slab_sorted(c, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, tmax, &tr)
+                             : hrt_slab(c, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, tmax, &tr);
+      const int rl = hrt_float_as_int(n1.z), rr = hrt_float_as_int(n3.z);
       cnt.box(2u);
       if (hl && hr) {
         const bool left_first = tl <= tr;

@@ -713,7 +713,7 @@ template <class K> static cudaError_t allow_smem(K kernel, size_t bytes)
 }
 
 typedef void (*BounceFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t);
-typedef void (*ScatterFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t, uint32_t);
+typedef void (*ScatterFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t, uint32_t, uint32_t);
 
 /* [smem][brute][count]; the instrumented build exists for BVH traversal only */
 static BounceFn bounce_fn(bool smem, bool brute, bool count)
@@ -1002,7 +1002,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   /* scatter kernel shared memory: scene + receivers + reduction table */
   const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
   const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 110 * 1024;
-  const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
+  size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
+  /* per-thread chain cache (hrt_origin_chain) behind the scene and the receiver tables,
+   * while two blocks still fit an SM */
+  uint32_t cc_off = 0;
+  {
+    const size_t cc_sb = (size_t)(HRT_CHAIN_CACHE_LEVELS + 1) * HRT_BLOCK * 4;
+    const size_t at = (scat_sb + 15) & ~(size_t)15;
+    if (smem && !brute && at + cc_sb <= 112 * 1024 && !getenv("HRT_NO_CHAIN_CACHE")) { cc_off = (uint32_t)at; scat_sb = at + cc_sb; }
+  }
   /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
    * thanks to the direction sort) whenever there are enough hits to fill the
    * machine; a warp per hit (lanes over receivers) for few rays x many RX */
@@ -1216,7 +1224,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+      f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok, cc_off);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
       if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 3], st)); ev_used += 4; }

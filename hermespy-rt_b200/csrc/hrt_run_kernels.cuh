@@ -30,14 +30,15 @@ struct HrtSharedMem {
   uint32_t node_addr, tri_addr;     /* byte addresses in the shared window */
   __device__ __forceinline__ float4 node(int i, int k) const { return lds128(node_addr + ((uint32_t)i << 6) + ((uint32_t)k << 4)); }
   __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return lds128(tri_addr + s * 48u + ((uint32_t)k << 4)); }
-  __device__ __forceinline__ void node_z(int i, uint32_t right, float *z0, float *z1) const
+  __device__ __forceinline__ void child_at(uint32_t off, float4 *xy, float4 *zr) const
   {
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(*z0), "=f"(*z1) : "r"(node_addr + ((uint32_t)i << 6) + 32u + (right << 3)));
+    *xy = lds128(node_addr + off); *zr = lds128(node_addr + off + 16u);
   }
-  __device__ __forceinline__ void node_refs(int i, int *rl, int *rr) const
-  {
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(*rl), "=r"(*rr) : "r"(node_addr + ((uint32_t)i << 6) + 48u));
-  }
+  __device__ __forceinline__ int child_ref(int i, uint32_t right) const
+  { return (int)lds32(node_addr + ((uint32_t)i << 6) + (right ? 56u : 24u)); }
+  /* entry `lvl` of a thread's chain cache (hrt_origin_chain) */
+  __device__ __forceinline__ uint32_t cache_word(uint32_t cache_addr, uint32_t lvl) const
+  { return lds32(cache_addr + lvl * (HRT_BLOCK * 4u)); }
   __device__ __forceinline__ void select_octant(uint32_t oct, uint32_t stride)
   {
     node_addr += oct * stride * 16u;
@@ -77,7 +78,7 @@ static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris, uint32_t o
 { return (size_t)num_nodes * 64 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
 
 template <bool SMEM, bool BRUTE, class Cnt>
-__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, HrtChain chain = HrtChain{0u, 0u})
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, HrtChain chain = hrt_no_chain())
 {
   if (SMEM) {
     HrtSharedMem m;
@@ -95,14 +96,21 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
   }
 }
 
-/* the chain of node boxes that contain `o` (hrt_origin_chain), on the plain node copy */
+/* the chain of node boxes that contain `o` (hrt_origin_chain), on the plain node
+ * copy; cc_off != 0: byte offset of the block's chain cache in shared memory */
 template <bool SMEM>
-__device__ __forceinline__ HrtChain origin_chain(const SceneDev &sc, V3 o)
+__device__ __forceinline__ HrtChain origin_chain(const SceneDev &sc, V3 o, uint32_t cc_off)
 {
-  if (sc.no_chain) return HrtChain{0u, 0u};
+  if (sc.no_chain) return hrt_no_chain();
   if (SMEM) {
     HrtSharedMem m;
     m.node_addr = smem_base_addr(); m.tri_addr = 0;
+    if (cc_off) {
+      uint32_t *mine = (uint32_t *)((char *)hrt_smem4 + cc_off) + threadIdx.x;
+      HrtChain ch = hrt_origin_chain(m, sc.root_ref, sc.num_tris, o, mine, (uint32_t)HRT_BLOCK, HRT_CHAIN_CACHE_LEVELS);
+      ch.cache_addr = smem_base_addr() + cc_off + 4u * threadIdx.x;
+      return ch;
+    }
     return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
   }
   HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
@@ -411,7 +419,7 @@ struct PairAcc {
  * output paths. */
 template <bool SMEM, bool BRUTE, bool WARP, bool COUNT, bool LEAN = false>
 __global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
-k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
+k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok, uint32_t cc_off)
 {
   typename CntSel<COUNT>::type wc; cnt_init(wc);
   uint32_t used4 = 0;
@@ -466,7 +474,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
     const V3 mv = ld3(sc.mesh_vel, mesh);
     float theta_carry = r2.w;
-    const HrtChain chain = BRUTE ? HrtChain{0u, 0u} : origin_chain<SMEM>(sc, s.o);
+    const HrtChain chain = BRUTE ? hrt_no_chain() : origin_chain<SMEM>(sc, s.o, cc_off);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const uint64_t hkey = hrt_mix64((path << 32) | gid);
 

@@ -92,7 +92,7 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   }
 }
 
-static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute, HrtChain chain = HrtChain{0u, 0u})
+static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute, HrtChain chain = hrt_no_chain())
 {
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
   HrtNoCount nc;
@@ -201,7 +201,7 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
         const HrtMaterial &mat = mats.m[E.mesh_mat[mesh]];
         hrt_bounce_update(s, mat, k, h.t, n, theta);
         float carry = theta;
-        const HrtChain chain = brute == 1 ? HrtChain{0u, 0u} : chain_of(E, s.o);
+        const HrtChain chain = brute == 1 ? hrt_no_chain() : chain_of(E, s.o);
         for (size_t r = 0; r < R; ++r) {
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
