@@ -787,7 +787,7 @@ extern "C" int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_
 
 static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t B, uint32_t flags)
 {
-  const uint32_t shape_flags = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_SUMMARY | HRT_FLAG_TRACE);
+  const uint32_t shape_flags = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_TRACE);   /* the flags that own buffers */
   if (ctx->cap_n >= n && ctx->cap_R == R && ctx->cap_T == T && ctx->cap_B == B && ctx->cap_flags == shape_flags)
     return HRT_OK;
   free_run_dev(ctx);

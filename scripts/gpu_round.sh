@@ -33,7 +33,7 @@ python scripts/run_c5.py 6.25e7 1024 256 65536 > $OUT/c5_shard.json 2> $OUT/c5.e
 
 if [ "${NCU:-1}" = "1" ]; then
 echo "== ncu launch list"
-export HRT_BENCH_RAYS=2e6 HRT_REF_PATHS=100
+export HRT_BENCH_RAYS=8e6 HRT_REF_PATHS=100
 python bench.py --steps 1 --warmup 0 > $OUT/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 0 > $OUT/ncu_launches.log 2>&1
