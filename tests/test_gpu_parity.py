@@ -259,6 +259,62 @@ def test_scene_advance_refit_and_rebuild(ctx, tmp_path):
     ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
 
 
+def test_degenerate_scenes_builder_and_ties(ctx, tmp_path):
+    """Builder corner cases: many coincident triangles (identical centroids: the
+    SAH bins cannot separate them, nodes are halved by position), long thin
+    slivers, a single triangle, three triangles.  Closest hits (ids incl. the
+    lowest-id-wins tie rule among coincident triangles) and t equal the oracle's."""
+    from hrt_b200 import scenes
+    rng = np.random.default_rng(12)
+    quad = np.array([[-2, -2, 1], [2, -2, 1], [2, 2, 1], [-2, 2, 1]], np.float32)
+    cases = {}
+    # 1) 40 copies of the same two triangles + one big floor
+    vs = np.concatenate([quad] * 20 + [np.array([[-9, -9, 0], [9, -9, 0], [9, 9, 0], [-9, 9, 0]], np.float32)])
+    tris = np.concatenate([np.array([[0, 1, 2], [0, 2, 3]], np.uint32) + 4 * k for k in range(21)])
+    cases["coincident"] = [dict(vs=vs, tris=tris, material=1, velocity=np.zeros(3, np.float32))]
+    # 2) slivers: 60 needle triangles along x, 1e-3 wide
+    v, t = [], []
+    for k in range(60):
+        y = -3 + 0.1 * k
+        v += [[-5, y, 0.5 + 0.01 * k], [5, y + 1e-3, 0.5 + 0.01 * k], [5, y - 1e-3, 0.5 + 0.01 * k]]
+        t.append([3 * k, 3 * k + 1, 3 * k + 2])
+    cases["slivers"] = [dict(vs=np.array(v, np.float32), tris=np.array(t, np.uint32), material=2, velocity=np.zeros(3, np.float32))]
+    cases["single"] = [dict(vs=quad[:3], tris=np.array([[0, 1, 2]], np.uint32), material=1, velocity=np.zeros(3, np.float32))]
+    cases["three"] = [dict(vs=np.concatenate([quad, quad[:3] + [0, 0, 1]]), tris=np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6]], np.uint32),
+                           material=1, velocity=np.zeros(3, np.float32))]
+    for name, meshes in cases.items():
+        path = str(tmp_path / (name + ".hrt")); scenes.write_hrt(path, meshes)
+        n = 60000
+        o = rng.uniform(-6, 6, (n, 3)) * [1, 1, 0.5] + [0, 0, 2.5]
+        d = rng.normal(size=(n, 3)); d[:, 2] = -np.abs(d[:, 2]) - 0.2; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        # half of the rays aimed at random points of random triangles (thin slivers are hard to hit by chance)
+        corners = np.concatenate([m["vs"][m["tris"]] for m in meshes]).astype(np.float64)
+        w = rng.random((n // 2, 3)); w /= w.sum(1, keepdims=True)
+        tgt = (corners[rng.integers(0, len(corners), n // 2)] * w[:, :, None]).sum(1)
+        d[: n // 2] = tgt - o[: n // 2]; d[: n // 2] /= np.linalg.norm(d[: n // 2], axis=1, keepdims=True)
+        rays = np.ascontiguousarray(np.concatenate([o, d], 1).astype(np.float32))
+        tri_o, t_o, _ = tl.oracle_closest(path, rays)
+        for env in ({}, {"HRT_BVH_LBVH": "1"}):
+            os_env = dict(env)
+            import os
+            os.environ.update(os_env)
+            try:
+                ctx.load_scene(path)
+                tri_g, t_g, _ = ctx.closest_hits(rays)
+            finally:
+                for k in os_env:
+                    del os.environ[k]
+            assert (tri_o != tl.NONE).sum() > n // 20, name
+            assert np.array_equal(tri_o, tri_g) and np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32)), (name, env)
+        # and a full run: BVH kernels == brute-force kernels
+        rx = np.array([[0.5, 0.3, 3.0], [-3.0, 1.0, 2.0]], np.float32); tx = np.array([[0.1, -0.2, 4.0]], np.float32)
+        a = ctx.run(rx, tx, np.zeros_like(rx), np.zeros_like(tx), 3.5, 20000, 3, summary=True)
+        b = ctx.run(rx, tx, np.zeros_like(rx), np.zeros_like(tx), 3.5, 20000, 3, summary=True, brute_force=True)
+        for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+            assert np.array_equal(a["pair"][k], b["pair"][k]), (name, k)
+    ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
+
+
 def test_launch_directions_bit_exact(ctx):
     """Fibonacci launch directions incl. the host-recomputed ambiguous ones
     (hrt_core.cuh, hrt_launch_dir) == glibc results of the oracle, every ray."""
