@@ -968,6 +968,16 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const uint64_t n_shard = shard_count(P, rank, world, blk);
   size_t chunk = 1u << 23;
   if (const char *s = getenv("HRT_CHUNK")) { long long v = atoll(s); if (v >= 32) chunk = (size_t)v; }
+  {
+    /* per-ray state (two 64-byte records, three queue words, two key words per TX,
+     * sort scratch) must fit: at most half of the free device memory */
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b) {
+      const size_t have = free_b + (ctx->cap_n ? ctx->cap_n * ctx->cap_T * 160 : 0);   /* our own buffers are reusable */
+      const size_t lim = (have / 2) / (T * 176 + 40);
+      if (chunk > lim) chunk = lim < 32 ? 32 : lim;
+    }
+  }
   if (flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE)) {
     /* bound the dense staging buffers to ~6 GB */
     const size_t per_path = R * T * B * 40 + T * (B + 1) * 24 + 64 * T;
