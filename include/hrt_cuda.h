@@ -14,6 +14,11 @@
  *                           for one shard of the (tx, path) space
  *   hrt_closest_hits ...... moeller_trumbore() (src/compute_paths.c:237-287)
  *                           for a batch of rays (unit-test / validation entry)
+ *   hrt_scene_advance ..... no reference counterpart: moves the meshes by their
+ *                           Mesh.velocity (inc/scene.h:21-22) and refits the BVH
+ * Output modes of hrt_run beyond the reference's dense arrays (HRT_FLAG_*):
+ * per-(rx, tx, bounce) summaries, the delay-binned impulse response, and the
+ * compact list of valid paths -- see HrtRunParams.
  *
  * Every function returns HRT_OK (0) or a negative HRT_E_* code;
  * hrt_last_error() gives the message.  There is no CPU fallback anywhere:
