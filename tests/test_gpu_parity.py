@@ -315,6 +315,27 @@ def test_degenerate_scenes_builder_and_ties(ctx, tmp_path):
     ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
 
 
+@pytest.mark.parametrize("P,B,R,T", [(1, 1, 1, 1), (7, 2, 3, 1), (33, 1, 1, 3), (257, 12, 2, 2), (1000, 3, 70, 1)])
+def test_ragged_and_tiny_sizes(ctx, P, B, R, T):
+    """Sizes around every granularity of the implementation (warps of 32, chunks,
+    receiver tiles of 32, one path, one bounce, many bounces with few rays): dense
+    outputs, RaysInfo and the hit trace against the oracle."""
+    scene = "simple_street_canyon_with_cars"
+    grid, txs = tl.canyon_c4_positions()
+    rng = np.random.default_rng(P * 131 + B)
+    rx = np.concatenate([grid, grid + [0.7, 0.3, 0.5]])[:R]
+    tx = txs[:T] + rng.uniform(-0.5, 0.5, (T, 3))
+    rxv, txv = rng.uniform(-3, 3, rx.shape), rng.uniform(-10, 10, tx.shape)
+    a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, 3.5, P, B, fill=0x00)
+    b, _ = tl.run_oracle(scene, rx, tx, rxv, txv, 3.5, P, B, fill=0x5A, trace=False)
+    mask = tl.written_mask(a, b)
+    ctx.load_scene(tl.scene_path(scene))
+    res = ctx.run(rx, tx, rxv, txv, 3.5, P, B, dense=True, raysinfo=True, trace=True, summary=True)
+    _compare_dense(a, mask, res["out"], tr, res["trace"])
+    pair, bounce = tl.oracle_summaries(a, tr)
+    tl.assert_summaries_equal(pair, bounce, res["pair"], res["bounce"])
+
+
 def test_launch_directions_bit_exact(ctx):
     """Fibonacci launch directions incl. the host-recomputed ambiguous ones
     (hrt_core.cuh, hrt_launch_dir) == glibc results of the oracle, every ray."""
