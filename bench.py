@@ -330,10 +330,22 @@ def main_gpu(args):
                             "bound; its DRAM traffic is the gather of per-hit state" % (tj["source"], l0["duration_ms"]))
         except Exception:
             pass
+        isect_share, isect_note = None, None
+        try:
+            sj = json.load(open(os.path.join(ROOT, "profiles", "k_scatter_shares.json")))
+            isect_share = sj["intersection_share_of_issue_slots"]
+            isect_note = ("k_scatter fuses the reference's per-path scattering math (0 counted flops) with the closest-hit "
+                          "query; by ncu source-level instruction counts (%s) %.0f %% of its issue slots are the query. "
+                          "frac_of_intersection_slots = frac / that share" % (sj["source"], 100 * isect_share))
+        except Exception:
+            pass
         roofline = {
             "bound": "fp32", "kernel": "k_scatter", "achieved": achieved, "peak": peak_unfused,
             "unit": "TFLOP/s", "frac": (achieved / peak_unfused) if achieved and peak_unfused else None,
             "traffic": traffic, "traffic_note": traffic_note,
+            "intersection_share_of_issue_slots": isect_share,
+            "frac_of_intersection_slots": (achieved / peak_unfused / isect_share) if achieved and peak_unfused and isect_share else None,
+            "intersection_note": isect_note,
             "peak_source": "measured in this run with separately rounded FMUL+FADD chains "
                            "(hrt_fp32_peak); MEASURED_PEAKS.json has no fp32 figure. nominal "
                            f"unfused {nominal:.1f}, measured FFMA {peak_fma:.1f} TFLOP/s",

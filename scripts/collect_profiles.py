@@ -74,6 +74,16 @@ def source_shares(rep, kernel_substr, out_path):
         agg[seq[k][0]] += c; thr[seq[k][0]] += t
         fn = func(seq[k][0]); fa[fn] += c; ft[fn] += t
     tot = sum(agg.values()); tt = sum(thr.values())
+    # share of the issue slots spent on the closest-hit query itself (traversal, slab and
+    # triangle tests, their loads and ray set-up) as opposed to the per-path math after it
+    INTERSECTION = {"hrt_closest_hit", "hrt_mt_test", "hrt_slab_sorted", "hrt_slab", "hrt_fma_pair", "v3_dot", "v3_cross",
+                    "v3_sub", "lds128", "lds32", "smem_base_addr", "node", "tri", "child_at", "child_ref", "cache_word",
+                    "hrt_safe_inv", "hrt_octant", "hrt_ray_cull", "hrt_origin_chain", "select_octant", "query", "origin_chain"}
+    share = sum(c for fn, c in fa.items() if fn in INTERSECTION) / max(tot, 1)
+    json.dump({"kernel": kernel_substr, "intersection_share_of_issue_slots": share,
+               "functions": {fn: c / tot for fn, c in fa.most_common(30)},
+               "source": os.path.relpath(out_path, ROOT)},
+              open(out_path.replace("_by_source.txt", "_shares.json"), "w"), indent=1)
     with open(out_path, "w") as f:
         f.write(f"kernel {kernel_substr}: {len(data)} SASS instructions, {tot:.4e} warp-instructions executed, "
                 f"{tt / tot:.2f} active threads per instruction\n\nby function (share of issued warp-instructions, active threads):\n")
@@ -119,6 +129,8 @@ for rep, kern, tag in (("prof_scatter.ncu-rep", "_Z9k_scatterILb1ELb0ELb0ELb0ELb
         tr.append({"kernel": r.get("Kernel Name"), "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                    "duration_ms": dur * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(du, 1) if dur is not None else None})
     json.dump({"source": f"ncu --set full --clock-control none, {rep}", "launches": tr}, open(os.path.join(OUT, f"{tag}_traffic.json"), "w"), indent=1)
+    if tag == "k_scatter":
+        shutil.copy(os.path.join(OUT, "k_scatter_shares.json"), os.path.join(ROOT, "profiles", "k_scatter_shares.json"))
     if tag == "k_scatter":   # what bench.py reports as roofline.traffic
         json.dump({"source": f"profiles/{name}/{tag}_traffic.json (ncu --set full, one launch of the 8e6-ray bench step)", "launches": tr},
                   open(os.path.join(ROOT, "profiles", "k_scatter_traffic.json"), "w"), indent=1)
