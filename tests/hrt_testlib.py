@@ -368,3 +368,25 @@ def assert_summaries_equal(pair_ref, bounce_ref, pair, bounce, rtol=GAIN_RTOL * 
         assert np.array_equal(pair_ref[k], pair[k]), f"pair.{k}"
     for k in ("power_te", "power_tm"):
         np.testing.assert_allclose(pair[k], pair_ref[k], rtol=rtol, atol=1e-300, err_msg=k)
+
+
+# ------------------------------------------------------------ plain C caller
+
+def build_c_caller(out_dir: str) -> str:
+    """Compiles tests/c_caller/caller.c (written against include/ under the
+    reference's header names) as C11 with -Wall -Wextra -Werror and links it
+    against the product library.  Returns the executable's path."""
+    exe = os.path.join(out_dir, "caller")
+    pkg = os.path.join(ROOT, "hermespy-rt_b200")
+    cmd = ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_caller", "caller.c"), "-L", pkg, "-lhermespy_rt",
+           "-Wl,-rpath," + pkg, "-lm", "-o", exe]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    return exe
+
+
+C_CALLER_RX = [[0.0, 0.0, 0.5], [0.4, -0.3, 1.25]]
+C_CALLER_TX = [[0.0, 0.0, 0.5]]
+C_CALLER_RXV = [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]
+C_CALLER_TXV = [[0.0, 2.0, 0.0]]

@@ -336,6 +336,24 @@ def test_ragged_and_tiny_sizes(ctx, P, B, R, T):
     tl.assert_summaries_equal(pair, bounce, res["pair"], res["bounce"])
 
 
+@pytest.mark.parametrize("scene,P,B,f", [("simple_reflector", 30000, 3, 3.0), ("box", 20000, 3, 3.0)])
+def test_plain_c_caller_vs_oracle(tmp_path, scene, P, B, f):
+    """tests/c_caller/caller.c -- a C program in the style of the reference's
+    test/test.c:17-72 (its path count, bounce count and frequency for the
+    reflector) -- run as its own process against the library: path count, the sum
+    of the tau bit patterns and the LoS delays equal the oracle's."""
+    import json, subprocess
+    exe = tl.build_c_caller(str(tmp_path))
+    p = subprocess.run([exe, tl.scene_path(scene), str(P), str(B), repr(f)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    got = json.loads(p.stdout.strip().splitlines()[-1])
+    a, tr = tl.run_oracle(scene, tl.C_CALLER_RX, tl.C_CALLER_TX, tl.C_CALLER_RXV, tl.C_CALLER_TXV, f, P, B, fill=0x00)
+    tau = a.scat["tau"].reshape(-1)
+    assert got["paths"] == int((tau != 0).sum()) and got["paths"] > 1000
+    assert got["tau_bits"] == int(tau.view(np.uint32)[tau != 0].astype(np.uint64).sum())
+    assert got["los_tau_bits"] == a.los["tau"].reshape(-1).view(np.uint32).tolist()
+
+
 def test_launch_directions_bit_exact(ctx):
     """Fibonacci launch directions incl. the host-recomputed ambiguous ones
     (hrt_core.cuh, hrt_launch_dir) == glibc results of the oracle, every ray."""

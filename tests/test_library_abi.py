@@ -126,3 +126,17 @@ def test_python_module_imports_and_refuses_without_gpu():
     with pytest.raises(ValueError):
         m.compute_paths(tl.scene_path("box"), np.zeros((2, 3)), np.ones((1, 3)), np.zeros((1, 3)),
                         np.zeros((1, 3)), 3.0, 1, 1, 10, 1)
+
+
+def test_plain_c_caller_compiles_links_and_refuses_without_gpu(tmp_path):
+    """The drop-in boundary at source level: a C11 program written against the
+    reference's header names (compute_paths.h, scene.h, vec3.h, ray.h) compiles
+    warning-free against include/ and links against libhermespy_rt.so.  Without a
+    GPU it ends like the reference's I/O errors do: message + exit(8)."""
+    import subprocess
+    import torch
+    exe = tl.build_c_caller(str(tmp_path))
+    if torch.cuda.is_available():
+        return
+    p = subprocess.run([exe, tl.scene_path("simple_reflector"), "100", "2", "3.0"], capture_output=True, text=True)
+    assert p.returncode == 8 and "hermespy_rt" in p.stderr
