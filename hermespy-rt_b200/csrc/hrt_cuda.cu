@@ -925,6 +925,171 @@ static cudaError_t run_copy_tiles(hrt_ctx *ctx, cudaStream_t st, const std::vect
   return cudaSuccess;
 }
 
+/* RaysInfo activity masks, bits outside TX 0's path range */
+static void raysinfo_tail_bits(const HrtRunParams *p, const uint8_t tail_dead[8])
+{
+  const size_t T = p->num_tx, B = p->num_bounces;
+  const uint64_t P = p->num_paths;
+  /* bits outside TX 0's path range: row 0 is all ones (:470); in later rows
+   * the tail bits of the last byte stay set for T == 1 */
+  uint8_t *A = p->rays_scat->rays_active;
+  const size_t rowb = P / 8 + 1;
+  memset(A, 0xff, rowb);
+  for (size_t t = 0; t < T; ++t)
+    for (size_t b = 0; b < B; ++b) {
+      uint8_t *row = A + (t * B + b + 1) * rowb;
+      for (uint64_t bit = P; bit < rowb * 8; ++bit) {
+        /* global bit index `bit` = TX 1, path bit-P (if it exists): its state
+         * when the reference copies the row, i.e. after bounce b for t >= 1,
+         * after bounce b-1 for t == 0 */
+        bool on = true;
+        const uint64_t j = bit - P;
+        if (T > 1 && j < P && j < 8) {
+          const int done = (int)b - (t == 0 ? 1 : 0);     /* last bounce TX 1 has finished */
+          on = done < 0 || (int)tail_dead[j] > done;
+        }
+        if (on) row[bit >> 3] |= (uint8_t)(1u << (bit & 7)); else row[bit >> 3] &= (uint8_t)~(1u << (bit & 7));
+      }
+    }
+}
+
+/* per-(rx, tx, bounce) and per-(tx, bounce) tables of this call -> added to the caller's (host or device) */
+static int flush_summaries(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd, uint32_t flags, cudaStream_t st)
+{
+  const size_t R = p->num_rx, T = p->num_tx, B = p->num_bounces;
+  HrtRunStats &S = ctx->stats;
+  const size_t np = R * T * B, nb = T * B;
+  if (flags & HRT_FLAG_SUMMARY_DEV) {
+    /* pair: fields 4,5 of each 6-word record are doubles */
+    unsigned char *d_isd = nullptr;
+    unsigned char *h_isd = (unsigned char *)calloc(np * 6, 1);
+    if (!h_isd) return fail(ctx, HRT_E_NOMEM, "out of host memory");
+    for (size_t i = 0; i < np; ++i) h_isd[6 * i + 4] = h_isd[6 * i + 5] = 1;
+    cudaError_t e = cudaMalloc((void **)&d_isd, np * 6);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_isd, h_isd, np * 6, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      k_add_u64<<<nblk(np * 6), 256, 0, st>>>((unsigned long long *)p->pair_summary, (const unsigned long long *)rd.pair, np * 6, d_isd);
+      k_add_u64<<<nblk(nb * 4), 256, 0, st>>>((unsigned long long *)p->bounce_summary, (const unsigned long long *)rd.bounce, nb * 4, nullptr);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_isd); free(h_isd);
+    CK(e);
+    S.kernel_launches += 2;
+  } else {
+    HrtPairSummary *hp = (HrtPairSummary *)malloc(np * sizeof(HrtPairSummary));
+    HrtBounceSummary *hb = (HrtBounceSummary *)malloc(nb * sizeof(HrtBounceSummary));
+    if (!hp || !hb) { free(hp); free(hb); return fail(ctx, HRT_E_NOMEM, "out of host memory"); }
+    cudaError_t e = cudaMemcpyAsync(hp, rd.pair, np * sizeof(HrtPairSummary), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb, rd.bounce, nb * sizeof(HrtBounceSummary), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+      for (size_t i = 0; i < np; ++i) {
+        p->pair_summary[i].n_valid += hp[i].n_valid; p->pair_summary[i].n_occluded += hp[i].n_occluded;
+        p->pair_summary[i].hit_hash += hp[i].hit_hash; p->pair_summary[i].tau_bits += hp[i].tau_bits;
+        p->pair_summary[i].power_te += hp[i].power_te; p->pair_summary[i].power_tm += hp[i].power_tm;
+      }
+      for (size_t i = 0; i < nb; ++i) {
+        p->bounce_summary[i].n_traced += hb[i].n_traced; p->bounce_summary[i].n_hit += hb[i].n_hit;
+        p->bounce_summary[i].hit_hash += hb[i].hit_hash; p->bounce_summary[i].t_bits += hb[i].t_bits;
+      }
+    }
+    free(hp); free(hb);
+    CK(e);
+  }
+  return HRT_OK;
+}
+
+/* compact path list -> the caller's buffer (unless it already lives in device memory), and the count */
+static int flush_path_list(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd, uint32_t flags, cudaStream_t st)
+{
+  unsigned long long found = 0;
+  CK(cudaMemcpyAsync(&found, rd.counters + 14, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const unsigned long long kept = found < p->paths_capacity ? found : p->paths_capacity;
+  if (!(flags & HRT_FLAG_PATHLIST_DEV)) {
+    CK(cudaMemcpyAsync(p->paths, ctx->d_plist, (size_t)kept * sizeof(HrtPathRecord), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  *p->paths_count = found;
+  return HRT_OK;
+}
+
+/* impulse response of this call -> added to the caller's array, LoS paths included (rank 0) */
+static int flush_cir(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd, uint32_t rank, cudaStream_t st)
+{
+  const size_t R = p->num_rx, T = p->num_tx;
+  HrtRunStats &S = ctx->stats;
+  const size_t ncir = R * T * (size_t)p->cir_bins * 4;
+  float *h = (float *)malloc(ncir * sizeof(float));
+  if (!h) return fail(ctx, HRT_E_NOMEM, "out of host memory");
+  unsigned long long dropped = 0;
+  cudaError_t e = cudaMemcpyAsync(h, ctx->d_cir, ncir * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&dropped, rd.counters + 15, 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) {
+    for (size_t i = 0; i < ncir; ++i) p->cir[i] += h[i];
+    S.cir_dropped = dropped;
+    /* the LoS paths (reference :556-577), written to p->los above */
+    if (p->los && rank == 0)
+      for (size_t k = 0; k < R * T; ++k) {
+        if (p->los->a_te_re[k] == 0.f && p->los->tau[k] == 0.f) continue;   /* blocked */
+        const float fb = (p->los->tau[k] - p->cir_tau0_s) * rd.cir_inv_dt;
+        if (fb >= 0.f && fb < (float)p->cir_bins) {
+          float *dst = p->cir + (k * p->cir_bins + (size_t)fb) * 4;
+          dst[0] += p->los->a_te_re[k]; dst[1] += p->los->a_te_im[k];
+          dst[2] += p->los->a_tm_re[k]; dst[3] += p->los->a_tm_im[k];
+        } else S.cir_dropped++;
+      }
+  }
+  free(h);
+  CK(e);
+  return HRT_OK;
+}
+
+/* Line of sight (reference :514-577): one query per (rx, tx) pair on the GPU,
+ * results and RaysInfo bits into the caller's host arrays. */
+static int run_los(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd, const SceneDev &sc, bool smem, bool brute,
+                   size_t scene_sb, cudaStream_t st)
+{
+  const size_t R = p->num_rx, T = p->num_tx;
+  HrtRunStats &S = ctx->stats;
+  const size_t npair = R * T;
+  if (ctx->cap_los < npair) { if (ctx->d_los) cudaFree(ctx->d_los); CK(cudaMalloc(&ctx->d_los, npair * sizeof(HrtLosOut))); ctx->cap_los = npair; }
+  DISPATCH2(k_los, smem, brute, nblk(npair, HRT_BLOCK), HRT_BLOCK, smem ? scene_sb : 0, st, rd, sc, (HrtLosOut *)ctx->d_los);
+  CK(cudaGetLastError());
+  S.kernel_launches++; S.los_queries = npair;
+  HrtLosOut *h = (HrtLosOut *)malloc(npair * sizeof(HrtLosOut));
+  if (!h) return fail(ctx, HRT_E_NOMEM, "out of host memory");
+  cudaError_t e = cudaMemcpyAsync(h, ctx->d_los, npair * sizeof(HrtLosOut), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { free(h); CK(e); }
+  ChannelInfo *L = p->los;
+  for (size_t k = 0; k < npair; ++k) {
+    const size_t r = k / T, t = k % T;
+    L->a_te_im[k] = L->a_tm_im[k] = 0.f;                                     /* reference :515-516 */
+    if (p->rays_los && p->rays_los->rays) {                                  /* reference :526-528 */
+      Ray *lr = &p->rays_los->rays[k];
+      lr->o = p->tx_pos[t];
+      lr->d = vec3_sub(&p->rx_pos[r], &lr->o);
+    }
+    uint8_t *bits = (p->rays_los && p->rays_los->rays_active) ? p->rays_los->rays_active : nullptr;
+    if (h[k].state == 0) {                                                   /* blocked, reference :548-554 */
+      L->a_te_re[k] = L->a_tm_re[k] = L->tau[k] = 0.f;
+      if (bits) bits[k / 8] &= (uint8_t)~(1u << (k % 8));
+      continue;
+    }
+    L->directions_tx[k].x = h[k].dir_tx.x; L->directions_tx[k].y = h[k].dir_tx.y; L->directions_tx[k].z = h[k].dir_tx.z;
+    L->directions_rx[k].x = h[k].dir_rx.x; L->directions_rx[k].y = h[k].dir_rx.y; L->directions_rx[k].z = h[k].dir_rx.z;
+    L->a_te_re[k] = L->a_tm_re[k] = h[k].a;
+    L->tau[k] = h[k].tau;
+    L->freq_shift[k] = h[k].freq;
+    if (bits) bits[k / 8] |= (uint8_t)(1u << (k % 8));
+  }
+  free(h);
+  return HRT_OK;
+}
+
 extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
 {
   if (!ctx || !p) return HRT_E_ARG;
@@ -1080,41 +1245,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   CK(cudaEventRecord(ctx->ev[0], st));
 
   /* ---- line of sight (rank 0 of the shard group only) ---- */
-  if (p->los && rank == 0) {
-    const size_t npair = R * T;
-    if (ctx->cap_los < npair) { if (ctx->d_los) cudaFree(ctx->d_los); CK(cudaMalloc(&ctx->d_los, npair * sizeof(HrtLosOut))); ctx->cap_los = npair; }
-    DISPATCH2(k_los, smem, brute, nblk(npair, HRT_BLOCK), HRT_BLOCK, smem ? scene_sb : 0, st, rd, sc, (HrtLosOut *)ctx->d_los);
-    CK(cudaGetLastError());
-    S.kernel_launches++; S.los_queries = npair;
-    HrtLosOut *h = (HrtLosOut *)malloc(npair * sizeof(HrtLosOut));
-    if (!h) return fail(ctx, HRT_E_NOMEM, "out of host memory");
-    cudaError_t e = cudaMemcpyAsync(h, ctx->d_los, npair * sizeof(HrtLosOut), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { free(h); CK(e); }
-    ChannelInfo *L = p->los;
-    for (size_t k = 0; k < npair; ++k) {
-      const size_t r = k / T, t = k % T;
-      L->a_te_im[k] = L->a_tm_im[k] = 0.f;                                     /* reference :515-516 */
-      if (p->rays_los && p->rays_los->rays) {                                  /* reference :526-528 */
-        Ray *lr = &p->rays_los->rays[k];
-        lr->o = p->tx_pos[t];
-        lr->d = vec3_sub(&p->rx_pos[r], &lr->o);
-      }
-      uint8_t *bits = (p->rays_los && p->rays_los->rays_active) ? p->rays_los->rays_active : nullptr;
-      if (h[k].state == 0) {                                                   /* blocked, reference :548-554 */
-        L->a_te_re[k] = L->a_tm_re[k] = L->tau[k] = 0.f;
-        if (bits) bits[k / 8] &= (uint8_t)~(1u << (k % 8));
-        continue;
-      }
-      L->directions_tx[k].x = h[k].dir_tx.x; L->directions_tx[k].y = h[k].dir_tx.y; L->directions_tx[k].z = h[k].dir_tx.z;
-      L->directions_rx[k].x = h[k].dir_rx.x; L->directions_rx[k].y = h[k].dir_rx.y; L->directions_rx[k].z = h[k].dir_rx.z;
-      L->a_te_re[k] = L->a_tm_re[k] = h[k].a;
-      L->tau[k] = h[k].tau;
-      L->freq_shift[k] = h[k].freq;
-      if (bits) bits[k / 8] |= (uint8_t)(1u << (k % 8));
-    }
-    free(h);
-  }
+  if (p->los && rank == 0) { rc = run_los(ctx, p, rd, sc, smem, brute, scene_sb, st); if (rc) return rc; }
   CK(cudaEventRecord(ctx->ev[1], st));
 
   if (flags & HRT_FLAG_SUMMARY) {
@@ -1314,109 +1445,11 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   }
   S.shadow_queries = S.primary_hits * R;
 
-  if ((flags & HRT_FLAG_RAYSINFO) && p->rays_scat->rays_active && rank == 0) {
-    /* bits outside TX 0's path range: row 0 is all ones (:470); in later rows
-     * the tail bits of the last byte stay set for T == 1 */
-    uint8_t *A = p->rays_scat->rays_active;
-    const size_t rowb = P / 8 + 1;
-    memset(A, 0xff, rowb);
-    for (size_t t = 0; t < T; ++t)
-      for (size_t b = 0; b < B; ++b) {
-        uint8_t *row = A + (t * B + b + 1) * rowb;
-        for (uint64_t bit = P; bit < rowb * 8; ++bit) {
-          /* global bit index `bit` = TX 1, path bit-P (if it exists): its state
-           * when the reference copies the row, i.e. after bounce b for t >= 1,
-           * after bounce b-1 for t == 0 */
-          bool on = true;
-          const uint64_t j = bit - P;
-          if (T > 1 && j < P && j < 8) {
-            const int done = (int)b - (t == 0 ? 1 : 0);     /* last bounce TX 1 has finished */
-            on = done < 0 || (int)tail_dead[j] > done;
-          }
-          if (on) row[bit >> 3] |= (uint8_t)(1u << (bit & 7)); else row[bit >> 3] &= (uint8_t)~(1u << (bit & 7));
-        }
-      }
-  }
+  if ((flags & HRT_FLAG_RAYSINFO) && p->rays_scat->rays_active && rank == 0) raysinfo_tail_bits(p, tail_dead);
 
-  if (flags & HRT_FLAG_SUMMARY) {
-    const size_t np = R * T * B, nb = T * B;
-    if (flags & HRT_FLAG_SUMMARY_DEV) {
-      /* pair: fields 4,5 of each 6-word record are doubles */
-      unsigned char *d_isd = nullptr;
-      unsigned char *h_isd = (unsigned char *)calloc(np * 6, 1);
-      if (!h_isd) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
-      for (size_t i = 0; i < np; ++i) h_isd[6 * i + 4] = h_isd[6 * i + 5] = 1;
-      cudaError_t e = cudaMalloc((void **)&d_isd, np * 6);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(d_isd, h_isd, np * 6, cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) {
-        k_add_u64<<<nblk(np * 6), 256, 0, st>>>((unsigned long long *)p->pair_summary, (const unsigned long long *)rd.pair, np * 6, d_isd);
-        k_add_u64<<<nblk(nb * 4), 256, 0, st>>>((unsigned long long *)p->bounce_summary, (const unsigned long long *)rd.bounce, nb * 4, nullptr);
-        e = cudaGetLastError();
-      }
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      cudaFree(d_isd); free(h_isd);
-      CKR(e);
-      S.kernel_launches += 2;
-    } else {
-      HrtPairSummary *hp = (HrtPairSummary *)malloc(np * sizeof(HrtPairSummary));
-      HrtBounceSummary *hb = (HrtBounceSummary *)malloc(nb * sizeof(HrtBounceSummary));
-      if (!hp || !hb) { free(hp); free(hb); rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
-      cudaError_t e = cudaMemcpyAsync(hp, rd.pair, np * sizeof(HrtPairSummary), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(hb, rd.bounce, nb * sizeof(HrtBounceSummary), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e == cudaSuccess) {
-        for (size_t i = 0; i < np; ++i) {
-          p->pair_summary[i].n_valid += hp[i].n_valid; p->pair_summary[i].n_occluded += hp[i].n_occluded;
-          p->pair_summary[i].hit_hash += hp[i].hit_hash; p->pair_summary[i].tau_bits += hp[i].tau_bits;
-          p->pair_summary[i].power_te += hp[i].power_te; p->pair_summary[i].power_tm += hp[i].power_tm;
-        }
-        for (size_t i = 0; i < nb; ++i) {
-          p->bounce_summary[i].n_traced += hb[i].n_traced; p->bounce_summary[i].n_hit += hb[i].n_hit;
-          p->bounce_summary[i].hit_hash += hb[i].hit_hash; p->bounce_summary[i].t_bits += hb[i].t_bits;
-        }
-      }
-      free(hp); free(hb);
-      CKR(e);
-    }
-  }
-
-  if (flags & HRT_FLAG_PATHLIST) {
-    unsigned long long found = 0;
-    CKR(cudaMemcpyAsync(&found, rd.counters + 14, 8, cudaMemcpyDeviceToHost, st));
-    CKR(cudaStreamSynchronize(st));
-    const unsigned long long kept = found < p->paths_capacity ? found : p->paths_capacity;
-    if (!(flags & HRT_FLAG_PATHLIST_DEV)) {
-      CKR(cudaMemcpyAsync(p->paths, ctx->d_plist, (size_t)kept * sizeof(HrtPathRecord), cudaMemcpyDeviceToHost, st));
-      CKR(cudaStreamSynchronize(st));
-    }
-    *p->paths_count = found;
-  }
-  if (flags & HRT_FLAG_CIR) {
-    const size_t ncir = R * T * (size_t)p->cir_bins * 4;
-    float *h = (float *)malloc(ncir * sizeof(float));
-    if (!h) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
-    unsigned long long dropped = 0;
-    cudaError_t e = cudaMemcpyAsync(h, ctx->d_cir, ncir * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&dropped, rd.counters + 15, 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) {
-      for (size_t i = 0; i < ncir; ++i) p->cir[i] += h[i];
-      S.cir_dropped = dropped;
-      /* the LoS paths (reference :556-577), written to p->los above */
-      if (p->los && rank == 0)
-        for (size_t k = 0; k < R * T; ++k) {
-          if (p->los->a_te_re[k] == 0.f && p->los->tau[k] == 0.f) continue;   /* blocked */
-          const float fb = (p->los->tau[k] - p->cir_tau0_s) * rd.cir_inv_dt;
-          if (fb >= 0.f && fb < (float)p->cir_bins) {
-            float *dst = p->cir + (k * p->cir_bins + (size_t)fb) * 4;
-            dst[0] += p->los->a_te_re[k]; dst[1] += p->los->a_te_im[k];
-            dst[2] += p->los->a_tm_re[k]; dst[3] += p->los->a_tm_im[k];
-          } else S.cir_dropped++;
-        }
-    }
-    free(h);
-    CKR(e);
-  }
+  if (flags & HRT_FLAG_SUMMARY) { rc = flush_summaries(ctx, p, rd, flags, st); if (rc) goto run_done; }
+  if (flags & HRT_FLAG_PATHLIST) { rc = flush_path_list(ctx, p, rd, flags, st); if (rc) goto run_done; }
+  if (flags & HRT_FLAG_CIR) { rc = flush_cir(ctx, p, rd, rank, st); if (rc) goto run_done; }
 
   if (count) {
     unsigned long long hc[16];
