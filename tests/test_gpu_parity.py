@@ -148,7 +148,11 @@ def test_run_dense_vs_oracle(ctx, cfg, P, B, n_rx, moving, T):
     # work order give the very same bits
     import os
     for env in ({"HRT_SCATTER_MODE": "t"}, {"HRT_SCATTER_MODE": "w"}, {"HRT_NO_SORT": "1"},
-                {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "w"}):
+                {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "w"},
+                # traversal-order variants: no origin chain, chain without its shared-memory cache,
+                # hit sort forced on in the warp mapping
+                {"HRT_NO_CHAIN": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_NO_CHAIN_CACHE": "1", "HRT_SCATTER_MODE": "t"},
+                {"HRT_NO_CHAIN_CACHE": "1", "HRT_SCATTER_MODE": "w"}, {"HRT_HIT_SORT_ALWAYS": "1", "HRT_SCATTER_MODE": "w"}):
         os.environ.update(env)
         try:
             alt = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, trace=True, summary=True)
