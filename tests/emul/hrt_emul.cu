@@ -244,3 +244,44 @@ extern "C" int emul_bvh_stats(const Scene *sc, int leaf_max, uint32_t *num_nodes
   *num_nodes = E.num_nodes; *num_tris = E.n;
   return 0;
 }
+
+/* The kernels' one-reciprocal form of a scatter path (hrt_scatter_path_fast)
+ * against the division-for-division form that follows the reference line by line
+ * (hrt_scatter_path), same libm on both sides: worst complex relative deviation of
+ * the gains over n random (state, material, geometry) samples; tau, direction and
+ * Doppler term must be identical.  Returns the number of non-identical exact words. */
+extern "C" int emul_scatter_fast_vs_exact(size_t n, uint32_t seed, float f_ghz, double *worst_rel)
+{
+  HrtMaterialTable mats;
+  memset(&mats, 0, sizeof mats);
+  for (uint32_t i = 0; i < NUM_G_MATERIALS; ++i) hrt_materials_derive(i, f_ghz, (HrtMaterialDerived *)&mats.m[i]);
+  uint64_t st = 0x9E3779B97F4A7C15ull ^ seed;
+  auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (float)((st >> 40) * (1.0 / 16777216.0)); };
+  HrtRunConst k;
+  const float f_hz = (float)((double)f_ghz * 1e9);
+  k.fsl_k = 4.f * HRT_PI * f_hz / HRT_C0; k.dop_k = f_hz / HRT_C0;
+  int bad = 0; double worst = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    HrtRayState s;
+    s.o = v3(rnd() * 100.f - 50.f, rnd() * 100.f - 50.f, rnd() * 20.f);
+    s.d = v3_normalize(v3(rnd() - .5f, rnd() - .5f, rnd() - .5f));
+    s.te_r = rnd() - .5f; s.te_i = rnd() - .5f; s.tm_r = rnd() - .5f; s.tm_i = rnd() - .5f;
+    s.tau = rnd() * 1e-6f;
+    const HrtMaterial &m = mats.m[1 + (size_t)(rnd() * 15.99f)];
+    const V3 nrm = v3_normalize(v3(rnd() - .5f, rnd() - .5f, rnd() - .5f));
+    const V3 mv = v3(rnd() * 30.f - 15.f, rnd() * 30.f - 15.f, 0.f);
+    float dist;
+    const V3 sd = hrt_shadow_dir(s.o, v3(rnd() * 100.f - 50.f, rnd() * 100.f - 50.f, 1.5f), &dist);
+    if (i % 7 == 0) dist = rnd() * 1e-3f;                 /* free-space factor below 1: no division by it */
+    const float theta_i = rnd() * 1.5707f;
+    const HrtScatterOut a = hrt_scatter_path(s, m, k, nrm, mv, sd, dist, theta_i);
+    const HrtScatterOut b = hrt_scatter_path_fast(s, hrt_scat_const(m), k, nrm, mv, sd, dist, theta_i);
+    if (memcmp(&a.tau, &b.tau, 4) || memcmp(&a.dfreq, &b.dfreq, 4) || memcmp(&a.dir_rx, &b.dir_rx, 12)) ++bad;
+    const double e_te = hypot((double)a.te_r - b.te_r, (double)a.te_i - b.te_i), m_te = hypot((double)a.te_r, (double)a.te_i);
+    const double e_tm = hypot((double)a.tm_r - b.tm_r, (double)a.tm_i - b.tm_i), m_tm = hypot((double)a.tm_r, (double)a.tm_i);
+    if (m_te > 0 && e_te / m_te > worst) worst = e_te / m_te;
+    if (m_tm > 0 && e_tm / m_tm > worst) worst = e_tm / m_tm;
+  }
+  *worst_rel = worst;
+  return bad;
+}

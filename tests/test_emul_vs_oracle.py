@@ -50,3 +50,18 @@ def test_two_tx_doppler_layout():
     o, _ = tl.run_emul(scene, rx, tx, rxv, txv, f, 2000, 3)
     keys = ["scat.tau", "scat.freq_shift", "scat.directions_rx"] + list(tl.GAIN_KEYS)
     tl.assert_exact(tl.outputs_words(a), mask, tl.outputs_words(o), keys=keys)
+
+
+def test_one_reciprocal_gains_stay_within_a_few_ulp():
+    """hrt_scatter_path_fast (what k_scatter runs: one reciprocal for the two gain
+    normalisations) against hrt_scatter_path (the reference's eight divisions), both
+    on the CPU with the same libm: delay, direction and Doppler term identical, gains
+    within a few fp32 ulp -- three orders of magnitude inside the 1e-4 tolerance."""
+    import ctypes as C
+    lib = tl.emul_lib()
+    lib.emul_scatter_fast_vs_exact.argtypes = [C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_double)]
+    for seed, f in ((1, 3.5), (2, 28.0), (3, 0.9)):
+        worst = C.c_double(0)
+        bad = lib.emul_scatter_fast_vs_exact(200000, seed, f, C.byref(worst))
+        assert bad == 0
+        assert 0 < worst.value < 1e-6, worst.value
