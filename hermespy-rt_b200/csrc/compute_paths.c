@@ -143,3 +143,29 @@ size_t compute_cir(
   hrt_get_stats(ctx, &st);
   return (size_t)st.cir_dropped;
 }
+
+/* The valid scatter paths of the same path set as compact records (HrtPathRecord,
+ * include/hrt_cuda.h) instead of dense arrays: what the reference writes into
+ * the slots of living rays and unoccluded receivers, nothing for the others.
+ * Stores at most `capacity` records into `paths` (arbitrary order) and returns
+ * the number of valid paths found (> capacity: a subset was stored). */
+size_t compute_path_list(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    HrtPathRecord *paths, size_t capacity)
+{
+  if (!scene || !paths || !capacity) die("compute_path_list", "NULL scene or output");
+  hrt_ctx *ctx = prepare(scene, carrier_frequency_GHz);
+  HrtRunParams p;
+  memset(&p, 0, sizeof p);
+  p.num_rx = num_rx; p.num_tx = num_tx; p.num_paths = num_rays; p.num_bounces = num_bounces;
+  p.carrier_frequency_GHz = carrier_frequency_GHz;
+  p.rx_pos = rx_pos; p.tx_pos = tx_pos; p.rx_vel = rx_vel; p.tx_vel = tx_vel;
+  p.shard_world = 1;
+  p.flags = HRT_FLAG_PATHLIST;
+  uint64_t found = 0;
+  p.paths = paths; p.paths_capacity = capacity; p.paths_count = &found;
+  if (hrt_run(ctx, &p) != HRT_OK) die("compute_path_list failed", hrt_last_error(ctx));
+  return (size_t)found;
+}

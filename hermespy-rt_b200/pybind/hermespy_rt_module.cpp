@@ -18,6 +18,8 @@
 #include <complex>
 #include <stdexcept>
 #include <string>
+#include <vector>
+#include <cstring>
 
 #include "../../include/hrt_cuda.h"   // extern "C" inside
 
@@ -139,6 +141,47 @@ compute_cir_py(const std::string &mesh_filepath, farr rx_positions, farr tx_posi
   return {std::move(cir), dropped};
 }
 
+// Extension: the valid scatter paths as a structured array (no dense slots for
+// dead rays / occluded receivers).  Returns (records[:min(found, capacity)], found).
+std::pair<py::array, size_t>
+compute_path_list_py(const std::string &mesh_filepath, farr rx_positions, farr tx_positions, farr rx_velocities,
+                     farr tx_velocities, float carrier_frequency, size_t num_rx, size_t num_tx, size_t num_paths,
+                     size_t num_bounces, size_t capacity)
+{
+  if (!num_rx || !num_tx || !num_paths || !num_bounces || !capacity || !(carrier_frequency > 0.f))
+    throw std::invalid_argument("num_rx, num_tx, num_paths, num_bounces, capacity and carrier_frequency must be > 0");
+  const Vec3 *rx = as_vec3(rx_positions, num_rx, "rx_positions");
+  const Vec3 *tx = as_vec3(tx_positions, num_tx, "tx_positions");
+  const Vec3 *rxv = as_vec3(rx_velocities, num_rx, "rx_velocities");
+  const Vec3 *txv = as_vec3(tx_velocities, num_tx, "tx_velocities");
+  if (hrt_device_count() <= 0)
+    throw std::runtime_error("hermespy_rt: no CUDA device available (this build has no CPU path)");
+  if (FILE *f = fopen(mesh_filepath.c_str(), "rb")) fclose(f);
+  else throw std::runtime_error("hermespy_rt: cannot open scene file " + mesh_filepath);
+  std::vector<HrtPathRecord> buf(capacity);
+  size_t found = 0;
+  {
+    py::gil_scoped_release nogil;
+    Scene scene = scene_load(mesh_filepath.c_str());
+    found = compute_path_list(&scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency, num_rx, num_tx,
+                              num_paths, num_bounces, buf.data(), capacity);
+    free_scene(&scene);
+  }
+  const size_t kept = found < capacity ? found : capacity;
+  py::list fields;
+  const char *names[] = {"path", "rx", "tx", "bounce", "a_te_re", "a_te_im", "a_tm_re", "a_tm_im", "tau", "freq_shift", "direction_rx"};
+  const char *fmts[] = {"<u4", "<u4", "<u2", "<u2", "<f4", "<f4", "<f4", "<f4", "<f4", "<f4", "<f4"};
+  for (int k = 0; k < 11; ++k) {
+    if (k == 10) fields.append(py::make_tuple(names[k], fmts[k], py::make_tuple(3)));
+    else fields.append(py::make_tuple(names[k], fmts[k]));
+  }
+  py::dtype dt = py::dtype::from_args(fields);
+  if ((size_t)dt.itemsize() != sizeof(HrtPathRecord)) throw std::runtime_error("hermespy_rt: path record layout mismatch");
+  py::array out(dt, std::vector<py::ssize_t>{(py::ssize_t)kept});
+  memcpy(out.mutable_data(), buf.data(), kept * sizeof(HrtPathRecord));
+  return {std::move(out), found};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(hermespy_rt, m)
@@ -164,4 +207,11 @@ PYBIND11_MODULE(hermespy_rt, m)
         py::arg("rx_velocities"), py::arg("tx_velocities"), py::arg("carrier_frequency"),
         py::arg("num_rx"), py::arg("num_tx"), py::arg("num_paths"), py::arg("num_bounces"),
         py::arg("tau0"), py::arg("dt"), py::arg("num_bins"));
+  m.def("compute_path_list", &compute_path_list_py,
+        "The valid scatter paths of the compute_paths() path set as a structured array of 48-byte records "
+        "(path, rx, tx, bounce, a_te_re, a_te_im, a_tm_re, a_tm_im, tau, freq_shift, direction_rx); "
+        "returns (records, number of valid paths found)",
+        py::arg("mesh_filepath"), py::arg("rx_positions"), py::arg("tx_positions"),
+        py::arg("rx_velocities"), py::arg("tx_velocities"), py::arg("carrier_frequency"),
+        py::arg("num_rx"), py::arg("num_tx"), py::arg("num_paths"), py::arg("num_bounces"), py::arg("capacity"));
 }

@@ -213,6 +213,15 @@ int  hrt_materials_set(hrt_ctx *ctx, const HrtMaterialDerived table[NUM_G_MATERI
 
 int hrt_run(hrt_ctx *ctx, const HrtRunParams *p);
 
+/* One-call form of the path-list mode on the implicit context of compute_paths()
+ * (hermespy-rt_b200/csrc/compute_paths.c): compute_paths' arguments, then the
+ * caller's record buffer.  Returns the number of valid scatter paths found. */
+size_t compute_path_list(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    HrtPathRecord *paths, size_t capacity);
+
 /* The shard partition as pure host arithmetic (no GPU): how many of the
  * num_paths paths rank `rank` of `world` owns, and the global path index of its
  * local index L.  Every path belongs to exactly one rank. */

@@ -605,6 +605,17 @@ def test_pybind_module_matches_golden():
             n_out += 1
     assert dropped == n_out and ins.sum() > 100
     assert (np.abs(cir[0, 0] - ref) <= 1e-5 * mag + 1e-30).all()
+    # compute_path_list(): the valid paths as records == the valid slots of the module's dense output
+    recs, found = rt.compute_path_list(tl.scene_path(g["scene"]), g["rx"], g["tx"], g["rxv"], g["txv"], g["f"],
+                                       1, 1, P, B, B * P)
+    assert found == int(valid.sum()) == len(recs) and recs.dtype.itemsize == 48
+    order = np.lexsort((recs["path"], recs["bounce"]))
+    recs = recs[order]
+    idx = recs["bounce"].astype(np.int64) * P + recs["path"]
+    assert np.array_equal(idx, np.flatnonzero(valid))
+    assert np.array_equal(recs["tau"].view(np.uint32), tau[idx].view(np.uint32))
+    assert np.array_equal(recs["a_te_re"].view(np.uint32), a_te.real[idx].astype(np.float32).view(np.uint32))
+    assert np.array_equal(recs["direction_rx"].view(np.uint32), sc.directions_rx.reshape(-1, 3)[idx].view(np.uint32))
 
 
 def test_large_scene_global_memory_bvh(ctx, tmp_path):

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
                        capture_output=True)
     L = hrt.lib()
     want = _declared_symbols()
-    assert {"compute_paths", "compute_cir", "scene_load", "scene_save", "get_material_index", "hrt_run", "hrt_scene_advance",
+    assert {"compute_paths", "compute_cir", "compute_path_list", "scene_load", "scene_save", "get_material_index", "hrt_run", "hrt_scene_advance",
             "hrt_scene_upload", "hrt_ctx_create", "hrt_closest_hits"} <= want
     for s in sorted(want):
         assert hasattr(L, s), f"libhermespy_rt.so does not export {s}"
