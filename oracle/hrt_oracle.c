@@ -429,3 +429,14 @@ void oracle_launch_dirs(size_t first, size_t n, size_t num_paths, Vec3 *out)
 {
   for (size_t i = 0; i < n; ++i) out[i] = orc_launch_dir(first + i, num_paths);
 }
+
+/* Unit normals of every triangle in (mesh, face) order -- what the reference's
+ * precompute_normals (:208-224) stores in Mesh.ns; `out` holds sum(num_triangles). */
+int oracle_normals(const Scene *scene, Vec3 *out)
+{
+  OrcTris ft;
+  if (orc_flatten(scene, &ft)) return -1;
+  memcpy(out, ft.n, (size_t)ft.num_tris * sizeof(Vec3));
+  orc_free_tris(&ft);
+  return 0;
+}

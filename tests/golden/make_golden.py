@@ -24,11 +24,16 @@ GOLDEN = {
     "box_generic": ("box_generic", 3000, 3, [[2.0, 2.0, 4.0]], True),
     "2cars_raised": ("2cars_raised", 3000, 5, [[-6.0, 4.0, 1.0]], True),
     "canyon_3rx": ("canyon_1x1", 2500, 5, [[20.0, 2.0, 1.5], [-30.0, -2.0, 1.5]], True),
+    # moving meshes (Mesh.velocity != 0): reference src/compute_paths.c:720-722
+    "canyon_moving": ("canyon_moving", 2500, 5, [[20.0, 2.0, 1.5], [-30.0, -2.0, 1.5]], True),
 }
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, (cfg, P, B, extra, moving) in GOLDEN.items():
+        if only and name not in only:
+            continue
         scene, rx, tx, f = tl.CONFIGS[cfg]
         rx = list(rx) + extra
         rxv = [[0.5 * i, -1.0, 0.25] if moving else [0, 0, 0] for i in range(len(rx))]

@@ -145,6 +145,10 @@ CONFIGS = {
     "2cars_origin": ("2cars", [[0, 0, 0]], [[0, 0, 0]], 70.0),
     "2cars_raised": ("2cars", [[2, -1, 1.5]], [[0, 0, 1.5]], 70.0),
     "canyon_1x1": ("simple_street_canyon_with_cars", [[0, 0, 1.5]], [[0, 0, 10]], 3.5),
+    # scripts/make_moving_scene.py: the canyon with non-zero Mesh.velocity (cars +-14 m/s,
+    # drifting ground, moving buildings) and real materials -- the mesh-velocity
+    # Doppler term of reference src/compute_paths.c:720-722
+    "canyon_moving": ("canyon_moving", [[0, 0, 1.5]], [[0, 0, 10]], 3.5),
 }
 
 
@@ -160,7 +164,7 @@ def canyon_c4_positions(num_tx=4, num_rx=64):
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_NAMES = ("reflector_testc", "reflector_testpy", "box_generic", "2cars_raised",
-                "canyon_3rx")
+                "canyon_3rx", "canyon_moving")
 
 
 def load_golden(name: str) -> dict:
@@ -293,6 +297,78 @@ def random_rays(scene_name, n, seed=0):
     d[2 * k:3 * k] = pts - o[2 * k:3 * k]
     rays = np.concatenate([o, d.astype(np.float32)], axis=1).astype(np.float32)
     return np.ascontiguousarray(rays)
+
+
+def scene_triangles(scene_name):
+    """(N, 3, 3) float64 corners of every triangle in (mesh, face) order"""
+    lib = oracle_lib()
+    sc = lib.scene_load(scene_path(scene_name).encode())
+    tris, *_ = abi.scene_to_numpy(sc)
+    abi.free_scene(sc)
+    return tris.astype(np.float64)
+
+
+def grazing_rays(scene_name, n, seed=0, lo_exp=-7.5, hi_exp=-2.0):
+    """Adversarial rays for conservative culling: each ray passes
+    through a point on an EDGE of a random triangle while running almost inside
+    that triangle's plane, |d.n| log-uniform in [10^lo_exp, 10^hi_exp].  Near
+    |d.n| ~ 1e-7 the reference's fp32 det is rounding noise and its u, v, t can
+    land inside the acceptance windows for a ray that passes metres away."""
+    T = scene_triangles(scene_name)
+    rng = np.random.default_rng(seed)
+    tt = T[rng.integers(0, len(T), n)]
+    e1 = tt[:, 1] - tt[:, 0]; e2 = tt[:, 2] - tt[:, 0]
+    nrm = np.cross(e1, e2); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    ed = rng.integers(0, 3, n); w = rng.random(n)
+    a = tt[np.arange(n), ed]; b = tt[np.arange(n), (ed + 1) % 3]
+    pt = a + (b - a) * w[:, None]
+    u = e1 / np.linalg.norm(e1, axis=1, keepdims=True)
+    v = np.cross(nrm, u)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    d = u * np.cos(ang)[:, None] + v * np.sin(ang)[:, None]
+    d = d + nrm * (10.0 ** rng.uniform(lo_exp, hi_exp, n) * rng.choice([-1, 1], n))[:, None]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = pt - d * rng.uniform(0.5, 60, n)[:, None]
+    return np.ascontiguousarray(np.concatenate([o, d], 1).astype(np.float32))
+
+
+def phantom_hit_report(scene_name, rays, tri_ref, t_ref, tri, t):
+    """Classifies the rays on which a BVH result differs from the reference loop:
+    returns (indices, |d.n| of the reference's triangle).  See DESIGN.md,
+    'phantom hits'."""
+    bad = np.flatnonzero((tri_ref != tri) | (t_ref.view(np.uint32) != t.view(np.uint32)))
+    if bad.size == 0:
+        return bad, np.zeros(0)
+    T = scene_triangles(scene_name)
+    # the triangle the two disagree about: the reference's if it hit one, else ours
+    which = np.where(tri_ref[bad] != NONE, tri_ref[bad], tri[bad])
+    tt = T[which]
+    nrm = np.cross(tt[:, 1] - tt[:, 0], tt[:, 2] - tt[:, 0]); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    d = rays[bad, 3:6].astype(np.float64); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return bad, np.abs((d * nrm).sum(1))
+
+
+def oracle_normals(scene_name):
+    """(N, 3) float32 unit normals in (mesh, face) order (reference :208-224)."""
+    lib = oracle_lib()
+    sc = lib.scene_load(scene_path(scene_name).encode())
+    n = sum(sc.meshes[m].num_triangles for m in range(sc.num_meshes))
+    out = np.zeros((n, 3), np.float32)
+    lib.oracle_normals.argtypes = [C.POINTER(abi.Scene), C.c_void_p]
+    assert lib.oracle_normals(C.byref(sc), out.ctypes.data) == 0
+    abi.free_scene(sc)
+    return out
+
+
+def mesh_normals(scene) -> np.ndarray:
+    """Mesh.ns of a Scene struct after a compute_paths() call, concatenated."""
+    parts = []
+    for m in range(scene.num_meshes):
+        me = scene.meshes[m]
+        assert bool(me.ns), f"mesh {m}: ns not filled"
+        parts.append(np.ctypeslib.as_array(C.cast(me.ns, C.POINTER(C.c_float)),
+                                           (me.num_triangles, 3)).copy())
+    return np.concatenate(parts)
 
 
 def oracle_closest(scene_name, rays):

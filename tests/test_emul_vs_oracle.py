@@ -65,3 +65,31 @@ def test_one_reciprocal_gains_stay_within_a_few_ulp():
         bad = lib.emul_scatter_fast_vs_exact(200000, seed, f, C.byref(worst))
         assert bad == 0
         assert 0 < worst.value < 1e-6, worst.value
+
+
+@pytest.mark.parametrize("scene", ["simple_street_canyon_with_cars", "2cars", "box"])
+def test_grazing_rays_phantom_hits(scene):
+    """rays running almost inside a triangle's plane.  The
+    triangle test itself equals the reference on every ray (brute force over the
+    same hrt_mt_test: bit-equal).  With BVH culling a few results differ, and ONLY
+    where the reference reports a 'phantom hit': |d.n| < 1e-5, where its fp32 det is
+    rounding noise and the accepted (u, v, t) belong to a ray that never comes near
+    the triangle's bounding box -- no conservative box can contain it.  Documented
+    in DESIGN.md section 4; the rate on this adversarial generator stays < 1e-3
+    and is zero for |d.n| >= 1e-5."""
+    rays = tl.grazing_rays(scene, 200000, seed=3)
+    tri_o, t_o, _ = tl.oracle_closest(scene, rays)
+    tri_b, t_b, _ = tl.emul_closest(scene, rays, brute=1)
+    assert np.array_equal(tri_o, tri_b) and np.array_equal(t_o.view(np.uint32), t_b.view(np.uint32))
+    assert (tri_o != tl.NONE).mean() > 0.3
+    for brute in (0, 2):
+        tri_e, t_e, _ = tl.emul_closest(scene, rays, brute=brute)
+        bad, dn = tl.phantom_hit_report(scene, rays, tri_o, t_o, tri_e, t_e)
+        assert bad.size < 1e-3 * len(rays), bad.size
+        if bad.size:
+            assert dn.max() < 1e-5, dn.max()
+    # the same generator restricted to |d.n| >= 1e-5: no difference at all
+    rays = tl.grazing_rays(scene, 100000, seed=4, lo_exp=-5.0)
+    tri_o, t_o, _ = tl.oracle_closest(scene, rays)
+    tri_e, t_e, _ = tl.emul_closest(scene, rays)
+    assert np.array_equal(tri_o, tri_e) and np.array_equal(t_o.view(np.uint32), t_e.view(np.uint32))

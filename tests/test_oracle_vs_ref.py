@@ -18,6 +18,8 @@ CASES = [
     ("2cars_origin", 20000, 5, None, False),
     ("2cars_raised", 20000, 5, [[-6.0, 4.0, 1.0]], True),
     ("canyon_1x1", 6000, 5, [[20.0, 2.0, 1.5], [-30.0, -2.0, 1.5]], True),
+    # non-zero Mesh.velocity on cars, ground and buildings (scenes/canyon_moving.hrt)
+    ("canyon_moving", 6000, 5, [[20.0, 2.0, 1.5], [-30.0, -2.0, 1.5]], True),
 ]
 
 
@@ -43,6 +45,12 @@ def test_oracle_bit_exact_vs_reference(name, P, B, extra_rx, moving):
         assert np.array_equal(mask[k], mask_o[k]), k
     # trace consistency: slot_state != 0  <=>  tau word is determined
     assert np.array_equal(tr["slot_state"].reshape(-1) != 0, mask["scat.tau"])
+    if name == "canyon_moving":
+        # the mesh-velocity term really is in play: freq_shift of valid paths is not just the TX base value
+        fs = o.scat["freq_shift"].reshape(-1)
+        valid = tr["slot_state"].reshape(-1) == 1
+        assert mask["scat.freq_shift"][valid].all()
+        assert np.unique(fs[valid]).size > 5000
 
 
 def test_two_tx_layout_quirks():
@@ -78,3 +86,18 @@ def test_material_table_matches_reference():
         tl.oracle_lib().get_material_index.argtypes = [C.c_char_p]
         assert tl.ref_lib().get_material_index(nm.encode()) == \
             tl.oracle_lib().get_material_index(nm.encode())
+
+
+@pytest.mark.parametrize("scene", ["simple_reflector", "box", "2cars", "simple_street_canyon_with_cars", "canyon_moving"])
+def test_normals_match_reference(scene):
+    """oracle_normals() == the Mesh.ns the reference's precompute_normals leaves
+    in the caller's scene (src/compute_paths.c:208-224), bit for bit."""
+    from hrt_b200 import abi
+    lib = tl.ref_lib()
+    sc = lib.scene_load(tl.scene_path(scene).encode())
+    try:
+        abi.call_compute_paths(lib, sc, [[0, 0, 1.5]], [[0, 0, 3.0]], [[0, 0, 0]], [[0, 0, 0]], 3.0, 8, 1)
+        ns = tl.mesh_normals(sc)
+    finally:
+        abi.free_scene(sc)
+    assert np.array_equal(ns.view(np.uint32), tl.oracle_normals(scene).view(np.uint32))
