@@ -745,6 +745,159 @@ HRT_HD HrtScatterOut hrt_scatter_path_fast(const HrtRayState &s, const HrtScatCo
   return r;
 }
 
+/* ------------------------------------------- closed form of a scatter path
+ * The reference L2-normalises its four scattering coefficients (:399-405)
+ * whenever their norm exceeds 1e-6.  All four carry the common factor
+ * A = s * exp(-alpha |theta_s - theta_i|) * cos(theta_s), so after the
+ * normalisation only its SIGN is left:
+ *   (te_r, te_i, tm_r, tm_i) = sign(A) * (1, p, g, g p) / sqrt((1 + g^2)(1 + p^2)),
+ *   g = rough * cos(theta_i) + (1 - rough),  p = sin(0.1 alpha sin(theta_i)),
+ * with cos(theta_i) = |n_i . d| and sin(theta_i) = sqrt(1 - (n_i . d)^2) for the
+ * folded incidence angle (:280-283).  No acos / acosf / expf / cosf / sinf per
+ * path; the result agrees with the reference's fp32 evaluation to ~1e-6
+ * relative (tests/emul: emul_scatter_cf_vs_exact), 100x inside the 1e-4 gain
+ * tolerance.  The closed form is used only when a cheap estimate proves the
+ * norm test passes with 1 % to spare; everything else -- norm near or below
+ * 1e-6, s = 0 (metal), alpha = 0, |n_i . d| > 1 (NaN in the reference) --
+ * takes the libm path above (hrt_scatter_path_fast). */
+HRT_HD float hrt_sqrt_fast(float v)
+{
+#if defined(__CUDA_ARCH__)
+  float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#else
+  return sqrtf(v);
+#endif
+}
+HRT_HD float hrt_rsqrt_fast(float v)
+{
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#else
+  return 1.0f / sqrtf(v);
+#endif
+}
+HRT_HD float hrt_rcp_fast(float v)
+{
+#if defined(__CUDA_ARCH__)
+  float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#else
+  return 1.0f / v;
+#endif
+}
+HRT_HD float hrt_exp2_fast(float v)
+{
+#if defined(__CUDA_ARCH__)
+  float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#else
+  return exp2f(v);
+#endif
+}
+/* acos to 7e-5 rad on [-1, 1] (Abramowitz-Stegun 4.4.45): for the norm ESTIMATE only */
+HRT_HD float hrt_acos_est(float x)
+{
+  const float a = fminf(fabsf(x), 1.f);
+  float p = HRT_FMA(-0.0187293f, a, 0.0742610f);
+  p = HRT_FMA(p, a, -0.2121144f);
+  p = HRT_FMA(p, a, 1.5707288f);
+  const float r = hrt_sqrt_fast(1.f - a) * p;
+  return x < 0.f ? HRT_PI - r : r;
+}
+
+struct HrtScatCf {
+  float rough, omr;       /* 1/(1+alpha), 1 - rough (:382-384)              */
+  float ph_k;             /* 0.1 alpha (:394)                                */
+  float lobe_lb;          /* s exp(-alpha pi) <= lobe factor                 */
+  float s, alpha_l2e;     /* for the estimate: s, alpha log2(e)              */
+  float ok;               /* 1: closed form allowed for this material, else 0 */
+};
+HRT_HD HrtScatCf hrt_scat_cf(const HrtMaterial &m)
+{
+  HrtScatCf c;
+  c.rough = HRT_DIV(1.0f, HRT_ADD(1.0f, m.s1_alpha));
+  c.omr = HRT_SUB(1.0f, c.rough);
+  c.ph_k = 0.1f * m.s1_alpha;
+  c.s = m.s; c.alpha_l2e = m.s1_alpha * 1.4426950408889634f;
+  c.lobe_lb = m.s * hrt_exp2_fast(-c.alpha_l2e * HRT_PI) * 0.98f;
+  c.ok = (m.s > 0.f && m.s1_alpha >= 1.f && c.ph_k <= 0.5f) ? 1.f : 0.f;
+  return c;
+}
+
+/* (g, p, 1/sqrt((1+g^2)(1+p^2))) from cos and sin of the incidence angle */
+HRT_HD void hrt_scat_unit(const HrtScatCf &m, float ci, float si, float *g, float *p, float *inv_n)
+{
+  *g = HRT_FMA(m.rough, ci, m.omr);
+  const float ph = m.ph_k * si, q = ph * ph;              /* sin(ph), 0 <= ph <= 0.5: |rel err| < 1e-8 */
+  *p = ph * HRT_FMA(q, HRT_FMA(q, HRT_FMA(q, -1.f / 5040.f, 1.f / 120.f), -1.f / 6.f), 1.f);
+  *inv_n = hrt_rsqrt_fast(HRT_FMA(*g, *g, 1.f) * HRT_FMA(*p, *p, 1.f));
+}
+
+/* Gains of one scatter path in closed form.  xs = d . n (scattering direction
+ * against the surface normal), (ci, si) the carried incidence angle, th_i_est
+ * any 1e-3-accurate value of that angle.  Returns false when the closed form
+ * must not be used (caller falls back to hrt_scatter_path_fast); the delay,
+ * direction and Doppler terms are formed by the caller exactly as before. */
+HRT_HD bool hrt_scatter_gains_cf(const HrtRayState &s, const HrtScatCf &m, float fsl_k, float xs, float dist,
+                                 float ci, float si, float *te_r, float *te_i, float *tm_r, float *tm_i)
+{
+  if (!(m.ok != 0.f) || !(ci <= 1.f)) return false;
+  float g, p, inv_n;
+  hrt_scat_unit(m, ci, si, &g, &p, &inv_n);
+  const float ax = fabsf(xs);
+  /* norm = lobe |cos theta_s| sqrt((1+g^2)(1+p^2)) >= lobe_lb |xs|: clearly above 1e-6? */
+  if (!(m.lobe_lb * ax > 1.02e-6f)) {
+    /* estimate with approximate angles: 1e-3 relative, 2 % margin */
+    const float dth = fabsf(hrt_acos_est(xs) - hrt_acos_est(ci));
+    const float est = m.s * hrt_exp2_fast(-m.alpha_l2e * dth) * ax;
+    if (!(est * inv_n * 0.98f > 1.02e-6f * inv_n * inv_n)) return false;     /* est / inv_n > 1.02e-6 / 0.98 */
+  }
+  float k = xs < 0.f ? -inv_n : inv_n;
+  float l2 = HRT_MUL(fsl_k, dist);                                             /* :711 */
+  l2 = HRT_MUL(l2, l2);
+  if (l2 > 1.f) k *= hrt_rcp_fast(l2);                                         /* :713 */
+  const float gk = g * k;
+  *te_r = HRT_FMA(-s.te_i, p, s.te_r) * k;                                     /* :698 */
+  *te_i = HRT_FMA(s.te_r, p, s.te_i) * k;
+  *tm_r = HRT_FMA(-s.tm_i, p, s.tm_r) * gk;
+  *tm_i = HRT_FMA(s.tm_r, p, s.tm_i) * gk;
+  return true;
+}
+
+/* cos / sin of the folded incidence angle from the fp32 dot product the
+ * reference hands to acos (:281): |x| and sqrt(1 - x^2) */
+HRT_HD void hrt_fold_cos_sin(float x, float *ci, float *si)
+{
+  *ci = fabsf(x);
+  *si = hrt_sqrt_fast(fmaxf(HRT_FMA(-x, x, 1.f), 0.f));
+}
+
+/* One scatter path as the kernels form it: closed-form gains when allowed, the
+ * libm formulas otherwise.  cx_i: fp32 dot product n.d of the shadow hit whose
+ * angle is carried (what the reference feeds to acos, :281), or 2 = none yet:
+ * the primary incidence angle theta_p with (ci_p, si_p) = (cosf, sinf)(theta_p). */
+#define HRT_CX_PRIMARY 2.f
+HRT_HD HrtScatterOut hrt_scatter_path_auto(const HrtRayState &s, const HrtScatConst &m, const HrtScatCf &mcf,
+                                           const HrtRunConst &k, V3 n, V3 mesh_vel, V3 sd, float dist,
+                                           float cx_i, float theta_p, float ci_p, float si_p)
+{
+  HrtScatterOut r;
+  float ci = ci_p, si = si_p;
+  if (cx_i != HRT_CX_PRIMARY) hrt_fold_cos_sin(cx_i, &ci, &si);
+  const float xs = v3_dot(sd, n);                                              /* :694, argument of acosf */
+  if (hrt_scatter_gains_cf(s, mcf, k.fsl_k, xs, dist, ci, si, &r.te_r, &r.te_i, &r.tm_r, &r.tm_i)) {
+    r.dir_rx = v3(-sd.x, -sd.y, -sd.z);                                        /* :707 */
+    r.tau = HRT_ADD(s.tau, HRT_DIV(dist, HRT_C0));                             /* :709 */
+    r.dfreq = HRT_MUL(v3_dot(v3_sub(sd, s.d), mesh_vel), k.dop_k);             /* :720-721 */
+    return r;
+  }
+  /* norm test not clear-cut, s = 0, alpha = 0, |n.d| > 1 ...: the reference's formulas with libm */
+  float theta_i = theta_p;
+  if (cx_i != HRT_CX_PRIMARY) {
+    theta_i = (float)acos((double)cx_i);                                       /* :281-283 */
+    if ((double)theta_i > (double)HRT_PI / 2.) theta_i = HRT_SUB(HRT_PI, theta_i);
+  }
+  return hrt_scatter_path_fast(s, m, k, n, mesh_vel, sd, dist, theta_i);
+}
+
 /* ------------------------------------------------------------------ LoS
  * reference :520-577 for one (rx, tx) pair, query result passed in. */
 struct HrtLosOut {

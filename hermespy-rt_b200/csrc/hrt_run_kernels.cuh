@@ -472,8 +472,14 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const uint32_t gid = tri_gid_of<SMEM>(sc, slot);
     const uint32_t mesh = sc.mesh_of[gid];
     const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
+    const HrtScatCf mcf = hrt_scat_cf(mats.m[sc.mesh_mat[mesh]]);
     const V3 mv = ld3(sc.mesh_vel, mesh);
-    float theta_carry = r2.w;
+    /* incidence angle handed to scat_coefs (appendix A-4): carried as the fp32 dot
+     * product n.d of the most recent shadow hit (what the reference feeds to acos,
+     * :281); 2 = "none yet: the primary angle theta_p" */
+    const float theta_p = r2.w;
+    float cx_carry = HRT_CX_PRIMARY, ci_p, si_p;
+    sincosf(theta_p, &si_p, &ci_p);
     const HrtChain chain = BRUTE ? hrt_no_chain() : origin_chain<SMEM>(sc, s.o, cc_off);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const uint64_t hkey = hrt_mix64((path << 32) | gid);
@@ -482,35 +488,35 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     for (uint32_t r0 = 0; r0 < R; r0 += step) {
       const uint32_t r = WARP ? r0 + lane : r0;
       const bool act = WARP ? r < R : valid;
-      float dist = 0.f, th_sh = 0.f;
+      float dist = 0.f, cx_sh = HRT_CX_PRIMARY;
       V3 sd = v3(0.f, 0.f, 1.f);
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
         h = query<SMEM, BRUTE>(sc, s.o, sd, wc, chain);                       /* :682 */
-        if (h.gid != HRT_NONE) th_sh = hrt_theta_fold(tri_normal<SMEM>(sc, h.slot), sd);
+        if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM>(sc, h.slot), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;
-      float theta_i;
+      float cx_i;
       if (WARP) {
-        /* theta handed to scat_coefs: the fold angle of the most recent shadow
-         * query (this receiver included) that hit anything, else the primary
-         * incidence angle (appendix A-4) */
+        /* angle handed to scat_coefs: that of the most recent shadow query (this
+         * receiver included) that hit anything, else the primary incidence angle
+         * (appendix A-4): inclusive "last lane that hit" scan over ballot bits */
         const unsigned m = __ballot_sync(0xFFFFFFFFu, shit);
         const unsigned below = m & (0xFFFFFFFFu >> (31u - lane));
         const int src = below ? 31 - __clz((int)below) : 0;
-        const float from = __shfl_sync(0xFFFFFFFFu, th_sh, src);
-        theta_i = below ? from : theta_carry;
-        if (m) theta_carry = __shfl_sync(0xFFFFFFFFu, th_sh, 31 - __clz((int)m));
+        const float from = __shfl_sync(0xFFFFFFFFu, cx_sh, src);
+        cx_i = below ? from : cx_carry;
+        if (m) cx_carry = __shfl_sync(0xFFFFFFFFu, cx_sh, 31 - __clz((int)m));
       } else {
-        if (shit) theta_carry = th_sh;
-        theta_i = theta_carry;
+        if (shit) cx_carry = cx_sh;
+        cx_i = cx_carry;
       }
       const bool occ = shit && h.t <= 1.f;                                     /* :683 */
       const bool ok = act && !occ;
       HrtScatterOut p;
       p.te_r = p.te_i = p.tm_r = p.tm_i = p.tau = p.dfreq = 0.f; p.dir_rx = v3(0.f, 0.f, 0.f);
-      if (ok) p = hrt_scatter_path_fast(s, mat, rd.k, n, mv, sd, dist, theta_i); /* :694-721 */
+      if (ok) p = hrt_scatter_path_auto(s, mat, mcf, rd.k, n, mv, sd, dist, cx_i, theta_p, ci_p, si_p);   /* :694-721 */
       if (act && (dense || trace)) {
         const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;          /* :674 */
         if (dense) {
@@ -559,8 +565,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         }
       }
       if (summary) {
-        const double pte = (double)p.te_r * p.te_r + (double)p.te_i * p.te_i;
-        const double ptm = (double)p.tm_r * p.tm_r + (double)p.tm_i * p.tm_i;
+        const float pte32 = HRT_FMA(p.te_r, p.te_r, p.te_i * p.te_i), ptm32 = HRT_FMA(p.tm_r, p.tm_r, p.tm_i * p.tm_i);
+        const double pte = (double)pte32, ptm = (double)ptm32;
         if (WARP) {
           if (occ) {
             if (smem_rx_ok) atomicAdd(&s_acc[r].n_occl, 1u);
@@ -586,7 +592,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
            * update per warp */
           const unsigned m_ok = __ballot_sync(0xFFFFFFFFu, ok), m_occ = __ballot_sync(0xFFFFFFFFu, occ);
           unsigned long long hsum = 0ull, tsum = 0ull;
-          double e = ok ? pte : 0.0, m2 = ok ? ptm : 0.0;
+          double e = 0.0, m2 = 0.0;
           if (m_ok) {
             /* integer sums: one REDUX per 16-bit digit (32 x 65535 fits 32 bits) */
             const unsigned long long hk = ok ? hkey : 0ull;
@@ -599,11 +605,14 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
                  + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb >> 16) << 16);
             /* both power sums in one butterfly: after the first exchange the lower
              * half-warp carries the TE sum, the upper half the TM sum */
+            /* (the <= 32 terms of a warp are added in fp32: 2e-6 relative at worst; across
+             * warps, blocks and launches the sums are kept in double) */
             const bool upper = lane >= 16u;
-            double keep = upper ? m2 : e;
-            keep += __shfl_xor_sync(0xFFFFFFFFu, upper ? e : m2, 16);
+            const float e32 = ok ? pte32 : 0.f, m32 = ok ? ptm32 : 0.f;
+            float keep = upper ? m32 : e32;
+            keep += __shfl_xor_sync(0xFFFFFFFFu, upper ? e32 : m32, 16);
             for (int o = 8; o; o >>= 1) keep += __shfl_xor_sync(0xFFFFFFFFu, keep, o);
-            e = keep; m2 = keep;       /* lanes 0-15: e is the total; lanes 16-31: m2 is the total */
+            e = (double)keep; m2 = e;       /* lanes 0-15: e is the TE total; lanes 16-31: m2 is the TM total */
           }
           if (smem_rx_ok) {
             /* the sums are in every lane: lanes 0-2 add the three integer words with ONE

@@ -135,8 +135,10 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
                                   size_t R, size_t T, size_t P, size_t B,
                                   ChannelInfo *los, ChannelInfo *scat,
                                   uint32_t *tr_hit, uint8_t *tr_state,
-                                  int leaf_max, float pad_ulps, int brute)
+                                  int leaf_max, float pad_ulps, int brute_and_mode)
 {
+  const int brute = brute_and_mode & 0xFF;
+  const bool closed_form = (brute_and_mode & 0x100) != 0;   /* gains as k_scatter forms them */
   EmulScene E;
   float ma = 0.f;
   for (size_t i = 0; i < R; ++i) ma = fmaxf(ma, fmaxf(fabsf(rx_pos[i].x), fmaxf(fabsf(rx_pos[i].y), fabsf(rx_pos[i].z))));
@@ -200,16 +202,20 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
         const uint32_t mesh = E.mesh_of[h.gid];
         const HrtMaterial &mat = mats.m[E.mesh_mat[mesh]];
         hrt_bounce_update(s, mat, k, h.t, n, theta);
-        float carry = theta;
+        float carry = theta, cx_carry = HRT_CX_PRIMARY;
+        const float ci_p = cosf(theta), si_p = sinf(theta);
         const HrtChain chain = brute == 1 ? hrt_no_chain() : chain_of(E, s.o);
         for (size_t r = 0; r < R; ++r) {
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
           const HrtHit sh = query(E, s.o, sd, brute, chain);
-          if (sh.gid != HRT_NONE) carry = hrt_theta_fold(nrm(E, sh.slot), sd);
+          if (sh.gid != HRT_NONE) { carry = hrt_theta_fold(nrm(E, sh.slot), sd); cx_carry = v3_dot(nrm(E, sh.slot), sd); }
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
-          const HrtScatterOut o = hrt_scatter_path(s, mat, k, n, E.mesh_vel[mesh], sd, dist, carry);
+          /* closed_form: what k_scatter runs (hrt_scatter_path_auto); else the reference's formulas line by line */
+          const HrtScatterOut o = closed_form
+            ? hrt_scatter_path_auto(s, hrt_scat_const(mat), hrt_scat_cf(mat), k, n, E.mesh_vel[mesh], sd, dist, cx_carry, theta, ci_p, si_p)
+            : hrt_scatter_path(s, mat, k, n, E.mesh_vel[mesh], sd, dist, carry);
           scat->a_te_re[so] = o.te_r; scat->a_te_im[so] = o.te_i; scat->a_tm_re[so] = o.tm_r; scat->a_tm_im[so] = o.tm_i;
           scat->tau[so] = o.tau;
           scat->freq_shift[so] = HRT_SUB(scat->freq_shift[so], o.dfreq);
@@ -283,5 +289,68 @@ extern "C" int emul_scatter_fast_vs_exact(size_t n, uint32_t seed, float f_ghz, 
     if (m_tm > 0 && e_tm / m_tm > worst) worst = e_tm / m_tm;
   }
   *worst_rel = worst;
+  return bad;
+}
+
+/* The closed form of the normalised scattering vector (hrt_scatter_path_auto, what
+ * k_scatter runs) against the reference's formulas line by line (hrt_scatter_path),
+ * same libm for the latter's transcendentals: worst complex relative deviation of the
+ * gains over n random samples -- all 17 materials, incidence angle given as the dot
+ * product the reference feeds to acos (or as a primary angle), scattering directions
+ * down to grazing.  tau, direction and Doppler term must be identical.  *n_closed =
+ * samples that took the closed form.  Returns the number of non-identical exact words. */
+extern "C" int emul_scatter_cf_vs_exact(size_t n, uint32_t seed, float f_ghz, double *worst_rel, size_t *n_closed)
+{
+  HrtMaterialTable mats;
+  memset(&mats, 0, sizeof mats);
+  for (uint32_t i = 0; i < NUM_G_MATERIALS; ++i) hrt_materials_derive(i, f_ghz, (HrtMaterialDerived *)&mats.m[i]);
+  uint64_t st = 0x9E3779B97F4A7C15ull ^ seed;
+  auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (float)((st >> 40) * (1.0 / 16777216.0)); };
+  HrtRunConst k;
+  const float f_hz = (float)((double)f_ghz * 1e9);
+  k.fsl_k = 4.f * HRT_PI * f_hz / HRT_C0; k.dop_k = f_hz / HRT_C0;
+  int bad = 0; double worst = 0.0; size_t closed = 0;
+  for (size_t i = 0; i < n; ++i) {
+    HrtRayState s;
+    s.o = v3(rnd() * 100.f - 50.f, rnd() * 100.f - 50.f, rnd() * 20.f);
+    s.d = v3_normalize(v3(rnd() - .5f, rnd() - .5f, rnd() - .5f));
+    s.te_r = rnd() - .5f; s.te_i = rnd() - .5f; s.tm_r = rnd() - .5f; s.tm_i = rnd() - .5f;
+    s.tau = rnd() * 1e-6f;
+    const HrtMaterial &m = mats.m[(size_t)(rnd() * 16.99f)];
+    float dist;
+    const V3 rxp = v3(rnd() * 100.f - 50.f, rnd() * 100.f - 50.f, 1.5f);
+    const V3 sd = hrt_shadow_dir(s.o, rxp, &dist);
+    /* surface normal: random, or nearly perpendicular to the scattering direction (grazing, |cos theta_s| down to 1e-7) */
+    V3 nrm = v3_normalize(v3(rnd() - .5f, rnd() - .5f, rnd() - .5f));
+    if (i % 3 == 0) {
+      const V3 perp = v3_normalize(v3_cross(sd, nrm));
+      const float eps = powf(10.f, -7.f * rnd()) * (rnd() < .5f ? -1.f : 1.f);
+      nrm = v3_normalize(v3_add(perp, v3_scale(sd, eps)));
+    }
+    const V3 mv = v3(rnd() * 30.f - 15.f, rnd() * 30.f - 15.f, 0.f);
+    if (i % 7 == 0) dist = rnd() * 1e-3f;
+    /* incidence: a shadow-hit dot product in [-1, 1] (dense near 0 and +-1), or the primary angle */
+    float cx = HRT_CX_PRIMARY, theta_p = rnd() * 1.5707f, theta_i = theta_p;
+    if (i % 5 != 0) {
+      const float u = rnd();
+      cx = (i % 2) ? (2.f * u - 1.f) : ((i % 4) ? powf(10.f, -7.f * u) : 1.f - powf(10.f, -7.f * u));
+      if (rnd() < .5f) cx = -cx;
+      theta_i = (float)acos((double)cx);
+      if ((double)theta_i > (double)HRT_PI / 2.) theta_i = HRT_SUB(HRT_PI, theta_i);
+    }
+    const HrtScatterOut a = hrt_scatter_path(s, m, k, nrm, mv, sd, dist, theta_i);
+    const HrtScatCf mcf = hrt_scat_cf(m);
+    float t0, t1, t2, t3, ci = cosf(theta_p), si = sinf(theta_p);
+    if (cx != HRT_CX_PRIMARY) hrt_fold_cos_sin(cx, &ci, &si);
+    if (hrt_scatter_gains_cf(s, mcf, k.fsl_k, v3_dot(sd, nrm), dist, ci, si, &t0, &t1, &t2, &t3)) ++closed;
+    const HrtScatterOut b = hrt_scatter_path_auto(s, hrt_scat_const(m), mcf, k, nrm, mv, sd, dist, cx, theta_p, cosf(theta_p), sinf(theta_p));
+    if (memcmp(&a.tau, &b.tau, 4) || memcmp(&a.dfreq, &b.dfreq, 4) || memcmp(&a.dir_rx, &b.dir_rx, 12)) ++bad;
+    const double e_te = hypot((double)a.te_r - b.te_r, (double)a.te_i - b.te_i), m_te = hypot((double)a.te_r, (double)a.te_i);
+    const double e_tm = hypot((double)a.tm_r - b.tm_r, (double)a.tm_i - b.tm_i), m_tm = hypot((double)a.tm_r, (double)a.tm_i);
+    if (m_te > 0 && e_te / m_te > worst) worst = e_te / m_te;
+    if (m_tm > 0 && e_tm / m_tm > worst) worst = e_tm / m_tm;
+    if ((m_te == 0 && e_te != 0) || (m_tm == 0 && e_tm != 0)) ++bad;
+  }
+  *worst_rel = worst; *n_closed = closed;
   return bad;
 }

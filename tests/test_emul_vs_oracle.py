@@ -93,3 +93,37 @@ def test_grazing_rays_phantom_hits(scene):
     tri_o, t_o, _ = tl.oracle_closest(scene, rays)
     tri_e, t_e, _ = tl.emul_closest(scene, rays)
     assert np.array_equal(tri_o, tri_e) and np.array_equal(t_o.view(np.uint32), t_e.view(np.uint32))
+
+
+def test_closed_form_scatter_gains():
+    """hrt_scatter_path_auto (what k_scatter runs): the normalised scattering vector
+    in closed form -- no acos/acosf/expf/cosf/sinf per path -- against the reference's
+    formulas line by line (glibc), 17 materials, grazing scattering directions,
+    incidence dot products dense near 0 and +-1.  Delay / direction / Doppler term
+    identical; gains within 2e-6 (the 1e-4 tolerance has 50x headroom); most samples
+    take the closed form, the rest falls back to the libm formulas."""
+    import ctypes as C
+    lib = tl.emul_lib()
+    lib.emul_scatter_cf_vs_exact.argtypes = [C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_size_t)]
+    for seed, f in ((1, 3.5), (2, 28.0), (3, 0.9), (4, 70.0)):
+        worst = C.c_double(0); nc = C.c_size_t(0)
+        n = 400000
+        bad = lib.emul_scatter_cf_vs_exact(n, seed, f, C.byref(worst), C.byref(nc))
+        assert bad == 0
+        assert worst.value < 2e-6, worst.value
+        assert nc.value > 0.5 * n, nc.value
+
+
+@pytest.mark.parametrize("name", tl.GOLDEN_NAMES)
+def test_compute_paths_closed_form_matches_golden(name):
+    """The whole path with the kernels' closed-form gains against the reference's
+    vectors: exact words bit-equal, gains within the 1e-4 tolerance (1e-5 asserted)."""
+    g = tl.load_golden(name)
+    o, tr = tl.run_emul(g["scene"], g["rx"], g["tx"], g["rxv"], g["txv"], g["f"], g["P"], g["B"], closed_form=True)
+    w = tl.outputs_words(o)
+    ref = {k[4:]: v for k, v in g.items() if k.startswith("out.")}
+    mask = {k[5:]: v for k, v in g.items() if k.startswith("mask.")}
+    keys = [k for k in tl.EXACT_KEYS if not k.startswith(("scat_rays", "scat_active", "los_rays", "los_active"))]
+    tl.assert_exact(ref, mask, w, keys=keys)
+    tl.assert_gains_close(ref, mask, w, rtol=1e-5)
+    assert np.array_equal(tr["slot_state"], g["trace.slot_state"])
