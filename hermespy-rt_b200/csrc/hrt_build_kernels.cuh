@@ -354,3 +354,60 @@ __global__ void k_sah_refit(int first, int last, const int2 *raw_ref, float *raw
   }
 }
 
+/* ---- binary -> 4-wide collapse (hrt_bvh.cuh, "4-wide nodes") ----
+ * bn: the emitted binary nodes (plain copy, boxes padded).  Generic over the
+ * builder: only child refs are followed. */
+__global__ void k_wide_parent(const float4 *bn, int n, int *parent)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0) parent[0] = -1;                   /* node 0 is the root, nobody's child */
+  const int l = __float_as_int(bn[4 * (size_t)i + 1].z), r = __float_as_int(bn[4 * (size_t)i + 3].z);
+  if (l >= 0) parent[l] = i;
+  if (r >= 0) parent[r] = i;
+}
+
+/* even[i] = 1 when binary node i sits at even depth (it becomes a wide node) */
+__global__ void k_wide_depth(int n, const int *parent, uint8_t *even)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = 0;
+  for (int j = parent[i]; j >= 0; j = parent[j]) ++d;
+  even[i] = (uint8_t)((d & 1) == 0);
+}
+
+/* exclusive prefix count of the flags, one block: wide nodes are numbered in
+ * binary index order (deterministic; level order for the SAH builder) */
+__global__ void __launch_bounds__(1024) k_wide_scan(int n, const uint8_t *even, uint32_t *widx, uint32_t *total)
+{
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + (int)threadIdx.x;
+    const uint32_t f = i < n ? even[i] : 0u;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, f != 0u);
+    if (lane == 0) warp_sum[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
+    if (i < n) widx[i] = base + before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    __syncthreads();
+    if (threadIdx.x == 1023) base += before + (uint32_t)__popc(m);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = base;
+}
+
+__global__ void k_wide_emit(const float4 *bn, int n, const uint8_t *even, const uint32_t *widx,
+                            float4 *wnodes, size_t oct_stride4, uint32_t octants)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !even[i]) return;
+  HrtWideChild ch[4];
+  const int c = hrt_wide_children(bn, i, widx, ch);
+  hrt_wide_emit(wnodes, oct_stride4, octants, widx[i], ch, c);
+}

@@ -139,3 +139,82 @@ HRT_HD float hrt_box_pad(float max_abs_coord, float ulps)
 {
   return ulps * FLT_EPSILON * fmaxf(max_abs_coord, 1.0f);
 }
+
+/* ---- 4-wide nodes (BVH4) ----
+ * The traversal kernels walk a 4-wide tree collapsed from the binary one: a
+ * binary node at even depth becomes a wide node whose children are its
+ * grandchildren (or its children where those are leaves).  One visit tests four
+ * boxes with one set of loads and NO ordering decision: there is one node copy
+ * per ray-direction octant (as for the binary nodes), and inside a copy the
+ * children are stored front-to-back for that octant (by the box centre along the
+ * octant's diagonal), with the near / far plane of every axis pre-selected.
+ *
+ * Wide node, 7 x float4 = 112 B, structure of arrays over the four children:
+ *   w0 near.x[4]  w1 far.x[4]  w2 near.y[4]  w3 far.y[4]  w4 near.z[4]  w5 far.z[4]
+ *   w6 ref[4]     >= 0 wide node index, < 0 leaf (as hrt_leaf_ref), empty slot:
+ *                 HRT_WIDE_EMPTY with a box no ray can enter (near +3e38, far -3e38)
+ * Pure traversal order, as with every other tree shape: the result is the
+ * minimum over (t, triangle id). */
+#define HRT_WIDE_F4 7u          /* float4s per wide node */
+
+struct HrtWideChild { int ref; V3 lo, hi; };
+
+/* writes the `octants` copies of wide node `w`; copies are `oct_stride4` float4s apart */
+HRT_HD void hrt_wide_emit(float4 *nodes, size_t oct_stride4, uint32_t octants, uint32_t w,
+                          const HrtWideChild *ch, int n)
+{
+  for (uint32_t oct = 0; oct < octants; ++oct) {
+    /* front-to-back order for this octant: ascending centre along (+-1, +-1, +-1) */
+    int order[4] = { 0, 1, 2, 3 };
+    float key[4];
+    for (int k = 0; k < 4; ++k) {
+      if (k >= n) { key[k] = 3.0e38f; continue; }
+      const float cx = ch[k].lo.x + ch[k].hi.x, cy = ch[k].lo.y + ch[k].hi.y, cz = ch[k].lo.z + ch[k].hi.z;
+      key[k] = ((oct & 1u) ? -cx : cx) + ((oct & 2u) ? -cy : cy) + ((oct & 4u) ? -cz : cz);
+    }
+    for (int i = 1; i < 4; ++i)
+      for (int j = i; j > 0 && key[order[j]] < key[order[j - 1]]; --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    float v[7][4];
+    for (int s = 0; s < 4; ++s) {
+      const int k = order[s];
+      if (k >= n) {
+        v[0][s] = v[2][s] = v[4][s] = 3.0e38f; v[1][s] = v[3][s] = v[5][s] = -3.0e38f;
+        if (oct & 1u) { v[0][s] = -3.0e38f; v[1][s] = 3.0e38f; }
+        if (oct & 2u) { v[2][s] = -3.0e38f; v[3][s] = 3.0e38f; }
+        if (oct & 4u) { v[4][s] = -3.0e38f; v[5][s] = 3.0e38f; }
+        v[6][s] = hrt_int_as_float(HRT_WIDE_EMPTY);
+        continue;
+      }
+      v[0][s] = (oct & 1u) ? ch[k].hi.x : ch[k].lo.x; v[1][s] = (oct & 1u) ? ch[k].lo.x : ch[k].hi.x;
+      v[2][s] = (oct & 2u) ? ch[k].hi.y : ch[k].lo.y; v[3][s] = (oct & 2u) ? ch[k].lo.y : ch[k].hi.y;
+      v[4][s] = (oct & 4u) ? ch[k].hi.z : ch[k].lo.z; v[5][s] = (oct & 4u) ? ch[k].lo.z : ch[k].hi.z;
+      v[6][s] = hrt_int_as_float(ch[k].ref);
+    }
+    float4 *dst = nodes + (size_t)oct * oct_stride4 + (size_t)w * HRT_WIDE_F4;
+    for (int q = 0; q < 7; ++q) { dst[q].x = v[q][0]; dst[q].y = v[q][1]; dst[q].z = v[q][2]; dst[q].w = v[q][3]; }
+  }
+}
+
+/* children of wide node = children of binary node `i` (plain octant-0 copy of
+ * the emitted binary nodes, boxes already padded), inner children replaced by
+ * their own two children.  widx maps an (even-depth) binary node to its wide
+ * index.  Returns the number of children written to ch[0..3]. */
+HRT_HD int hrt_wide_children(const float4 *bn, int i, const uint32_t *widx, HrtWideChild *ch)
+{
+  int n = 0;
+  for (int s = 0; s < 2; ++s) {
+    const float4 a = bn[4 * (size_t)i + 2 * s], b = bn[4 * (size_t)i + 2 * s + 1];
+    const int ref = hrt_float_as_int(b.z);
+    if (ref < 0) {
+      ch[n].ref = ref; ch[n].lo = v3(a.x, a.z, b.x); ch[n].hi = v3(a.y, a.w, b.y); ++n;
+      continue;
+    }
+    for (int g = 0; g < 2; ++g) {
+      const float4 c = bn[4 * (size_t)ref + 2 * g], e = bn[4 * (size_t)ref + 2 * g + 1];
+      const int gref = hrt_float_as_int(e.z);
+      ch[n].ref = gref < 0 ? gref : (int)widx[gref];
+      ch[n].lo = v3(c.x, c.z, e.x); ch[n].hi = v3(c.y, c.w, e.y); ++n;
+    }
+  }
+  return n;
+}

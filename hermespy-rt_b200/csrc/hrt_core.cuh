@@ -302,6 +302,23 @@ struct HrtGlobalMem {
     *xy = q[0]; *zr = q[1];
 #endif
   }
+  /* 4-wide nodes (hrt_bvh.cuh): float4 k of wide node i of the selected octant copy */
+  const float4 *wnodes;
+  HRT_HD float4 wide(int i, int k) const
+  {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&wnodes[7 * (size_t)i + k]);
+#else
+    return wnodes[7 * (size_t)i + k];
+#endif
+  }
+  HRT_HD void select_wide_octant(uint32_t oct, size_t stride4)
+  {
+    wnodes += (size_t)oct * stride4;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(wnodes));
+#endif
+  }
   HRT_HD uint32_t cache_word(uint32_t, uint32_t) const { return 0u; }   /* no chain cache for global-memory scenes */
   HRT_HD int child_ref(int i, uint32_t right) const
   {
@@ -485,6 +502,107 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref
     if (!got) done = true;
   }
   return h;
+}
+
+/* Closest hit over the 4-wide tree (hrt_bvh.cuh, "4-wide nodes"): the same
+ * minimum over (t, triangle id) as the reference's loop over every triangle.
+ * One visit = seven 16-byte loads, four slab tests, no ordering decision (the
+ * octant copy stores the children front to back); the children that are hit are
+ * pushed in reverse order and the nearest is popped straight away.
+ * SORTED: `mem.wnodes` holds 8 octant copies `oct_stride4` float4s apart; else a
+ * single plain copy (lo/hi per axis, min/max in the slab test).
+ * root_ref: wide node index, a leaf ref, or anything with num_tris == 0. */
+#define HRT_WSTACK 96   /* 3 pushes per level, depth <= (32 + log2 n) / 2 + 1 */
+#define HRT_WIDE_EMPTY ((int)0x80000000)   /* ref of an unused child slot */
+template <bool SORTED, class Mem, class Gid, class Cnt>
+HRT_HD HrtHit hrt_closest_hit_wide(const Mem &mem_in, const Gid tri_gid, int root_ref,
+                                   uint32_t num_tris, V3 o, V3 d, Cnt &cnt, size_t oct_stride4 = 0)
+{
+  HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
+  if (num_tris == 0) return h;
+  HrtRayCull c = hrt_ray_cull(o, d);
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+f"(c.ood.x), "+f"(c.ood.y), "+f"(c.ood.z));
+#endif
+  Mem mem = mem_in;
+  if (SORTED) mem.select_wide_octant(hrt_octant(c), oct_stride4);
+  float tmax = HRT_T_MAX * 1.0001f;
+  HrtStackEntry stack[HRT_WSTACK];
+  int sp = 0, cur = root_ref;
+  for (;;) {
+    while (cur >= 0) {
+      /* axis by axis, so that at most two plane vectors are live next to the running
+       * entry / exit distances of the four children */
+      float tn[4], tf[4]; bool hit[4]; int ref[4];
+      {
+        const float4 n4 = mem.wide(cur, 0), f4 = mem.wide(cur, 1);
+        if (SORTED) {
+          tn[0] = fmaxf(HRT_FMA(n4.x, c.inv.x, c.ood.x), 0.f); tn[1] = fmaxf(HRT_FMA(n4.y, c.inv.x, c.ood.x), 0.f);
+          tn[2] = fmaxf(HRT_FMA(n4.z, c.inv.x, c.ood.x), 0.f); tn[3] = fmaxf(HRT_FMA(n4.w, c.inv.x, c.ood.x), 0.f);
+          tf[0] = fminf(HRT_FMA(f4.x, c.inv.x, c.ood.x), tmax); tf[1] = fminf(HRT_FMA(f4.y, c.inv.x, c.ood.x), tmax);
+          tf[2] = fminf(HRT_FMA(f4.z, c.inv.x, c.ood.x), tmax); tf[3] = fminf(HRT_FMA(f4.w, c.inv.x, c.ood.x), tmax);
+        } else {
+#define HRT_WIDE_AX0(K, M) { const float a = HRT_FMA(n4.M, c.inv.x, c.ood.x), b = HRT_FMA(f4.M, c.inv.x, c.ood.x); \
+                             tn[K] = fmaxf(fminf(a, b), 0.f); tf[K] = fminf(fmaxf(a, b), tmax); }
+          HRT_WIDE_AX0(0, x) HRT_WIDE_AX0(1, y) HRT_WIDE_AX0(2, z) HRT_WIDE_AX0(3, w)
+#undef HRT_WIDE_AX0
+        }
+      }
+#define HRT_WIDE_AX(K, M, INV, OOD)                                                                  \
+      { const float a = HRT_FMA(n4.M, INV, OOD), b = HRT_FMA(f4.M, INV, OOD);                           \
+        if (SORTED) { tn[K] = fmaxf(tn[K], a); tf[K] = fminf(tf[K], b); }                              \
+        else { tn[K] = fmaxf(tn[K], fminf(a, b)); tf[K] = fminf(tf[K], fmaxf(a, b)); } }
+      {
+        const float4 n4 = mem.wide(cur, 2), f4 = mem.wide(cur, 3);
+        HRT_WIDE_AX(0, x, c.inv.y, c.ood.y) HRT_WIDE_AX(1, y, c.inv.y, c.ood.y)
+        HRT_WIDE_AX(2, z, c.inv.y, c.ood.y) HRT_WIDE_AX(3, w, c.inv.y, c.ood.y)
+      }
+      {
+        const float4 n4 = mem.wide(cur, 4), f4 = mem.wide(cur, 5);
+        HRT_WIDE_AX(0, x, c.inv.z, c.ood.z) HRT_WIDE_AX(1, y, c.inv.z, c.ood.z)
+        HRT_WIDE_AX(2, z, c.inv.z, c.ood.z) HRT_WIDE_AX(3, w, c.inv.z, c.ood.z)
+      }
+#undef HRT_WIDE_AX
+      {
+        const float4 rf = mem.wide(cur, 6);
+        ref[0] = hrt_float_as_int(rf.x); ref[1] = hrt_float_as_int(rf.y);
+        ref[2] = hrt_float_as_int(rf.z); ref[3] = hrt_float_as_int(rf.w);
+      }
+      for (int k = 0; k < 4; ++k) hit[k] = tn[k] <= tf[k] && (SORTED || ref[k] != HRT_WIDE_EMPTY);
+      cnt.box((uint32_t)(ref[0] != HRT_WIDE_EMPTY) + (uint32_t)(ref[1] != HRT_WIDE_EMPTY) +
+              (uint32_t)(ref[2] != HRT_WIDE_EMPTY) + (uint32_t)(ref[3] != HRT_WIDE_EMPTY));
+      /* far to near onto the stack, then take the nearest back off */
+      if (hit[3]) { HrtStackEntry e; e.ref = ref[3]; e.tn = tn[3]; stack[sp++] = e; }
+      if (hit[2]) { HrtStackEntry e; e.ref = ref[2]; e.tn = tn[2]; stack[sp++] = e; }
+      if (hit[1]) { HrtStackEntry e; e.ref = ref[1]; e.tn = tn[1]; stack[sp++] = e; }
+      if (hit[0]) { cur = ref[0]; continue; }
+      bool got = false;
+      while (sp > 0) {
+        const HrtStackEntry e = stack[--sp];
+        if (e.tn <= tmax) { cur = e.ref; got = true; break; }
+      }
+      if (!got) return h;
+    }
+    {
+      const uint32_t code = (uint32_t)~cur;
+      const uint32_t first = code >> 3, ntri = (code & 7u) + 1u;
+      for (uint32_t k = 0; k < ntri; ++k) {
+        const uint32_t s = first + k;
+        float t;
+        const uint32_t gid = tri_gid[s];
+        if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) {
+          h.t = t; h.gid = gid; h.slot = s;
+          tmax = HRT_FMA(t, 1.0001f, 1e-30f);
+        }
+      }
+    }
+    /* pop, skipping subtrees that start beyond the current best */
+    for (;;) {
+      if (sp == 0) return h;
+      const HrtStackEntry e = stack[--sp];
+      if (e.tn <= tmax) { cur = e.ref; break; }
+    }
+  }
 }
 
 /* Brute force over every triangle in leaf order -- debug/validation path of

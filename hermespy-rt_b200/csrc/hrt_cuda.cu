@@ -61,11 +61,13 @@ struct SceneDev {
   const uint32_t *mesh_mat;    /* by mesh */
   const float *mesh_vel;       /* 3 per mesh */
   uint32_t num_tris, num_nodes;
-  uint32_t octants;            /* node copies: 8 (one per direction octant) or 1 */
+  uint32_t octants;            /* copies of the binary nodes (1: they only feed the collapse and the refit) */
   int root_ref;
+  const float4 *wnodes;        /* 4-wide nodes the kernels traverse (hrt_bvh.cuh), wide_octants copies */
+  uint32_t num_wide, wide_octants;   /* copies: 8 (one per direction octant) or 1 */
+  int wroot;
   float key_lo[3], key_scale[3];   /* vertex bounds -> 10-bit grid of the hit-order keys */
   float key_log;                   /* > 0: logarithmic x/y grid around the TX, cells per octave */
-  uint32_t no_chain;               /* HRT_NO_CHAIN=1: shadow rays start at the root (A/B switch) */
 };
 
 struct RunDev {
@@ -188,6 +190,10 @@ struct hrt_ctx {
   float scene_lo[3], scene_hi[3];
   float4 *d_tris; uint32_t *d_tri_gid; uint32_t *d_mesh_of; uint32_t *d_mesh_mat; float *d_mesh_vel;
   float4 *d_nodes;
+  /* 4-wide nodes collapsed from d_nodes (build_wide) and the collapse scratch */
+  float4 *d_wnodes; size_t cap_wnodes;
+  int *d_wparent; uint8_t *d_weven; uint32_t *d_widx, *d_wtotal; size_t cap_wscratch;
+  uint32_t num_wide, wide_octants; int wroot;
   /* builder arrays kept for re-padding */
   int *d_kl, *d_kr, *d_kfirst, *d_klast, *d_newidx;
   float *d_box;            /* [(2n-1)][6] lo.xyz hi.xyz; inner nodes then leaves */
@@ -291,6 +297,8 @@ static void free_scene_dev(hrt_ctx *c)
   dev_free(c->d_kfirst); dev_free(c->d_klast); dev_free(c->d_newidx); dev_free(c->d_box);
   dev_free(c->d_raw_ref); dev_free(c->d_raw_box);
   dev_free(c->d_verts); dev_free(c->d_idx3); dev_free(c->d_vmesh); dev_free(c->d_recs); dev_free(c->d_tboxes); dev_free(c->d_bounds);
+  dev_free(c->d_wnodes); dev_free(c->d_wparent); dev_free(c->d_weven); dev_free(c->d_widx); dev_free(c->d_wtotal);
+  c->cap_wnodes = c->cap_wscratch = 0; c->num_wide = 0;
   c->have_scene = false;
 }
 
@@ -331,23 +339,58 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
 
 static inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-/* (re)emit traversal nodes with the given padding */
-static int emit_nodes(hrt_ctx *ctx, float pad)
+/* binary nodes in d_nodes -> the 4-wide nodes the kernels traverse (hrt_bvh.cuh):
+ * parents, depth parity, numbering of the even-depth nodes, emission of the
+ * octant copies.  Works for either builder; redone whenever the boxes change
+ * (re-padding, refit).  Everything on `st`. */
+static int build_wide(hrt_ctx *ctx, cudaStream_t st)
+{
+  const uint32_t n = ctx->num_nodes;
+  ctx->wroot = ctx->root_ref; ctx->num_wide = 0;
+  if (n == 0) return HRT_OK;
+  if (ctx->cap_wscratch < n) {
+    dev_free(ctx->d_wparent); dev_free(ctx->d_weven); dev_free(ctx->d_widx); dev_free(ctx->d_wtotal);
+    ctx->cap_wscratch = 0;
+    CK(dev_alloc(&ctx->d_wparent, n)); CK(dev_alloc(&ctx->d_weven, n)); CK(dev_alloc(&ctx->d_widx, n)); CK(dev_alloc(&ctx->d_wtotal, 1));
+    ctx->cap_wscratch = n;
+  }
+  k_wide_parent<<<nblk(n), 256, 0, st>>>(ctx->d_nodes, (int)n, ctx->d_wparent);
+  k_wide_depth<<<nblk(n), 256, 0, st>>>((int)n, ctx->d_wparent, ctx->d_weven);
+  k_wide_scan<<<1, 1024, 0, st>>>((int)n, ctx->d_weven, ctx->d_widx, ctx->d_wtotal);
+  CK(cudaGetLastError());
+  uint32_t total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->d_wtotal, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->num_wide = total;
+  ctx->wide_octants = octant_copies(total);
+  const size_t need = (size_t)total * HRT_WIDE_F4 * ctx->wide_octants;
+  if (ctx->cap_wnodes < need) {
+    dev_free(ctx->d_wnodes); ctx->cap_wnodes = 0;
+    CK(dev_alloc(&ctx->d_wnodes, need)); ctx->cap_wnodes = need;
+  }
+  k_wide_emit<<<nblk(n), 256, 0, st>>>(ctx->d_nodes, (int)n, ctx->d_weven, ctx->d_widx, ctx->d_wnodes,
+                                       (size_t)total * HRT_WIDE_F4, ctx->wide_octants);
+  CK(cudaGetLastError());
+  ctx->wroot = 0;
+  return HRT_OK;
+}
+
+/* (re)emit the traversal nodes with the given padding, on stream `st` */
+static int emit_nodes(hrt_ctx *ctx, float pad, cudaStream_t st)
 {
   const int n = (int)ctx->num_tris;
   ctx->pad = pad;
-  if (ctx->num_nodes == 0) return HRT_OK;
+  if (ctx->num_nodes == 0) { ctx->wroot = ctx->root_ref; ctx->num_wide = 0; return HRT_OK; }
   if (ctx->sah) {
-    k_emit_raw<<<nblk(ctx->num_nodes), 256, 0, ctx->stream>>>((int)ctx->num_nodes, ctx->d_raw_ref, ctx->d_raw_box, pad,
-                                                             ctx->d_nodes, ctx->octants, ctx->num_nodes);
-    CK(cudaGetLastError());
-    return HRT_OK;
+    k_emit_raw<<<nblk(ctx->num_nodes), 256, 0, st>>>((int)ctx->num_nodes, ctx->d_raw_ref, ctx->d_raw_box, pad,
+                                                    ctx->d_nodes, ctx->octants, ctx->num_nodes);
+  } else {
+    k_emit<<<nblk(n - 1), 256, 0, st>>>(n, ctx->d_kl, ctx->d_kr, ctx->d_kfirst, ctx->d_klast,
+                                        ctx->d_newidx + n /* used flags live behind newidx */,
+                                        ctx->d_newidx, ctx->d_box, ctx->leaf_max, pad, ctx->d_nodes, ctx->octants, ctx->num_nodes);
   }
-  k_emit<<<nblk(n - 1), 256, 0, ctx->stream>>>(n, ctx->d_kl, ctx->d_kr, ctx->d_kfirst, ctx->d_klast,
-                                               ctx->d_newidx + n /* used flags live behind newidx */,
-                                               ctx->d_newidx, ctx->d_box, ctx->leaf_max, pad, ctx->d_nodes, ctx->octants, ctx->num_nodes);
   CK(cudaGetLastError());
-  return HRT_OK;
+  return build_wide(ctx, st);
 }
 
 /* binned-SAH build over the triangle boxes; fills d_tris / d_tri_gid in leaf
@@ -496,7 +539,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
     CKG(cudaMemcpyAsync(ctx->d_mesh_vel, h_vel, (size_t)M * 12, cudaMemcpyHostToDevice, st));
     const unsigned init_bounds[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
     CKG(cudaMemcpyAsync(d_bounds, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
-    ctx->num_nodes = 0; ctx->root_ref = 0; ctx->octants = 8;
+    ctx->num_nodes = 0; ctx->root_ref = 0; ctx->octants = 1; ctx->wide_octants = 8; ctx->num_wide = 0; ctx->wroot = 0;
     if (n > 0) {
       k_tri_setup<<<nblk(n), 256, 0, st>>>(d_v, d_i, n, d_recs, d_boxes, d_bounds);
       ctx->sah = !getenv("HRT_BVH_LBVH");
@@ -504,7 +547,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         CKG(cudaGetLastError());
         const int brc = build_sah(ctx, n, d_boxes, d_recs);
         if (brc) { rc = brc; goto done; }
-        ctx->octants = octant_copies(ctx->num_nodes);
+        ctx->octants = 1;
         CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
         goto built;
       }
@@ -542,16 +585,14 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         CKG(es);
         ctx->num_nodes = (uint32_t)(last_idx + last_used);
         ctx->root_ref = 0;
-        /* small scenes get one node copy per ray-direction octant (shared-memory
-         * traversal without per-axis min/max, hrt_slab_sorted) */
-        ctx->octants = octant_copies(ctx->num_nodes);
+        ctx->octants = 1;
         CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
       }
     }
 built:
     ctx->pad = hrt_box_pad(max_abs, ctx->pad_ulps);
-    if (ctx->num_nodes) {
-      int erc = emit_nodes(ctx, ctx->pad);
+    {
+      int erc = emit_nodes(ctx, ctx->pad, st);
       if (erc) { rc = erc; goto done; }
     }
     if (normals_out && n) {
@@ -609,7 +650,7 @@ extern "C" int hrt_scene_advance(hrt_ctx *ctx, float dt_s, int rebuild)
     ctx->sah = true;
     const int rc = build_sah(ctx, n, ctx->d_tboxes, ctx->d_recs);
     if (rc) { ctx->have_scene = false; return rc; }
-    ctx->octants = octant_copies(ctx->num_nodes);
+    ctx->octants = 1;
     CK(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
     ctx->root_ref = 0;
   } else {
@@ -621,7 +662,7 @@ extern "C" int hrt_scene_advance(hrt_ctx *ctx, float dt_s, int rebuild)
     }
     CK(cudaGetLastError());
   }
-  const int erc = emit_nodes(ctx, pad);
+  const int erc = emit_nodes(ctx, pad, st);
   if (erc) return erc;
   CK(cudaStreamSynchronize(st));
   return HRT_OK;
@@ -685,15 +726,20 @@ static SceneDev scene_dev(const hrt_ctx *c)
     /* 511 cells for log2(1 + 2 * ext / 5 cm) octaves: covers a TX anywhere inside the bounds */
     s.key_log = (ext > 256.f && !getenv("HRT_KEY_UNIFORM")) ? 511.f / log2f(1.f + 2.f * ext * 20.f) : 0.f;
   }
-  s.no_chain = getenv("HRT_NO_CHAIN") ? 1u : 0u;
+  s.wnodes = c->d_wnodes; s.num_wide = c->num_wide; s.wide_octants = c->wide_octants; s.wroot = c->wroot;
   return s;
 }
 
 /* make sure boxes are padded for ray origins as far out as max_abs */
-static int ensure_pad(hrt_ctx *ctx, float max_abs)
+static int ensure_pad(hrt_ctx *ctx, float max_abs, cudaStream_t st)
 {
   const float need = hrt_box_pad(fmaxf(max_abs, ctx->scene_max_abs), ctx->pad_ulps);
-  if (need > ctx->pad) return emit_nodes(ctx, need);
+  /* the nodes are rewritten on the stream the traversal kernels will run on: a
+   * caller-supplied stream is ordered behind any earlier work on the context's own */
+  if (need > ctx->pad) {
+    if (st != ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
+    return emit_nodes(ctx, need, st);
+  }
   return HRT_OK;
 }
 
@@ -713,7 +759,7 @@ template <class K> static cudaError_t allow_smem(K kernel, size_t bytes)
 }
 
 typedef void (*BounceFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t);
-typedef void (*ScatterFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t, uint32_t, uint32_t);
+typedef void (*ScatterFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t, uint32_t);
 
 /* [smem][brute][count]; the instrumented build exists for BVH traversal only */
 static BounceFn bounce_fn(bool smem, bool brute, bool count)
@@ -761,13 +807,13 @@ extern "C" int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_
   CK(cudaSetDevice(ctx->device));
   float max_abs = 0.f;
   for (size_t i = 0; i < n; ++i) { max_abs = fmaxf(max_abs, fmaxf(fabsf(rays[i].o.x), fmaxf(fabsf(rays[i].o.y), fabsf(rays[i].o.z)))); }
-  int rc = ensure_pad(ctx, max_abs); if (rc) return rc;
+  int rc = ensure_pad(ctx, max_abs, ctx->stream); if (rc) return rc;
   Ray *d_r = nullptr; uint32_t *d_tri = nullptr; float *d_t = nullptr, *d_th = nullptr;
   cudaStream_t st = ctx->stream;
   CK(dev_alloc(&d_r, n)); CK(dev_alloc(&d_tri, n)); CK(dev_alloc(&d_t, n)); CK(dev_alloc(&d_th, n));
   CK(cudaMemcpyAsync(d_r, rays, n * sizeof(Ray), cudaMemcpyHostToDevice, st));
-  const size_t sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris, ctx->octants);
-  const bool smem = ctx->octants == 8 && sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM"), brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
+  const size_t sb = scene_smem_bytes(ctx->num_wide, ctx->num_tris, ctx->wide_octants);
+  const bool smem = ctx->wide_octants == 8 && sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM"), brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
   const SceneDev sc = scene_dev(ctx);
   const unsigned grid = (unsigned)min((size_t)sm_count(ctx->device) * 2, (n + HRT_BLOCK - 1) / HRT_BLOCK);
   if (smem) {
@@ -1120,7 +1166,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   for (size_t i = 0; i < R; ++i) max_abs = fmaxf(max_abs, fmaxf(fabsf(p->rx_pos[i].x), fmaxf(fabsf(p->rx_pos[i].y), fabsf(p->rx_pos[i].z))));
   for (size_t i = 0; i < T; ++i) max_abs = fmaxf(max_abs, fmaxf(fabsf(p->tx_pos[i].x), fmaxf(fabsf(p->tx_pos[i].y), fabsf(p->tx_pos[i].z))));
   if (!(max_abs < 1e30f)) return fail(ctx, HRT_E_ARG, "non-finite position");
-  int rc = ensure_pad(ctx, max_abs); if (rc) return rc;
+  int rc = ensure_pad(ctx, max_abs, st); if (rc) return rc;
   const size_t npos = 6 * (R + T);
   if (ctx->cap_pos < npos) { dev_free(ctx->d_pos); CK(dev_alloc(&ctx->d_pos, npos)); ctx->cap_pos = npos; }
   float *d_rx = ctx->d_pos, *d_tx = d_rx + 3 * R, *d_rxv = d_tx + 3 * T, *d_txv = d_rxv + 3 * R;
@@ -1168,8 +1214,8 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   S.num_tris = ctx->num_tris; S.num_nodes = ctx->num_nodes; S.box_pad = ctx->pad;
   S.bvh_sah = ctx->sah; S.bvh_levels = (uint32_t)ctx->build_levels; S.bvh_build_ms = ctx->build_ms;
   const SceneDev sc = scene_dev(ctx);
-  const size_t scene_sb = scene_smem_bytes(ctx->num_nodes, ctx->num_tris, ctx->octants);
-  const bool smem = ctx->octants == 8 && scene_sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM");
+  const size_t scene_sb = scene_smem_bytes(ctx->num_wide, ctx->num_tris, ctx->wide_octants);
+  const bool smem = ctx->wide_octants == 8 && scene_sb <= HRT_SMEM_SCENE_LIMIT && !getenv("HRT_NO_SMEM");
   const bool brute = (flags & HRT_FLAG_BRUTE_FORCE) != 0;
   S.scene_in_smem = smem;
   const int sms = sm_count(ctx->device);
@@ -1177,15 +1223,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   /* scatter kernel shared memory: scene + receivers + reduction table */
   const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
   const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 110 * 1024;
-  size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
-  /* per-thread chain cache (hrt_origin_chain) behind the scene and the receiver tables,
-   * while two blocks still fit an SM */
-  uint32_t cc_off = 0;
-  {
-    const size_t cc_sb = (size_t)(HRT_CHAIN_CACHE_LEVELS + 1) * HRT_BLOCK * 4;
-    const size_t at = (scat_sb + 15) & ~(size_t)15;
-    if (smem && !brute && at + cc_sb <= 112 * 1024 && !getenv("HRT_NO_CHAIN_CACHE")) { cc_off = (uint32_t)at; scat_sb = at + cc_sb; }
-  }
+  const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
   /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
    * thanks to the direction sort) whenever there are enough hits to fill the
    * machine; a warp per hit (lanes over receivers) for few rays x many RX */
@@ -1365,7 +1403,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok, cc_off);
+      f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
       if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 3], st)); ev_used += 4; }

@@ -27,22 +27,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 __device__ __forceinline__ uint32_t smem_base_addr() { return (uint32_t)__cvta_generic_to_shared(hrt_smem4); }
 
 struct HrtSharedMem {
-  uint32_t node_addr, tri_addr;     /* byte addresses in the shared window */
-  __device__ __forceinline__ float4 node(int i, int k) const { return lds128(node_addr + ((uint32_t)i << 6) + ((uint32_t)k << 4)); }
+  uint32_t wnode_addr, tri_addr;     /* byte addresses in the shared window */
+  __device__ __forceinline__ float4 wide(int i, int k) const { return lds128(wnode_addr + (uint32_t)i * 112u + ((uint32_t)k << 4)); }
   __device__ __forceinline__ float4 tri(uint32_t s, int k) const { return lds128(tri_addr + s * 48u + ((uint32_t)k << 4)); }
-  __device__ __forceinline__ void child_at(uint32_t off, float4 *xy, float4 *zr) const
+  __device__ __forceinline__ void select_wide_octant(uint32_t oct, size_t stride4)
   {
-    *xy = lds128(node_addr + off); *zr = lds128(node_addr + off + 16u);
-  }
-  __device__ __forceinline__ int child_ref(int i, uint32_t right) const
-  { return (int)lds32(node_addr + ((uint32_t)i << 6) + (right ? 56u : 24u)); }
-  /* entry `lvl` of a thread's chain cache (hrt_origin_chain) */
-  __device__ __forceinline__ uint32_t cache_word(uint32_t cache_addr, uint32_t lvl) const
-  { return lds32(cache_addr + lvl * (HRT_BLOCK * 4u)); }
-  __device__ __forceinline__ void select_octant(uint32_t oct, uint32_t stride)
-  {
-    node_addr += oct * stride * 16u;
-    asm volatile("" : "+r"(node_addr));   /* keep it in a register: do not recompute per node */
+    wnode_addr += oct * (uint32_t)stride4 * 16u;
+    asm volatile("" : "+r"(wnode_addr));   /* keep it in a register: do not recompute per node */
   }
 };
 
@@ -56,65 +47,48 @@ struct HrtSharedGid {
  * first free float4 slot after them */
 __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
 {
-  const uint32_t nn = sc.num_nodes * 4u * sc.octants, nt = sc.num_tris * 3u;
-  for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.nodes[i];
+  const uint32_t nn = sc.num_wide * HRT_WIDE_F4 * sc.wide_octants, nt = sc.num_tris * 3u;
+  for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.wnodes[i];
   for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) hrt_smem4[nn + i] = sc.tris[i];
   uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
   for (uint32_t i = threadIdx.x; i < sc.num_tris; i += blockDim.x) gid[i] = sc.tri_gid[i];
   return nn + nt + (sc.num_tris + 3u) / 4u;
 }
 
-/* Eight node copies (one per ray-direction octant, planes pre-ordered: no
- * per-axis min/max in the slab test) whenever they fit the budget -- shared
+/* Eight copies of the 4-wide nodes (one per ray-direction octant: planes and
+ * child order pre-selected, hrt_bvh.cuh) whenever they fit the budget -- shared
  * memory for small scenes, HBM (HRT_OCTANT_BYTES_MAX, default 4 GB) otherwise. */
-static uint32_t octant_copies(uint32_t num_nodes)
+static uint32_t octant_copies(uint32_t num_wide)
 {
   size_t lim = (size_t)4 << 30;
   if (const char *e = getenv("HRT_OCTANT_BYTES_MAX")) lim = (size_t)atoll(e);
-  return (size_t)num_nodes * 64 * 8 <= lim ? 8u : 1u;
+  return (size_t)num_wide * 112 * 8 <= lim ? 8u : 1u;
 }
 
-static size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_tris, uint32_t octants = 8)
-{ return (size_t)num_nodes * 64 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
+static size_t scene_smem_bytes(uint32_t num_wide, uint32_t num_tris, uint32_t octants = 8)
+{ return (size_t)num_wide * 112 * octants + (size_t)num_tris * 48 + (size_t)((num_tris + 3) / 4) * 16; }
+
+/* byte offset of the triangle records behind the wide nodes of a staged scene */
+__device__ __forceinline__ uint32_t scene_tri_off(const SceneDev &sc) { return sc.num_wide * 112u * sc.wide_octants; }
 
 template <bool SMEM, bool BRUTE, class Cnt>
-__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, HrtChain chain = hrt_no_chain())
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt)
 {
+  const size_t stride4 = (size_t)sc.num_wide * HRT_WIDE_F4;
   if (SMEM) {
     HrtSharedMem m;
-    m.node_addr = smem_base_addr();
-    m.tri_addr = m.node_addr + sc.num_nodes * 512u;         /* 8 octant copies of the nodes first */
+    m.wnode_addr = smem_base_addr();
+    m.tri_addr = m.wnode_addr + scene_tri_off(sc);
     HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
-    asm volatile("" : "+r"(m.tri_addr), "+r"(gid.addr));   /* keep both bases in registers across the leaf loop (+1.4 %) */
+    asm volatile("" : "+r"(m.tri_addr), "+r"(gid.addr));   /* keep both bases in registers across the leaf loop */
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
-    return hrt_closest_hit<true>(m, gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
+    return hrt_closest_hit_wide<true>(m, gid, sc.wroot, sc.num_tris, o, d, cnt, stride4);
   } else {
-    HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
+    HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris; m.wnodes = sc.wnodes;
     if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
-    if (sc.octants == 8) return hrt_closest_hit<true>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, sc.num_nodes * 4u, chain);
-    return hrt_closest_hit<false>(m, sc.tri_gid, sc.root_ref, sc.num_tris, o, d, cnt, 0u, chain);
+    if (sc.wide_octants == 8) return hrt_closest_hit_wide<true>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt, stride4);
+    return hrt_closest_hit_wide<false>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt);
   }
-}
-
-/* the chain of node boxes that contain `o` (hrt_origin_chain), on the plain node
- * copy; cc_off != 0: byte offset of the block's chain cache in shared memory */
-template <bool SMEM>
-__device__ __forceinline__ HrtChain origin_chain(const SceneDev &sc, V3 o, uint32_t cc_off)
-{
-  if (sc.no_chain) return hrt_no_chain();
-  if (SMEM) {
-    HrtSharedMem m;
-    m.node_addr = smem_base_addr(); m.tri_addr = 0;
-    if (cc_off) {
-      uint32_t *mine = (uint32_t *)((char *)hrt_smem4 + cc_off) + threadIdx.x;
-      HrtChain ch = hrt_origin_chain(m, sc.root_ref, sc.num_tris, o, mine, (uint32_t)HRT_BLOCK, HRT_CHAIN_CACHE_LEVELS);
-      ch.cache_addr = smem_base_addr() + cc_off + 4u * threadIdx.x;
-      return ch;
-    }
-    return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
-  }
-  HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris;
-  return hrt_origin_chain(m, sc.root_ref, sc.num_tris, o);
 }
 
 template <bool COUNT> struct CntSel { typedef HrtNoCount type; };
@@ -128,14 +102,14 @@ __device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long 
 template <bool SMEM>
 __device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
 {
-  const float4 q2 = SMEM ? lds128(smem_base_addr() + sc.num_nodes * 512u + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
+  const float4 q2 = SMEM ? lds128(smem_base_addr() + scene_tri_off(sc) + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
   return v3(q2.y, q2.z, q2.w);
 }
 
 template <bool SMEM>
 __device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
 {
-  if (SMEM) return lds32(smem_base_addr() + sc.num_nodes * 512u + sc.num_tris * 48u + 4u * slot);
+  if (SMEM) return lds32(smem_base_addr() + scene_tri_off(sc) + sc.num_tris * 48u + 4u * slot);
   return sc.tri_gid[slot];
 }
 
@@ -419,7 +393,7 @@ struct PairAcc {
  * output paths. */
 template <bool SMEM, bool BRUTE, bool WARP, bool COUNT, bool LEAN = false>
 __global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
-k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok, uint32_t cc_off)
+k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
 {
   typename CntSel<COUNT>::type wc; cnt_init(wc);
   uint32_t used4 = 0;
@@ -480,7 +454,6 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const float theta_p = r2.w;
     float cx_carry = HRT_CX_PRIMARY, ci_p, si_p;
     sincosf(theta_p, &si_p, &ci_p);
-    const HrtChain chain = BRUTE ? hrt_no_chain() : origin_chain<SMEM>(sc, s.o, cc_off);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const uint64_t hkey = hrt_mix64((path << 32) | gid);
 
@@ -493,7 +466,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = query<SMEM, BRUTE>(sc, s.o, sd, wc, chain);                       /* :682 */
+        h = query<SMEM, BRUTE>(sc, s.o, sd, wc);                              /* :682 */
         if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM>(sc, h.slot), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;
@@ -565,8 +538,9 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
         }
       }
       if (summary) {
-        const float pte32 = HRT_FMA(p.te_r, p.te_r, p.te_i * p.te_i), ptm32 = HRT_FMA(p.tm_r, p.tm_r, p.tm_i * p.tm_i);
-        const double pte = (double)pte32, ptm = (double)ptm32;
+        /* squared in double: gains of ~1e-26 (70 GHz, second bounce) would underflow in fp32 */
+        const double pte = (double)p.te_r * p.te_r + (double)p.te_i * p.te_i;
+        const double ptm = (double)p.tm_r * p.tm_r + (double)p.tm_i * p.tm_i;
         if (WARP) {
           if (occ) {
             if (smem_rx_ok) atomicAdd(&s_acc[r].n_occl, 1u);
@@ -592,7 +566,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
            * update per warp */
           const unsigned m_ok = __ballot_sync(0xFFFFFFFFu, ok), m_occ = __ballot_sync(0xFFFFFFFFu, occ);
           unsigned long long hsum = 0ull, tsum = 0ull;
-          double e = 0.0, m2 = 0.0;
+          double e = ok ? pte : 0.0, m2 = ok ? ptm : 0.0;
           if (m_ok) {
             /* integer sums: one REDUX per 16-bit digit (32 x 65535 fits 32 bits) */
             const unsigned long long hk = ok ? hkey : 0ull;
@@ -605,14 +579,11 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
                  + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, tb >> 16) << 16);
             /* both power sums in one butterfly: after the first exchange the lower
              * half-warp carries the TE sum, the upper half the TM sum */
-            /* (the <= 32 terms of a warp are added in fp32: 2e-6 relative at worst; across
-             * warps, blocks and launches the sums are kept in double) */
             const bool upper = lane >= 16u;
-            const float e32 = ok ? pte32 : 0.f, m32 = ok ? ptm32 : 0.f;
-            float keep = upper ? m32 : e32;
-            keep += __shfl_xor_sync(0xFFFFFFFFu, upper ? e32 : m32, 16);
+            double keep = upper ? m2 : e;
+            keep += __shfl_xor_sync(0xFFFFFFFFu, upper ? e : m2, 16);
             for (int o = 8; o; o >>= 1) keep += __shfl_xor_sync(0xFFFFFFFFu, keep, o);
-            e = (double)keep; m2 = e;       /* lanes 0-15: e is the TE total; lanes 16-31: m2 is the TM total */
+            e = keep; m2 = keep;       /* lanes 0-15: e is the total; lanes 16-31: m2 is the total */
           }
           if (smem_rx_ok) {
             /* the sums are in every lane: lanes 0-2 add the three integer words with ONE

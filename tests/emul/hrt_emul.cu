@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/hrt_cuda.h"
 #include "../../hermespy-rt_b200/csrc/hrt_bvh.cuh"
@@ -20,7 +21,36 @@ struct EmulScene {
   std::vector<uint32_t> gid, mesh_of, mesh_mat;
   std::vector<V3> mesh_vel;
   uint32_t n = 0; int root = 0; uint32_t num_nodes = 0;
+  std::vector<float4> wnodes;          /* 4-wide nodes, 8 octant copies */
+  uint32_t num_wide = 0; int wroot = 0;
 };
+
+/* binary nodes (octant-0 copy) -> 4-wide nodes, as hrt_cuda.cu's collapse kernels do:
+ * even-depth binary nodes become wide nodes, numbered in binary index order */
+static void collapse_wide(EmulScene &E)
+{
+  E.wroot = E.root; E.num_wide = 0;
+  if (E.num_nodes == 0) return;
+  std::vector<int> depth(E.num_nodes, -1);
+  std::vector<int> todo(1, 0); depth[0] = 0;
+  while (!todo.empty()) {
+    const int i = todo.back(); todo.pop_back();
+    for (int s = 0; s < 2; ++s) {
+      const int ref = hrt_float_as_int(E.nodes[4 * (size_t)i + 2 * s + 1].z);
+      if (ref >= 0) { depth[ref] = depth[i] + 1; todo.push_back(ref); }
+    }
+  }
+  std::vector<uint32_t> widx(E.num_nodes, 0);
+  for (uint32_t i = 0; i < E.num_nodes; ++i) if (depth[i] >= 0 && !(depth[i] & 1)) widx[i] = E.num_wide++;
+  E.wnodes.assign((size_t)E.num_wide * HRT_WIDE_F4 * 8, float4());
+  for (uint32_t i = 0; i < E.num_nodes; ++i) {
+    if (depth[i] < 0 || (depth[i] & 1)) continue;
+    HrtWideChild ch[4];
+    const int n = hrt_wide_children(E.nodes.data(), (int)i, widx.data(), ch);
+    hrt_wide_emit(E.wnodes.data(), (size_t)E.num_wide * HRT_WIDE_F4, 8u, widx[i], ch, n);
+  }
+  E.wroot = 0;
+}
 
 static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, float extra_abs)
 {
@@ -60,7 +90,7 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
     E.gid[s] = g;
     blo[n - 1 + s] = S[g].lo; bhi[n - 1 + s] = S[g].hi;
   }
-  if (n <= leaf_max) { E.root = hrt_leaf_ref(0u, (uint32_t)n); return; }
+  if (n <= leaf_max) { E.root = E.wroot = hrt_leaf_ref(0u, (uint32_t)n); return; }
   std::vector<int> kl(n - 1), kr(n - 1), kf(n - 1), kla(n - 1), parent(2 * (size_t)n, -1), arrive(n - 1, 0);
   for (int i = 0; i < n - 1; ++i) {
     hrt_karras_node(keys.data(), n, i, &kl[i], &kr[i], &kf[i], &kla[i]);
@@ -90,21 +120,24 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
                     hrt_child_ref(kr[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
                     blo[kl[i]], bhi[kl[i]], blo[kr[i]], bhi[kr[i]], pad, oct);
   }
+  collapse_wide(E);
 }
 
 static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute, HrtChain chain = hrt_no_chain())
 {
-  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
   HrtNoCount nc;
   if (brute == 1) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
-  if (brute == 2) return hrt_closest_hit<false>(m, E.gid.data(), E.root, E.n, o, d, nc, 0u, chain);   /* plain node copy */
-  return hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, o, d, nc, E.num_nodes * 4u, chain);  /* octant copies */
+  if (brute == 2) return hrt_closest_hit<false>(m, E.gid.data(), E.root, E.n, o, d, nc, 0u, chain);   /* binary, plain node copy */
+  if (brute == 3) return hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, o, d, nc, E.num_nodes * 4u, chain);  /* binary, octant copies */
+  if (brute == 4) return hrt_closest_hit_wide<false>(m, E.gid.data(), E.wroot, E.n, o, d, nc);        /* 4-wide, plain copy (octant 0) */
+  return hrt_closest_hit_wide<true>(m, E.gid.data(), E.wroot, E.n, o, d, nc, (size_t)E.num_wide * HRT_WIDE_F4);  /* 4-wide: what the kernels run */
 }
 
 /* the shadow rays of a hit point start from its origin chain, as in k_scatter */
 static HrtChain chain_of(const EmulScene &E, V3 o)
 {
-  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
   return hrt_origin_chain(m, E.root, E.n, o);
 }
 
@@ -231,11 +264,15 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
 extern "C" int emul_count_work(const Scene *sc, const Ray *rays, size_t n, int leaf_max, double out[6])
 {
   EmulScene E; build(sc, E, leaf_max, 64.f, 0.f);
-  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data();
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
   HrtCount c;
   unsigned long long tot[5] = {0, 0, 0, 0, 0};
+  const bool binary = getenv("EMUL_COUNT_BINARY") != nullptr;
   for (size_t i = 0; i < n; ++i) {
     for (int k = 0; k < 5; ++k) c.c[k] = 0;
+    if (binary) hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c, E.num_nodes * 4u);
+    else hrt_closest_hit_wide<true>(m, E.gid.data(), E.wroot, E.n, tov(rays[i].o), tov(rays[i].d), c, (size_t)E.num_wide * HRT_WIDE_F4);
+    if (0)
     hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c, E.num_nodes * 4u);
     for (int k = 0; k < 5; ++k) tot[k] += c.c[k];
   }
