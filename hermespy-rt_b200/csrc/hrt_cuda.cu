@@ -33,6 +33,7 @@
 
 #include "../../include/hrt_cuda.h"
 #include "hrt_bvh.cuh"
+#include "hrt_rxmap.cuh"
 
 /* host C helpers (host_math.c): glibc double trig, as the reference uses */
 extern "C" void hrt_host_launch_dir(uint64_t path, uint64_t num_paths, float out[3]);
@@ -68,6 +69,14 @@ struct SceneDev {
   int wroot;
   float key_lo[3], key_scale[3];   /* vertex bounds -> 10-bit grid of the hit-order keys */
   float key_log;                   /* > 0: logarithmic x/y grid around the TX, cells per octave */
+};
+
+/* receiver maps (hrt_rxmap.cuh).  Cell word: (offset of the cell's list inside the
+ * receiver's item range << 8) | length; items are leaf slots. */
+struct RxMapDev {
+  const uint32_t *cells;       /* [R][6 G G] */
+  const uint16_t *items;       /* [R][items_per_rx] */
+  uint32_t G, items_per_rx;
 };
 
 struct RunDev {
@@ -110,6 +119,7 @@ struct RunDev {
   float cir_tau0, cir_inv_dt;
   uint32_t cir_bins;
   uint32_t flags;
+  RxMapDev map;          /* k_scatter<..., MAP>: receiver maps of this run's receivers */
 };
 
 /* global path index of shard-local index L (blocks dealt round-robin) */
@@ -208,6 +218,14 @@ struct hrt_ctx {
   size_t num_verts;
   int level_first[256];
   float max_speed;
+
+  /* receiver maps (hrt_rxmap.cuh) of the last run's receivers, reused while the
+   * receivers, the scene and the padding stay the same */
+  uint32_t *d_map_cells; uint16_t *d_map_items; uint32_t *d_map_cursor;   /* cursor[R], then status[1] */
+  size_t cap_map_cells, cap_map_items, cap_map_cursor;
+  uint32_t map_G, map_items_per_rx, map_R; bool map_valid;
+  uint64_t map_key, scene_version;
+  float map_build_ms;
 
   bool have_mats;
   HrtMaterialTable mats;
@@ -324,6 +342,7 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   cudaStreamSynchronize(c->stream);
   free_scene_dev(c); free_run_dev(c);
   dev_free(c->d_pos);
+  dev_free(c->d_map_cells); dev_free(c->d_map_items); dev_free(c->d_map_cursor);
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
   if (c->d_cir) { cudaFree(c->d_cir); c->d_cir = nullptr; }
   if (c->d_plist) { cudaFree(c->d_plist); c->d_plist = nullptr; }
@@ -380,6 +399,7 @@ static int emit_nodes(hrt_ctx *ctx, float pad, cudaStream_t st)
 {
   const int n = (int)ctx->num_tris;
   ctx->pad = pad;
+  ctx->scene_version++;          /* geometry, tree or padding changed: receiver maps are stale */
   if (ctx->num_nodes == 0) { ctx->wroot = ctx->root_ref; ctx->num_wide = 0; return HRT_OK; }
   if (ctx->sah) {
     k_emit_raw<<<nblk(ctx->num_nodes), 256, 0, st>>>((int)ctx->num_nodes, ctx->d_raw_ref, ctx->d_raw_box, pad,
@@ -785,6 +805,75 @@ static ScatterFn scatter_fn(bool smem, bool brute, bool warp, bool count)
         { k_scatter<true, true, true, false>,    k_scatter<true, true, true, false> } } } };
   return tab[smem][brute][warp][count];
 }
+/* shadow queries through receiver maps (shared-memory scenes, no brute force): [warp][count], lean [warp] */
+static ScatterFn scatter_fn_map(bool warp, bool count)
+{
+  static const ScatterFn tab[2][2] = {
+    { k_scatter<true, false, false, false, false, true>, k_scatter<true, false, false, true, false, true> },
+    { k_scatter<true, false, true, false, false, true>,  k_scatter<true, false, true, true, false, true> } };
+  return tab[warp][count];
+}
+static ScatterFn scatter_fn_map_lean(bool warp)
+{
+  static const ScatterFn tab[2] = { k_scatter<true, false, false, false, true, true>, k_scatter<true, false, true, false, true, true> };
+  return tab[warp];
+}
+
+/* Receiver maps for this run's receivers (hrt_rxmap.cuh), built on `st` unless the
+ * cached ones still apply.  *use = false (and no error) when maps do not apply or
+ * a list overflowed: the run then walks the BVH. */
+static uint64_t hash_bytes(const void *p, size_t n, uint64_t h)
+{
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
+  return h;
+}
+
+static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, cudaStream_t st, bool *use)
+{
+  *use = false;
+  const size_t R = p->num_rx;
+  uint32_t G = 128;
+  if (const char *e = getenv("HRT_RXMAP_G")) { int v = atoi(e); if (v >= 8 && v <= 1024) G = (uint32_t)v & ~7u; }
+  const size_t cells = R * 6 * (size_t)G * G;
+  if (ctx->num_tris == 0 || ctx->num_tris > 65535 || cells * 4 > ((size_t)2 << 30)) return HRT_OK;
+  uint64_t key = hash_bytes(p->rx_pos, R * sizeof(Vec3), 0xCBF29CE484222325ull);
+  key = hash_bytes(&ctx->scene_version, 8, key); key = hash_bytes(&G, 4, key);
+  if (ctx->map_valid && ctx->map_key == key && ctx->map_R == R && ctx->map_G == G) { *use = true; return HRT_OK; }
+  ctx->map_valid = false;
+  uint32_t per_rx = (uint32_t)(6 * (size_t)G * G * 4);            /* items per receiver: 4 per cell on average, grown on overflow */
+  if (const char *e = getenv("HRT_RXMAP_ITEMS_PER_CELL")) { int v = atoi(e); if (v >= 1 && v <= 64) per_rx = (uint32_t)(6 * (size_t)G * G * v); }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (per_rx >= (1u << 24)) per_rx = (1u << 24) - 1;
+    if (ctx->cap_map_cells < cells) { dev_free(ctx->d_map_cells); ctx->cap_map_cells = 0; CK(dev_alloc(&ctx->d_map_cells, cells)); ctx->cap_map_cells = cells; }
+    if (ctx->cap_map_items < R * (size_t)per_rx) { dev_free(ctx->d_map_items); ctx->cap_map_items = 0; CK(dev_alloc(&ctx->d_map_items, R * (size_t)per_rx)); ctx->cap_map_items = R * (size_t)per_rx; }
+    if (ctx->cap_map_cursor < R + 1) { dev_free(ctx->d_map_cursor); ctx->cap_map_cursor = 0; CK(dev_alloc(&ctx->d_map_cursor, R + 1)); ctx->cap_map_cursor = R + 1; }
+    if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); }
+    CK(cudaMemsetAsync(ctx->d_map_cursor, 0, (R + 1) * 4, st));
+    CK(cudaEventRecord(e0, st));
+    const SceneDev sc = scene_dev(ctx);
+    const uint32_t nb = G / HRT_RXMAP_BLOCK;
+    k_rxmap_build<<<dim3(nb * nb, 6, (unsigned)R), 64, 0, st>>>(sc, d_rx, G, 4.f * ctx->pad, ctx->d_map_cells, ctx->d_map_items,
+                                                               per_rx, ctx->d_map_cursor, ctx->d_map_cursor + R);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, st));
+    uint32_t status = 0;
+    CK(cudaMemcpyAsync(&status, ctx->d_map_cursor + R, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->map_build_ms, e0, e1);
+    ctx->stats.kernel_launches++;
+    if (!status) {
+      ctx->map_valid = true; ctx->map_key = key; ctx->map_R = (uint32_t)R; ctx->map_G = G; ctx->map_items_per_rx = per_rx;
+      *use = true;
+      break;
+    }
+    per_rx *= 4;                                                   /* some list did not fit: more room, once or twice */
+  }
+  if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  return HRT_OK;
+}
+
 /* summary-only runs without instrumentation: the lean instantiations */
 static ScatterFn scatter_fn_lean(bool smem, bool warp)
 {
@@ -1220,10 +1309,6 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   S.scene_in_smem = smem;
   const int sms = sm_count(ctx->device);
 
-  /* scatter kernel shared memory: scene + receivers + reduction table */
-  const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
-  const bool smem_rx_ok = (smem ? scene_sb : 0) + rx_sb <= 110 * 1024;
-  const size_t scat_sb = (smem ? scene_sb : 0) + (smem_rx_ok ? rx_sb : 0);
   /* scatter mapping: a thread per hit (receivers in sequence, coherent lanes
    * thanks to the direction sort) whenever there are enough hits to fill the
    * machine; a warp per hit (lanes over receivers) for few rays x many RX */
@@ -1233,7 +1318,25 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
   const bool lean = !brute && !count && !(flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE | HRT_FLAG_CIR | HRT_FLAG_PATHLIST));
   if ((flags & HRT_FLAG_PATHLIST_DEV) && !(flags & HRT_FLAG_PATHLIST)) return fail(ctx, HRT_E_ARG, "PATHLIST_DEV needs PATHLIST");
-  const ScatterFn f_scatter = lean ? scatter_fn_lean(smem, warp_mode) : scatter_fn(smem, brute, warp_mode, count);
+  /* receiver maps instead of the tree walk for the shadow queries: scenes that live in
+   * shared memory, enough receivers for the build (a few ms) to pay off */
+  bool use_map = false;
+  {
+    size_t min_rx = 8;
+    if (const char *e = getenv("HRT_RXMAP_MIN_RX")) min_rx = (size_t)atoll(e);
+    const char *force = getenv("HRT_RXMAP");          /* 0: never, 1: whenever possible */
+    const bool want = force ? force[0] == '1' : (R >= min_rx && (uint64_t)T * P * R >= (1ull << 22));
+    if (want && smem && !brute) { rc = ensure_rxmap(ctx, p, d_rx, st, &use_map); if (rc) return rc; }
+  }
+  rd.map.cells = ctx->d_map_cells; rd.map.items = ctx->d_map_items; rd.map.G = ctx->map_G; rd.map.items_per_rx = ctx->map_items_per_rx;
+  const ScatterFn f_scatter = use_map ? (lean ? scatter_fn_map_lean(warp_mode) : scatter_fn_map(warp_mode, count))
+                                      : lean ? scatter_fn_lean(smem, warp_mode) : scatter_fn(smem, brute, warp_mode, count);
+  S.rx_map = use_map; S.rx_map_build_ms = use_map ? ctx->map_build_ms : 0.f; S.rx_map_cells = use_map ? ctx->map_G : 0;
+  /* scatter kernel shared memory: scene (with receiver maps: its triangle records only) + receivers + reduction table */
+  const size_t scat_scene_sb = use_map ? scene_smem_bytes(0, ctx->num_tris, 0) : (smem ? scene_sb : 0);
+  const size_t rx_sb = ((3 * R + 3) / 4) * 16 + ((flags & HRT_FLAG_SUMMARY) ? R * sizeof(PairAcc) : 0);
+  const bool smem_rx_ok = scat_scene_sb + rx_sb <= 110 * 1024;
+  const size_t scat_sb = scat_scene_sb + (smem_rx_ok ? rx_sb : 0);
   if (smem) {
     CK(allow_smem(f_bounce, scene_sb));
     CK(allow_smem(k_los<true, true>, scene_sb)); CK(allow_smem(k_los<true, false>, scene_sb));

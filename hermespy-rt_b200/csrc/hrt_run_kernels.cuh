@@ -45,9 +45,10 @@ struct HrtSharedGid {
 
 /* copies nodes, triangle records and ids into shared memory; returns the
  * first free float4 slot after them */
+template <bool NODES = true>
 __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
 {
-  const uint32_t nn = sc.num_wide * HRT_WIDE_F4 * sc.wide_octants, nt = sc.num_tris * 3u;
+  const uint32_t nn = NODES ? sc.num_wide * HRT_WIDE_F4 * sc.wide_octants : 0u, nt = sc.num_tris * 3u;
   for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.wnodes[i];
   for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) hrt_smem4[nn + i] = sc.tris[i];
   uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
@@ -91,6 +92,101 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
   }
 }
 
+/* ------------------------------------------------------- receiver maps
+ * (hrt_rxmap.cuh).  Cell word: (offset of the cell's list inside the receiver's
+ * item range << 8) | length; items are leaf slots (uint16). */
+/* shadow query through the map of receiver r: exact tests of the candidates of
+ * cells (+d) and (-d); triangle records staged in shared memory at offset 0 */
+template <class Cnt>
+__device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, Cnt &cnt)
+{
+  HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
+  HrtSharedMem m;
+  m.wnode_addr = 0u; m.tri_addr = smem_base_addr();
+  const uint32_t gid_addr = m.tri_addr + sc.num_tris * 48u;
+  const uint32_t *cells = mp.cells + (size_t)r * 6u * mp.G * mp.G;
+  const uint16_t *items = mp.items + (size_t)r * mp.items_per_rx;
+  const uint32_t w0 = __ldg(&cells[hrt_rxmap_cell(d, mp.G)]);
+  const uint32_t w1 = __ldg(&cells[hrt_rxmap_cell(v3(-d.x, -d.y, -d.z), mp.G)]);
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const uint32_t w = side ? w1 : w0;
+    const uint16_t *it = items + (w >> 8);
+    const uint32_t n = w & 255u;
+#pragma unroll 1
+    for (uint32_t k = 0; k < n; ++k) {
+      const uint32_t s = __ldg(&it[k]);
+      float t;
+      const uint32_t gid = lds32(gid_addr + 4u * s);
+      if (hrt_mt_test(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) { h.t = t; h.gid = gid; h.slot = s; }
+    }
+  }
+  return h;
+}
+
+/* One block of 64 threads per 8 x 8 cells of one face of one receiver's cube map:
+ * (1) the triangles that can touch the block's pyramid, (2) per cell the ones
+ * that can touch the cell's pyramid -- counted, space reserved with one atomic
+ * per block, then written.  status[0] |= 1 on any overflow (the host then falls
+ * back to the BVH for this run). */
+#define HRT_RXMAP_CAND 1024
+__global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx_pos, uint32_t G, float pad,
+                                                    uint32_t *cells, uint16_t *items, uint32_t items_per_rx,
+                                                    uint32_t *cursor, uint32_t *status)
+{
+  __shared__ uint16_t cand[HRT_RXMAP_CAND];
+  __shared__ uint32_t ncand, base, wtot[2];
+  const uint32_t nb = G / HRT_RXMAP_BLOCK, face = blockIdx.y, r = blockIdx.z;
+  const uint32_t bi = blockIdx.x % nb, bj = blockIdx.x / nb, tid = threadIdx.x;
+  const V3 apex = v3(rx_pos[3 * r], rx_pos[3 * r + 1], rx_pos[3 * r + 2]);
+  if (tid == 0) ncand = 0;
+  __syncthreads();
+  {
+    const HrtPyramid bp = hrt_rxmap_pyramid(face, G, bi * HRT_RXMAP_BLOCK, (bi + 1u) * HRT_RXMAP_BLOCK,
+                                            bj * HRT_RXMAP_BLOCK, (bj + 1u) * HRT_RXMAP_BLOCK);
+    for (uint32_t s = tid; s < sc.num_tris; s += 64u) {
+      V3 va, vb, vc;
+      hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
+      if (hrt_rxmap_overlap(bp, va, vb, vc, pad)) {
+        const uint32_t k = atomicAdd(&ncand, 1u);
+        if (k < HRT_RXMAP_CAND) cand[k] = (uint16_t)s;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t nc = ncand;
+  if (nc > HRT_RXMAP_CAND) { if (tid == 0) atomicOr(status, 1u); nc = HRT_RXMAP_CAND; }
+  const uint32_t i = bi * HRT_RXMAP_BLOCK + (tid & 7u), j = bj * HRT_RXMAP_BLOCK + (tid >> 3);
+  const HrtPyramid cp = hrt_rxmap_pyramid(face, G, i, i + 1u, j, j + 1u);
+  uint32_t count = 0;
+  for (uint32_t k = 0; k < nc; ++k) {
+    const uint32_t s = cand[k];
+    V3 va, vb, vc;
+    hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
+    count += hrt_rxmap_overlap(cp, va, vb, vc, pad) ? 1u : 0u;
+  }
+  /* exclusive scan of the 64 counts */
+  uint32_t incl = count;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31u) >= (uint32_t)o) incl += v; }
+  if ((tid & 31u) == 31u) wtot[tid >> 5] = incl;
+  __syncthreads();
+  const uint32_t my = incl - count + (tid >= 32u ? wtot[0] : 0u), total = wtot[0] + wtot[1];
+  if (tid == 0) base = atomicAdd(&cursor[r], total);
+  __syncthreads();
+  const uint32_t off = base + my;
+  const bool fits = base + total <= items_per_rx && off < (1u << 24) && count <= 255u;
+  if (!fits) atomicOr(status, 1u);
+  cells[((size_t)(r * 6u + face) * G + j) * G + i] = fits ? ((off << 8) | count) : 0u;
+  if (!fits) return;
+  uint16_t *dst = items + (size_t)r * items_per_rx + off;
+  for (uint32_t k = 0; k < nc; ++k) {
+    const uint32_t s = cand[k];
+    V3 va, vb, vc;
+    hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
+    if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) *dst++ = (uint16_t)s;
+  }
+}
+
 template <bool COUNT> struct CntSel { typedef HrtNoCount type; };
 template <> struct CntSel<true> { typedef HrtCount type; };
 __device__ __forceinline__ void cnt_init(HrtNoCount &) {}
@@ -99,17 +195,17 @@ __device__ __forceinline__ void cnt_flush(const HrtNoCount &, unsigned long long
 __device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long *dst)
 { for (int k = 0; k < 5; ++k) if (c.c[k]) atomicAdd(&dst[k], (unsigned long long)c.c[k]); }
 
-template <bool SMEM>
+template <bool SMEM, bool MAP = false>
 __device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
 {
-  const float4 q2 = SMEM ? lds128(smem_base_addr() + scene_tri_off(sc) + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
+  const float4 q2 = SMEM ? lds128(smem_base_addr() + (MAP ? 0u : scene_tri_off(sc)) + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
   return v3(q2.y, q2.z, q2.w);
 }
 
-template <bool SMEM>
+template <bool SMEM, bool MAP = false>
 __device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
 {
-  if (SMEM) return lds32(smem_base_addr() + scene_tri_off(sc) + sc.num_tris * 48u + 4u * slot);
+  if (SMEM) return lds32(smem_base_addr() + (MAP ? 0u : scene_tri_off(sc)) + sc.num_tris * 48u + 4u * slot);
   return sc.tri_gid[slot];
 }
 
@@ -391,13 +487,15 @@ struct PairAcc {
 /* LEAN: summary tables only (no dense / trace / CIR / path-list outputs) --
  * the streaming configuration of large runs, compiled without the other
  * output paths. */
-template <bool SMEM, bool BRUTE, bool WARP, bool COUNT, bool LEAN = false>
+/* MAP: shadow queries through receiver maps (rd.map, hrt_rxmap.cuh) instead of the
+ * tree walk; only the triangle records are staged in shared memory. */
+template <bool SMEM, bool BRUTE, bool WARP, bool COUNT, bool LEAN = false, bool MAP = false>
 __global__ void __launch_bounds__(HRT_BLOCK, HRT_MIN_BLOCKS)
 k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
 {
   typename CntSel<COUNT>::type wc; cnt_init(wc);
   uint32_t used4 = 0;
-  if (SMEM) used4 = stage_scene(sc);
+  if (SMEM) used4 = MAP ? stage_scene<false>(sc) : stage_scene<true>(sc);
   const uint32_t R = rd.R, T = rd.T, B = rd.B;
   /* receivers (and, in summary mode, the reduction table) in shared memory */
   float *s_rx = (float *)(hrt_smem4 + used4);
@@ -442,8 +540,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     s.o = v3(r0.x, r0.y, r0.z); s.d = v3(r0.w, r1.x, r1.y);
     s.te_r = r1.z; s.te_i = r1.w; s.tm_r = r2.x; s.tm_i = r2.y; s.tau = r2.z;
     const uint32_t slot = __float_as_uint(r3.x), l = __float_as_uint(r3.y);
-    const V3 n = tri_normal<SMEM>(sc, slot);
-    const uint32_t gid = tri_gid_of<SMEM>(sc, slot);
+    const V3 n = tri_normal<SMEM, MAP>(sc, slot);
+    const uint32_t gid = tri_gid_of<SMEM, MAP>(sc, slot);
     const uint32_t mesh = sc.mesh_of[gid];
     const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
     const HrtScatCf mcf = hrt_scat_cf(mats.m[sc.mesh_mat[mesh]]);
@@ -466,8 +564,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = query<SMEM, BRUTE>(sc, s.o, sd, wc);                              /* :682 */
-        if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM>(sc, h.slot), sd);   /* :281, argument of acos */
+        h = MAP ? query_map(sc, rd.map, r, s.o, sd, wc) : query<SMEM, BRUTE>(sc, s.o, sd, wc);   /* :682 */
+        if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM, MAP>(sc, h.slot), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;
       float cx_i;

@@ -1,0 +1,138 @@
+/* hrt_rxmap.cuh -- receiver maps: the shadow queries of k_scatter without a
+ * tree walk.
+ *
+ * Every shadow ray of the reference's per-receiver loop (src/compute_paths.c:
+ * 670-683) runs from a hit point o towards a receiver R and on to infinity: it
+ * lies on a line through R.  Which triangles a line through R can touch depends
+ * on its direction only.  For every receiver the directions around R are
+ * therefore divided into the cells of a cube map (6 faces x G x G), and each
+ * cell gets the list of triangles some line through R inside that cell could
+ * touch -- a conservative rasterisation of the scene as seen from R, every
+ * triangle at every depth, not only the visible ones.  A shadow query then is
+ * two cell look-ups (direction +d: beyond the receiver, -d: between receiver
+ * and hit point, and behind it) and the exact Moeller-Trumbore test of the
+ * listed triangles, a handful instead of ~24 box and ~4 triangle tests.
+ *
+ * As with the BVH this only decides WHICH triangles get the exact test
+ * (hrt_mt_test, the reference's arithmetic): the result is the minimum over
+ * (t, triangle id) of the accepted candidates.  The lists are conservative:
+ *   - a triangle is left out of a cell only if it is separated from the cell's
+ *     pyramid (apex R) by one of the pyramid's four side planes by more than
+ *     `pad` metres, or if the pyramid lies outside the plane through R and one
+ *     of the triangle's edges by more than the angle pad subtends at that edge;
+ *   - cells are enlarged by HRT_RXMAP_EPS in cube-map coordinates (the query
+ *     computes its cell in fp32);
+ *   - pad covers the distance by which the fp32 direction normalize(R - o)
+ *     misses R (<= 1e-7 |R - o|) and the reference's epsilon windows.
+ * The same documented exception as for the BVH applies: "phantom hits" of rays
+ * within ~1e-5 rad of a triangle's plane.
+ *
+ * The element functions are __host__ __device__ so that tests/emul builds the
+ * same maps serially and checks conservativeness against the oracle on the CPU.
+ */
+#pragma once
+
+#include "hrt_core.cuh"
+
+#define HRT_RXMAP_EPS 2e-4f          /* cell enlargement in cube-map coordinates ([-1, 1] per face) */
+#define HRT_RXMAP_BLOCK 8u           /* cells per side of a build block */
+
+/* linear cell index of direction w (any length, not all zero): face-major,
+ * then row j, then column i.  Face = 2 * major axis + (negative ? 1 : 0); the
+ * two remaining components, in x < y < z order, divided by |major|, are the
+ * cell coordinates (a, b) in [-1, 1]. */
+HRT_HD uint32_t hrt_rxmap_cell(V3 w, uint32_t G)
+{
+  const float ax = fabsf(w.x), ay = fabsf(w.y), az = fabsf(w.z);
+  uint32_t face; float m, a, b;
+  if (ax >= ay && ax >= az) { face = w.x < 0.f ? 1u : 0u; m = ax; a = w.y; b = w.z; }
+  else if (ay >= az)        { face = w.y < 0.f ? 3u : 2u; m = ay; a = w.x; b = w.z; }
+  else                      { face = w.z < 0.f ? 5u : 4u; m = az; a = w.x; b = w.y; }
+  const float half = 0.5f * (float)G, inv = half / m;
+  const float fi = fminf(fmaxf(HRT_FMA(a, inv, half), 0.f), (float)(G - 1u));
+  const float fj = fminf(fmaxf(HRT_FMA(b, inv, half), 0.f), (float)(G - 1u));
+  return (face * G + (uint32_t)fj) * G + (uint32_t)fi;
+}
+
+/* direction of cube-map point (a, b) on `face` */
+HRT_HD V3 hrt_rxmap_dir(uint32_t face, float a, float b)
+{
+  const float s = (face & 1u) ? -1.f : 1.f;
+  switch (face >> 1) {
+    case 0:  return v3(s, a, b);
+    case 1:  return v3(a, s, b);
+    default: return v3(a, b, s);
+  }
+}
+
+/* the pyramid of the cell range [i0, i1) x [j0, j1) of `face`: four inward side
+ * plane normals (planes through the apex), unit length, and four unit corner
+ * directions */
+struct HrtPyramid { V3 m[4]; V3 c[4]; };
+
+HRT_HD HrtPyramid hrt_rxmap_pyramid(uint32_t face, uint32_t G, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1)
+{
+  const float g = 2.f / (float)G;
+  const float a0 = (float)i0 * g - 1.f - HRT_RXMAP_EPS, a1 = (float)i1 * g - 1.f + HRT_RXMAP_EPS;
+  const float b0 = (float)j0 * g - 1.f - HRT_RXMAP_EPS, b1 = (float)j1 * g - 1.f + HRT_RXMAP_EPS;
+  HrtPyramid p;
+  p.c[0] = hrt_rxmap_dir(face, a0, b0); p.c[1] = hrt_rxmap_dir(face, a1, b0);
+  p.c[2] = hrt_rxmap_dir(face, a1, b1); p.c[3] = hrt_rxmap_dir(face, a0, b1);
+  const V3 mid = hrt_rxmap_dir(face, 0.5f * (a0 + a1), 0.5f * (b0 + b1));
+  for (int k = 0; k < 4; ++k) {
+    const V3 u = p.c[k], v = p.c[(k + 1) & 3];
+    V3 n = v3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+    const float l = 1.f / sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    const float sgn = (n.x * mid.x + n.y * mid.y + n.z * mid.z) < 0.f ? -l : l;
+    p.m[k] = v3(n.x * sgn, n.y * sgn, n.z * sgn);
+  }
+  for (int k = 0; k < 4; ++k) {
+    const V3 u = p.c[k];
+    const float l = 1.f / sqrtf(u.x * u.x + u.y * u.y + u.z * u.z);
+    p.c[k] = v3(u.x * l, u.y * l, u.z * l);
+  }
+  return p;
+}
+
+HRT_HD float hrt_dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+/* May a line through the apex inside the pyramid touch the triangle (va, vb, vc:
+ * corners relative to the apex) or anything within `pad` of it?  false only
+ * when provably not (see the file header). */
+HRT_HD bool hrt_rxmap_overlap(const HrtPyramid &p, V3 va, V3 vb, V3 vc, float pad)
+{
+  /* (a) a side plane of the pyramid separates the padded triangle from it */
+  for (int k = 0; k < 4; ++k)
+    if (hrt_dot3(va, p.m[k]) < -pad && hrt_dot3(vb, p.m[k]) < -pad && hrt_dot3(vc, p.m[k]) < -pad) return false;
+  /* (b) the pyramid lies outside the plane through the apex and one edge.  Only
+   * when the apex is well off the triangle's plane (else its image on the sphere
+   * of directions degenerates and "inside" has no sign). */
+  const V3 e1 = v3(vb.x - va.x, vb.y - va.y, vb.z - va.z), e2 = v3(vc.x - va.x, vc.y - va.y, vc.z - va.z);
+  const V3 n = v3(e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x);
+  const float nl = sqrtf(hrt_dot3(n, n));
+  const float h = hrt_dot3(va, n);                       /* distance of the apex from the plane, times nl */
+  if (!(fabsf(h) > 16.f * pad * nl)) return true;
+  const V3 vs[3] = { va, vb, vc };
+  for (int k = 0; k < 3; ++k) {
+    const V3 u = vs[k], v = vs[(k + 1) % 3], w = vs[(k + 2) % 3];
+    const V3 e = v3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);   /* normal of the plane (apex, edge) */
+    const V3 ed = v3(v.x - u.x, v.y - u.y, v.z - u.z);
+    const float sgn = hrt_dot3(w, e) < 0.f ? -1.f : 1.f;
+    /* |e| / |edge| = distance of the apex from the edge's line: the pad subtends
+     * pad |edge| / |e| there (twice that for safety); corners are unit vectors */
+    const float lim = -2.f * pad * sqrtf(hrt_dot3(ed, ed));
+    bool out = true;
+    for (int c = 0; c < 4; ++c) out = out && (sgn * hrt_dot3(p.c[c], e) < lim);
+    if (out) return false;
+  }
+  return true;
+}
+
+/* corners of triangle record (q0, q1, q2) relative to apex r */
+HRT_HD void hrt_rxmap_corners(float4 q0, float4 q1, float4 q2, V3 r, V3 *va, V3 *vb, V3 *vc)
+{
+  const V3 a = v3(q0.x - r.x, q0.y - r.y, q0.z - r.z);
+  *va = a;
+  *vb = v3(a.x + q0.w, a.y + q1.x, a.z + q1.y);
+  *vc = v3(a.x + q1.z, a.y + q1.w, a.z + q2.x);
+}

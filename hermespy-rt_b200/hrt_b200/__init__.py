@@ -77,6 +77,7 @@ class RunStats(C.Structure):
         ("work_bounce", C.c_uint64 * 5), ("work_scatter", C.c_uint64 * 5),
         ("bvh_sah", C.c_uint32), ("bvh_levels", C.c_uint32), ("bvh_build_ms", C.c_float), ("ms_sort", C.c_float),
         ("cir_dropped", C.c_uint64),
+        ("rx_map", C.c_uint32), ("rx_map_cells", C.c_uint32), ("rx_map_build_ms", C.c_float),
     ]
 
     def as_dict(self):

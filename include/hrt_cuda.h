@@ -186,6 +186,10 @@ typedef struct {
   float    bvh_build_ms;       /* GPU time of the last build */
   float    ms_sort;            /* hit-queue ordering, part of ms_total */
   uint64_t cir_dropped;        /* HRT_FLAG_CIR: valid paths whose delay fell outside the window */
+  /* shadow queries went through receiver maps (csrc/hrt_rxmap.cuh) instead of the BVH:
+   * 1/0, cells per cube-map face edge, GPU time of the map build (0 when the cached maps applied) */
+  uint32_t rx_map, rx_map_cells;
+  float    rx_map_build_ms;
 } HrtRunStats;
 
 int  hrt_device_count(void);

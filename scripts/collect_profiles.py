@@ -78,7 +78,8 @@ def source_shares(rep, kernel_substr, out_path):
     # triangle tests, their loads and ray set-up) as opposed to the per-path math after it
     INTERSECTION = {"hrt_closest_hit", "hrt_mt_test", "hrt_slab_sorted", "hrt_slab", "hrt_fma_pair", "v3_dot", "v3_cross",
                     "v3_sub", "lds128", "lds32", "smem_base_addr", "node", "tri", "child_at", "child_ref", "cache_word",
-                    "hrt_safe_inv", "hrt_octant", "hrt_ray_cull", "hrt_origin_chain", "select_octant", "query", "origin_chain"}
+                    "hrt_safe_inv", "hrt_octant", "hrt_ray_cull", "hrt_origin_chain", "select_octant", "query", "origin_chain",
+                    "hrt_closest_hit_wide", "wide", "select_wide_octant", "scene_tri_off"}
     share = sum(c for fn, c in fa.items() if fn in INTERSECTION) / max(tot, 1)
     json.dump({"kernel": kernel_substr, "intersection_share_of_issue_slots": share,
                "functions": {fn: c / tot for fn, c in fa.most_common(30)},

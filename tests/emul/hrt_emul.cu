@@ -15,6 +15,7 @@
 
 #include "../../include/hrt_cuda.h"
 #include "../../hermespy-rt_b200/csrc/hrt_bvh.cuh"
+#include "../../hermespy-rt_b200/csrc/hrt_rxmap.cuh"
 
 struct EmulScene {
   std::vector<float4> tris, nodes;
@@ -23,6 +24,7 @@ struct EmulScene {
   uint32_t n = 0; int root = 0; uint32_t num_nodes = 0;
   std::vector<float4> wnodes;          /* 4-wide nodes, 8 octant copies */
   uint32_t num_wide = 0; int wroot = 0;
+  float pad = 0.f;                     /* node padding (hrt_box_pad) */
 };
 
 /* binary nodes (octant-0 copy) -> 4-wide nodes, as hrt_cuda.cu's collapse kernels do:
@@ -70,6 +72,7 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   }
   const int n = (int)A.size();
   E.n = n;
+  E.pad = hrt_box_pad(max_abs, pad_ulps);
   if (n == 0) return;
   std::vector<HrtTriSetup> S(n);
   V3 slo = v3(1e30f, 1e30f, 1e30f), shi = v3(-1e30f, -1e30f, -1e30f);
@@ -141,6 +144,60 @@ static HrtChain chain_of(const EmulScene &E, V3 o)
   return hrt_origin_chain(m, E.root, E.n, o);
 }
 
+/* receiver maps (hrt_rxmap.cuh), built serially with the same two-level scheme and
+ * element functions as the kernels k_rxmap_* */
+struct EmulRxMap { uint32_t G = 0; std::vector<uint32_t> start, count; std::vector<uint16_t> items; };
+
+static void build_rxmap(const EmulScene &E, const Vec3 *rx, size_t R, uint32_t G, float pad, EmulRxMap &M)
+{
+  M.G = G; M.start.assign(R * 6 * G * G, 0); M.count.assign(R * 6 * G * G, 0); M.items.clear();
+  const uint32_t nb = G / HRT_RXMAP_BLOCK;
+  std::vector<uint32_t> cand;
+  for (size_t r = 0; r < R; ++r) {
+    const V3 apex = v3(rx[r].x, rx[r].y, rx[r].z);
+    for (uint32_t f = 0; f < 6; ++f)
+      for (uint32_t bj = 0; bj < nb; ++bj)
+        for (uint32_t bi = 0; bi < nb; ++bi) {
+          const HrtPyramid bp = hrt_rxmap_pyramid(f, G, bi * HRT_RXMAP_BLOCK, (bi + 1) * HRT_RXMAP_BLOCK, bj * HRT_RXMAP_BLOCK, (bj + 1) * HRT_RXMAP_BLOCK);
+          cand.clear();
+          for (uint32_t s = 0; s < E.n; ++s) {
+            V3 va, vb, vc; hrt_rxmap_corners(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], apex, &va, &vb, &vc);
+            if (hrt_rxmap_overlap(bp, va, vb, vc, pad)) cand.push_back(s);
+          }
+          for (uint32_t cj = 0; cj < HRT_RXMAP_BLOCK; ++cj)
+            for (uint32_t ci = 0; ci < HRT_RXMAP_BLOCK; ++ci) {
+              const uint32_t i = bi * HRT_RXMAP_BLOCK + ci, j = bj * HRT_RXMAP_BLOCK + cj;
+              const HrtPyramid cp = hrt_rxmap_pyramid(f, G, i, i + 1, j, j + 1);
+              const size_t cell = ((r * 6 + f) * G + j) * G + i;
+              M.start[cell] = (uint32_t)M.items.size();
+              for (uint32_t s : cand) {
+                V3 va, vb, vc; hrt_rxmap_corners(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], apex, &va, &vb, &vc);
+                if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) M.items.push_back((uint16_t)s);
+              }
+              M.count[cell] = (uint32_t)M.items.size() - M.start[cell];
+            }
+        }
+  }
+}
+
+/* shadow query through the receiver map: the exact test of the candidates of cells (+d) and (-d) */
+static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, V3 d, unsigned long long *tests = nullptr)
+{
+  HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
+  HrtNoCount nc;
+  for (int side = 0; side < 2; ++side) {
+    const V3 w = side ? v3(-d.x, -d.y, -d.z) : d;
+    const size_t cell = r * 6 * M.G * M.G + hrt_rxmap_cell(w, M.G);
+    for (uint32_t k = 0; k < M.count[cell]; ++k) {
+      const uint32_t s = M.items[M.start[cell] + k];
+      float t;
+      if (tests) ++*tests;
+      if (hrt_mt_test(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], o, d, h.t, h.gid, E.gid[s], &t, nc)) { h.t = t; h.gid = E.gid[s]; h.slot = s; }
+    }
+  }
+  return h;
+}
+
 static V3 nrm(const EmulScene &E, uint32_t slot) { const float4 q = E.tris[3 * slot + 2]; return v3(q.y, q.z, q.w); }
 static V3 tov(Vec3 a) { return v3(a.x, a.y, a.z); }
 
@@ -172,6 +229,7 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
 {
   const int brute = brute_and_mode & 0xFF;
   const bool closed_form = (brute_and_mode & 0x100) != 0;   /* gains as k_scatter forms them */
+  const bool use_map = (brute_and_mode & 0x200) != 0;       /* shadow queries through receiver maps */
   EmulScene E;
   float ma = 0.f;
   for (size_t i = 0; i < R; ++i) ma = fmaxf(ma, fmaxf(fabsf(rx_pos[i].x), fmaxf(fabsf(rx_pos[i].y), fabsf(rx_pos[i].z))));
@@ -183,6 +241,11 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
   HrtRunConst k;
   const float f_hz = (float)((double)f_ghz * 1e9);
   k.fsl_k = 4.f * HRT_PI * f_hz / HRT_C0; k.dop_k = f_hz / HRT_C0;
+  EmulRxMap M;
+  if (use_map) {
+    const char *g = getenv("EMUL_RXMAP_G");
+    build_rxmap(E, rx_pos, R, g ? (uint32_t)atoi(g) : 64u, 4.f * E.pad, M);   /* 4 x the node padding, as hrt_cuda.cu */
+  }
 
   for (size_t r = 0, q = 0; r < R; ++r)
     for (size_t t = 0; t < T; ++t, ++q) {
@@ -242,7 +305,7 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
-          const HrtHit sh = query(E, s.o, sd, brute, chain);
+          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd) : query(E, s.o, sd, brute, chain);
           if (sh.gid != HRT_NONE) { carry = hrt_theta_fold(nrm(E, sh.slot), sd); cx_carry = v3_dot(nrm(E, sh.slot), sd); }
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
           /* closed_form: what k_scatter runs (hrt_scatter_path_auto); else the reference's formulas line by line */
@@ -389,5 +452,37 @@ extern "C" int emul_scatter_cf_vs_exact(size_t n, uint32_t seed, float f_ghz, do
     if ((m_te == 0 && e_te != 0) || (m_tm == 0 && e_tm != 0)) ++bad;
   }
   *worst_rel = worst; *n_closed = closed;
+  return bad;
+}
+
+/* Receiver maps against the brute-force loop over every triangle (same
+ * hrt_mt_test): for every origin x receiver the shadow query through the map must
+ * return the same (triangle, t).  Returns the number of differing queries;
+ * *avg_tests = triangle tests per query through the map. */
+extern "C" long emul_rxmap_vs_brute(const Scene *sc, const Vec3 *rx, size_t R, const Vec3 *origins, size_t n,
+                                    uint32_t G, double *avg_tests, double *avg_list)
+{
+  EmulScene E;
+  float ma = 0.f;
+  for (size_t i = 0; i < R; ++i) ma = fmaxf(ma, fmaxf(fabsf(rx[i].x), fmaxf(fabsf(rx[i].y), fabsf(rx[i].z))));
+  for (size_t i = 0; i < n; ++i) ma = fmaxf(ma, fmaxf(fabsf(origins[i].x), fmaxf(fabsf(origins[i].y), fabsf(origins[i].z))));
+  build(sc, E, 2, 64.f, ma);
+  EmulRxMap M;
+  build_rxmap(E, rx, R, G, 4.f * E.pad, M);
+  unsigned long long tests = 0; long bad = 0;
+  HrtNoCount nc;
+  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
+  for (size_t i = 0; i < n; ++i)
+    for (size_t r = 0; r < R; ++r) {
+      float dist;
+      const V3 o = tov(origins[i]);
+      const V3 sd = hrt_shadow_dir(o, tov(rx[r]), &dist);
+      if (!(dist > 0.f)) continue;
+      const HrtHit a = query_map(E, M, r, o, sd, &tests);
+      const HrtHit b = hrt_closest_hit_brute(m, E.gid.data(), E.n, o, sd, nc);
+      if (a.gid != b.gid || (a.gid != HRT_NONE && memcmp(&a.t, &b.t, 4))) ++bad;
+    }
+  *avg_tests = (double)tests / (double)(n * R);
+  *avg_list = (double)M.items.size() / (double)M.start.size();
   return bad;
 }

@@ -251,7 +251,8 @@ def emul_lib() -> C.CDLL:
     return _emul
 
 
-def run_emul(scene, rx, tx, rxv, txv, f_ghz, P, B, leaf_max=2, pad_ulps=64.0, brute=0, closed_form=False):
+def run_emul(scene, rx, tx, rxv, txv, f_ghz, P, B, leaf_max=2, pad_ulps=64.0, brute=0, closed_form=False,
+             rx_map=False):
     lib = emul_lib()
     sc = lib.scene_load(scene_path(scene).encode())
     rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
@@ -266,7 +267,7 @@ def run_emul(scene, rx, tx, rxv, txv, f_ghz, P, B, leaf_max=2, pad_ulps=64.0, br
                                     txv.ctypes.data, C.c_float(f_ghz), R, T, P, B,
                                     C.byref(los), C.byref(scs), tr["hit_tri"].ctypes.data,
                                     tr["slot_state"].ctypes.data, leaf_max, C.c_float(pad_ulps),
-                                    int(brute) | (0x100 if closed_form else 0))
+                                    int(brute) | (0x100 if closed_form else 0) | (0x200 if rx_map else 0))
         assert rc == 0
     finally:
         abi.free_scene(sc)

@@ -127,3 +127,57 @@ def test_compute_paths_closed_form_matches_golden(name):
     tl.assert_exact(ref, mask, w, keys=keys)
     tl.assert_gains_close(ref, mask, w, rtol=1e-5)
     assert np.array_equal(tr["slot_state"], g["trace.slot_state"])
+
+
+@pytest.mark.parametrize("scene,G", [("simple_street_canyon_with_cars", 64), ("simple_street_canyon_with_cars", 32),
+                                     ("canyon_moving", 64), ("2cars", 64), ("box", 64), ("simple_reflector", 32)])
+def test_receiver_maps_are_conservative(scene, G):
+    """hrt_rxmap.cuh: shadow queries through the receiver maps (two cell look-ups +
+    exact tests of the listed triangles) against the brute-force loop over every
+    triangle, same hrt_mt_test: identical (triangle, t) for every query.  Origins:
+    points on and near the surfaces (as hit points are), random points in the
+    volume, points very close to receivers; receivers incl. one 1 mm above a
+    surface and one far outside the scene."""
+    import ctypes as C
+    from hrt_b200 import abi
+    lib = tl.emul_lib()
+    lib.emul_rxmap_vs_brute.restype = C.c_long
+    lib.emul_rxmap_vs_brute.argtypes = [C.POINTER(abi.Scene), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    T = tl.scene_triangles(scene)
+    rng = np.random.default_rng(17)
+    lo, hi = T.reshape(-1, 3).min(0), T.reshape(-1, 3).max(0)
+    n = 1500
+    w = rng.random((n, 3)); w /= w.sum(1, keepdims=True)
+    tt = T[rng.integers(0, len(T), n)]
+    nrm = np.cross(tt[:, 1] - tt[:, 0], tt[:, 2] - tt[:, 0]); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    on_surface = (tt * w[:, :, None]).sum(1) + nrm * (1e-4 * rng.choice([-1, 1], n))[:, None]   # the reference's 1e-4 offset
+    volume = lo + rng.random((n // 2, 3)) * (hi - lo)
+    grid, _ = tl.canyon_c4_positions()
+    rx = np.concatenate([grid[::7][:8], lo[None] + (hi - lo) * rng.random((4, 3)),
+                         on_surface[:1] + nrm[:1] * 1e-3, (hi + 30.0)[None]]).astype(np.float32)
+    near_rx = rx[rng.integers(0, len(rx), 200)] + rng.normal(size=(200, 3)) * 1e-2
+    origins = np.ascontiguousarray(np.concatenate([on_surface, volume, near_rx]).astype(np.float32))
+    sc = lib.scene_load(tl.scene_path(scene).encode())
+    avg, lst = C.c_double(0), C.c_double(0)
+    bad = lib.emul_rxmap_vs_brute(C.byref(sc), rx.ctypes.data, len(rx), origins.ctypes.data, len(origins), G,
+                                  C.byref(avg), C.byref(lst))
+    abi.free_scene(sc)
+    assert bad == 0, bad
+    assert avg.value < 0.6 * len(T) + 4, avg.value     # the lists really are short
+
+
+@pytest.mark.parametrize("name", ["canyon_3rx", "canyon_moving", "2cars_raised", "box_generic"])
+def test_compute_paths_receiver_maps_match_golden(name):
+    """The whole path with shadow queries through receiver maps (and closed-form
+    gains), as k_scatter runs it, against the reference's vectors."""
+    g = tl.load_golden(name)
+    o, tr = tl.run_emul(g["scene"], g["rx"], g["tx"], g["rxv"], g["txv"], g["f"], g["P"], g["B"], closed_form=True, rx_map=True)
+    w = tl.outputs_words(o)
+    ref = {k[4:]: v for k, v in g.items() if k.startswith("out.")}
+    mask = {k[5:]: v for k, v in g.items() if k.startswith("mask.")}
+    keys = [k for k in tl.EXACT_KEYS if not k.startswith(("scat_rays", "scat_active", "los_rays", "los_active"))]
+    tl.assert_exact(ref, mask, w, keys=keys)
+    tl.assert_gains_close(ref, mask, w, rtol=1e-5)
+    assert np.array_equal(tr["slot_state"], g["trace.slot_state"])
+    assert np.array_equal(tr["hit_tri"], g["trace.hit_tri"])

@@ -153,16 +153,23 @@ def test_run_dense_vs_oracle(ctx, cfg, P, B, n_rx, moving, T):
     import os
     for env in ({"HRT_SCATTER_MODE": "t"}, {"HRT_SCATTER_MODE": "w"}, {"HRT_NO_SORT": "1"},
                 {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_NO_SMEM": "1", "HRT_SCATTER_MODE": "w"},
-                # traversal-order variants: no origin chain, chain without its shared-memory cache,
-                # hit sort forced on in the warp mapping
-                {"HRT_NO_CHAIN": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_NO_CHAIN_CACHE": "1", "HRT_SCATTER_MODE": "t"},
-                {"HRT_NO_CHAIN_CACHE": "1", "HRT_SCATTER_MODE": "w"}, {"HRT_HIT_SORT_ALWAYS": "1", "HRT_SCATTER_MODE": "w"}):
+                # hit sort forced on in the warp mapping; single plain copy of the wide nodes
+                {"HRT_HIT_SORT_ALWAYS": "1", "HRT_SCATTER_MODE": "w"}, {"HRT_OCTANT_BYTES_MAX": "0", "HRT_RELOAD": "1"},
+                # shadow queries through receiver maps (hrt_rxmap.cuh) instead of the BVH, both mappings, coarse and fine cells
+                {"HRT_RXMAP": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_RXMAP": "1", "HRT_SCATTER_MODE": "w"},
+                {"HRT_RXMAP": "1", "HRT_RXMAP_G": "32"}, {"HRT_RXMAP": "1", "HRT_RXMAP_G": "256", "HRT_RXMAP_ITEMS_PER_CELL": "1"}):
         os.environ.update(env)
         try:
+            if "HRT_RELOAD" in env:
+                ctx.load_scene(tl.scene_path(scene))
             alt = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, trace=True, summary=True)
         finally:
             for k in env:
                 del os.environ[k]
+            if "HRT_RELOAD" in env:
+                ctx.load_scene(tl.scene_path(scene))
+        if "HRT_RXMAP" in env:
+            assert alt["stats"]["rx_map"] == 1, env
         _compare_dense(a, mask, alt["out"], tr, alt["trace"])
         tl.assert_summaries_equal(pair, bounce, alt["pair"], alt["bounce"])
         for k in ("tau", "a_te_re", "a_tm_im", "freq_shift", "directions_rx"):
@@ -540,13 +547,22 @@ def test_bvh_equals_brute_force_c4_workload(ctx):
     rx, tx = tl.canyon_c4_positions()
     zr, zt = np.zeros_like(rx), np.zeros_like(tx)
     ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
-    a = ctx.run(rx, tx, zr, zt, 3.5, 200_000, 5, summary=True)
+    import os
     b = ctx.run(rx, tx, zr, zt, 3.5, 200_000, 5, summary=True, brute_force=True)
-    for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
-        assert np.array_equal(a["pair"][k], b["pair"][k]), k
-    for k in ("n_traced", "n_hit", "hit_hash", "t_bits"):
-        assert np.array_equal(a["bounce"][k], b["bounce"][k]), k
-    assert a["stats"]["shadow_queries"] > 90_000_000
+    for mode in ("1", "0"):                   # receiver maps (what this workload runs by default), then the BVH
+        os.environ["HRT_RXMAP"] = mode
+        try:
+            a = ctx.run(rx, tx, zr, zt, 3.5, 200_000, 5, summary=True)
+        finally:
+            del os.environ["HRT_RXMAP"]
+        assert a["stats"]["rx_map"] == int(mode)
+        for k in ("n_valid", "n_occluded", "hit_hash", "tau_bits"):
+            assert np.array_equal(a["pair"][k], b["pair"][k]), (mode, k)
+        for k in ("n_traced", "n_hit", "hit_hash", "t_bits"):
+            assert np.array_equal(a["bounce"][k], b["bounce"][k]), (mode, k)
+        np.testing.assert_allclose(a["pair"]["power_te"], b["pair"]["power_te"], rtol=1e-9)
+        assert a["stats"]["shadow_queries"] > 90_000_000
+    assert ctx.run(rx, tx, zr, zt, 3.5, 200_000, 5, summary=True)["stats"]["rx_map"] == 1
 
 
 def test_python_api_shapes():
@@ -754,13 +770,15 @@ def test_c4_geometry_vs_oracle(ctx):
     ctx.load_scene(tl.scene_path(scene))
     pair, bounce = tl.oracle_summaries(a, tr)
     import os
-    for env in ({}, {"HRT_SCATTER_MODE": "t"}, {"HRT_SCATTER_MODE": "w"}):
+    for env in ({"HRT_RXMAP": "0"}, {"HRT_RXMAP": "0", "HRT_SCATTER_MODE": "t"}, {"HRT_RXMAP": "0", "HRT_SCATTER_MODE": "w"},
+                {"HRT_RXMAP": "1", "HRT_SCATTER_MODE": "t"}, {"HRT_RXMAP": "1", "HRT_SCATTER_MODE": "w"}):
         os.environ.update(env)
         try:
             res = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, trace=True, summary=True)
         finally:
             for k in env:
                 del os.environ[k]
+        assert res["stats"]["rx_map"] == int(env["HRT_RXMAP"])
         _compare_dense(a, mask, res["out"], tr, res["trace"])
         tl.assert_summaries_equal(pair, bounce, res["pair"], res["bounce"])
     assert int(pair["n_valid"].sum()) > 500_000
