@@ -138,7 +138,9 @@ struct HrtHit {
  * thresholds that sit 1e-5 away from the reference's, while IEEE division is
  * monotonic and off by at most 2^-24 relative -- so the shortcut never changes
  * a decision, it only skips divisions. */
-template <class Cnt>
+/* TIE_ONLY_T: accept on t <= best and leave the (t == best) tie to the caller
+ * (who then looks up the triangle id): saves fetching the id of every candidate. */
+template <class Cnt, bool TIE_ONLY_T = false>
 HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
                         float best, uint32_t best_gid, uint32_t gid, float *t_out, Cnt &cnt)
 {
@@ -185,6 +187,7 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   if (snt > HRT_MUL(HRT_MUL(best, ad), 1.00001f)) return false;   /* clearly behind the best hit so far */
   const float t = HRT_DIV(nt, det);                      /* :274 */
   if (!(t > HRT_EPS)) return false;                      /* :275 */
+  if (TIE_ONLY_T) { if (t <= best) { *t_out = t; return true; } return false; }
   if (t < best || (t == best && gid < best_gid)) { *t_out = t; return true; }
   return false;
 }

@@ -96,9 +96,12 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
  * (hrt_rxmap.cuh).  Cell word: (offset of the cell's list inside the receiver's
  * item range << 8) | length; items are leaf slots (uint16). */
 /* shadow query through the map of receiver r: exact tests of the candidates of
- * cells (+d) and (-d); triangle records staged in shared memory at offset 0 */
+ * cell (-d) -- between hit point and receiver, and behind the hit point -- and,
+ * unless that already produced a hit in front of the receiver (dist: distance
+ * to it), of cell (+d), beyond the receiver.  Triangle records staged in shared
+ * memory at offset 0. */
 template <class Cnt>
-__device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, Cnt &cnt)
+__device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, float dist, Cnt &cnt)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   HrtSharedMem m;
@@ -106,20 +109,26 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
   const uint32_t gid_addr = m.tri_addr + sc.num_tris * 48u;
   const uint32_t *cells = mp.cells + (size_t)r * 6u * mp.G * mp.G;
   const uint16_t *items = mp.items + (size_t)r * mp.items_per_rx;
-  const uint32_t w0 = __ldg(&cells[hrt_rxmap_cell(d, mp.G)]);
-  const uint32_t w1 = __ldg(&cells[hrt_rxmap_cell(v3(-d.x, -d.y, -d.z), mp.G)]);
+  uint32_t c_pos, c_neg;
+  hrt_rxmap_cells2(d, mp.G, &c_pos, &c_neg);
+  uint32_t w = __ldg(&cells[c_neg]);
+  const uint32_t w_pos = __ldg(&cells[c_pos]);
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
-    const uint32_t w = side ? w1 : w0;
     const uint16_t *it = items + (w >> 8);
     const uint32_t n = w & 255u;
 #pragma unroll 1
     for (uint32_t k = 0; k < n; ++k) {
       const uint32_t s = __ldg(&it[k]);
       float t;
-      const uint32_t gid = lds32(gid_addr + 4u * s);
-      if (hrt_mt_test(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) { h.t = t; h.gid = gid; h.slot = s; }
+      if (hrt_mt_test<Cnt, true>(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, 0u, 0u, &t, cnt)) {
+        const uint32_t gid = lds32(gid_addr + 4u * s);
+        if (t < h.t || gid < h.gid) { h.t = t; h.gid = gid; h.slot = s; }     /* t == h.t: lowest id wins (:275) */
+      }
     }
+    /* a hit clearly in front of the receiver: nothing beyond it can be closer */
+    if (h.t < dist * 0.999f) break;
+    w = w_pos;
   }
   return h;
 }
@@ -564,7 +573,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = MAP ? query_map(sc, rd.map, r, s.o, sd, wc) : query<SMEM, BRUTE>(sc, s.o, sd, wc);   /* :682 */
+        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc) : query<SMEM, BRUTE>(sc, s.o, sd, wc);   /* :682 */
         if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM, MAP>(sc, h.slot), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;

@@ -54,6 +54,33 @@ HRT_HD uint32_t hrt_rxmap_cell(V3 w, uint32_t G)
   return (face * G + (uint32_t)fj) * G + (uint32_t)fi;
 }
 
+/* Both cells of a line through the apex at once: cell of direction w and of -w.
+ * The opposite direction lies on the opposite face (face ^ 1) with both cell
+ * coordinates mirrored: G - 1 - i, G - 1 - j.  (For a coordinate exactly on a
+ * cell boundary the mirrored index is the neighbour of the exact one; such a
+ * direction belongs to both enlarged cells, HRT_RXMAP_EPS.)  1/|major| may be an
+ * approximate reciprocal: 2^-22 relative is 1e-4 of a cell, inside the same margin. */
+HRT_HD void hrt_rxmap_cells2(V3 w, uint32_t G, uint32_t *cell_pos, uint32_t *cell_neg)
+{
+  const float ax = fabsf(w.x), ay = fabsf(w.y), az = fabsf(w.z);
+  uint32_t face; float m, a, b;
+  if (ax >= ay && ax >= az) { face = w.x < 0.f ? 1u : 0u; m = ax; a = w.y; b = w.z; }
+  else if (ay >= az)        { face = w.y < 0.f ? 3u : 2u; m = ay; a = w.x; b = w.z; }
+  else                      { face = w.z < 0.f ? 5u : 4u; m = az; a = w.x; b = w.y; }
+  const float half = 0.5f * (float)G;
+#if defined(__CUDA_ARCH__)
+  float inv; asm("rcp.approx.f32 %0, %1;" : "=f"(inv) : "f"(m));
+  inv *= half;
+#else
+  const float inv = half / m;
+#endif
+  const float top = (float)(G - 1u);
+  const uint32_t i = (uint32_t)fminf(fmaxf(HRT_FMA(a, inv, half), 0.f), top);
+  const uint32_t j = (uint32_t)fminf(fmaxf(HRT_FMA(b, inv, half), 0.f), top);
+  *cell_pos = (face * G + j) * G + i;
+  *cell_neg = ((face ^ 1u) * G + (G - 1u - j)) * G + (G - 1u - i);
+}
+
 /* direction of cube-map point (a, b) on `face` */
 HRT_HD V3 hrt_rxmap_dir(uint32_t face, float a, float b)
 {

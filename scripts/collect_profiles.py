@@ -111,7 +111,7 @@ def launch_shares(csv_path, out_path):
             f.write(f"  {v:12.1f} us  {n[k]:4d}x  {100 * v / tot:5.1f}%  {k}\n")
 
 
-for rep, kern, tag in (("prof_scatter.ncu-rep", "_Z9k_scatterILb1ELb0ELb0ELb0ELb1EE", "k_scatter"),
+for rep, kern, tag in (("prof_scatter.ncu-rep", os.environ.get("HRT_PROF_KERNEL", "_Z9k_scatterILb1ELb0ELb0ELb0ELb1ELb1EE"), "k_scatter"),
                        ("prof_c5.ncu-rep", "_Z9k_scatterILb0ELb0ELb0ELb0ELb1EE", "k_scatter_c5")):
     p = os.path.join(G, rep)
     if not os.path.exists(p): continue

@@ -181,19 +181,23 @@ static void build_rxmap(const EmulScene &E, const Vec3 *rx, size_t R, uint32_t G
 }
 
 /* shadow query through the receiver map: the exact test of the candidates of cells (+d) and (-d) */
-static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, V3 d, unsigned long long *tests = nullptr)
+static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, V3 d, float dist, unsigned long long *tests = nullptr)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   HrtNoCount nc;
+  uint32_t c_pos, c_neg;
+  hrt_rxmap_cells2(d, M.G, &c_pos, &c_neg);          /* as the kernel: (-d) first, (+d) only if nothing in front of the receiver */
   for (int side = 0; side < 2; ++side) {
-    const V3 w = side ? v3(-d.x, -d.y, -d.z) : d;
-    const size_t cell = r * 6 * M.G * M.G + hrt_rxmap_cell(w, M.G);
+    const size_t cell = r * 6 * M.G * M.G + (side ? c_pos : c_neg);
     for (uint32_t k = 0; k < M.count[cell]; ++k) {
       const uint32_t s = M.items[M.start[cell] + k];
       float t;
       if (tests) ++*tests;
-      if (hrt_mt_test(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], o, d, h.t, h.gid, E.gid[s], &t, nc)) { h.t = t; h.gid = E.gid[s]; h.slot = s; }
+      if (hrt_mt_test<HrtNoCount, true>(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], o, d, h.t, 0u, 0u, &t, nc)) {
+        if (t < h.t || E.gid[s] < h.gid) { h.t = t; h.gid = E.gid[s]; h.slot = s; }
+      }
     }
+    if (h.t < dist * 0.999f) break;
   }
   return h;
 }
@@ -305,7 +309,7 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
-          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd) : query(E, s.o, sd, brute, chain);
+          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist) : query(E, s.o, sd, brute, chain);
           if (sh.gid != HRT_NONE) { carry = hrt_theta_fold(nrm(E, sh.slot), sd); cx_carry = v3_dot(nrm(E, sh.slot), sd); }
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
           /* closed_form: what k_scatter runs (hrt_scatter_path_auto); else the reference's formulas line by line */
@@ -478,7 +482,7 @@ extern "C" long emul_rxmap_vs_brute(const Scene *sc, const Vec3 *rx, size_t R, c
       const V3 o = tov(origins[i]);
       const V3 sd = hrt_shadow_dir(o, tov(rx[r]), &dist);
       if (!(dist > 0.f)) continue;
-      const HrtHit a = query_map(E, M, r, o, sd, &tests);
+      const HrtHit a = query_map(E, M, r, o, sd, dist, &tests);
       const HrtHit b = hrt_closest_hit_brute(m, E.gid.data(), E.n, o, sd, nc);
       if (a.gid != b.gid || (a.gid != HRT_NONE && memcmp(&a.t, &b.t, 4))) ++bad;
     }
