@@ -185,10 +185,92 @@ def workload_config():
 
 # ------------------------------------------------------------------ GPU arm
 
+def dense_e2e_block(hrt, abi, tl):
+    """The drop-in C symbol compute_paths() itself (host buffers in, host buffers
+    out: scene upload, BVH build, trace, D2H of every dense array inside) on
+    BASELINE configs[1] and configs[2] at their stated sizes, each checked against
+    the oracle in this run (style of the reference's test/test.c:62-72)."""
+    out = []
+    L = hrt.lib()
+    for name, cfg, P, B in (("configs[1] box.hrt 1e6 rays x 3 bounces", "box_generic", 1_000_000, 3),
+                            ("configs[2] 2cars.hrt 1e7 rays x 5 bounces, 70 GHz", "2cars_raised", 10_000_000, 5)):
+        scene, rx, tx, f = tl.CONFIGS[cfg]
+        zr, zt = [[0.0, 0.0, 0.0]], [[0.0, 0.0, 0.0]]
+        sc = L.scene_load(tl.scene_path(scene).encode())
+        o = abi.alloc_outputs(1, 1, P, B, 0)
+        times = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            abi.call_compute_paths(L, sc, rx, tx, zr, zt, f, P, B, out=o)
+            times.append(time.perf_counter() - t0)
+        abi.free_scene(sc)
+        t_o = time.perf_counter()
+        a, tr = tl.run_oracle(scene, rx, tx, zr, zt, f, P, B, fill=0)
+        t_o = time.perf_counter() - t_o
+        st = tr["slot_state"].reshape(-1)
+        wr, va = st != 0, st == 1
+        tau_ok = bool(np.array_equal(a.scat["tau"].reshape(-1).view(np.uint32)[wr], o.scat["tau"].reshape(-1).view(np.uint32)[wr]))
+        dir_ok = bool(np.array_equal(a.scat["directions_rx"].reshape(-1, 3).view(np.uint32)[va],
+                                     o.scat["directions_rx"].reshape(-1, 3).view(np.uint32)[va]))
+        worst = 0.0
+        for pol in ("te", "tm"):
+            ar = a.scat[f"a_{pol}_re"].reshape(-1)[wr].astype(np.float64); ai = a.scat[f"a_{pol}_im"].reshape(-1)[wr].astype(np.float64)
+            br = o.scat[f"a_{pol}_re"].reshape(-1)[wr].astype(np.float64); bi = o.scat[f"a_{pol}_im"].reshape(-1)[wr].astype(np.float64)
+            mag = np.hypot(ar, ai); err = np.hypot(ar - br, ai - bi)
+            nz = mag > 0
+            if nz.any():
+                worst = max(worst, float((err[nz] / mag[nz]).max()))
+            if (~nz).any():
+                worst = max(worst, float(err[~nz].max() > 0))
+        rb = int((tr["hit_tri"] != tl.IDLE).sum())
+        d2h = sum(v.nbytes for k, v in o.scat.items() if k != "directions_tx") + o.scat_rays.nbytes + o.scat_active.nbytes
+        best = min(times[1:])
+        out.append({"config": name, "entry": "compute_paths() (C symbol, host arrays)", "seconds": best, "first_call_seconds": times[0],
+                    "ray_bounces": rb, "ray_bounces_per_s": rb / best, "d2h_bytes": int(d2h),
+                    "oracle_check": {"slots_written": int(wr.sum()), "valid_paths": int(va.sum()), "tau_bit_exact": tau_ok,
+                                     "directions_bit_exact": dir_ok, "worst_gain_rel_err": worst, "tolerance": tl.GAIN_RTOL,
+                                     "oracle_seconds_1_core": t_o}})
+        del a, tr, o
+    return out
+
+
+def c5_block(hrt, rank, world, local, peak_unfused):
+    """BASELINE configs[4] (C5): the synthetic 64 x 64 tiled canyon (958,464
+    triangles, mixed ITU materials), 16 TX / 1024 RX / 6 bounces.  The full job is
+    3.4e12 closest-hit queries, so every rank traces ONE shard of 256 of it (shard
+    `rank`: 65,536-path blocks dealt round-robin, i.e. the ray density and
+    coherence of the full job) -- weak scaling in the number of GPUs."""
+    from hrt_b200 import scenes
+    meshes, pitch = scenes.tiled_canyon(SCENE, 64, 64)
+    path = f"/tmp/c5_tiled_canyon_{rank}.hrt"
+    scenes.write_hrt(path, meshes)
+    rx, tx = scenes.c5_positions(pitch, 64, 64, n_tx=16, n_rx=1024)
+    zr, zt = np.zeros_like(rx), np.zeros_like(tx)
+    ctx = hrt.Context(local)
+    t0 = time.perf_counter(); ctx.load_scene(path); t_up = time.perf_counter() - t0
+    P, SH = 62_500_000, 256
+    ctx.run(rx, tx, zr, zt, 3.5, 200_000, 6, summary=True, los=False)          # warm-up (buffers, clocks)
+    r = ctx.run(rx, tx, zr, zt, 3.5, P, 6, summary=True, shard=(rank % SH, SH), shard_block=1 << 16)
+    s = r["stats"]
+    c = ctx.run(rx, tx, zr, zt, 3.5, 20_000, 6, summary=True, count_work=True, los=False)["stats"]
+    ctx.close()
+    os.remove(path)
+    fq = work_flops(c["work_scatter"]) / max(c["shadow_queries"], 1)
+    return {"ms": s["ms_total"], "ms_scatter": s["ms_scatter"], "ray_bounces": s["ray_bounces"], "shadow_queries": s["shadow_queries"],
+            "valid_paths": int(r["pair"]["n_valid"].sum()), "flops_per_shadow_query": fq,
+            "box_tests_per_shadow_query": c["work_scatter"][0] / max(c["shadow_queries"], 1),
+            "tri_tests_per_shadow_query": c["work_scatter"][1] / max(c["shadow_queries"], 1),
+            "counted_on_rays_per_tx": 20_000, "triangles": s["num_tris"], "bvh_build_ms": s["bvh_build_ms"],
+            "scene_load_upload_bvh_s": t_up, "scene_in_smem": bool(s["scene_in_smem"]),
+            "achieved_tflops": fq * s["shadow_queries"] / (s["ms_scatter"] * 1e-3) / 1e12 if s["ms_scatter"] else None,
+            "peak": peak_unfused}
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
     import hrt_b200 as hrt
+    from hrt_b200 import abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,21 +296,25 @@ def main_gpu(args):
     ctx.load_scene(SCENE)
     R, T, B = NUM_RX, NUM_TX, BOUNCES
 
-    # per-rank summary tables live in torch device memory so that NCCL can gather them
-    pair_dev = torch.zeros(R * T * B * 6, dtype=torch.int64, device="cuda")
-    bounce_dev = torch.zeros(T * B * 4, dtype=torch.int64, device="cuda")
-    gathered = torch.zeros(world * pair_dev.numel(), dtype=torch.int64, device="cuda") if world > 1 else None
-    gathered_b = torch.zeros(world * bounce_dev.numel(), dtype=torch.int64, device="cuda") if world > 1 else None
-    stream = torch.cuda.current_stream().cuda_stream
+    # ONE explicit stream carries everything of a step: the zeroing of the tables,
+    # every kernel of hrt_run (p.stream), the NCCL all-gathers and the timing events
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        # per-rank summary tables live in torch device memory so that NCCL can gather them
+        pair_dev = torch.zeros(R * T * B * 6, dtype=torch.int64, device="cuda")
+        bounce_dev = torch.zeros(T * B * 4, dtype=torch.int64, device="cuda")
+        gathered = torch.zeros(world * pair_dev.numel(), dtype=torch.int64, device="cuda") if world > 1 else None
+        gathered_b = torch.zeros(world * bounce_dev.numel(), dtype=torch.int64, device="cuda") if world > 1 else None
 
     def step():
-        pair_dev.zero_(); bounce_dev.zero_()
-        r = ctx.run(rx, tx, zr, zt, F_GHZ, P, B, summary=True, los=(rank == 0),
-                    shard=(rank, world), shard_block=SHARD_BLOCK,
-                    summary_dev_ptrs=(pair_dev.data_ptr(), bounce_dev.data_ptr()), stream=stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, pair_dev)
-            dist.all_gather_into_tensor(gathered_b, bounce_dev)
+        with torch.cuda.stream(stream):
+            pair_dev.zero_(); bounce_dev.zero_()
+            r = ctx.run(rx, tx, zr, zt, F_GHZ, P, B, summary=True, los=(rank == 0),
+                        shard=(rank, world), shard_block=SHARD_BLOCK,
+                        summary_dev_ptrs=(pair_dev.data_ptr(), bounce_dev.data_ptr()), stream=stream.cuda_stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, pair_dev)
+                dist.all_gather_into_tensor(gathered_b, bounce_dev)
         return r["stats"]
 
     def sync():
@@ -244,9 +330,9 @@ def main_gpu(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
-    e0.record()
+    e0.record(stream)
     stats = [step() for _ in range(args.steps)]
-    e1.record()
+    e1.record(stream)
     sync()
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
@@ -292,42 +378,92 @@ def main_gpu(args):
     # every path of the job
     PL = int(os.environ.get("HRT_BENCH_LIST_PATHS", "40000"))          # rays per TX of the listed job
     cap = int(PL * T * B * R * 0.6 / world) + 4096                      # records per rank (C4: ~0.42 valid per slot)
-    lbuf = torch.empty(cap * 48, dtype=torch.uint8, device="cuda")
-    g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    sync()
-    g0.record()
-    lr = ctx.run(rx, tx, zr, zt, F_GHZ, PL, B, los=False, shard=(rank, world), shard_block=4096,
-                 path_list_dev=(lbuf.data_ptr(), cap), stream=stream)
-    g1.record()
-    allrec, counts = hrt.gather_path_lists(lbuf, min(lr["paths_found"], cap), cap)
-    g2.record()
+    with torch.cuda.stream(stream):
+        lbuf = torch.empty(cap * 48, dtype=torch.uint8, device="cuda")
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        sync()
+        g0.record(stream)
+        lr = ctx.run(rx, tx, zr, zt, F_GHZ, PL, B, los=False, shard=(rank, world), shard_block=4096,
+                     path_list_dev=(lbuf.data_ptr(), cap), stream=stream.cuda_stream)
+        g1.record(stream)
+        allrec, counts = hrt.gather_path_lists(lbuf, min(lr["paths_found"], cap), cap)
+        g2.record(stream)
     sync()
     gather = {"job": f"{PL} rays per TX, same scene/TX/RX/bounces", "records": int(allrec.shape[0]),
               "record_bytes": 48, "bytes_gathered_per_rank": int(world * cap * 48),
               "overflow": bool(lr["paths_found"] > cap), "trace_and_list_ms": g0.elapsed_time(g1),
               "all_gather_ms": g1.elapsed_time(g2), "backend": "nccl" if world > 1 else "single rank"}
+    del lbuf, allrec
+
+    peak_unfused, peak_fma = ctx.fp32_peak()
+
+    # ---- BASELINE configs[4]: one shard of 256 of the C5 job per rank (weak scaling)
+    c5 = None
+    if not os.environ.get("HRT_BENCH_SKIP_C5"):
+        mine = c5_block(hrt, rank, world, local, peak_unfused)
+        vec = torch.tensor([mine["ms"], float(mine["ray_bounces"]), float(mine["shadow_queries"]), mine["ms_scatter"]],
+                           device="cuda", dtype=torch.float64)
+        mx, sm = vec.clone(), vec.clone()
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_s = float(mx[0]) * 1e-3
+        c5 = {"workload": "BASELINE configs[4]: synthetic 64x64 tiled street canyon (958,464 triangles, mixed ITU materials), "
+                          "16 TX / 1024 RX, 6 bounces, 6.25e7 rays per TX; every rank traces one shard of 256 of the job "
+                          "(blocks of 65,536 paths dealt round-robin: the full job's ray density)",
+              "scaling": "weak", "n_gpus": world, "shards_traced": world, "of_shards": 256,
+              "seconds": t_s, "ray_bounces_per_s": float(sm[1]) / t_s,
+              "closest_hit_queries_per_s": (float(sm[1]) + float(sm[2])) / t_s,
+              "full_job_seconds_at_this_rate": 256.0 / world * t_s,
+              "target_rb_per_s_north_star": 1e10,
+              "roofline": {"bound": "fp32", "kernel": "k_scatter (global-memory scene, 4-wide BVH)",
+                           "achieved": mine["achieved_tflops"], "peak": peak_unfused, "unit": "TFLOP/s",
+                           "frac": mine["achieved_tflops"] / peak_unfused if mine["achieved_tflops"] else None,
+                           "flops_per_shadow_query": mine["flops_per_shadow_query"],
+                           "box_tests_per_shadow_query": mine["box_tests_per_shadow_query"],
+                           "tri_tests_per_shadow_query": mine["tri_tests_per_shadow_query"],
+                           "counted_on_rays_per_tx": mine["counted_on_rays_per_tx"]},
+              "rank0": {k: mine[k] for k in ("ms", "ms_scatter", "valid_paths", "triangles", "bvh_build_ms",
+                                             "scene_load_upload_bvh_s", "scene_in_smem")}}
 
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel (k_scatter): counted work / live launch time
-        cnt = ctx.run(rx, tx, zr, zt, F_GHZ, min(P, 1 << 20), B, summary=True, los=False,
-                      count_work=True)["stats"]
+        P_cnt = min(P, 1 << 20)
+        cnt = ctx.run(rx, tx, zr, zt, F_GHZ, P_cnt, B, summary=True, los=False, count_work=True)["stats"]
         flops_per_shadow = work_flops(cnt["work_scatter"]) / max(cnt["shadow_queries"], 1)
         flops_per_primary = work_flops(cnt["work_bounce"]) / max(cnt["ray_bounces"], 1)
         s0 = stats[0]
         ms_scatter = sum(s["ms_scatter"] for s in stats)
         n_scatter = sum(s["n_scatter_launches"] for s in stats)
         shadow_rank0 = sum(s["shadow_queries"] for s in stats)
-        peak_unfused, peak_fma = ctx.fp32_peak()
         achieved = flops_per_shadow * shadow_rank0 / (ms_scatter * 1e-3) / 1e12 if ms_scatter else None
         nominal = 148 * 128 * 1.965e9 / 1e12
+        # the same step with the shadow queries walking the BVH instead of the receiver maps
+        # (rank 0's shard): more counted work per query, more time
+        bvh_mode = None
+        if s0["rx_map"] and not os.environ.get("HRT_BENCH_SKIP_BVH_MODE"):
+            os.environ["HRT_RXMAP"] = "0"
+            try:
+                ctx.run(rx, tx, zr, zt, F_GHZ, P, B, summary=True, los=False, shard=(rank, world), shard_block=SHARD_BLOCK)
+                sb = ctx.run(rx, tx, zr, zt, F_GHZ, P, B, summary=True, los=False, shard=(rank, world), shard_block=SHARD_BLOCK)["stats"]
+                cb = ctx.run(rx, tx, zr, zt, F_GHZ, P_cnt, B, summary=True, los=False, count_work=True)["stats"]
+            finally:
+                del os.environ["HRT_RXMAP"]
+            fb = work_flops(cb["work_scatter"]) / max(cb["shadow_queries"], 1)
+            ab = fb * sb["shadow_queries"] / (sb["ms_scatter"] * 1e-3) / 1e12
+            bvh_mode = {"how": "HRT_RXMAP=0: the same step, shadow queries through the 4-wide BVH", "ms_scatter": sb["ms_scatter"],
+                        "ms_total": sb["ms_total"], "ray_bounces_per_s": sb["ray_bounces"] / (sb["ms_total"] * 1e-3),
+                        "flops_per_shadow_query": fb, "box_tests_per_shadow_query": cb["work_scatter"][0] / max(cb["shadow_queries"], 1),
+                        "tri_tests_per_shadow_query": cb["work_scatter"][1] / max(cb["shadow_queries"], 1),
+                        "achieved": ab, "frac": ab / peak_unfused if peak_unfused else None}
         traffic, traffic_note = None, "no ncu capture committed under profiles/"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "k_scatter_traffic.json")))
             l0 = tj["launches"][0]
             traffic = l0["dram_bytes_read"] + l0["dram_bytes_write"]
             traffic_note = ("DRAM bytes of ONE k_scatter launch under ncu (%s, %.1f ms launch): the kernel is fp32-issue "
-                            "bound; its DRAM traffic is the gather of per-hit state" % (tj["source"], l0["duration_ms"]))
+                            "bound; its DRAM traffic is the gather of per-hit state and the receiver-map cells" % (tj["source"], l0["duration_ms"]))
         except Exception:
             pass
         isect_share, isect_note = None, None
@@ -343,6 +479,11 @@ def main_gpu(args):
             "bound": "fp32", "kernel": "k_scatter", "achieved": achieved, "peak": peak_unfused,
             "unit": "TFLOP/s", "frac": (achieved / peak_unfused) if achieved and peak_unfused else None,
             "traffic": traffic, "traffic_note": traffic_note,
+            "convention": "SURVEY 8(d): flops of the tests PERFORMED (22 per ray-box test; Moeller-Trumbore 14/9/16/6 by stage reached), "
+                          "counted by the instrumented kernels, x shadow queries / k_scatter time.  With receiver maps a shadow "
+                          "query performs no box test at all, so the counted work per query is a third of the BVH walk's while the "
+                          "kernel finishes sooner: compare bvh_mode (same step, HRT_RXMAP=0)",
+            "bvh_mode": bvh_mode,
             "intersection_share_of_issue_slots": isect_share,
             "frac_of_intersection_slots": (achieved / peak_unfused / isect_share) if achieved and peak_unfused and isect_share else None,
             "intersection_note": isect_note,
@@ -350,6 +491,9 @@ def main_gpu(args):
                            "(hrt_fp32_peak); MEASURED_PEAKS.json has no fp32 figure. nominal "
                            f"unfused {nominal:.1f}, measured FFMA {peak_fma:.1f} TFLOP/s",
             "flops_per_shadow_query": flops_per_shadow, "flops_per_primary_query": flops_per_primary,
+            "counted_on_rays_per_tx": P_cnt, "timed_rays_per_tx": P,
+            "counted_note": "work per query is counted on a separate pass of the instrumented kernels at counted_on_rays_per_tx "
+                            "rays per TX; per-query work does not depend on the ray count",
             "launches": n_scatter, "avg_launch_ms": ms_scatter / n_scatter if n_scatter else None,
             "kernel_share_of_step": ms_scatter / (ms_total if world == 1 else sum(s["ms_total"] for s in stats)),
             "box_tests_per_shadow_query": cnt["work_scatter"][0] / max(cnt["shadow_queries"], 1),
@@ -363,6 +507,12 @@ def main_gpu(args):
                 cpu = {"value": r[0] / r[1], "unit": "ray-bounces/s", "cores": 1, "kind": "reference",
                        "sample": f"same scene/TX/RX/bounces, {os.environ.get('HRT_REF_PATHS', '1000')} rays per TX "
                                  f"({r[0]} ray-bounces, {r[1]:.1f} s of compute_paths())"}
+        # ---- the drop-in entry itself on configs[1] and configs[2] (N = 1 only: host-memory heavy)
+        dense = None
+        if world == 1 and not os.environ.get("HRT_BENCH_SKIP_DENSE"):
+            ctx.close(); ctx = None
+            import hrt_testlib as tl
+            dense = dense_e2e_block(hrt, abi, tl)
         value = rb_total / (ms_total * 1e-3)
         out = {
             "metric": METRIC, "value": value, "unit": "ray-bounces/s", "n_gpus": world,
@@ -374,6 +524,7 @@ def main_gpu(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
+            "dense_e2e": dense, "c5": c5,
             "path_list_gather": gather,
             "closest_hit_queries_per_s": (rb_total + shadow_total) / (ms_total * 1e-3),
             "shadow_queries_per_step": shadow_total / args.steps,
@@ -382,12 +533,16 @@ def main_gpu(args):
             "ambiguous_dirs_per_step": s0["ambiguous_dirs"],
             "bvh": {"triangles": s0["num_tris"], "nodes": s0["num_nodes"], "builder": "binned SAH" if s0["bvh_sah"] else "LBVH",
                     "build_ms": s0["bvh_build_ms"], "scene_in_smem": bool(s0["scene_in_smem"]), "box_pad_m": s0["box_pad"]},
+            "receiver_maps": {"used": bool(s0["rx_map"]), "cells_per_face_edge": s0["rx_map_cells"],
+                              "build_ms_first_step": stats[0]["rx_map_build_ms"]},
             "ms_breakdown_rank0_last_step": {"scatter": stats[-1]["ms_scatter"], "bounce": stats[-1]["ms_bounce"],
                                              "hit_sort": stats[-1]["ms_sort"], "total": stats[-1]["ms_total"]},
         }
         os.write(json_fd, (json.dumps(out) + "\n").encode())
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -1095,21 +1095,11 @@ static int flush_summaries(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd
   HrtRunStats &S = ctx->stats;
   const size_t np = R * T * B, nb = T * B;
   if (flags & HRT_FLAG_SUMMARY_DEV) {
-    /* pair: fields 4,5 of each 6-word record are doubles */
-    unsigned char *d_isd = nullptr;
-    unsigned char *h_isd = (unsigned char *)calloc(np * 6, 1);
-    if (!h_isd) return fail(ctx, HRT_E_NOMEM, "out of host memory");
-    for (size_t i = 0; i < np; ++i) h_isd[6 * i + 4] = h_isd[6 * i + 5] = 1;
-    cudaError_t e = cudaMalloc((void **)&d_isd, np * 6);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_isd, h_isd, np * 6, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-      k_add_u64<<<nblk(np * 6), 256, 0, st>>>((unsigned long long *)p->pair_summary, (const unsigned long long *)rd.pair, np * 6, d_isd);
-      k_add_u64<<<nblk(nb * 4), 256, 0, st>>>((unsigned long long *)p->bounce_summary, (const unsigned long long *)rd.bounce, nb * 4, nullptr);
-      e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_isd); free(h_isd);
-    CK(e);
+    /* added on the device, on the run's stream; pair records: words 4, 5 of 6 are doubles */
+    k_add_u64<<<nblk(np * 6), 256, 0, st>>>((unsigned long long *)p->pair_summary, (const unsigned long long *)rd.pair, np * 6, 6u, 4u);
+    k_add_u64<<<nblk(nb * 4), 256, 0, st>>>((unsigned long long *)p->bounce_summary, (const unsigned long long *)rd.bounce, nb * 4, 0u, 0u);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
     S.kernel_launches += 2;
   } else {
     HrtPairSummary *hp = (HrtPairSummary *)malloc(np * sizeof(HrtPairSummary));

@@ -757,11 +757,12 @@ __global__ void k_fold_counts(RunDev rd)
   rd.bounce[k].n_hit += rd.qcount[(b + 1) * rd.T + t];
 }
 
-__global__ void k_add_u64(unsigned long long *dst, const unsigned long long *src, size_t n, const unsigned char *is_double)
+/* dst += src, word by word; words with (index % period) >= first_double are doubles (period 0: none) */
+__global__ void k_add_u64(unsigned long long *dst, const unsigned long long *src, size_t n, uint32_t period, uint32_t first_double)
 {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (is_double && is_double[i]) ((double *)dst)[i] += ((const double *)src)[i];
+  if (period && (uint32_t)(i % period) >= first_double) ((double *)dst)[i] += ((const double *)src)[i];
   else dst[i] += src[i];
 }
 
