@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -241,6 +242,7 @@ struct hrt_ctx {
   float *d_cir; size_t cap_cir;
   float4 *d_plist; size_t cap_plist;
   HostPool *pool; char *stage[2]; cudaEvent_t stage_ev[2];
+  float *h_patch; float *d_patch;     /* pinned / device staging of host-recomputed launch directions */
   HrtRunStats stats;
 };
 
@@ -343,6 +345,8 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   free_scene_dev(c); free_run_dev(c);
   dev_free(c->d_pos);
   dev_free(c->d_map_cells); dev_free(c->d_map_items); dev_free(c->d_map_cursor);
+  dev_free(c->d_patch);
+  if (c->h_patch) { cudaFreeHost(c->h_patch); c->h_patch = nullptr; }
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
   if (c->d_cir) { cudaFree(c->d_cir); c->d_cir = nullptr; }
   if (c->d_plist) { cudaFree(c->d_plist); c->d_plist = nullptr; }
@@ -772,10 +776,19 @@ static int ensure_pad(hrt_ctx *ctx, float max_abs, cudaStream_t st)
                 else       KERNEL<false, false><<<grid, block, shbytes, st>>>(__VA_ARGS__); } \
   } while (0)
 
+/* opt-in to > 48 KB of dynamic shared memory, once per (kernel, device, size): the
+ * attribute call is not free and hrt_run is called per step */
 template <class K> static cudaError_t allow_smem(K kernel, size_t bytes)
 {
   if (bytes <= 48 * 1024) return cudaSuccess;
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static std::mutex mu;
+  static std::vector<std::pair<std::pair<const void *, int>, size_t>> done;
+  int dev = 0; cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto &d : done) if (d.first.first == (const void *)kernel && d.first.second == dev && d.second >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.push_back({{(const void *)kernel, dev}, bytes});
+  return e;
 }
 
 typedef void (*BounceFn)(RunDev, SceneDev, HrtMaterialTable, uint32_t);
@@ -1218,6 +1231,8 @@ static int run_los(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd, const 
 extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
 {
   if (!ctx || !p) return HRT_E_ARG;
+  const auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
   if (!ctx->have_scene) return fail(ctx, HRT_E_STATE, "hrt_run before hrt_scene_upload");
   if (!ctx->have_mats) return fail(ctx, HRT_E_STATE, "hrt_run before hrt_materials_set");
   const size_t R = p->num_rx, T = p->num_tx, B = p->num_bounces;
@@ -1258,7 +1273,11 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const uint64_t n_shard = shard_count(P, rank, world, blk);
   size_t chunk = 1u << 23;
   if (const char *s = getenv("HRT_CHUNK")) { long long v = atoll(s); if (v >= 32) chunk = (size_t)v; }
-  {
+  const uint32_t shape_flags_now = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_TRACE);
+  const bool buffers_fit = ctx->cap_n && ctx->cap_R == R && ctx->cap_T == T && ctx->cap_B == B && ctx->cap_flags == shape_flags_now;
+  if (buffers_fit && ctx->cap_n >= (n_shard < chunk ? n_shard : chunk)) {
+    /* the buffers of the previous run already hold a full chunk of this shape: no memory query */
+  } else {
     /* per-ray state (two 64-byte records, three queue words, two key words per TX,
      * sort scratch) must fit: at most half of the free device memory */
     size_t free_b = 0, total_b = 0;
@@ -1274,8 +1293,10 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     const size_t lim = (size_t)6e9 / per_path;
     if (chunk > lim) chunk = lim < 32 ? 32 : lim;
   }
-  if (world > 1) { chunk = (chunk / blk) * blk; if (chunk == 0) chunk = blk; }
-  else chunk &= ~(size_t)31;
+  /* whole warps of paths; a chunk need not be a whole number of shard blocks (k_raygen,
+   * d2h_columns and the RaysInfo bookkeeping split runs at block boundaries themselves) */
+  chunk &= ~(size_t)31;
+  if (chunk == 0) chunk = 32;
   if (chunk > n_shard) chunk = n_shard ? n_shard : 32;
   rc = ensure_run_buffers(ctx, chunk, R, T, B, flags); if (rc) return rc;
 
@@ -1373,6 +1394,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     }
   }
 
+  const float host_setup = host_ms();
   CK(cudaEventRecord(ctx->ev[0], st));
 
   /* ---- line of sight (rank 0 of the shard group only) ---- */
@@ -1421,20 +1443,27 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       CKR(cudaMemcpyAsync(&namb, rd.amb_count, 4, cudaMemcpyDeviceToHost, st));
       CKR(cudaStreamSynchronize(st));
       if (namb) {
-        /* recompute the flagged directions with the host libm (see hrt_launch_dir) */
+        /* recompute the flagged directions with the host libm (see hrt_launch_dir): indices down,
+         * values up in ONE transfer through a pinned buffer, written in place by k_patch_dirs */
         if (namb > HRT_AMB_CAP) { rc = fail(ctx, HRT_E_STATE, "ambiguous-direction list overflow (%u)", namb); goto run_done; }
-        uint32_t *idx = (uint32_t *)malloc(namb * 4);
-        if (!idx) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
-        cudaError_t e = cudaMemcpyAsync(idx, rd.amb_list, namb * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        for (uint32_t k = 0; k < namb && e == cudaSuccess; ++k) {
-          float d[3];
-          hrt_host_launch_dir(hrt_gpath(l0 + idx[k], rank, world, blk), P, d);
-          e = cudaMemcpyAsync(rd.dirs + 3 * (size_t)idx[k], d, 12, cudaMemcpyHostToDevice, st);
-          if (e == cudaSuccess) e = cudaStreamSynchronize(st);   /* d is a stack temporary */
+        if (!ctx->h_patch) {
+          CKR(cudaHostAlloc((void **)&ctx->h_patch, (size_t)HRT_AMB_CAP * 16, cudaHostAllocDefault));
+          CKR(dev_alloc(&ctx->d_patch, (size_t)HRT_AMB_CAP * 4));
         }
-        free(idx);
-        CKR(e);
+        uint32_t *idx = (uint32_t *)ctx->h_patch;              /* [namb] indices, then reused as (index, x, y, z) records */
+        CKR(cudaMemcpyAsync(idx, rd.amb_list, namb * 4, cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        for (uint32_t k = namb; k-- > 0;) {                    /* back to front: record k overwrites indices >= 4k only */
+          const uint32_t l = idx[k];
+          float d[3];
+          hrt_host_launch_dir(hrt_gpath(l0 + l, rank, world, blk), P, d);
+          float *rec = ctx->h_patch + 4 * (size_t)k;
+          memcpy(rec, &l, 4); rec[1] = d[0]; rec[2] = d[1]; rec[3] = d[2];
+        }
+        CKR(cudaMemcpyAsync(ctx->d_patch, ctx->h_patch, (size_t)namb * 16, cudaMemcpyHostToDevice, st));
+        k_patch_dirs<<<nblk(namb), 256, 0, st>>>(rd, (const float4 *)ctx->d_patch, namb);
+        CKR(cudaGetLastError());
+        S.kernel_launches++;
         S.ambiguous_dirs += namb;
       }
     }
@@ -1606,6 +1635,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     S.n_bounce_launches = S.n_scatter_launches = (uint32_t)(ev_used / 4);
     S.ms_total = a; S.ms_bounce = ms_bounce; S.ms_scatter = ms_scatter;
     S.ms_other = b;
+    S.host_ms_setup = host_setup; S.host_ms_total = host_ms();
   }
 run_done:
 #undef CKR

@@ -294,6 +294,18 @@ __global__ void k_raygen(RunDev rd)
   }
 }
 
+/* host-recomputed launch directions (index, x, y, z) written over the GPU's values;
+ * the direction-order key of the path is refreshed with them */
+__global__ void k_patch_dirs(RunDev rd, const float4 *recs, uint32_t n)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float4 r = recs[k];
+  const uint32_t l = __float_as_uint(r.x);
+  rd.dirs[3 * l] = r.y; rd.dirs[3 * l + 1] = r.z; rd.dirs[3 * l + 2] = r.w;
+  rd.dkey[l] = dir_key(v3(r.y, r.z, r.w));
+}
+
 /* per-ray state (reference :453-472) and output initialisation: gains/tau
  * zero, freq_shift = Doppler base value with the reference's index algebra
  * (:494-508) */

@@ -78,6 +78,7 @@ class RunStats(C.Structure):
         ("bvh_sah", C.c_uint32), ("bvh_levels", C.c_uint32), ("bvh_build_ms", C.c_float), ("ms_sort", C.c_float),
         ("cir_dropped", C.c_uint64),
         ("rx_map", C.c_uint32), ("rx_map_cells", C.c_uint32), ("rx_map_build_ms", C.c_float),
+        ("host_ms_setup", C.c_float), ("host_ms_total", C.c_float),
     ]
 
     def as_dict(self):

@@ -190,6 +190,9 @@ typedef struct {
    * 1/0, cells per cube-map face edge, GPU time of the map build (0 when the cached maps applied) */
   uint32_t rx_map, rx_map_cells;
   float    rx_map_build_ms;
+  /* host wall clock of the call: entry -> first kernel of the run queued (argument checks,
+   * position upload, buffer and map management), and entry -> return */
+  float    host_ms_setup, host_ms_total;
 } HrtRunStats;
 
 int  hrt_device_count(void);

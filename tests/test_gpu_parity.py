@@ -422,6 +422,19 @@ def test_summary_mode_and_shards(ctx):
     for k in ("n_traced", "n_hit", "hit_hash", "t_bits"):
         assert np.array_equal(acc_bounce[k], full["bounce"][k]), k
     np.testing.assert_allclose(acc_pair["power_te"], full["pair"]["power_te"], rtol=1e-9)
+    # chunks that are not a whole number of shard blocks: 3 shards, block 4096, chunk 4992
+    os.environ["HRT_CHUNK"] = "5000"
+    try:
+        o2 = abi.alloc_outputs(len(rx), len(tx), P, B, 0)
+        for r in range(3):
+            ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True, out=o2, shard=(r, 3), shard_block=4096, los=(r == 0))
+    finally:
+        del os.environ["HRT_CHUNK"]
+    fr = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, raysinfo=True)["out"]
+    for k in ("tau", "a_te_re", "a_tm_im", "freq_shift", "directions_rx"):
+        assert np.array_equal(o2.scat[k].view(np.uint32), fr.scat[k].view(np.uint32)), k
+    assert np.array_equal(o2.scat_rays.view(np.uint32), fr.scat_rays.view(np.uint32))
+    assert np.array_equal(o2.scat_active, fr.scat_active)
     os.environ["HRT_CHUNK"] = "8192"
     try:
         ch = ctx.run(rx, tx, rxv, txv, f, P, B, dense=True, summary=True)
