@@ -8,21 +8,33 @@
  *     :171-206) -- 17 rows through the host libm, then uploaded;
  *   - Mesh.ns: the reference mallocs per-mesh normals into the caller's scene
  *     (:208-224); callers may read them (the viewer does), so they are filled
- *     from the GPU-computed normals.  Like the reference this allocates on
- *     every call and leaves freeing to free_scene().
+ *     from the GPU-computed normals (cached with the uploaded scene).  A
+ *     previous array is freed before the new one is attached -- the reference
+ *     leaks it on repeated calls; freeing the last one is free_scene()'s job.
  * Errors follow the reference convention: message on stderr and exit(8)
  * (inc/common.h:20-25).  There is no CPU fallback.
  *
  * Environment:
- *   HRT_DEVICE=<n>        CUDA device of the implicit context (default 0)
+ *   HRT_DEVICES=0,1,...   CUDA devices of the implicit context: the job is sharded
+ *                         over them inside the library (hrt_multi_*); "all" = every
+ *                         device of the box.  Default: HRT_DEVICE or device 0
+ *   HRT_DEVICE=<n>        single CUDA device (default 0)
  *   HRT_NO_RAYSINFO=1     do not fill raysInfo_scat (saves the largest copy)
+ *   HRT_NO_SCENE_CACHE=1  re-upload the scene and rebuild the BVH on every call
  */
 #include "../../include/hrt_cuda.h"
 
 #include <stdio.h>
 
-static hrt_ctx *g_ctx = NULL;
-static int g_ctx_device = -1;
+static hrt_multi *g_ctx = NULL;
+static char g_ctx_devices[256] = "";
+/* the scene the devices currently hold: content hash and its normals (reference
+ * :208-224), so that repeated calls on the same scene neither re-upload it nor
+ * rebuild the BVH (the reference's binding re-reads the file on every call,
+ * compute_paths_pybind11.cpp:119) */
+static uint64_t g_scene_hash = 0;
+static Vec3 *g_scene_normals = NULL;
+static size_t g_scene_tris = 0;
 
 static void die(const char *what, const char *detail)
 {
@@ -30,41 +42,87 @@ static void die(const char *what, const char *detail)
   exit(8);
 }
 
-static void drop_ctx(void) { if (g_ctx) { hrt_ctx_destroy(g_ctx); g_ctx = NULL; } }
-
-static hrt_ctx *implicit_ctx(void)
+static void drop_ctx(void)
 {
-  int dev = 0;
-  const char *s = getenv("HRT_DEVICE");
-  if (s) dev = atoi(s);
-  if (g_ctx && g_ctx_device == dev) return g_ctx;
+  if (g_ctx) { hrt_multi_destroy(g_ctx); g_ctx = NULL; }
+  free(g_scene_normals); g_scene_normals = NULL; g_scene_hash = 0; g_scene_tris = 0;
+}
+
+static hrt_multi *implicit_ctx(void)
+{
+  char want[256];
+  const char *ds = getenv("HRT_DEVICES"), *d1 = getenv("HRT_DEVICE");
+  snprintf(want, sizeof want, "%s", ds && *ds ? ds : (d1 && *d1 ? d1 : "0"));
+  if (g_ctx && !strcmp(want, g_ctx_devices)) return g_ctx;
   drop_ctx();
-  if (hrt_ctx_create(dev, &g_ctx) != HRT_OK) die("cannot create CUDA context", hrt_last_error(NULL));
-  g_ctx_device = dev;
+  int devs[64], n = 0;
+  if (!strcmp(want, "all")) n = 0;
+  else {
+    const char *q = want;
+    while (*q && n < 64) {
+      char *end;
+      const long v = strtol(q, &end, 10);
+      if (end == q) die("bad HRT_DEVICES", want);
+      devs[n++] = (int)v;
+      q = end;
+      while (*q == ',' || *q == ' ') ++q;
+    }
+    if (n == 0) die("bad HRT_DEVICES", want);
+  }
+  if (hrt_multi_create(n ? devs : NULL, n, &g_ctx) != HRT_OK) die("cannot create CUDA context", hrt_multi_last_error(NULL));
+  snprintf(g_ctx_devices, sizeof g_ctx_devices, "%s", want);
   static int registered = 0;
   if (!registered) { atexit(drop_ctx); registered = 1; }
   return g_ctx;
 }
 
-/* scene -> GPU (flatten, normals, BVH) and the material table at f; fills
- * Mesh.ns like the reference's precompute_normals */
-static hrt_ctx *prepare(Scene *scene, float carrier_frequency_GHz)
+static uint64_t fnv(const void *p, size_t n, uint64_t h)
 {
-  hrt_ctx *ctx = implicit_ctx();
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
+  return h;
+}
+
+/* content hash of everything the GPU side reads from the scene */
+static uint64_t scene_hash(const Scene *scene)
+{
+  uint64_t h = fnv(&scene->num_meshes, 4, 0xCBF29CE484222325ull);
+  for (uint32_t m = 0; m < scene->num_meshes; ++m) {
+    const Mesh *me = &scene->meshes[m];
+    h = fnv(&me->num_vertices, 4, h); h = fnv(&me->num_triangles, 4, h);
+    h = fnv(me->vs, (size_t)me->num_vertices * sizeof(Vec3), h);
+    h = fnv(me->is, (size_t)me->num_triangles * 12, h);
+    h = fnv(&me->material_index, 4, h); h = fnv(&me->velocity, sizeof(Vec3), h);
+  }
+  return h ? h : 1;
+}
+
+/* scene -> GPUs (flatten, normals, BVH; skipped when they already hold this
+ * scene) and the material table at f; fills Mesh.ns like the reference's
+ * precompute_normals -- a previous array is freed first (the reference leaks it) */
+static hrt_multi *prepare(Scene *scene, float carrier_frequency_GHz)
+{
+  hrt_multi *ctx = implicit_ctx();
   size_t total = 0;
   for (uint32_t m = 0; m < scene->num_meshes; ++m) total += scene->meshes[m].num_triangles;
-  Vec3 *normals = (Vec3 *)malloc((total ? total : 1) * sizeof(Vec3));
-  if (!normals) die("compute_paths", "out of memory");
-  if (hrt_scene_upload(ctx, scene, normals) != HRT_OK) die("scene upload failed", hrt_last_error(ctx));
+  const uint64_t h = scene_hash(scene);
+  if (h != g_scene_hash || total != g_scene_tris || !g_scene_normals || getenv("HRT_NO_SCENE_CACHE")) {
+    free(g_scene_normals);
+    g_scene_normals = (Vec3 *)malloc((total ? total : 1) * sizeof(Vec3));
+    if (!g_scene_normals) die("compute_paths", "out of memory");
+    g_scene_hash = 0;
+    if (hrt_multi_scene_upload(ctx, scene, g_scene_normals) != HRT_OK) die("scene upload failed", hrt_multi_last_error(ctx));
+    g_scene_hash = h; g_scene_tris = total;
+  }
   size_t off = 0;
   for (uint32_t m = 0; m < scene->num_meshes; ++m) {
     Mesh *me = &scene->meshes[m];
+    free(me->ns);
     me->ns = (Vec3 *)malloc((me->num_triangles ? me->num_triangles : 1) * sizeof(Vec3));
     if (!me->ns) die("compute_paths", "out of memory");
-    memcpy(me->ns, normals + off, (size_t)me->num_triangles * sizeof(Vec3));
+    memcpy(me->ns, g_scene_normals + off, (size_t)me->num_triangles * sizeof(Vec3));
     off += me->num_triangles;
   }
-  free(normals);
 
   /* material constants at this frequency: only the materials the scene uses
    * are (re)computed, the others stay zero (reference :176-180) */
@@ -74,7 +132,7 @@ static hrt_ctx *prepare(Scene *scene, float carrier_frequency_GHz)
     uint32_t mi = scene->meshes[m].material_index;
     hrt_materials_derive(mi, carrier_frequency_GHz, &table[mi]);
   }
-  if (hrt_materials_set(ctx, table) != HRT_OK) die("material upload failed", hrt_last_error(ctx));
+  if (hrt_multi_materials_set(ctx, table) != HRT_OK) die("material upload failed", hrt_multi_last_error(ctx));
   return ctx;
 }
 
@@ -86,19 +144,18 @@ void compute_paths(
     ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat)
 {
   if (!scene || !chanInfo_scat) die("compute_paths", "NULL scene or scatter output");
-  hrt_ctx *ctx = prepare(scene, carrier_frequency_GHz);
+  hrt_multi *ctx = prepare(scene, carrier_frequency_GHz);
 
   HrtRunParams p;
   memset(&p, 0, sizeof p);
   p.num_rx = num_rx; p.num_tx = num_tx; p.num_paths = num_rays; p.num_bounces = num_bounces;
   p.carrier_frequency_GHz = carrier_frequency_GHz;
   p.rx_pos = rx_pos; p.tx_pos = tx_pos; p.rx_vel = rx_vel; p.tx_vel = tx_vel;
-  p.shard_world = 1;
   p.flags = HRT_FLAG_DENSE;
   if (raysInfo_scat && !getenv("HRT_NO_RAYSINFO")) p.flags |= HRT_FLAG_RAYSINFO;
   p.los = chanInfo_los; p.rays_los = raysInfo_los;
   p.scat = chanInfo_scat; p.rays_scat = raysInfo_scat;
-  if (hrt_run(ctx, &p) != HRT_OK) die("compute_paths failed", hrt_last_error(ctx));
+  if (hrt_multi_run(ctx, &p) != HRT_OK) die("compute_paths failed", hrt_multi_last_error(ctx));
 }
 
 /* Streaming consumer of the same path set: instead of
@@ -114,7 +171,7 @@ size_t compute_cir(
     float tau0_s, float dt_s, size_t num_bins, float *cir)
 {
   if (!scene || !cir || !num_bins) die("compute_cir", "NULL scene or output");
-  hrt_ctx *ctx = prepare(scene, carrier_frequency_GHz);
+  hrt_multi *ctx = prepare(scene, carrier_frequency_GHz);
   const size_t nl = num_rx * num_tx;
   memset(cir, 0, nl * num_bins * 4 * sizeof(float));
 
@@ -133,14 +190,13 @@ size_t compute_cir(
   p.num_rx = num_rx; p.num_tx = num_tx; p.num_paths = num_rays; p.num_bounces = num_bounces;
   p.carrier_frequency_GHz = carrier_frequency_GHz;
   p.rx_pos = rx_pos; p.tx_pos = tx_pos; p.rx_vel = rx_vel; p.tx_vel = tx_vel;
-  p.shard_world = 1;
   p.flags = HRT_FLAG_CIR;
   p.los = &los;
   p.cir = cir; p.cir_tau0_s = tau0_s; p.cir_dt_s = dt_s; p.cir_bins = (uint32_t)num_bins;
-  if (hrt_run(ctx, &p) != HRT_OK) die("compute_cir failed", hrt_last_error(ctx));
+  if (hrt_multi_run(ctx, &p) != HRT_OK) die("compute_cir failed", hrt_multi_last_error(ctx));
   free(buf);
   HrtRunStats st;
-  hrt_get_stats(ctx, &st);
+  hrt_multi_get_stats(ctx, &st);
   return (size_t)st.cir_dropped;
 }
 
@@ -156,16 +212,15 @@ size_t compute_path_list(
     HrtPathRecord *paths, size_t capacity)
 {
   if (!scene || !paths || !capacity) die("compute_path_list", "NULL scene or output");
-  hrt_ctx *ctx = prepare(scene, carrier_frequency_GHz);
+  hrt_multi *ctx = prepare(scene, carrier_frequency_GHz);
   HrtRunParams p;
   memset(&p, 0, sizeof p);
   p.num_rx = num_rx; p.num_tx = num_tx; p.num_paths = num_rays; p.num_bounces = num_bounces;
   p.carrier_frequency_GHz = carrier_frequency_GHz;
   p.rx_pos = rx_pos; p.tx_pos = tx_pos; p.rx_vel = rx_vel; p.tx_vel = tx_vel;
-  p.shard_world = 1;
   p.flags = HRT_FLAG_PATHLIST;
   uint64_t found = 0;
   p.paths = paths; p.paths_capacity = capacity; p.paths_count = &found;
-  if (hrt_run(ctx, &p) != HRT_OK) die("compute_path_list failed", hrt_last_error(ctx));
+  if (hrt_multi_run(ctx, &p) != HRT_OK) die("compute_path_list failed", hrt_multi_last_error(ctx));
   return (size_t)found;
 }

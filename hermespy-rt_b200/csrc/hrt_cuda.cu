@@ -243,6 +243,7 @@ struct hrt_ctx {
   float4 *d_plist; size_t cap_plist;
   HostPool *pool; char *stage[2]; cudaEvent_t stage_ev[2];
   float *h_patch; float *d_patch;     /* pinned / device staging of host-recomputed launch directions */
+  uint8_t tail_dead[8];               /* RaysInfo: bounce at which paths 0..7 of TX 1 died in the last run (appendix A-9) */
   HrtRunStats stats;
 };
 
@@ -1101,6 +1102,10 @@ static void raysinfo_tail_bits(const HrtRunParams *p, const uint8_t tail_dead[8]
     }
 }
 
+#define HRT_FLAG_INTERNAL_NO_TAIL 0x80000000u   /* hrt_multi.cu: leave the RaysInfo tail bits to the caller */
+extern "C" void hrt_internal_raysinfo_tail(const hrt_ctx *rank0, const HrtRunParams *p)
+{ if (rank0 && p && p->rays_scat && p->rays_scat->rays_active) raysinfo_tail_bits(p, rank0->tail_dead); }
+
 /* per-(rx, tx, bounce) and per-(tx, bounce) tables of this call -> added to the caller's (host or device) */
 static int flush_summaries(hrt_ctx *ctx, const HrtRunParams *p, const RunDev &rd, uint32_t flags, cudaStream_t st)
 {
@@ -1605,7 +1610,9 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   }
   S.shadow_queries = S.primary_hits * R;
 
-  if ((flags & HRT_FLAG_RAYSINFO) && p->rays_scat->rays_active && rank == 0) raysinfo_tail_bits(p, tail_dead);
+  memcpy(ctx->tail_dead, tail_dead, 8);
+  /* (a multi-device run sets the tail bits once all devices are done: hrt_internal_raysinfo_tail) */
+  if ((flags & HRT_FLAG_RAYSINFO) && p->rays_scat->rays_active && rank == 0 && !(flags & HRT_FLAG_INTERNAL_NO_TAIL)) raysinfo_tail_bits(p, tail_dead);
 
   if (flags & HRT_FLAG_SUMMARY) { rc = flush_summaries(ctx, p, rd, flags, st); if (rc) goto run_done; }
   if (flags & HRT_FLAG_PATHLIST) { rc = flush_path_list(ctx, p, rd, flags, st); if (rc) goto run_done; }

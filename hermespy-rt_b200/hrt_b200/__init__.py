@@ -116,6 +116,21 @@ def lib() -> C.CDLL:
         L.hrt_closest_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.hrt_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.hrt_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.hrt_multi_destroy.argtypes = [C.c_void_p]
+        L.hrt_multi_last_error.restype = C.c_char_p
+        L.hrt_multi_last_error.argtypes = [C.c_void_p]
+        L.hrt_multi_num_devices.argtypes = [C.c_void_p]
+        L.hrt_multi_ctx.restype = C.c_void_p
+        L.hrt_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+        L.hrt_multi_scene_upload.argtypes = [C.c_void_p, C.POINTER(abi.Scene), C.c_void_p]
+        L.hrt_multi_scene_advance.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        L.hrt_multi_materials_set.argtypes = [C.c_void_p, C.POINTER(MaterialDerived)]
+        L.hrt_multi_get_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
+        L.hrt_multi_run.argtypes = [C.c_void_p, C.POINTER(RunParams)]
+        L.hrt_multi_run_gathered.argtypes = [C.c_void_p, C.POINTER(RunParams), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_void_p), C.c_uint64, C.POINTER(C.c_uint64)]
+        L.hrt_multi_nccl_version.argtypes = [C.c_void_p]
         L.hrt_shard_count.restype = C.c_uint64
         L.hrt_shard_count.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
         L.hrt_shard_path.restype = C.c_uint64
@@ -319,7 +334,7 @@ class Context:
             p.paths, p.paths_capacity = int(path_list_dev[0]), int(path_list_dev[1])
             p.paths_count = C.pointer(n_found)
         p.flags = flags
-        self._check(lib().hrt_run(self._h, C.byref(p)), "hrt_run")
+        self._check(self._run_call(p), "hrt_run")
         if path_list_dev is not None:
             res["paths_found"] = int(n_found.value)
         if path_list is not None:
@@ -328,6 +343,9 @@ class Context:
         res["stats"] = self.stats()
         del keep
         return res
+
+    def _run_call(self, p):
+        return lib().hrt_run(self._h, C.byref(p))
 
     def stats(self) -> dict:
         s = RunStats()
@@ -350,6 +368,91 @@ class Context:
                                            tri.ctypes.data, t.ctypes.data, th.ctypes.data),
                     "hrt_closest_hits")
         return tri, t, th
+
+
+class MultiContext(Context):
+    """Several GPUs of one box behind one call (hrt_multi_*, include/hrt_cuda.h):
+    the job is sharded by ray inside the C library, one host thread per device."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        L = lib()
+        n = 0 if devices is None else len(devices)
+        arr = (C.c_int * max(n, 1))(*(devices or [0]))
+        rc = L.hrt_multi_create(arr if devices is not None else None, n, C.byref(self._h))
+        if rc != 0:
+            raise HrtError(f"hrt_multi_create failed ({rc}): {L.hrt_multi_last_error(None).decode()}")
+        self._scene = None
+        self.num_devices = L.hrt_multi_num_devices(self._h)
+        self.device = None
+
+    def close(self):
+        if self._h:
+            lib().hrt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+        if self._scene is not None:
+            abi.free_scene(self._scene)
+            self._scene = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise HrtError(f"{what} failed ({rc}): {lib().hrt_multi_last_error(self._h).decode()}")
+
+    def load_scene(self, path: str, want_normals: bool = False):
+        L = lib()
+        if self._scene is not None:
+            abi.free_scene(self._scene)
+        if not os.path.exists(path):
+            raise HrtError(f"scene file not found: {path}")
+        self._scene = L.scene_load(path.encode())
+        ntri = sum(self._scene.meshes[m].num_triangles for m in range(self._scene.num_meshes))
+        normals = np.zeros((max(ntri, 1), 3), np.float32) if want_normals else None
+        self._check(L.hrt_multi_scene_upload(self._h, C.byref(self._scene), normals.ctypes.data if want_normals else None),
+                    "hrt_multi_scene_upload")
+        self.num_tris = ntri
+        return normals[:ntri] if want_normals else None
+
+    def set_frequency(self, f_ghz: float):
+        L = lib()
+        tab = (MaterialDerived * 17)()
+        for m in range(self._scene.num_meshes):
+            mi = self._scene.meshes[m].material_index
+            L.hrt_materials_derive(mi, C.c_float(f_ghz), C.byref(tab[mi]))
+        self._check(L.hrt_multi_materials_set(self._h, tab), "hrt_multi_materials_set")
+
+    def advance(self, dt_s: float, rebuild: bool = False):
+        self._check(lib().hrt_multi_scene_advance(self._h, C.c_float(dt_s), int(rebuild)), "hrt_multi_scene_advance")
+
+    def _run_call(self, p):
+        return lib().hrt_multi_run(self._h, C.byref(p))
+
+    def stats(self) -> dict:
+        s = RunStats()
+        self._check(lib().hrt_multi_get_stats(self._h, C.byref(s)), "hrt_multi_get_stats")
+        return s.as_dict()
+
+    def run_gathered(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, pair_ptrs, bounce_ptrs, paths_ptrs=None,
+                     paths_capacity_each=0, shard_block=1 << 16, los=False):
+        """hrt_multi_run_gathered(): device pointers per device (lists of ints); returns per-device path counts."""
+        rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
+        R, T = rx.shape[0], tx.shape[0]
+        rxv = abi.vec3_array(rx_vel, R); txv = abi.vec3_array(tx_vel, T)
+        self.set_frequency(f_ghz)
+        p = RunParams()
+        p.num_rx, p.num_tx, p.num_paths, p.num_bounces = R, T, P, B
+        p.carrier_frequency_GHz = f_ghz
+        p.rx_pos, p.tx_pos, p.rx_vel, p.tx_vel = (a.ctypes.data for a in (rx, tx, rxv, txv))
+        p.shard_block = shard_block
+        n = self.num_devices
+        pa = (C.c_void_p * n)(*pair_ptrs); ba = (C.c_void_p * n)(*bounce_ptrs)
+        la = (C.c_void_p * n)(*paths_ptrs) if paths_ptrs else None
+        counts = (C.c_uint64 * n)()
+        self._check(lib().hrt_multi_run_gathered(self._h, C.byref(p), pa, ba, la, int(paths_capacity_each), counts),
+                    "hrt_multi_run_gathered")
+        return [int(c) for c in counts]
+
+    def nccl_version(self) -> int:
+        return lib().hrt_multi_nccl_version(self._h)
 
 
 # ------------------------------------------------- reference-shaped Python API

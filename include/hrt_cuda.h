@@ -247,6 +247,48 @@ int hrt_fp32_peak(hrt_ctx *ctx, float *tflops_unfused, float *tflops_fma);
 int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_t flags,
                      uint32_t *tri, float *t, float *theta);
 
+/* ------------------------------------------------------------------------
+ * Several GPUs of one box behind one call.
+ * The job is sharded by ray inside the library: device i of n traces the
+ * 65,536-path blocks b = i (mod n) of every transmitter's path range on its
+ * own replica of the scene and BVH, driven by its own host thread; results are
+ * those of hrt_run on one device.  Replaces nothing in the reference (which is
+ * single-threaded): it is how compute_paths() uses a whole 8 x B200 box
+ * (HRT_DEVICES=0,1,...).
+ */
+typedef struct hrt_multi hrt_multi;
+
+/* devices == NULL: devices 0 .. n-1; n <= 0: every device of the box */
+int  hrt_multi_create(const int *devices, int n, hrt_multi **out);
+void hrt_multi_destroy(hrt_multi *m);
+const char *hrt_multi_last_error(const hrt_multi *m);     /* m may be NULL: creation errors */
+int  hrt_multi_num_devices(const hrt_multi *m);
+hrt_ctx *hrt_multi_ctx(hrt_multi *m, int i);              /* the i-th device's context (borrowed) */
+int  hrt_multi_scene_upload(hrt_multi *m, const Scene *scene, Vec3 *normals_out);   /* replicated, built in parallel */
+int  hrt_multi_scene_advance(hrt_multi *m, float dt_s, int rebuild);
+int  hrt_multi_materials_set(hrt_multi *m, const HrtMaterialDerived table[NUM_G_MATERIALS]);
+int  hrt_multi_get_stats(const hrt_multi *m, HrtRunStats *out);   /* counters summed, times = slowest device */
+
+/* One job over all devices, HOST results (every hrt_run flag except the *_DEV
+ * ones; shard_* must be unset).  Dense arrays: each device writes its own
+ * disjoint columns -- no collective.  Summaries / impulse response: ADDED to,
+ * as with hrt_run.  Path list: stored up to its capacity, *paths_count = found. */
+int  hrt_multi_run(hrt_multi *m, const HrtRunParams *p);
+
+/* One job over all devices, DEVICE-RESIDENT results on EVERY device, exchanged
+ * with ncclAllGather over NVLink (ncclCommInitAll, one communicator per device
+ * in this process; NCCL is bound at run time, HRT_E_STATE if it is absent):
+ *   pair_dev[i] / bounce_dev[i]  device memory on device i ([R][T][B] / [T][B]):
+ *                                overwritten with the whole job's tables
+ *   paths_dev[i] (or NULL)       device memory on device i, n * paths_capacity_each
+ *                                records: segment j = device j's valid paths,
+ *                                counts[j] of them (host array [n])
+ * Summary and path-list results only. */
+int  hrt_multi_run_gathered(hrt_multi *m, const HrtRunParams *p,
+                            HrtPairSummary *const *pair_dev, HrtBounceSummary *const *bounce_dev,
+                            HrtPathRecord *const *paths_dev, uint64_t paths_capacity_each, uint64_t *counts);
+int  hrt_multi_nccl_version(const hrt_multi *m);          /* 0 until the gathered entry has run */
+
 #ifdef __cplusplus
 }
 #endif
