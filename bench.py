@@ -426,6 +426,44 @@ def main_gpu(args):
               "rank0": {k: mine[k] for k in ("ms", "ms_scatter", "valid_paths", "triangles", "bvh_build_ms",
                                              "scene_load_upload_bvh_s", "scene_in_smem")}}
 
+    # ---- the same job through ONE C call that shards it over all N GPUs inside the library
+    # (hrt_multi_run / hrt_multi_run_gathered: per-device host threads, ncclCommInitAll +
+    # ncclAllGather in this single process).  Rank 0 drives all devices; the other ranks idle.
+    inlib = None
+    if not os.environ.get("HRT_BENCH_SKIP_INLIB"):
+        sync()
+        if rank == 0:
+            try:
+                devs = list(range(world))
+                with hrt.MultiContext(devs) as mc:
+                    mc.load_scene(SCENE)
+                    mc.run(rx, tx, zr, zt, F_GHZ, P, B, summary=True, shard_block=SHARD_BLOCK)        # warm-up
+                    t0 = time.perf_counter()
+                    n_in = max(1, min(args.steps, 3))
+                    rb_in = 0
+                    for _ in range(n_in):
+                        rr = mc.run(rx, tx, zr, zt, F_GHZ, P, B, summary=True, shard_block=SHARD_BLOCK)
+                        rb_in += rr["stats"]["ray_bounces"]
+                    t_host = (time.perf_counter() - t0) / n_in
+                    pair_t = [torch.zeros(R * T * B * 6, dtype=torch.int64, device=f"cuda:{d}") for d in devs]
+                    bounce_t = [torch.zeros(T * B * 4, dtype=torch.int64, device=f"cuda:{d}") for d in devs]
+                    mc.run_gathered(rx, tx, zr, zt, F_GHZ, P, B, [t.data_ptr() for t in pair_t], [t.data_ptr() for t in bounce_t],
+                                    shard_block=SHARD_BLOCK)
+                    t0 = time.perf_counter()
+                    mc.run_gathered(rx, tx, zr, zt, F_GHZ, P, B, [t.data_ptr() for t in pair_t], [t.data_ptr() for t in bounce_t],
+                                    shard_block=SHARD_BLOCK)
+                    t_gath = time.perf_counter() - t0
+                    nv = [int(t.view(R * T * B, 6)[:, 0].sum().item()) for t in pair_t]
+                    inlib = {"entry": "hrt_multi_run (host summary tables) / hrt_multi_run_gathered (tables on every GPU via ncclAllGather)",
+                             "devices": world, "seconds_per_step_host_results": t_host,
+                             "ray_bounces_per_s_host_results": rb_in / n_in / t_host,
+                             "seconds_per_step_gathered": t_gath, "ray_bounces_per_s_gathered": rb_in / n_in / t_gath,
+                             "valid_paths_on_every_device": nv, "nccl_version": mc.nccl_version()}
+                    del pair_t, bounce_t
+            except Exception as e:                       # never lose the headline line to the extra block
+                inlib = {"error": repr(e)[:300]}
+        sync()
+
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel (k_scatter): counted work / live launch time
@@ -524,7 +562,7 @@ def main_gpu(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "dense_e2e": dense, "c5": c5,
+            "dense_e2e": dense, "c5": c5, "in_library_multi_gpu": inlib,
             "path_list_gather": gather,
             "closest_hit_queries_per_s": (rb_total + shadow_total) / (ms_total * 1e-3),
             "shadow_queries_per_step": shadow_total / args.steps,
