@@ -288,6 +288,9 @@ def main_gpu(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # host-side barrier for phases in which only rank 0 computes: an NCCL barrier would leave a
+    # spinning kernel on the idle ranks' GPUs, time-sliced against rank 0's work on them
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
 
     rx, tx = c4_positions()
     zr, zt = np.zeros_like(rx), np.zeros_like(tx)
@@ -462,6 +465,8 @@ def main_gpu(args):
                     del pair_t, bounce_t
             except Exception as e:                       # never lose the headline line to the extra block
                 inlib = {"error": repr(e)[:300]}
+        if world > 1:
+            dist.barrier(group=cpu_group)                # the other ranks wait here on the CPU, their GPUs idle
         sync()
 
     out = None
