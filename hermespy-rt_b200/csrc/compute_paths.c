@@ -136,12 +136,12 @@ static hrt_multi *prepare(Scene *scene, float carrier_frequency_GHz)
   return ctx;
 }
 
-void compute_paths(
+static void run_dense(
     Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
     float carrier_frequency_GHz,
     size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
     ChannelInfo *chanInfo_los, RaysInfo *raysInfo_los,
-    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat)
+    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat, float *a_te_c64, float *a_tm_c64)
 {
   if (!scene || !chanInfo_scat) die("compute_paths", "NULL scene or scatter output");
   hrt_multi *ctx = prepare(scene, carrier_frequency_GHz);
@@ -155,7 +155,33 @@ void compute_paths(
   if (raysInfo_scat && !getenv("HRT_NO_RAYSINFO")) p.flags |= HRT_FLAG_RAYSINFO;
   p.los = chanInfo_los; p.rays_los = raysInfo_los;
   p.scat = chanInfo_scat; p.rays_scat = raysInfo_scat;
+  if (a_te_c64) { p.flags |= HRT_FLAG_DENSE_C64; p.scat_a_te_c64 = a_te_c64; p.scat_a_tm_c64 = a_tm_c64; }
   if (hrt_multi_run(ctx, &p) != HRT_OK) die("compute_paths failed", hrt_multi_last_error(ctx));
+}
+
+void compute_paths(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    ChannelInfo *chanInfo_los, RaysInfo *raysInfo_los,
+    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat)
+{
+  run_dense(scene, rx_pos, tx_pos, rx_vel, tx_vel, carrier_frequency_GHz, num_rx, num_tx, num_rays, num_bounces,
+            chanInfo_los, raysInfo_los, chanInfo_scat, raysInfo_scat, NULL, NULL);
+}
+
+/* compute_paths() with the scatter gains as interleaved complex64 (include/hrt_cuda.h) */
+void compute_paths_c64(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    ChannelInfo *chanInfo_los, RaysInfo *raysInfo_los,
+    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat,
+    float *a_te_c64, float *a_tm_c64)
+{
+  if (!a_te_c64 || !a_tm_c64) die("compute_paths_c64", "NULL complex output");
+  run_dense(scene, rx_pos, tx_pos, rx_vel, tx_vel, carrier_frequency_GHz, num_rx, num_tx, num_rays, num_bounces,
+            chanInfo_los, raysInfo_los, chanInfo_scat, raysInfo_scat, a_te_c64, a_tm_c64);
 }
 
 /* Streaming consumer of the same path set: instead of

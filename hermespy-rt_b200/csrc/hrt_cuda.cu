@@ -105,6 +105,7 @@ struct RunDev {
   uint32_t *qkey, *qkey_alt; /* [T][n_alloc] Morton code of the hit point, order of the next queue */
   uint32_t *qcount;      /* [B+1][T] queue sizes, then [B][T] k_bounce and [B][T] k_scatter work cursors */
   float *out_f[6];       /* [R][T][B][n_alloc] te_re te_im tm_re tm_im tau freq */
+  uint32_t gain_stride;  /* 1; 2 with HRT_FLAG_DENSE_C64: te_im = te_re + 1 (interleaved complex), likewise tm */
   float *out_dir;        /* [R][T][B][n_alloc][3] */
   uint32_t *tr_hit;      /* [T][B][n_alloc] */
   float *tr_t;
@@ -330,7 +331,9 @@ static void free_run_dev(hrt_ctx *c)
   dev_free(r.dead_at); dev_free(r.queue[0]); dev_free(r.queue[1]);
   dev_free(r.queue_alt); dev_free(r.qkey); dev_free(r.qkey_alt);
   dev_free(r.qcount);
+  if (r.gain_stride == 2) { r.out_f[1] = nullptr; r.out_f[3] = nullptr; }     /* aliases of out_f[0] / out_f[2] */
   for (int k = 0; k < 6; ++k) dev_free(r.out_f[k]);
+  r.gain_stride = 1;
   dev_free(r.out_dir); dev_free(r.tr_hit); dev_free(r.tr_t); dev_free(r.tr_state);
   dev_free(r.pair); dev_free(r.bounce); dev_free(r.amb_list); dev_free(r.amb_count);
   dev_free(r.dkey); dev_free(r.dkey2); dev_free(r.perm); dev_free(r.perm2);
@@ -936,7 +939,7 @@ extern "C" int hrt_closest_hits(hrt_ctx *ctx, const Ray *rays, size_t n, uint32_
 
 static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t B, uint32_t flags)
 {
-  const uint32_t shape_flags = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_TRACE);   /* the flags that own buffers */
+  const uint32_t shape_flags = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_TRACE | HRT_FLAG_DENSE_C64);   /* the flags that own buffers */
   if (ctx->cap_n >= n && ctx->cap_R == R && ctx->cap_T == T && ctx->cap_B == B && ctx->cap_flags == shape_flags)
     return HRT_OK;
   free_run_dev(ctx);
@@ -952,7 +955,13 @@ static int ensure_run_buffers(hrt_ctx *ctx, size_t n, size_t R, size_t T, size_t
   CK(dev_alloc(&r.counters, 16));
   const size_t slots = R * T * B * n;
   if (flags & HRT_FLAG_DENSE) {
-    for (int k = 0; k < 6; ++k) CK(dev_alloc(&r.out_f[k], slots));
+    if (flags & HRT_FLAG_DENSE_C64) {
+      CK(dev_alloc(&r.out_f[0], slots * 2)); CK(dev_alloc(&r.out_f[2], slots * 2));
+      r.out_f[1] = r.out_f[0] + 1; r.out_f[3] = r.out_f[2] + 1; r.gain_stride = 2;
+      CK(dev_alloc(&r.out_f[4], slots)); CK(dev_alloc(&r.out_f[5], slots));
+    } else {
+      for (int k = 0; k < 6; ++k) CK(dev_alloc(&r.out_f[k], slots));
+    }
     CK(dev_alloc(&r.out_dir, slots * 3));
   }
   if (flags & HRT_FLAG_TRACE) {
@@ -1248,6 +1257,8 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   uint32_t flags = p->flags;
   if ((flags & HRT_FLAG_RAYSINFO) && !(flags & HRT_FLAG_DENSE)) return fail(ctx, HRT_E_ARG, "RAYSINFO needs DENSE");
   if ((flags & HRT_FLAG_DENSE) && !p->scat) return fail(ctx, HRT_E_ARG, "DENSE needs scat outputs");
+  if ((flags & HRT_FLAG_DENSE_C64) && (!(flags & HRT_FLAG_DENSE) || !p->scat_a_te_c64 || !p->scat_a_tm_c64))
+    return fail(ctx, HRT_E_ARG, "DENSE_C64 needs DENSE and both complex arrays");
   if ((flags & HRT_FLAG_RAYSINFO) && !p->rays_scat) flags &= ~HRT_FLAG_RAYSINFO;
   if ((flags & HRT_FLAG_SUMMARY) && (!p->pair_summary || !p->bounce_summary)) return fail(ctx, HRT_E_ARG, "SUMMARY needs both summary arrays");
   if ((flags & HRT_FLAG_HOST_DIRS) && !p->dirs) return fail(ctx, HRT_E_ARG, "HOST_DIRS needs dirs");
@@ -1278,7 +1289,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   const uint64_t n_shard = shard_count(P, rank, world, blk);
   size_t chunk = 1u << 23;
   if (const char *s = getenv("HRT_CHUNK")) { long long v = atoll(s); if (v >= 32) chunk = (size_t)v; }
-  const uint32_t shape_flags_now = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_TRACE);
+  const uint32_t shape_flags_now = flags & (HRT_FLAG_DENSE | HRT_FLAG_RAYSINFO | HRT_FLAG_TRACE | HRT_FLAG_DENSE_C64);
   const bool buffers_fit = ctx->cap_n && ctx->cap_R == R && ctx->cap_T == T && ctx->cap_B == B && ctx->cap_flags == shape_flags_now;
   if (buffers_fit && ctx->cap_n >= (n_shard < chunk ? n_shard : chunk)) {
     /* the buffers of the previous run already hold a full chunk of this shape: no memory query */
@@ -1548,6 +1559,11 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     if (flags & HRT_FLAG_DENSE) {
       ChannelInfo *O = p->scat;
       float *dst[6] = { O->a_te_re, O->a_te_im, O->a_tm_re, O->a_tm_im, O->tau, O->freq_shift };
+      if (flags & HRT_FLAG_DENSE_C64) {
+        CKR(d2h_columns(ctx, tiles, p->scat_a_te_c64, rd.out_f[0], 8, R * T * B, rd));
+        CKR(d2h_columns(ctx, tiles, p->scat_a_tm_c64, rd.out_f[2], 8, R * T * B, rd));
+        dst[0] = dst[1] = dst[2] = dst[3] = nullptr;
+      }
       for (int k = 0; k < 6; ++k) CKR(d2h_columns(ctx, tiles, dst[k], rd.out_f[k], 4, R * T * B, rd));
       CKR(d2h_columns(ctx, tiles, O->directions_rx, rd.out_dir, 12, R * T * B, rd));
     }

@@ -348,7 +348,8 @@ __global__ void k_init(RunDev rd)
           base = HRT_MUL(base, rd.k.dop_k);
           for (uint32_t r = 0; r < R; ++r) {
             const size_t s = ((size_t)(r * T + t) * B + b) * np + l;
-            rd.out_f[0][s] = 0.f; rd.out_f[1][s] = 0.f; rd.out_f[2][s] = 0.f; rd.out_f[3][s] = 0.f;
+            const size_t gs = s * rd.gain_stride;
+            rd.out_f[0][gs] = 0.f; rd.out_f[1][gs] = 0.f; rd.out_f[2][gs] = 0.f; rd.out_f[3][gs] = 0.f;
             rd.out_f[4][s] = 0.f; rd.out_f[5][s] = base;
             rd.out_dir[3 * s] = 0.f; rd.out_dir[3 * s + 1] = 0.f; rd.out_dir[3 * s + 2] = 0.f;
             if (rd.flags & HRT_FLAG_TRACE) rd.tr_state[s] = 0;
@@ -612,8 +613,9 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       if (act && (dense || trace)) {
         const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;          /* :674 */
         if (dense) {
-          rd.out_f[0][so] = p.te_r; rd.out_f[1][so] = p.te_i;                  /* zeros when occluded, :685-689 */
-          rd.out_f[2][so] = p.tm_r; rd.out_f[3][so] = p.tm_i;
+          const size_t gs = so * rd.gain_stride;                               /* 2: interleaved complex64 */
+          rd.out_f[0][gs] = p.te_r; rd.out_f[1][gs] = p.te_i;                  /* zeros when occluded, :685-689 */
+          rd.out_f[2][gs] = p.tm_r; rd.out_f[3][gs] = p.tm_i;
           rd.out_f[4][so] = p.tau;
           if (ok) {
             rd.out_f[5][so] = HRT_SUB(rd.out_f[5][so], p.dfreq);               /* :722 */

@@ -63,6 +63,7 @@ class RunParams(C.Structure):
         ("dirs", C.c_void_p), ("stream", C.c_void_p),
         ("cir", C.c_void_p), ("cir_tau0_s", C.c_float), ("cir_dt_s", C.c_float), ("cir_bins", C.c_uint32),
         ("paths", C.c_void_p), ("paths_capacity", C.c_uint64), ("paths_count", C.POINTER(C.c_uint64)),
+        ("scat_a_te_c64", C.c_void_p), ("scat_a_tm_c64", C.c_void_p),
     ]
 
 

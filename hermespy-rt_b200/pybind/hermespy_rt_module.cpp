@@ -6,20 +6,26 @@
 //
 // Differences from the reference binding, all of them fixes it needs anyway
 // (SURVEY section 8 row f1): the C headers are wrapped in extern "C" (the
-// reference module does not import on Linux), inputs are converted to
-// C-contiguous float32 and their shapes checked, outputs are zero-initialised
-// numpy arrays owned by Python (no leaks, no uninitialised slots), complex
-// gains are assembled once, RaysInfo is not materialised (the reference
-// computes and discards it, :172-176) and the GIL is released while the GPU
-// works.
+// reference module does not import on Linux); inputs are converted to
+// C-contiguous float32 and must have shape (n, 3); outputs are zero-initialised
+// numpy arrays owned by Python (no leaks, no uninitialised slots); the complex
+// gains are written by the device straight into the complex64 arrays Python
+// receives (compute_paths_c64: no re / im repack loop, :22-42); the scene file is
+// parsed once per (path, size, mtime) and the uploaded scene + BVH are reused
+// across calls (the reference re-reads the file on every call, :119); RaysInfo
+// is not materialised (the reference computes and discards it, :172-176); the
+// GIL is released while the GPU works.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 
+#include <sys/stat.h>
+
 #include <complex>
+#include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
-#include <cstring>
 
 #include "../../include/hrt_cuda.h"   // extern "C" inside
 
@@ -36,10 +42,31 @@ struct Channel {
 
 const Vec3 *as_vec3(const farr &a, size_t n, const char *what)
 {
-  if (a.size() != (py::ssize_t)(3 * n))
-    throw std::invalid_argument(std::string(what) + ": expected " + std::to_string(n) + " x 3 values");
+  if (a.ndim() != 2 || a.shape(0) != (py::ssize_t)n || a.shape(1) != 3)
+    throw std::invalid_argument(std::string(what) + ": expected an array of shape (" + std::to_string(n) + ", 3)");
   return reinterpret_cast<const Vec3 *>(a.data());
 }
+
+// The scene of the last call, kept parsed while the file is unchanged; the
+// library in turn keeps the uploaded copy and its BVH while the content is the
+// same (csrc/compute_paths.c).  One call at a time uses it (the implicit
+// context of compute_paths() is not re-entrant, like the reference).
+struct SceneCache {
+  std::mutex mu;
+  std::string path; off_t size = -1; time_t mtime_s = 0; long mtime_ns = 0;
+  Scene scene{}; bool loaded = false;
+  Scene *get(const std::string &p)
+  {
+    struct stat st;
+    if (stat(p.c_str(), &st) != 0) throw std::runtime_error("hermespy_rt: cannot open scene file " + p);
+    if (loaded && p == path && st.st_size == size && st.st_mtim.tv_sec == mtime_s && st.st_mtim.tv_nsec == mtime_ns) return &scene;
+    if (loaded) { free_scene(&scene); loaded = false; }
+    scene = scene_load(p.c_str());
+    path = p; size = st.st_size; mtime_s = st.st_mtim.tv_sec; mtime_ns = st.st_mtim.tv_nsec; loaded = true;
+    return &scene;
+  }
+};
+SceneCache g_scene_cache;
 
 py::array_t<float> zeros(std::vector<py::ssize_t> shape)
 {
@@ -60,12 +87,10 @@ Channel make_channel(size_t R, size_t T, size_t n)
   return c;
 }
 
-py::array_t<std::complex<float>> join(const std::vector<float> &re, const std::vector<float> &im,
-                                      size_t R, size_t T, size_t n)
+py::array_t<std::complex<float>> czeros(size_t R, size_t T, size_t n)
 {
   py::array_t<std::complex<float>> a({(py::ssize_t)R, (py::ssize_t)T, (py::ssize_t)n});
-  auto *p = a.mutable_data();
-  for (size_t i = 0; i < re.size(); ++i) p[i] = std::complex<float>(re[i], im[i]);
+  std::fill_n(a.mutable_data(), a.size(), std::complex<float>(0.f, 0.f));
   return a;
 }
 
@@ -82,32 +107,32 @@ std::pair<Channel, Channel> compute_paths_py(const std::string &mesh_filepath, f
   const Vec3 *txv = as_vec3(tx_velocities, num_tx, "tx_velocities");
   if (hrt_device_count() <= 0)
     throw std::runtime_error("hermespy_rt: no CUDA device available (this build has no CPU path)");
-  if (FILE *f = fopen(mesh_filepath.c_str(), "rb")) fclose(f);
-  else throw std::runtime_error("hermespy_rt: cannot open scene file " + mesh_filepath);
 
-  const size_t nl = num_rx * num_tx, ns = nl * num_bounces * num_paths;
+  const size_t nl = num_rx * num_tx;
   Channel los = make_channel(num_rx, num_tx, 1), sc = make_channel(num_rx, num_tx, num_bounces * num_paths);
-  std::vector<float> l_re[2], l_im[2], s_re[2], s_im[2];
-  for (int k = 0; k < 2; ++k) { l_re[k].assign(nl, 0.f); l_im[k].assign(nl, 0.f); s_re[k].assign(ns, 0.f); s_im[k].assign(ns, 0.f); }
+  los.a_te = czeros(num_rx, num_tx, 1); los.a_tm = czeros(num_rx, num_tx, 1);
+  sc.a_te = czeros(num_rx, num_tx, num_bounces * num_paths); sc.a_tm = czeros(num_rx, num_tx, num_bounces * num_paths);
+  std::vector<float> l_re[2], l_im[2];
+  for (int k = 0; k < 2; ++k) { l_re[k].assign(nl, 0.f); l_im[k].assign(nl, 0.f); }
 
   ChannelInfo ci_los = { 1, (Vec3 *)los.directions_rx.mutable_data(), (Vec3 *)los.directions_tx.mutable_data(),
                          l_re[0].data(), l_im[0].data(), l_re[1].data(), l_im[1].data(),
                          los.tau.mutable_data(), los.freq_shift.mutable_data() };
   ChannelInfo ci_sc = { (uint32_t)(num_bounces * num_paths), (Vec3 *)sc.directions_rx.mutable_data(),
-                        (Vec3 *)sc.directions_tx.mutable_data(),
-                        s_re[0].data(), s_im[0].data(), s_re[1].data(), s_im[1].data(),
+                        (Vec3 *)sc.directions_tx.mutable_data(), nullptr, nullptr, nullptr, nullptr,
                         sc.tau.mutable_data(), sc.freq_shift.mutable_data() };
+  float *te = reinterpret_cast<float *>(sc.a_te.mutable_data()), *tm = reinterpret_cast<float *>(sc.a_tm.mutable_data());
   {
     py::gil_scoped_release nogil;
-    Scene scene = scene_load(mesh_filepath.c_str());
-    compute_paths(&scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency,
-                  num_rx, num_tx, num_paths, num_bounces, &ci_los, nullptr, &ci_sc, nullptr);
-    free_scene(&scene);
+    std::lock_guard<std::mutex> lk(g_scene_cache.mu);
+    Scene *scene = g_scene_cache.get(mesh_filepath);
+    compute_paths_c64(scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency,
+                      num_rx, num_tx, num_paths, num_bounces, &ci_los, nullptr, &ci_sc, nullptr, te, tm);
   }
-  los.a_te = join(l_re[0], l_im[0], num_rx, num_tx, 1);
-  los.a_tm = join(l_re[1], l_im[1], num_rx, num_tx, 1);
-  sc.a_te = join(s_re[0], s_im[0], num_rx, num_tx, num_bounces * num_paths);
-  sc.a_tm = join(s_re[1], s_im[1], num_rx, num_tx, num_bounces * num_paths);
+  for (size_t k = 0; k < nl; ++k) {                        // num_rx * num_tx line-of-sight values
+    los.a_te.mutable_data()[k] = std::complex<float>(l_re[0][k], l_im[0][k]);
+    los.a_tm.mutable_data()[k] = std::complex<float>(l_re[1][k], l_im[1][k]);
+  }
   return {std::move(los), std::move(sc)};
 }
 
@@ -127,16 +152,14 @@ compute_cir_py(const std::string &mesh_filepath, farr rx_positions, farr tx_posi
   const Vec3 *txv = as_vec3(tx_velocities, num_tx, "tx_velocities");
   if (hrt_device_count() <= 0)
     throw std::runtime_error("hermespy_rt: no CUDA device available (this build has no CPU path)");
-  if (FILE *f = fopen(mesh_filepath.c_str(), "rb")) fclose(f);
-  else throw std::runtime_error("hermespy_rt: cannot open scene file " + mesh_filepath);
   py::array_t<std::complex<float>> cir({(py::ssize_t)num_rx, (py::ssize_t)num_tx, (py::ssize_t)num_bins, (py::ssize_t)2});
   size_t dropped = 0;
   {
     py::gil_scoped_release nogil;
-    Scene scene = scene_load(mesh_filepath.c_str());
-    dropped = compute_cir(&scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency, num_rx, num_tx,
+    std::lock_guard<std::mutex> lk(g_scene_cache.mu);
+    Scene *scene = g_scene_cache.get(mesh_filepath);
+    dropped = compute_cir(scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency, num_rx, num_tx,
                           num_paths, num_bounces, tau0, dt, num_bins, reinterpret_cast<float *>(cir.mutable_data()));
-    free_scene(&scene);
   }
   return {std::move(cir), dropped};
 }
@@ -156,16 +179,14 @@ compute_path_list_py(const std::string &mesh_filepath, farr rx_positions, farr t
   const Vec3 *txv = as_vec3(tx_velocities, num_tx, "tx_velocities");
   if (hrt_device_count() <= 0)
     throw std::runtime_error("hermespy_rt: no CUDA device available (this build has no CPU path)");
-  if (FILE *f = fopen(mesh_filepath.c_str(), "rb")) fclose(f);
-  else throw std::runtime_error("hermespy_rt: cannot open scene file " + mesh_filepath);
   std::vector<HrtPathRecord> buf(capacity);
   size_t found = 0;
   {
     py::gil_scoped_release nogil;
-    Scene scene = scene_load(mesh_filepath.c_str());
-    found = compute_path_list(&scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency, num_rx, num_tx,
+    std::lock_guard<std::mutex> lk(g_scene_cache.mu);
+    Scene *scene = g_scene_cache.get(mesh_filepath);
+    found = compute_path_list(scene, (Vec3 *)rx, (Vec3 *)tx, (Vec3 *)rxv, (Vec3 *)txv, carrier_frequency, num_rx, num_tx,
                               num_paths, num_bounces, buf.data(), capacity);
-    free_scene(&scene);
   }
   const size_t kept = found < capacity ? found : capacity;
   py::list fields;

@@ -64,6 +64,8 @@ typedef struct {
 #define HRT_FLAG_COUNT        0x80u  /* instrumented kernels: count box/triangle tests   */
 #define HRT_FLAG_CIR         0x100u  /* accumulate the delay-binned impulse response    */
 #define HRT_FLAG_PATHLIST    0x200u  /* emit the valid scatter paths as a compact list  */
+#define HRT_FLAG_DENSE_C64   0x800u  /* with DENSE: scatter gains as interleaved complex64 (scat_a_te_c64 /
+                                       scat_a_tm_c64) instead of the four re / im arrays of `scat` */
 #define HRT_FLAG_PATHLIST_DEV 0x400u /* ... into DEVICE memory (`paths`), e.g. a buffer
                                         that NCCL gathers next; paths_count stays host */
 
@@ -159,6 +161,13 @@ typedef struct {
   HrtPathRecord *paths;
   uint64_t       paths_capacity;
   uint64_t      *paths_count;
+
+  /* HRT_FLAG_DENSE_C64: [num_rx][num_tx][num_bounces][num_paths] complex64 each, as
+   * (re, im) float pairs -- what numpy / the reference's Python ChannelInfo hold
+   * (compute_paths_pybind11.cpp:22-42 repacks re / im arrays into these on the
+   * host; here the device writes them directly).  scat->a_*_re / _im are then
+   * not touched and may be NULL. */
+  float         *scat_a_te_c64, *scat_a_tm_c64;
 } HrtRunParams;
 
 /* Counters and timings of the last hrt_run on a context. */
@@ -223,6 +232,20 @@ int hrt_run(hrt_ctx *ctx, const HrtRunParams *p);
 /* One-call form of the path-list mode on the implicit context of compute_paths()
  * (hermespy-rt_b200/csrc/compute_paths.c): compute_paths' arguments, then the
  * caller's record buffer.  Returns the number of valid scatter paths found. */
+/* compute_paths() with the scatter gains delivered as interleaved complex64
+ * arrays (a_te_c64 / a_tm_c64: [num_rx][num_tx][num_bounces * num_rays] pairs of
+ * floats): the layout of the reference's Python ChannelInfo.a_te / a_tm, written
+ * by the device instead of being repacked on the host
+ * (compute_paths_pybind11.cpp:22-42).  chanInfo_scat's a_*_re / a_*_im members are
+ * ignored; everything else is as in compute_paths().  raysInfo_* may be NULL. */
+void compute_paths_c64(
+    Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
+    float carrier_frequency_GHz,
+    size_t num_rx, size_t num_tx, size_t num_rays, size_t num_bounces,
+    ChannelInfo *chanInfo_los, RaysInfo *raysInfo_los,
+    ChannelInfo *chanInfo_scat, RaysInfo *raysInfo_scat,
+    float *a_te_c64, float *a_tm_c64);
+
 size_t compute_path_list(
     Scene *scene, Vec3 *rx_pos, Vec3 *tx_pos, Vec3 *rx_vel, Vec3 *tx_vel,
     float carrier_frequency_GHz,

@@ -839,3 +839,56 @@ def test_grazing_rays_gpu(ctx, scene):
     tri_g, t_g, _ = ctx.closest_hits(rays)
     assert np.array_equal(tri_o, tri_g) and np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32))
     ctx.load_scene(tl.scene_path("simple_street_canyon_with_cars"))
+
+
+def test_complex64_entry_and_scene_cache(tmp_path):
+    """compute_paths_c64 (complex gains written by the device as
+    interleaved complex64, no host repack) == compute_paths' re / im arrays bit for
+    bit; repeated calls on one Scene reuse the uploaded scene (same results, Mesh.ns
+    replaced not leaked); the pybind module checks shapes and survives a rewritten
+    scene file (cache keyed by path, size and mtime)."""
+    import ctypes as C
+    import shutil
+    scene, rx, tx, f = tl.CONFIGS["canyon_moving"]
+    rx = list(rx) + [[20.0, 2.0, 1.5]]
+    rxv, txv = [[0.5, -1.0, 0.25], [0, 0, 0]], [[3.0, 1.0, -0.5]]
+    P, B = 20000, 4
+    L = hrt.lib()
+    L.compute_paths_c64.restype = None
+    sc = L.scene_load(tl.scene_path(scene).encode())
+    try:
+        o = abi.call_compute_paths(L, sc, rx, tx, rxv, txv, f, P, B, fill=0)
+        first_ns = C.cast(sc.meshes[0].ns, C.c_void_p).value
+        o2 = abi.alloc_outputs(2, 1, P, B, 0x5A)
+        te = np.zeros((2, 1, B, P), np.complex64); tm = np.zeros((2, 1, B, P), np.complex64)
+        rxa, txa = abi.vec3_array(rx), abi.vec3_array(tx)
+        rva, tva = abi.vec3_array(rxv, 2), abi.vec3_array(txv, 1)
+        los = abi.chan_struct(o2.los, 1); scs = abi.chan_struct(o2.scat, B * P)
+        scs.a_te_re = scs.a_te_im = scs.a_tm_re = scs.a_tm_im = None
+        L.compute_paths_c64(C.byref(sc), C.c_void_p(rxa.ctypes.data), C.c_void_p(txa.ctypes.data), C.c_void_p(rva.ctypes.data),
+                            C.c_void_p(tva.ctypes.data), C.c_float(f), C.c_size_t(2), C.c_size_t(1), C.c_size_t(P), C.c_size_t(B),
+                            C.byref(los), None, C.byref(scs), None, C.c_void_p(te.ctypes.data), C.c_void_p(tm.ctypes.data))
+        assert bool(sc.meshes[0].ns)
+    finally:
+        abi.free_scene(sc)
+    assert np.array_equal(te.real.view(np.uint32), o.scat["a_te_re"].view(np.uint32))
+    assert np.array_equal(te.imag.view(np.uint32), o.scat["a_te_im"].view(np.uint32))
+    assert np.array_equal(tm.real.view(np.uint32), o.scat["a_tm_re"].view(np.uint32))
+    assert np.array_equal(tm.imag.view(np.uint32), o.scat["a_tm_im"].view(np.uint32))
+    assert np.array_equal(o2.scat["tau"].view(np.uint32), o.scat["tau"].view(np.uint32))
+    assert (np.abs(te) > 0).sum() > 10000
+    # the Python module: shape checks, cache across calls, cache invalidation by file identity
+    import hermespy_rt as rt
+    path = str(tmp_path / "scene.hrt")
+    shutil.copy(tl.scene_path("box"), path)
+    args = (np.array([[-3.0, 1.5, 1.0]]), np.array([[1.0, -2.0, 2.5]]), np.zeros((1, 3)), np.zeros((1, 3)), 3.0, 1, 1, 5000, 2)
+    with pytest.raises(ValueError):
+        rt.compute_paths(path, np.zeros((3, 1)), *args[1:])
+    a1 = rt.compute_paths(path, *args)[1]
+    a2 = rt.compute_paths(path, *args)[1]
+    assert np.array_equal(a1.a_te.view(np.uint64), a2.a_te.view(np.uint64)) and np.array_equal(a1.tau, a2.tau)
+    assert a1.a_te.dtype == np.complex64 and a1.a_te.shape == (1, 1, 10000)
+    shutil.copy(tl.scene_path("simple_reflector"), path)
+    os_ = __import__("os"); os_.utime(path, None)
+    b1 = rt.compute_paths(path, np.array([[0.0, 0.0, 0.15]]), np.array([[0.0, 0.0, 0.151]]), *args[2:])[1]
+    assert not np.array_equal(a1.tau, b1.tau) and int((b1.tau > 0).sum()) > 1000
