@@ -112,7 +112,7 @@ def launch_shares(csv_path, out_path):
 
 
 for rep, kern, tag in (("prof_scatter.ncu-rep", os.environ.get("HRT_PROF_KERNEL", "_Z9k_scatterILb1ELb0ELb0ELb0ELb1ELb1EE"), "k_scatter"),
-                       ("prof_c5.ncu-rep", "_Z9k_scatterILb0ELb0ELb0ELb0ELb1EE", "k_scatter_c5")):
+                       ("prof_c5.ncu-rep", "_Z9k_scatterILb0ELb0ELb0ELb0ELb1ELb0EE", "k_scatter_c5")):
     p = os.path.join(G, rep)
     if not os.path.exists(p): continue
     open(os.path.join(OUT, f"{tag}_ncu_metrics.txt"), "w").write(sh([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), p]))
@@ -138,7 +138,7 @@ for rep, kern, tag in (("prof_scatter.ncu-rep", os.environ.get("HRT_PROF_KERNEL"
 if os.path.exists(os.path.join(G, "launches.csv")):
     shutil.copy(os.path.join(G, "launches.csv"), os.path.join(OUT, "launches.csv"))
     launch_shares(os.path.join(G, "launches.csv"), os.path.join(OUT, "launch_shares.txt"))
-for f in ("bench_full.json", "bench_ref.json", "bench_small.json", "pytest_gpu.log", "smoke.log", "c5_shard.json", "dense.json",
+for f in ("bench_full.json", "bench_ref.json", "bench_small.json", "pytest_gpu.log", "smoke.log", "c5_shard.json", "dense.json", "fp_ops.csv", "fp_ops_bvh.csv",
           "bench_n2.json", "bench_n4.json", "bench_n8.json", "gpu.txt", "c5_full.json"):
     if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(OUT, f))
 print("wrote", OUT, sorted(os.listdir(OUT)))

@@ -15,7 +15,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 
 tail -3 $OUT/smoke.log
 
 echo "== bench small (4e6 rays)"
-HRT_BENCH_RAYS=4e6 HRT_REF_PATHS=200 timeout 600 python bench.py --steps 2 --warmup 1 > $OUT/bench_small.json 2> $OUT/bench_small.err; echo "rc=$?"
+HRT_BENCH_RAYS=4e6 HRT_REF_PATHS=200 HRT_BENCH_SKIP_DENSE=1 HRT_BENCH_SKIP_C5=1 timeout 600 python bench.py --steps 2 --warmup 1 > $OUT/bench_small.json 2> $OUT/bench_small.err; echo "rc=$?"
 cat $OUT/bench_small.json | cut -c1-1500; tail -5 $OUT/bench_small.err
 
 if [ "${FULL:-1}" = "1" ]; then
@@ -33,11 +33,17 @@ python scripts/run_c5.py 6.25e7 1024 256 65536 > $OUT/c5_shard.json 2> $OUT/c5.e
 
 if [ "${NCU:-1}" = "1" ]; then
 echo "== ncu launch list"
-export HRT_BENCH_RAYS=8e6 HRT_REF_PATHS=100
+export HRT_BENCH_RAYS=8e6 HRT_REF_PATHS=100 HRT_BENCH_SKIP_DENSE=1 HRT_BENCH_SKIP_C5=1 HRT_BENCH_SKIP_INLIB=1 HRT_BENCH_SKIP_BVH_MODE=1
 python bench.py --steps 1 --warmup 0 > $OUT/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 0 > $OUT/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
+# SURVEY 8(d) cross-check: executed fp32 operations of k_scatter (ffma counts 2 flops), receiver maps and BVH mode
+ncu --metrics smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,gpu__time_duration.sum \
+    --clock-control none -k regex:k_scatter -c 5 --csv --log-file $OUT/fp_ops.csv python bench.py --steps 1 --warmup 0 > $OUT/ncu_fp.log 2>&1
+HRT_RXMAP=0 ncu --metrics smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,gpu__time_duration.sum \
+    --clock-control none -k regex:k_scatter -c 5 --csv --log-file $OUT/fp_ops_bvh.csv python bench.py --steps 1 --warmup 0 > $OUT/ncu_fp_bvh.log 2>&1
+echo "ncu fp ops rc=$?"
 python bench.py --steps 1 --warmup 0 > $OUT/ncu_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_scatter -s 1 -c 2 -f -o $OUT/prof_scatter \
     python bench.py --steps 1 --warmup 0 > $OUT/ncu_full.log 2>&1
