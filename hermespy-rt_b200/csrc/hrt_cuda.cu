@@ -35,6 +35,7 @@
 #include "../../include/hrt_cuda.h"
 #include "hrt_bvh.cuh"
 #include "hrt_rxmap.cuh"
+#include "hrt_ext.cuh"
 
 /* host C helpers (host_math.c): glibc double trig, as the reference uses */
 extern "C" void hrt_host_launch_dir(uint64_t path, uint64_t num_paths, float out[3]);
@@ -43,6 +44,10 @@ static_assert(sizeof(HrtMaterialDerived) == sizeof(HrtMaterial), "material ABI")
 static_assert(sizeof(Ray) == 24 && sizeof(Vec3) == 12, "reference ABI");
 static_assert(sizeof(HrtPairSummary) == 48 && sizeof(HrtBounceSummary) == 32, "summary ABI");
 static_assert(sizeof(HrtPathRecord) == 48, "path record ABI");
+static_assert(sizeof(HrtRefractRecord) == 48, "refraction record ABI");
+
+/* raw scattering parameters of g_materials for the opt-in extensions (hrt_ext.cuh) */
+__constant__ HrtExtTable c_ext;
 
 #ifndef HRT_BLOCK
 #define HRT_BLOCK 512   /* 2 blocks of 512 threads per SM: 64 registers, ~85 KB shared memory each */
@@ -122,6 +127,8 @@ struct RunDev {
   uint32_t cir_bins;
   uint32_t flags;
   RxMapDev map;          /* k_scatter<..., MAP>: receiver maps of this run's receivers */
+  float4 *refr;          /* [refr_cap][3] HrtRefractRecord, HRT_FLAG_EXT_REFRACT (count: counters[13]) */
+  unsigned long long refr_cap;
 };
 
 /* global path index of shard-local index L (blocks dealt round-robin) */
@@ -241,6 +248,7 @@ struct hrt_ctx {
   void *d_los;             /* HrtLosOut[R*T] */
   size_t cap_los;
   float *d_cir; size_t cap_cir;
+  float4 *d_refr; size_t cap_refr;
   float4 *d_plist; size_t cap_plist;
   HostPool *pool; char *stage[2]; cudaEvent_t stage_ev[2];
   float *h_patch; float *d_patch;     /* pinned / device staging of host-recomputed launch directions */
@@ -354,6 +362,7 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   if (c->d_los) { cudaFree(c->d_los); c->d_los = nullptr; }
   if (c->d_cir) { cudaFree(c->d_cir); c->d_cir = nullptr; }
   if (c->d_plist) { cudaFree(c->d_plist); c->d_plist = nullptr; }
+  if (c->d_refr) { cudaFree(c->d_refr); c->d_refr = nullptr; }
   delete c->pool; c->pool = nullptr;
   for (int k = 0; k < 2; ++k) if (c->stage[k]) { cudaFreeHost(c->stage[k]); cudaEventDestroy(c->stage_ev[k]); c->stage[k] = nullptr; }
   if (c->sort_tmp) { cudaFree(c->sort_tmp); c->sort_tmp = nullptr; }
@@ -1343,7 +1352,17 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   if (const char *m = getenv("HRT_SCATTER_MODE")) warp_mode = (m[0] == 'w') && R >= 2;
   const bool count = (flags & HRT_FLAG_COUNT) != 0 && !brute;
   const BounceFn f_bounce = bounce_fn(smem, brute, count);
-  const bool lean = !brute && !count && !(flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE | HRT_FLAG_CIR | HRT_FLAG_PATHLIST));
+  const bool lean = !brute && !count && !(flags & (HRT_FLAG_DENSE | HRT_FLAG_TRACE | HRT_FLAG_CIR | HRT_FLAG_PATHLIST | HRT_FLAG_EXT_LOBES));
+  if ((flags & HRT_FLAG_EXT_REFRACT) && (!p->refr_rays || !p->refr_capacity || !p->refr_count)) return fail(ctx, HRT_E_ARG, "EXT_REFRACT needs refr_rays, refr_capacity and refr_count");
+  if (flags & (HRT_FLAG_EXT_LOBES | HRT_FLAG_EXT_REFRACT)) {
+    HrtExtTable ext;
+    for (int i = 0; i < NUM_G_MATERIALS; ++i) {
+      ext.m[i].s1 = g_materials[i].s1; ext.m[i].s2 = g_materials[i].s2; ext.m[i].s3 = g_materials[i].s3;
+      ext.m[i].a1 = g_materials[i].s1_alpha; ext.m[i].a3 = g_materials[i].s3_alpha;
+    }
+    CK(cudaMemcpyToSymbolAsync(c_ext, &ext, sizeof ext, 0, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                 /* `ext` is a stack temporary */
+  }
   if ((flags & HRT_FLAG_PATHLIST_DEV) && !(flags & HRT_FLAG_PATHLIST)) return fail(ctx, HRT_E_ARG, "PATHLIST_DEV needs PATHLIST");
   /* receiver maps instead of the tree walk for the shadow queries: scenes that live in
    * shared memory, enough receivers for the build (a few ms) to pay off */
@@ -1384,6 +1403,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       rd.plist = ctx->d_plist;
     }
     rd.plist_cap = p->paths_capacity;
+  }
+  rd.refr = nullptr; rd.refr_cap = 0;
+  if (flags & HRT_FLAG_EXT_REFRACT) {
+    if (ctx->cap_refr < p->refr_capacity) {
+      if (ctx->d_refr) cudaFree(ctx->d_refr);
+      ctx->d_refr = nullptr; ctx->cap_refr = 0;
+      CK(dev_alloc(&ctx->d_refr, (size_t)p->refr_capacity * 3)); ctx->cap_refr = p->refr_capacity;
+    }
+    rd.refr = ctx->d_refr; rd.refr_cap = p->refr_capacity;
   }
   if (flags & HRT_FLAG_CIR) {
     const size_t ncir = R * T * (size_t)p->cir_bins * 4;
@@ -1633,6 +1661,15 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   if (flags & HRT_FLAG_SUMMARY) { rc = flush_summaries(ctx, p, rd, flags, st); if (rc) goto run_done; }
   if (flags & HRT_FLAG_PATHLIST) { rc = flush_path_list(ctx, p, rd, flags, st); if (rc) goto run_done; }
   if (flags & HRT_FLAG_CIR) { rc = flush_cir(ctx, p, rd, rank, st); if (rc) goto run_done; }
+  if (flags & HRT_FLAG_EXT_REFRACT) {
+    unsigned long long found = 0;
+    CKR(cudaMemcpyAsync(&found, rd.counters + 13, 8, cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    const unsigned long long kept = found < p->refr_capacity ? found : p->refr_capacity;
+    CKR(cudaMemcpyAsync(p->refr_rays, ctx->d_refr, (size_t)kept * sizeof(HrtRefractRecord), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    *p->refr_count = found;
+  }
 
   if (count) {
     unsigned long long hc[16];

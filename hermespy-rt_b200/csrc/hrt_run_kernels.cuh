@@ -445,6 +445,26 @@ k_bounce(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth)
         const V3 n = tri_normal<SMEM>(sc, h.slot);
         theta = hrt_theta_fold(n, s.d);                                        /* :281-283 */
         const uint32_t mat = sc.mesh_mat[sc.mesh_of[h.gid]];                   /* :622 */
+        if (rd.refr) {
+          /* HRT_FLAG_EXT_REFRACT (hrt_ext.cuh): the refraction ray of this hit, appended to the list */
+          V3 dt;
+          if (hrt_refract_dir(mats.m[mat], s.d, n, &dt)) {
+            const unsigned long long pos = atomicAdd(&rd.counters[13], 1ull);
+            if (pos < rd.refr_cap) {
+              float tc[4];
+              hrt_refr_coefs(mats.m[mat], theta, tc);
+              float l2 = rd.k.fsl_k * h.t; l2 *= l2; if (!(l2 > 1.f)) l2 = 1.f;
+              const float il = 1.f / l2;
+              const V3 hp = v3(s.o.x + s.d.x * h.t, s.o.y + s.d.y * h.t, s.o.z + s.d.z * h.t);
+              float4 *dst = rd.refr + 3 * pos;
+              dst[0] = make_float4(__uint_as_float((uint32_t)hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk)),
+                                   __uint_as_float(t | (depth << 16)), hp.x + 1e-4f * dt.x, hp.y + 1e-4f * dt.y);
+              dst[1] = make_float4(hp.z + 1e-4f * dt.z, dt.x, dt.y, dt.z);
+              dst[2] = make_float4((s.te_r * tc[0] - s.te_i * tc[1]) * il, (s.te_r * tc[1] + s.te_i * tc[0]) * il,
+                                   (s.tm_r * tc[2] - s.tm_i * tc[3]) * il, (s.tm_r * tc[3] + s.tm_i * tc[2]) * il);
+            }
+          }
+        }
         hrt_bounce_update(s, mats.m[mat], rd.k, h.t, n, theta);                /* :623-659 */
         if (rows) {
           float2 *wp = (float2 *)(rays_out + l);
@@ -565,8 +585,9 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     const V3 n = tri_normal<SMEM, MAP>(sc, slot);
     const uint32_t gid = tri_gid_of<SMEM, MAP>(sc, slot);
     const uint32_t mesh = sc.mesh_of[gid];
-    const HrtScatConst mat = hrt_scat_const(mats.m[sc.mesh_mat[mesh]]);
-    const HrtScatCf mcf = hrt_scat_cf(mats.m[sc.mesh_mat[mesh]]);
+    const uint32_t mat_index = sc.mesh_mat[mesh];
+    const HrtScatConst mat = hrt_scat_const(mats.m[mat_index]);
+    const HrtScatCf mcf = hrt_scat_cf(mats.m[mat_index]);
     const V3 mv = ld3(sc.mesh_vel, mesh);
     /* incidence angle handed to scat_coefs (appendix A-4): carried as the fp32 dot
      * product n.d of the most recent shadow hit (what the reference feeds to acos,
@@ -609,7 +630,18 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       const bool ok = act && !occ;
       HrtScatterOut p;
       p.te_r = p.te_i = p.tm_r = p.tm_i = p.tau = p.dfreq = 0.f; p.dir_rx = v3(0.f, 0.f, 0.f);
-      if (ok) p = hrt_scatter_path_auto(s, mat, mcf, rd.k, n, mv, sd, dist, cx_i, theta_p, ci_p, si_p);   /* :694-721 */
+      if (ok) {
+        if (!LEAN && (rd.flags & HRT_FLAG_EXT_LOBES)) {
+          /* opt-in three-lobe pattern (hrt_ext.cuh); incident direction = the reflected one mirrored back */
+          float ci = ci_p, si = si_p;
+          if (cx_i != HRT_CX_PRIMARY) hrt_fold_cos_sin(cx_i, &ci, &si);
+          const float two_dn = 2.f * (s.d.x * n.x + s.d.y * n.y + s.d.z * n.z);
+          const V3 k_inc = v3(s.d.x - two_dn * n.x, s.d.y - two_dn * n.y, s.d.z - two_dn * n.z);
+          p = hrt_scatter_path_ext(s, mcf, c_ext.m[mat_index], rd.k, n, mv, sd, dist, k_inc, ci, si);
+        } else {
+          p = hrt_scatter_path_auto(s, mat, mcf, rd.k, n, mv, sd, dist, cx_i, theta_p, ci_p, si_p);   /* :694-721 */
+        }
+      }
       if (act && (dense || trace)) {
         const size_t so = ((size_t)(r * T + t) * B + depth) * np + l;          /* :674 */
         if (dense) {

@@ -28,6 +28,10 @@ LIB_PATH = os.path.join(_HERE, "..", "libhermespy_rt.so")
 FLAG_DENSE, FLAG_RAYSINFO, FLAG_SUMMARY, FLAG_TRACE = 0x01, 0x02, 0x04, 0x08
 FLAG_BRUTE_FORCE, FLAG_HOST_DIRS, FLAG_SUMMARY_DEV, FLAG_COUNT = 0x10, 0x20, 0x40, 0x80
 FLAG_CIR, FLAG_PATHLIST, FLAG_PATHLIST_DEV = 0x100, 0x200, 0x400
+FLAG_DENSE_C64, FLAG_EXT_LOBES, FLAG_EXT_REFRACT = 0x800, 0x1000, 0x2000
+REFRACT_DTYPE = np.dtype([("path", "<u4"), ("tx", "<u2"), ("bounce", "<u2"), ("o", "<f4", (3,)), ("d", "<f4", (3,)),
+                          ("t_te_re", "<f4"), ("t_te_im", "<f4"), ("t_tm_re", "<f4"), ("t_tm_im", "<f4")])
+assert REFRACT_DTYPE.itemsize == 48
 PATH_DTYPE = np.dtype([("path", "<u4"), ("rx", "<u4"), ("tx", "<u2"), ("bounce", "<u2"),
                        ("a_te_re", "<f4"), ("a_te_im", "<f4"), ("a_tm_re", "<f4"), ("a_tm_im", "<f4"),
                        ("tau", "<f4"), ("freq_shift", "<f4"), ("direction_rx", "<f4", (3,))])
@@ -64,6 +68,7 @@ class RunParams(C.Structure):
         ("cir", C.c_void_p), ("cir_tau0_s", C.c_float), ("cir_dt_s", C.c_float), ("cir_bins", C.c_uint32),
         ("paths", C.c_void_p), ("paths_capacity", C.c_uint64), ("paths_count", C.POINTER(C.c_uint64)),
         ("scat_a_te_c64", C.c_void_p), ("scat_a_tm_c64", C.c_void_p),
+        ("refr_rays", C.c_void_p), ("refr_capacity", C.c_uint64), ("refr_count", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -247,7 +252,8 @@ class Context:
     def run(self, rx, tx, rx_vel, tx_vel, f_ghz, P, B, *, dense=False, raysinfo=False,
             summary=False, trace=False, brute_force=False, count_work=False, los=True, dirs=None,
             shard=(0, 1), shard_block=1 << 20, out: abi.Outputs | None = None,
-            summary_dev_ptrs=None, stream=None, cir=None, path_list=None, path_list_dev=None):
+            summary_dev_ptrs=None, stream=None, cir=None, path_list=None, path_list_dev=None,
+            ext_lobes=False, refract=None):
         """hrt_run().  Returns a dict with whatever was requested:
         'out' (abi.Outputs, dense), 'pair'/'bounce' (structured arrays, summary),
         'trace' (dict), 'stats'."""
@@ -334,8 +340,20 @@ class Context:
             flags |= FLAG_PATHLIST | FLAG_PATHLIST_DEV
             p.paths, p.paths_capacity = int(path_list_dev[0]), int(path_list_dev[1])
             p.paths_count = C.pointer(n_found)
+        n_refr = C.c_uint64(0)
+        if ext_lobes:
+            flags |= FLAG_EXT_LOBES
+        if refract is not None:
+            # refract = capacity: res["refract"] is a REFRACT_DTYPE array of the refraction rays spawned
+            rbuf = np.zeros(int(refract), REFRACT_DTYPE)
+            keep.append(rbuf)
+            flags |= FLAG_EXT_REFRACT
+            p.refr_rays = rbuf.ctypes.data; p.refr_capacity = int(refract); p.refr_count = C.pointer(n_refr)
         p.flags = flags
         self._check(self._run_call(p), "hrt_run")
+        if refract is not None:
+            res["refract_found"] = int(n_refr.value)
+            res["refract"] = rbuf[: min(int(n_refr.value), int(refract))]
         if path_list_dev is not None:
             res["paths_found"] = int(n_found.value)
         if path_list is not None:

@@ -66,6 +66,12 @@ typedef struct {
 #define HRT_FLAG_PATHLIST    0x200u  /* emit the valid scatter paths as a compact list  */
 #define HRT_FLAG_DENSE_C64   0x800u  /* with DENSE: scatter gains as interleaved complex64 (scat_a_te_c64 /
                                        scat_a_tm_c64) instead of the four re / im arrays of `scat` */
+/* Opt-in extensions the reference has as TODOs (no reference behaviour; definitions in
+ * csrc/hrt_ext.cuh, checked against the oracle's double-precision statement): */
+#define HRT_FLAG_EXT_LOBES  0x1000u  /* scatter gains from the three-lobe pattern (Material.s1/s2/s3, s1_alpha,
+                                        s3_alpha; reference TODO src/compute_paths.c:414) */
+#define HRT_FLAG_EXT_REFRACT 0x2000u /* list the refraction ray of every hit with ITU-R P.2040-3 (31c)/(31d)
+                                        gains (reference TODO :587, :726-728): refr_rays / refr_capacity / refr_count */
 #define HRT_FLAG_PATHLIST_DEV 0x400u /* ... into DEVICE memory (`paths`), e.g. a buffer
                                         that NCCL gathers next; paths_count stays host */
 
@@ -100,6 +106,18 @@ typedef struct {
   float tau, freq_shift;
   Vec3  direction_rx;
 } HrtPathRecord;
+
+/* One refraction ray (HRT_FLAG_EXT_REFRACT): spawned where path `path` of
+ * transmitter `tx` hits a surface at bounce `bounce`; origin 1e-4 m inside the
+ * surface along the refracted direction (Snell, n = Re sqrt(eta)); gains = the
+ * ray's gains before this bounce times T_TE / T_TM of eqs. (31c)/(31d), divided
+ * by the free-space factor of the segment like the reflected ray's (:627-634). */
+typedef struct {
+  uint32_t path; uint16_t tx, bounce;
+  float    o[3], d[3];
+  float    t_te_re, t_te_im, t_tm_re, t_tm_im;
+} HrtRefractRecord;
+
 
 typedef struct {
   /* problem (reference compute_paths arguments, inc/compute_paths.h:59-74) */
@@ -168,6 +186,12 @@ typedef struct {
    * host; here the device writes them directly).  scat->a_*_re / _im are then
    * not touched and may be NULL. */
   float         *scat_a_te_c64, *scat_a_tm_c64;
+
+  /* HRT_FLAG_EXT_REFRACT: host buffer of refr_capacity records, filled in no
+   * particular order; *refr_count = number spawned (may exceed the capacity) */
+  HrtRefractRecord *refr_rays;
+  uint64_t          refr_capacity;
+  uint64_t         *refr_count;
 } HrtRunParams;
 
 /* Counters and timings of the last hrt_run on a context. */

@@ -120,6 +120,114 @@ void orc_material(uint32_t index, float f_ghz, OrcMat *o)
   o->r = 1.f - m->s;                                                        /* :204 */
 }
 
+/* ---- extensions ----------------------------------
+ * NOT reference behaviour: the reference has these as TODOs (:587, :726-728,
+ * :414).  Double-precision statement of the definitions in
+ * hermespy-rt_b200/csrc/hrt_ext.cuh, which the opt-in HRT_FLAG_EXT_* modes of
+ * the product are tested against.  Active only through oracle_compute_paths_ext. */
+#define ORC_EXT_LOBES   1u
+#define ORC_EXT_REFRACT 2u
+typedef struct {
+  uint32_t path; uint16_t tx, bounce;
+  float o[3], d[3];
+  float t_te_re, t_te_im, t_tm_re, t_tm_im;
+} OrcRefractRecord;
+static unsigned g_ext = 0;
+static OrcRefractRecord *g_refr = NULL;
+static size_t g_refr_cap = 0, g_refr_n = 0;
+
+static void ext_csqrt(double re, double im, double *o_re, double *o_im)
+{
+  const double mag = sqrt(re * re + im * im);
+  *o_re = sqrt(fmax(0.5 * (mag + re), 0.0));
+  const double i = sqrt(fmax(0.5 * (mag - re), 0.0));
+  *o_im = im < 0.0 ? -i : i;
+}
+
+/* ITU-R P.2040-3 eqs. (31c), (31d), eta = eta' - j eta'' (eq. 9b) */
+void oracle_ext_refr_coefs(uint32_t material, float f_ghz, double theta1, double out[4])
+{
+  OrcMat m; orc_material(material, f_ghz, &m);
+  const double er = m.eta_re, ei = m.eta_im;
+  const double c1 = cos(theta1), s1 = sin(theta1);
+  double qr, qi, sr, si;
+  ext_csqrt(er - s1 * s1, -ei, &qr, &qi);
+  ext_csqrt(er, -ei, &sr, &si);
+  { const double dr = c1 + qr, di = qi, den = dr * dr + di * di;
+    out[0] = 2.0 * c1 * dr / den; out[1] = -2.0 * c1 * di / den; }
+  { const double nr = 2.0 * c1 * sr, ni = 2.0 * c1 * si, dr = er * c1 + qr, di = -ei * c1 + qi, den = dr * dr + di * di;
+    out[2] = (nr * dr + ni * di) / den; out[3] = (ni * dr - nr * di) / den; }
+}
+
+int oracle_ext_refract_dir(uint32_t material, float f_ghz, const double d[3], const double n_in[3], double out[3])
+{
+  OrcMat m; orc_material(material, f_ghz, &m);
+  double sr, si; ext_csqrt(m.eta_re, -(double)m.eta_im, &sr, &si);
+  const double n = fmax(sr, 1e-6);
+  double nn[3] = { n_in[0], n_in[1], n_in[2] };
+  double c1 = -(d[0] * nn[0] + d[1] * nn[1] + d[2] * nn[2]);
+  if (c1 < 0) { for (int k = 0; k < 3; ++k) nn[k] = -nn[k]; c1 = -c1; }
+  const double k = 1.0 / n, s2sq = k * k * fmax(1.0 - c1 * c1, 0.0);
+  if (s2sq > 1.0) return 0;
+  const double c2 = sqrt(1.0 - s2sq), f = k * c1 - c2;
+  double t[3], l = 0;
+  for (int q = 0; q < 3; ++q) { t[q] = k * d[q] + f * nn[q]; l += t[q] * t[q]; }
+  l = sqrt(l);
+  for (int q = 0; q < 3; ++q) out[q] = t[q] / l;
+  return 1;
+}
+
+static double ext_binom(int n, int k) { double r = 1; for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i; return floor(r + 0.5); }
+
+double oracle_ext_lobe_norm(int alpha, double cos_i, double sin_i)
+{
+  double sum = 0;
+  for (int k = 0; k <= alpha; ++k) {
+    double ik = 2.0 * 3.14159265358979323846 / (k + 1);
+    if (k & 1) {
+      double ser = 0;
+      for (int w = 0; w <= (k - 1) / 2; ++w) ser += ext_binom(2 * w, w) * pow(sin_i / 2.0, 2.0 * w);
+      ik *= cos_i * ser;
+    }
+    sum += ext_binom(alpha, k) * ik;
+  }
+  return sum / pow(2.0, alpha);
+}
+
+/* pi * f_s of the three-lobe model (Degli-Esposti 2007); ki towards the surface, ks away, n unit normal */
+double oracle_ext_pattern_pi(double s1, double s2, double s3, int a1, int a3,
+                             const double ki[3], const double ks[3], const double n_in[3])
+{
+  const double pi = 3.14159265358979323846;
+  double n[3] = { n_in[0], n_in[1], n_in[2] };
+  double cos_i = -(ki[0] * n[0] + ki[1] * n[1] + ki[2] * n[2]);
+  if (cos_i < 0) { for (int k = 0; k < 3; ++k) n[k] = -n[k]; cos_i = -cos_i; }
+  if (cos_i > 1) cos_i = 1;
+  const double sin_i = sqrt(fmax(1.0 - cos_i * cos_i, 0.0));
+  const double cos_s = ks[0] * n[0] + ks[1] * n[1] + ks[2] * n[2];
+  if (!(cos_s > 0)) return 0;
+  double kr[3], dir = 0, back = 0;
+  for (int k = 0; k < 3; ++k) { kr[k] = ki[k] + 2.0 * cos_i * n[k]; dir += kr[k] * ks[k]; back += ki[k] * ks[k]; }
+  dir = 0.5 * (1.0 + dir); back = 0.5 * (1.0 - back);
+  double f = s2 * cos_s;
+  if (s1 != 0) f += s1 * pi * pow(fmax(dir, 0.0), a1) / oracle_ext_lobe_norm(a1, cos_i, sin_i);
+  if (s3 != 0) f += s3 * pi * pow(fmax(back, 0.0), a3) / oracle_ext_lobe_norm(a3, cos_i, sin_i);
+  return f;
+}
+
+/* scattering coefficients of EXT_LOBES: s sqrt(pi f_s) times the reference's polarisation mix
+ * (1, p, g, g p) / sqrt((1 + g^2)(1 + p^2)) of scat_coefs (:382-396) */
+static void ext_scat(uint32_t material, const Vec3 *k_inc, const Vec3 *k_s, const Vec3 *nrm, float theta_i, float sc[4])
+{
+  const Material *m = &g_materials[material];
+  const double rough = 1.0 / (1.0 + m->s1_alpha), ci = cos((double)theta_i), si = sin((double)theta_i);
+  const double g = rough * ci + (1.0 - rough), p = sin(m->s1_alpha * si * 0.1);
+  const double ki[3] = { k_inc->x, k_inc->y, k_inc->z }, ks[3] = { k_s->x, k_s->y, k_s->z }, nn[3] = { nrm->x, nrm->y, nrm->z };
+  const double amp = m->s * sqrt(fmax(oracle_ext_pattern_pi(m->s1, m->s2, m->s3, m->s1_alpha, m->s3_alpha, ki, ks, nn), 0.0));
+  const double k = amp / sqrt((1.0 + g * g) * (1.0 + p * p));
+  sc[0] = (float)k; sc[1] = (float)(k * p); sc[2] = (float)(k * g); sc[3] = (float)(k * g * p);
+}
+
 /* ---- closest hit (reference moeller_trumbore :237-287) ------------------- */
 
 /* Returns 1 when something was hit.  *theta is only written on a hit, which is
@@ -334,6 +442,27 @@ int oracle_compute_paths(
 
         const uint32_t mesh = ft.mesh_of[tri];
         const uint32_t mat = scene->meshes[mesh].material_index;  /* :622 */
+        const Vec3 d_in = rays[i].d;                               /* incident direction (extensions only) */
+        if ((g_ext & ORC_EXT_REFRACT) && g_refr) {
+          /* the refraction ray the reference's TODO (:587, :726-728) would spawn here: state gains
+           * times (31c)/(31d), free-space loss of this segment as for the reflected ray (:627-634) */
+          double T4[4], dd[3] = { d_in.x, d_in.y, d_in.z }, nn[3] = { ft.n[tri].x, ft.n[tri].y, ft.n[tri].z }, dt[3];
+          oracle_ext_refr_coefs(mat, f_ghz, (double)theta, T4);
+          if (oracle_ext_refract_dir(mat, f_ghz, dd, nn, dt)) {
+            if (g_refr_n < g_refr_cap) {
+              OrcRefractRecord *q = &g_refr[g_refr_n];
+              double l = (double)(fsl_k * tt); l *= l; if (!(l > 1.0)) l = 1.0;
+              q->path = (uint32_t)p; q->tx = (uint16_t)t; q->bounce = (uint16_t)b;
+              for (int c = 0; c < 3; ++c) {
+                const double hp = (&rays[i].o.x)[c] + (double)(&d_in.x)[c] * tt;
+                q->o[c] = (float)(hp + 1e-4 * dt[c]); q->d[c] = (float)dt[c];
+              }
+              q->t_te_re = (float)((g_te_r[i] * T4[0] - g_te_i[i] * T4[1]) / l); q->t_te_im = (float)((g_te_r[i] * T4[1] + g_te_i[i] * T4[0]) / l);
+              q->t_tm_re = (float)((g_tm_r[i] * T4[2] - g_tm_i[i] * T4[3]) / l); q->t_tm_im = (float)((g_tm_r[i] * T4[3] + g_tm_i[i] * T4[2]) / l);
+            }
+            ++g_refr_n;
+          }
+        }
         float rc[4];
         orc_refl(&mats[mat], theta, rc);                           /* :623 */
         float fsl = fsl_k * tt;  fsl *= fsl;                       /* :627-628 */
@@ -377,7 +506,8 @@ int oracle_compute_paths(
           }
           float th_s = acosf(vec3_dot(&sh.d, &nrm));               /* :694 */
           float sc[4];
-          orc_scat(mat, th_s, theta, sc);                          /* :696 */
+          if (g_ext & ORC_EXT_LOBES) ext_scat(mat, &d_in, &sh.d, &nrm, theta, sc);
+          else orc_scat(mat, th_s, theta, sc);                     /* :696 */
           scat->a_te_re[s] = g_te_r[i] * sc[0] - g_te_i[i] * sc[1];   /* :698-705 */
           scat->a_te_im[s] = g_te_r[i] * sc[1] + g_te_i[i] * sc[0];
           scat->a_tm_re[s] = g_tm_r[i] * sc[2] - g_tm_i[i] * sc[3];
@@ -406,6 +536,22 @@ int oracle_compute_paths(
   free(delay); free(alive);
   orc_free_tris(&ft);
   return 0;
+}
+
+/* compute_paths with the opt-in extensions (ext: ORC_EXT_LOBES | ORC_EXT_REFRACT); refraction rays are
+ * appended to refr[0..cap), *n_refr = number spawned */
+int oracle_compute_paths_ext(
+    const Scene *scene,
+    const Vec3 *rx_pos, const Vec3 *tx_pos, const Vec3 *rx_vel, const Vec3 *tx_vel,
+    float f_ghz, size_t R, size_t T, size_t P, size_t B,
+    ChannelInfo *los, RaysInfo *rlos, ChannelInfo *scat, RaysInfo *rscat,
+    OrcTrace *trace, unsigned ext, OrcRefractRecord *refr, size_t cap, size_t *n_refr)
+{
+  g_ext = ext; g_refr = refr; g_refr_cap = cap; g_refr_n = 0;
+  const int rc = oracle_compute_paths(scene, rx_pos, tx_pos, rx_vel, tx_vel, f_ghz, R, T, P, B, los, rlos, scat, rscat, trace);
+  if (n_refr) *n_refr = g_refr_n;
+  g_ext = 0; g_refr = NULL; g_refr_cap = 0;
+  return rc;
 }
 
 /* Stand-alone closest hit over a scene for unit tests: `n` rays in, per ray

@@ -16,6 +16,7 @@
 #include "../../include/hrt_cuda.h"
 #include "../../hermespy-rt_b200/csrc/hrt_bvh.cuh"
 #include "../../hermespy-rt_b200/csrc/hrt_rxmap.cuh"
+#include "../../hermespy-rt_b200/csrc/hrt_ext.cuh"
 
 struct EmulScene {
   std::vector<float4> tris, nodes;
@@ -490,3 +491,18 @@ extern "C" long emul_rxmap_vs_brute(const Scene *sc, const Vec3 *rx, size_t R, c
   *avg_list = (double)M.items.size() / (double)M.start.size();
   return bad;
 }
+
+/* Opt-in extensions (hrt_ext.cuh), fp32 as the kernels evaluate them, for comparison with the
+ * oracle's double-precision statement (tests/test_extensions.py). */
+extern "C" void emul_ext_refr_coefs(uint32_t material, float f_ghz, float theta1, float out[4], float dir_in[3], float nrm[3], float dir_out[3], int *ok)
+{
+  HrtMaterial m; memset(&m, 0, sizeof m);
+  hrt_materials_derive(material, f_ghz, (HrtMaterialDerived *)&m);
+  hrt_refr_coefs(m, theta1, out);
+  V3 t;
+  *ok = hrt_refract_dir(m, v3(dir_in[0], dir_in[1], dir_in[2]), v3(nrm[0], nrm[1], nrm[2]), &t) ? 1 : 0;
+  dir_out[0] = t.x; dir_out[1] = t.y; dir_out[2] = t.z;
+}
+extern "C" float emul_ext_pattern_pi(float s1, float s2, float s3, int a1, int a3, const float ki[3], const float ks[3], const float n[3])
+{ return hrt_scat_pattern_pi(s1, s2, s3, a1, a3, v3(ki[0], ki[1], ki[2]), v3(ks[0], ks[1], ks[2]), v3(n[0], n[1], n[2])); }
+extern "C" float emul_ext_lobe_norm(int alpha, float cos_i, float sin_i) { return hrt_lobe_norm(alpha, cos_i, sin_i); }

@@ -80,8 +80,14 @@ def run_ref(scene, rx, tx, rxv, txv, f_ghz, P, B, fill=0):
         abi.free_scene(sc)
 
 
-def run_oracle(scene, rx, tx, rxv, txv, f_ghz, P, B, fill=0, trace=True):
-    """Our CPU restatement.  Returns (Outputs, trace dict)."""
+REFRACT_DTYPE = np.dtype([("path", "<u4"), ("tx", "<u2"), ("bounce", "<u2"), ("o", "<f4", (3,)), ("d", "<f4", (3,)),
+                          ("t_te_re", "<f4"), ("t_te_im", "<f4"), ("t_tm_re", "<f4"), ("t_tm_im", "<f4")])
+
+
+def run_oracle(scene, rx, tx, rxv, txv, f_ghz, P, B, fill=0, trace=True, ext=0, refract_capacity=0):
+    """Our CPU restatement.  Returns (Outputs, trace dict).  ext: 1 = three-lobe
+    scattering pattern, 2 = refraction rays (tr["refract"]) -- the opt-in
+    extensions of SURVEY 8 f4 (no reference behaviour), oracle_compute_paths_ext."""
     lib = oracle_lib()
     sc = lib.scene_load(scene_path(scene).encode())
     rx = abi.vec3_array(rx); tx = abi.vec3_array(tx)
@@ -104,11 +110,23 @@ def run_oracle(scene, rx, tx, rxv, txv, f_ghz, P, B, fill=0, trace=True):
     rl = abi.RaysInfo(1, 1, o.los_rays.ctypes.data, o.los_active.ctypes.data)
     rs = abi.RaysInfo(B + 1, P, o.scat_rays.ctypes.data, o.scat_active.ctypes.data)
     try:
-        rc = lib.oracle_compute_paths(C.byref(sc), rx.ctypes.data, tx.ctypes.data,
-                                      rxv.ctypes.data, txv.ctypes.data, C.c_float(f_ghz),
-                                      R, T, P, B, C.byref(los), C.byref(rl),
-                                      C.byref(scs), C.byref(rs),
-                                      C.byref(ot) if trace else None)
+        if ext:
+            lib.oracle_compute_paths_ext.restype = C.c_int
+            lib.oracle_compute_paths_ext.argtypes = lib.oracle_compute_paths.argtypes + [C.c_uint, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+            rbuf = np.zeros(max(int(refract_capacity), 1), REFRACT_DTYPE)
+            nref = C.c_size_t(0)
+            rc = lib.oracle_compute_paths_ext(C.byref(sc), rx.ctypes.data, tx.ctypes.data, rxv.ctypes.data, txv.ctypes.data,
+                                              C.c_float(f_ghz), R, T, P, B, C.byref(los), C.byref(rl), C.byref(scs), C.byref(rs),
+                                              C.byref(ot) if trace else None, int(ext), rbuf.ctypes.data, int(refract_capacity),
+                                              C.byref(nref))
+            tr["refract_found"] = int(nref.value)
+            tr["refract"] = rbuf[: min(int(nref.value), int(refract_capacity))]
+        else:
+            rc = lib.oracle_compute_paths(C.byref(sc), rx.ctypes.data, tx.ctypes.data,
+                                          rxv.ctypes.data, txv.ctypes.data, C.c_float(f_ghz),
+                                          R, T, P, B, C.byref(los), C.byref(rl),
+                                          C.byref(scs), C.byref(rs),
+                                          C.byref(ot) if trace else None)
         assert rc == 0
     finally:
         abi.free_scene(sc)
