@@ -862,7 +862,7 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
   uint32_t G = 128;
   if (const char *e = getenv("HRT_RXMAP_G")) { int v = atoi(e); if (v >= 8 && v <= 1024) G = (uint32_t)v & ~7u; }
   const size_t cells = R * 6 * (size_t)G * G;
-  if (ctx->num_tris == 0 || ctx->num_tris > 65535 || cells * 4 > ((size_t)2 << 30)) return HRT_OK;
+  if (ctx->num_tris == 0 || ctx->num_tris > 65535 || cells * 4 > ((size_t)2 << 30)) return HRT_OK;   /* (k_scatter indexes cells and items with 32 bits) */
   uint64_t key = hash_bytes(p->rx_pos, R * sizeof(Vec3), 0xCBF29CE484222325ull);
   key = hash_bytes(&ctx->scene_version, 8, key); key = hash_bytes(&G, 4, key);
   if (ctx->map_valid && ctx->map_key == key && ctx->map_R == R && ctx->map_G == G) { *use = true; return HRT_OK; }
@@ -872,6 +872,7 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (per_rx >= (1u << 24)) per_rx = (1u << 24) - 1;
+    if (R * (size_t)per_rx >= ((size_t)1 << 32)) break;          /* beyond the kernels' 32-bit item index: walk the BVH */
     if (ctx->cap_map_cells < cells) { dev_free(ctx->d_map_cells); ctx->cap_map_cells = 0; CK(dev_alloc(&ctx->d_map_cells, cells)); ctx->cap_map_cells = cells; }
     if (ctx->cap_map_items < R * (size_t)per_rx) { dev_free(ctx->d_map_items); ctx->cap_map_items = 0; CK(dev_alloc(&ctx->d_map_items, R * (size_t)per_rx)); ctx->cap_map_items = R * (size_t)per_rx; }
     if (ctx->cap_map_cursor < R + 1) { dev_free(ctx->d_map_cursor); ctx->cap_map_cursor = 0; CK(dev_alloc(&ctx->d_map_cursor, R + 1)); ctx->cap_map_cursor = R + 1; }

@@ -72,13 +72,14 @@ static size_t scene_smem_bytes(uint32_t num_wide, uint32_t num_tris, uint32_t oc
 /* byte offset of the triangle records behind the wide nodes of a staged scene */
 __device__ __forceinline__ uint32_t scene_tri_off(const SceneDev &sc) { return sc.num_wide * 112u * sc.wide_octants; }
 
+/* smem0: shared-window address of the staged scene; kernels compute it once and keep it in a register */
 template <bool SMEM, bool BRUTE, class Cnt>
-__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt)
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, uint32_t smem0 = smem_base_addr())
 {
   const size_t stride4 = (size_t)sc.num_wide * HRT_WIDE_F4;
   if (SMEM) {
     HrtSharedMem m;
-    m.wnode_addr = smem_base_addr();
+    m.wnode_addr = smem0;
     m.tri_addr = m.wnode_addr + scene_tri_off(sc);
     HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
     asm volatile("" : "+r"(m.tri_addr), "+r"(gid.addr));   /* keep both bases in registers across the leaf loop */
@@ -101,25 +102,26 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
  * to it), of cell (+d), beyond the receiver.  Triangle records staged in shared
  * memory at offset 0. */
 template <class Cnt>
-__device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, float dist, Cnt &cnt)
+__device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, float dist, Cnt &cnt,
+                                            uint32_t smem0)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   HrtSharedMem m;
-  m.wnode_addr = 0u; m.tri_addr = smem_base_addr();
+  m.wnode_addr = 0u; m.tri_addr = smem0;
   const uint32_t gid_addr = m.tri_addr + sc.num_tris * 48u;
-  const uint32_t *cells = mp.cells + (size_t)r * 6u * mp.G * mp.G;
-  const uint16_t *items = mp.items + (size_t)r * mp.items_per_rx;
+  /* 32-bit index arithmetic (the host checks that R * 6 G^2 and R * items_per_rx fit) */
+  const uint32_t cell0 = r * (6u * mp.G * mp.G);
+  const uint16_t *items = mp.items + r * mp.items_per_rx;
   uint32_t c_pos, c_neg;
   hrt_rxmap_cells2(d, mp.G, &c_pos, &c_neg);
-  uint32_t w = __ldg(&cells[c_neg]);
-  const uint32_t w_pos = __ldg(&cells[c_pos]);
+  uint32_t w = __ldg(&mp.cells[cell0 + c_neg]);
+  const uint32_t w_pos = __ldg(&mp.cells[cell0 + c_pos]);
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
-    const uint16_t *it = items + (w >> 8);
-    const uint32_t n = w & 255u;
+    const uint16_t *it = items + (w >> 8), *end = it + (w & 255u);
 #pragma unroll 1
-    for (uint32_t k = 0; k < n; ++k) {
-      const uint32_t s = __ldg(&it[k]);
+    for (; it != end; ++it) {
+      const uint32_t s = __ldg(it);
       float t;
       if (hrt_mt_test<Cnt, true>(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, 0u, 0u, &t, cnt)) {
         const uint32_t gid = lds32(gid_addr + 4u * s);
@@ -205,16 +207,16 @@ __device__ __forceinline__ void cnt_flush(const HrtCount &c, unsigned long long 
 { for (int k = 0; k < 5; ++k) if (c.c[k]) atomicAdd(&dst[k], (unsigned long long)c.c[k]); }
 
 template <bool SMEM, bool MAP = false>
-__device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot)
+__device__ __forceinline__ V3 tri_normal(const SceneDev &sc, uint32_t slot, uint32_t smem0 = smem_base_addr())
 {
-  const float4 q2 = SMEM ? lds128(smem_base_addr() + (MAP ? 0u : scene_tri_off(sc)) + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
+  const float4 q2 = SMEM ? lds128(smem0 + (MAP ? 0u : scene_tri_off(sc)) + slot * 48u + 32u) : __ldg(&sc.tris[3 * slot + 2]);
   return v3(q2.y, q2.z, q2.w);
 }
 
 template <bool SMEM, bool MAP = false>
-__device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot)
+__device__ __forceinline__ uint32_t tri_gid_of(const SceneDev &sc, uint32_t slot, uint32_t smem0 = smem_base_addr())
 {
-  if (SMEM) return lds32(smem_base_addr() + (MAP ? 0u : scene_tri_off(sc)) + sc.num_tris * 48u + 4u * slot);
+  if (SMEM) return lds32(smem0 + (MAP ? 0u : scene_tri_off(sc)) + sc.num_tris * 48u + 4u * slot);
   return sc.tri_gid[slot];
 }
 
@@ -553,6 +555,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
   }
   if (SMEM || smem_rx_ok) __syncthreads();
   const float *rxp = smem_rx_ok ? s_rx : rd.rx_pos;
+  uint32_t smem0 = smem_base_addr();
+  asm volatile("" : "+r"(smem0));             /* one register for the whole kernel instead of a recomputation per use */
 
   /* every block works through all transmitters, starting with "its own"
    * (blockIdx.y): when one TX runs out of hits its blocks help with the others */
@@ -582,8 +586,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     s.o = v3(r0.x, r0.y, r0.z); s.d = v3(r0.w, r1.x, r1.y);
     s.te_r = r1.z; s.te_i = r1.w; s.tm_r = r2.x; s.tm_i = r2.y; s.tau = r2.z;
     const uint32_t slot = __float_as_uint(r3.x), l = __float_as_uint(r3.y);
-    const V3 n = tri_normal<SMEM, MAP>(sc, slot);
-    const uint32_t gid = tri_gid_of<SMEM, MAP>(sc, slot);
+    const V3 n = tri_normal<SMEM, MAP>(sc, slot, smem0);
+    const uint32_t gid = tri_gid_of<SMEM, MAP>(sc, slot, smem0);
     const uint32_t mesh = sc.mesh_of[gid];
     const uint32_t mat_index = sc.mesh_mat[mesh];
     const HrtScatConst mat = hrt_scat_const(mats.m[mat_index]);
@@ -607,8 +611,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc) : query<SMEM, BRUTE>(sc, s.o, sd, wc);   /* :682 */
-        if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM, MAP>(sc, h.slot), sd);   /* :281, argument of acos */
+        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc, smem0) : query<SMEM, BRUTE>(sc, s.o, sd, wc, smem0);   /* :682 */
+        if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM, MAP>(sc, h.slot, smem0), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;
       float cx_i;
