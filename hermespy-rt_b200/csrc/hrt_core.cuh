@@ -572,6 +572,18 @@ HRT_HD HrtHit hrt_closest_hit_wide(const Mem &mem_in, const Gid tri_gid, int roo
         ref[2] = hrt_float_as_int(rf.z); ref[3] = hrt_float_as_int(rf.w);
       }
       for (int k = 0; k < 4; ++k) hit[k] = tn[k] <= tf[k] && (SORTED || ref[k] != HRT_WIDE_EMPTY);
+      if (!SORTED) {
+        /* single plain copy: its child order suits octant 0 only, so order the four by entry
+         * distance here (misses last) -- a 5-exchange network; the octant copies need none of it */
+#define HRT_WIDE_CSWAP(A, B)                                                                        \
+        if ((hit[B] && !hit[A]) || (hit[A] && hit[B] && tn[B] < tn[A])) {                            \
+          const float tt = tn[A]; tn[A] = tn[B]; tn[B] = tt;                                          \
+          const int rr = ref[A]; ref[A] = ref[B]; ref[B] = rr;                                        \
+          const bool hh = hit[A]; hit[A] = hit[B]; hit[B] = hh;                                       \
+        }
+        HRT_WIDE_CSWAP(0, 1) HRT_WIDE_CSWAP(2, 3) HRT_WIDE_CSWAP(0, 2) HRT_WIDE_CSWAP(1, 3) HRT_WIDE_CSWAP(1, 2)
+#undef HRT_WIDE_CSWAP
+      }
       cnt.box((uint32_t)(ref[0] != HRT_WIDE_EMPTY) + (uint32_t)(ref[1] != HRT_WIDE_EMPTY) +
               (uint32_t)(ref[2] != HRT_WIDE_EMPTY) + (uint32_t)(ref[3] != HRT_WIDE_EMPTY));
       /* far to near onto the stack, then take the nearest back off */
