@@ -118,7 +118,8 @@ HRT_HD int hrt_child_ref(int child, int n, const int *first, const int *last,
 /* `oct`: direction octant this copy of the node serves (bit k = component k of
  * the ray direction negative).  On those axes the two planes are stored
  * swapped, so that the first slot always holds the plane a ray of that octant
- * reaches first (hrt_slab_sorted).  oct = 0 is the plain (lo, hi) layout. */
+ * reaches first.  oct = 0 is the plain (lo, hi) layout -- the only one emitted since the
+ * kernels traverse the 4-wide nodes collapsed from these (hrt_wide_emit below). */
 HRT_HD void hrt_emit_node(float4 *out, int ref_l, int ref_r, V3 llo, V3 lhi, V3 rlo, V3 rhi, float pad,
                           uint32_t oct = 0)
 {

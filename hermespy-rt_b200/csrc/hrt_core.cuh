@@ -234,38 +234,6 @@ HRT_HD bool hrt_slab(const HrtRayCull &c, float lox, float hix, float loy, float
   return tn <= tf;
 }
 
-/* (a0, a1) * b + c in one issue slot: Blackwell's packed fp32 FMA (FFMA2, PTX
- * fma.rn.f32x2) with the scalars b, c broadcast; each half rounds like fmaf. */
-HRT_HD void hrt_fma_pair(float a0, float a1, float b, float c, float *r0, float *r1)
-{
-#if defined(__CUDA_ARCH__)
-  unsigned long long ra, rb, rc, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c), "f"(c));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(*r0), "=f"(*r1) : "l"(rd));
-#else
-  *r0 = fmaf(a0, b, c); *r1 = fmaf(a1, b, c);
-#endif
-}
-
-/* Same test when the node copy in use stores, per axis, the plane the ray
- * reaches first in the "lo" slot (one node copy per direction octant, see
- * hrt_emit_node): no per-axis min/max is needed. */
-HRT_HD bool hrt_slab_sorted(const HrtRayCull &c, float nx, float fx, float ny, float fy,
-                            float nz, float fz, float tmax, float *t_near)
-{
-  float x0, x1, y0, y1, z0, z1;
-  hrt_fma_pair(nx, fx, c.inv.x, c.ood.x, &x0, &x1);
-  hrt_fma_pair(ny, fy, c.inv.y, c.ood.y, &y0, &y1);
-  hrt_fma_pair(nz, fz, c.inv.z, c.ood.z, &z0, &z1);
-  const float tn = fmaxf(fmaxf(x0, y0), fmaxf(z0, 0.f));
-  const float tf = fminf(fminf(x1, y1), fminf(z1, tmax));
-  *t_near = tn;
-  return tn <= tf;
-}
-
 /* direction octant of a ray: bit k set when component k of 1/d is negative */
 HRT_HD uint32_t hrt_octant(const HrtRayCull &c)
 {
@@ -295,16 +263,6 @@ struct HrtGlobalMem {
     return tris[3 * s + k];
 #endif
   }
-  /* child record at byte offset `off` of the (octant's) node array */
-  HRT_HD void child_at(uint32_t off, float4 *xy, float4 *zr) const
-  {
-    const float4 *q = (const float4 *)((const char *)nodes + off);
-#if defined(__CUDA_ARCH__)
-    *xy = __ldg(q); *zr = __ldg(q + 1);
-#else
-    *xy = q[0]; *zr = q[1];
-#endif
-  }
   /* 4-wide nodes (hrt_bvh.cuh): float4 k of wide node i of the selected octant copy */
   const float4 *wnodes;
   HRT_HD float4 wide(int i, int k) const
@@ -322,23 +280,6 @@ struct HrtGlobalMem {
     asm volatile("" : "+l"(wnodes));
 #endif
   }
-  HRT_HD uint32_t cache_word(uint32_t, uint32_t) const { return 0u; }   /* no chain cache for global-memory scenes */
-  HRT_HD int child_ref(int i, uint32_t right) const
-  {
-    const int *q = (const int *)((const char *)nodes + ((size_t)i << 6) + (right ? 56u : 24u));
-#if defined(__CUDA_ARCH__)
-    return __ldg(q);
-#else
-    return *q;
-#endif
-  }
-  HRT_HD void select_octant(uint32_t oct, uint32_t stride)
-  {
-    nodes += (size_t)oct * stride;
-#if defined(__CUDA_ARCH__)
-    asm volatile("" : "+l"(nodes));   /* keep the octant's base in registers: do not recompute per node */
-#endif
-  }
 };
 
 #define HRT_STACK 64
@@ -348,163 +289,58 @@ struct __align__(8) HrtStackEntry { int ref; float tn; };
 struct HrtStackEntry { int ref; float tn; };
 #endif
 
-/* Origin chain.  Every shadow ray of one hit point starts inside the same
- * nested sequence of node boxes -- from the root down to (usually) the leaf of
- * the surface it starts on.  A ray that starts inside a box needs no test for
- * it, and which child contains the origin does not depend on the direction: the
- * walk down that chain is done once per hit point (`path`: bit k set = the
- * origin is in the RIGHT child at level k), and each of its rays then tests only
- * the SIBLING at every level -- one box test and no ordering decision instead of
- * two tests and a three-way branch.  Pure traversal order: results are the
- * minimum over (t, triangle id) as before. */
-struct HrtChain {
-  uint32_t path, depth;
-  uint32_t cached;      /* levels whose sibling record offsets sit in the per-thread cache (shared-memory scenes) */
-  uint32_t cache_addr;  /* shared-window byte address of this thread's entry 0; entries HRT_CHAIN_STRIDE bytes apart */
-};
-#define HRT_CHAIN_CACHE_LEVELS 6u
-HRT_HD HrtChain hrt_no_chain() { HrtChain c; c.path = 0u; c.depth = 0u; c.cached = 0u; c.cache_addr = 0u; return c; }
-
-/* `mem` must be the plain (octant 0) node copy: (lo, hi) per axis.  With
- * `cache` != NULL the byte offsets of the sibling records of the first
- * `max_cached` levels are stored at cache[level * stride_words], followed by the
- * ref at which that cached part of the chain ends. */
-template <class Mem>
-HRT_HD HrtChain hrt_origin_chain(const Mem &mem, int root_ref, uint32_t num_tris, V3 o,
-                                 uint32_t *cache = nullptr, uint32_t stride_words = 0, uint32_t max_cached = 0)
-{
-  HrtChain ch = hrt_no_chain();
-  if (num_tris == 0) return ch;
-  int cur = root_ref;
-  while (cur >= 0 && ch.depth < 32u) {
-    const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1), n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
-    const bool in_l = o.x >= n0.x && o.x <= n0.y && o.y >= n0.z && o.y <= n0.w && o.z >= n1.x && o.z <= n1.y;
-    const bool in_r = o.x >= n2.x && o.x <= n2.y && o.y >= n2.z && o.y <= n2.w && o.z >= n3.x && o.z <= n3.y;
-    if (!in_l && !in_r) break;
-    if (cache && ch.depth < max_cached) {
-      cache[ch.depth * stride_words] = ((uint32_t)cur << 6) + (in_l ? 32u : 0u);   /* the sibling's record */
-      ch.cached = ch.depth + 1u;
-    }
-    if (in_l) cur = hrt_float_as_int(n1.z);
-    else { ch.path |= 1u << ch.depth; cur = hrt_float_as_int(n3.z); }
-    ++ch.depth;
-    if (cache && ch.depth == ch.cached) cache[ch.depth * stride_words] = (uint32_t)cur;
-  }
-  return ch;
-}
-
-/* Closest hit over the BVH == the reference's loop over every triangle
- * (moeller_trumbore, :237-287): minimum t, ties to the lowest (mesh, face).
+/* Closest hit over the BINARY tree as built (plain node copy) == the reference's
+ * loop over every triangle (moeller_trumbore, :237-287): minimum t, ties to the
+ * lowest (mesh, face).  The kernels walk the 4-wide tree collapsed from it
+ * (hrt_closest_hit_wide); this walk is kept as the independent cross-check of
+ * the collapse that tests/emul runs against the oracle.
  * root_ref: inner node index, a leaf ref, or 0 with num_tris == 0. */
-/* SORTED: `mem_in.nodes` holds 8 consecutive copies of the node array, one per
- * direction octant (hrt_emit_node), `oct_stride` float4s apart. */
-template <bool SORTED, class Mem, class Gid, class Cnt>
-HRT_HD HrtHit hrt_closest_hit(const Mem &mem_in, const Gid tri_gid, int root_ref,
-                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt, uint32_t oct_stride = 0,
-                              HrtChain chain = hrt_no_chain())
+template <class Mem, class Gid, class Cnt>
+HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const Gid tri_gid, int root_ref,
+                              uint32_t num_tris, V3 o, V3 d, Cnt &cnt)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
-  HrtRayCull c = hrt_ray_cull(o, d);
-#if defined(__CUDA_ARCH__)
-  asm volatile("" : "+f"(c.ood.x), "+f"(c.ood.y), "+f"(c.ood.z));   /* likewise -o/d */
-#endif
-  Mem mem = mem_in;
-  if (SORTED) mem.select_octant(hrt_octant(c), oct_stride);
+  const HrtRayCull c = hrt_ray_cull(o, d);
   float tmax = HRT_T_MAX * 1.0001f;          /* far bound with slack */
-  HrtStackEntry stack[HRT_STACK];    /* (subtree ref, entry distance): one 8-byte store / load each */
+  HrtStackEntry stack[HRT_STACK];
   int sp = 0, cur = root_ref;
-  bool done = false;
-  /* the origin's chain (hrt_origin_chain): siblings only.  First the levels whose
-   * sibling record offsets were cached per thread, then the rest by path bits. */
-  for (uint32_t lvl = 0; lvl < chain.cached; ++lvl) {
-    float4 sxy, szr;
-    mem.child_at(mem.cache_word(chain.cache_addr, lvl), &sxy, &szr);
-    float ts;
-    const bool hs = SORTED ? hrt_slab_sorted(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts)
-                           : hrt_slab(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts);
-    cnt.box(1u);
-    if (hs) {
-      HrtStackEntry e;
-      e.ref = hrt_float_as_int(szr.z); e.tn = ts;
-      stack[sp++] = e;
-    }
-  }
-  if (chain.cached) cur = (int)mem.cache_word(chain.cache_addr, chain.cached);
-  for (uint32_t lvl = chain.cached; lvl < chain.depth; ++lvl) {
-    const uint32_t right = (chain.path >> lvl) & 1u;      /* origin in the right child: test the left */
-    float4 sxy, szr;
-    mem.child_at(((uint32_t)cur << 6) + (right ? 0u : 32u), &sxy, &szr);
-    float ts;
-    const bool hs = SORTED ? hrt_slab_sorted(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts)
-                           : hrt_slab(c, sxy.x, sxy.y, sxy.z, sxy.w, szr.x, szr.y, tmax, &ts);
-    cnt.box(1u);
-    if (hs) {
-      HrtStackEntry e;
-      e.ref = hrt_float_as_int(szr.z); e.tn = ts;
-      stack[sp++] = e;
-    }
-    cur = mem.child_ref(cur, right);
-  }
-  /* "while-while" traversal: every lane first walks inner nodes until it holds
-   * a leaf (or has nothing left), then the leaves are tested -- lanes of a warp
-   * meet in the triangle loop instead of interleaving box and triangle code. */
-  while (!done) {
+  for (;;) {
     while (cur >= 0) {
-      const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1);
-      const float4 n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
+      const float4 n0 = mem.node(cur, 0), n1 = mem.node(cur, 1), n2 = mem.node(cur, 2), n3 = mem.node(cur, 3);
       float tl, tr;
-      const bool hl = SORTED ? hrt_slab_sorted(c, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tmax, &tl)
-                             : hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tmax, &tl);
-      const bool hr = SORTED ? hrt_slab_sorted(c, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, tmax, &tr)
-                             : hrt_slab(c, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, tmax, &tr);
+      const bool hl = hrt_slab(c, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tmax, &tl);
+      const bool hr = hrt_slab(c, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, tmax, &tr);
       const int rl = hrt_float_as_int(n1.z), rr = hrt_float_as_int(n3.z);
       cnt.box(2u);
       if (hl && hr) {
         const bool left_first = tl <= tr;
         HrtStackEntry e;
-        e.ref = left_first ? rr : rl;
-        e.tn  = left_first ? tr : tl;
+        e.ref = left_first ? rr : rl; e.tn = left_first ? tr : tl;
         stack[sp++] = e;
         cur = left_first ? rl : rr;
-      } else if (hl) {
-        cur = rl;
-      } else if (hr) {
-        cur = rr;
-      } else {
-        /* pop, skipping subtrees that start beyond the current best */
+      } else if (hl) cur = rl;
+      else if (hr) cur = rr;
+      else {
         bool got = false;
-        while (sp > 0) {
-          --sp;
-          const HrtStackEntry e = stack[sp];
-          if (e.tn <= tmax) { cur = e.ref; got = true; break; }
-        }
-        if (!got) { done = true; break; }
+        while (sp > 0) { const HrtStackEntry e = stack[--sp]; if (e.tn <= tmax) { cur = e.ref; got = true; break; } }
+        if (!got) return h;
       }
     }
-    if (done) break;
-    {
-      const uint32_t code = (uint32_t)~cur;
-      const uint32_t first = code >> 3, ntri = (code & 7u) + 1u;
-      for (uint32_t k = 0; k < ntri; ++k) {
-        const uint32_t s = first + k;
-        float t;
-        const uint32_t gid = tri_gid[s];
-        if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) {
-          h.t = t; h.gid = gid; h.slot = s;
-          tmax = HRT_FMA(t, 1.0001f, 1e-30f);
-        }
+    const uint32_t code = (uint32_t)~cur, first = code >> 3, ntri = (code & 7u) + 1u;
+    for (uint32_t k = 0; k < ntri; ++k) {
+      const uint32_t s = first + k;
+      float t;
+      const uint32_t gid = tri_gid[s];
+      if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) {
+        h.t = t; h.gid = gid; h.slot = s;
+        tmax = HRT_FMA(t, 1.0001f, 1e-30f);
       }
     }
     bool got = false;
-    while (sp > 0) {
-      --sp;
-      const HrtStackEntry e = stack[sp];
-      if (e.tn <= tmax) { cur = e.ref; got = true; break; }
-    }
-    if (!got) done = true;
+    while (sp > 0) { const HrtStackEntry e = stack[--sp]; if (e.tn <= tmax) { cur = e.ref; got = true; break; } }
+    if (!got) return h;
   }
-  return h;
 }
 
 /* Closest hit over the 4-wide tree (hrt_bvh.cuh, "4-wide nodes"): the same

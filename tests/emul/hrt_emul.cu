@@ -114,11 +114,11 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   std::vector<int> used(n - 1), newidx(n - 1);
   int count = 0;
   for (int i = 0; i < n - 1; ++i) { used[i] = (kla[i] - kf[i] + 1) > leaf_max; newidx[i] = count; count += used[i]; }
-  E.num_nodes = count; E.nodes.resize(4 * (size_t)count * 8); E.root = 0;   /* 8 octant copies */
+  E.num_nodes = count; E.nodes.resize(4 * (size_t)count); E.root = 0;   /* one plain copy */
   const float pad = hrt_box_pad(max_abs, pad_ulps);
   for (int i = 0; i < n - 1; ++i) {
     if (!used[i]) continue;
-    for (uint32_t oct = 0; oct < 8; ++oct)
+    for (uint32_t oct = 0; oct < 1; ++oct)
       hrt_emit_node(&E.nodes[4 * ((size_t)oct * count + newidx[i])],
                     hrt_child_ref(kl[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
                     hrt_child_ref(kr[i], n, kf.data(), kla.data(), newidx.data(), leaf_max),
@@ -127,22 +127,14 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   collapse_wide(E);
 }
 
-static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute, HrtChain chain = hrt_no_chain())
+static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
 {
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
   HrtNoCount nc;
   if (brute == 1) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
-  if (brute == 2) return hrt_closest_hit<false>(m, E.gid.data(), E.root, E.n, o, d, nc, 0u, chain);   /* binary, plain node copy */
-  if (brute == 3) return hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, o, d, nc, E.num_nodes * 4u, chain);  /* binary, octant copies */
+  if (brute == 2) return hrt_closest_hit(m, E.gid.data(), E.root, E.n, o, d, nc);                        /* binary tree as built */
   if (brute == 4) return hrt_closest_hit_wide<false>(m, E.gid.data(), E.wroot, E.n, o, d, nc);        /* 4-wide, plain copy (octant 0) */
   return hrt_closest_hit_wide<true>(m, E.gid.data(), E.wroot, E.n, o, d, nc, (size_t)E.num_wide * HRT_WIDE_F4);  /* 4-wide: what the kernels run */
-}
-
-/* the shadow rays of a hit point start from its origin chain, as in k_scatter */
-static HrtChain chain_of(const EmulScene &E, V3 o)
-{
-  HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
-  return hrt_origin_chain(m, E.root, E.n, o);
 }
 
 /* receiver maps (hrt_rxmap.cuh), built serially with the same two-level scheme and
@@ -305,12 +297,11 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
         hrt_bounce_update(s, mat, k, h.t, n, theta);
         float carry = theta, cx_carry = HRT_CX_PRIMARY;
         const float ci_p = cosf(theta), si_p = sinf(theta);
-        const HrtChain chain = brute == 1 ? hrt_no_chain() : chain_of(E, s.o);
         for (size_t r = 0; r < R; ++r) {
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
-          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist) : query(E, s.o, sd, brute, chain);
+          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist) : query(E, s.o, sd, brute);
           if (sh.gid != HRT_NONE) { carry = hrt_theta_fold(nrm(E, sh.slot), sd); cx_carry = v3_dot(nrm(E, sh.slot), sd); }
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
           /* closed_form: what k_scatter runs (hrt_scatter_path_auto); else the reference's formulas line by line */
@@ -338,10 +329,8 @@ extern "C" int emul_count_work(const Scene *sc, const Ray *rays, size_t n, int l
   const bool binary = getenv("EMUL_COUNT_BINARY") != nullptr;
   for (size_t i = 0; i < n; ++i) {
     for (int k = 0; k < 5; ++k) c.c[k] = 0;
-    if (binary) hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c, E.num_nodes * 4u);
+    if (binary) hrt_closest_hit(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c);
     else hrt_closest_hit_wide<true>(m, E.gid.data(), E.wroot, E.n, tov(rays[i].o), tov(rays[i].d), c, (size_t)E.num_wide * HRT_WIDE_F4);
-    if (0)
-    hrt_closest_hit<true>(m, E.gid.data(), E.root, E.n, tov(rays[i].o), tov(rays[i].d), c, E.num_nodes * 4u);
     for (int k = 0; k < 5; ++k) tot[k] += c.c[k];
   }
   for (int k = 0; k < 5; ++k) out[k] = (double)tot[k] / (double)n;
