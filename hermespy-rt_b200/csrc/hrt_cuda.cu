@@ -78,10 +78,11 @@ struct SceneDev {
 };
 
 /* receiver maps (hrt_rxmap.cuh).  Cell word: (offset of the cell's list inside the
- * receiver's item range << 8) | length; items are leaf slots. */
+ * receiver's item range << 8) | length. */
 struct RxMapDev {
   const uint32_t *cells;       /* [R][6 G G] */
-  const uint16_t *items;       /* [R][items_per_rx] */
+  const uint32_t *items;       /* [R][items_per_rx]: slot | q_hi << 16 | q_lo << 24 (depth bounds, hrt_rxmap.cuh) */
+  const float *inv_step;       /* [R] depth quantisation of each receiver's items */
   uint32_t G, items_per_rx;
 };
 
@@ -230,7 +231,7 @@ struct hrt_ctx {
 
   /* receiver maps (hrt_rxmap.cuh) of the last run's receivers, reused while the
    * receivers, the scene and the padding stay the same */
-  uint32_t *d_map_cells; uint16_t *d_map_items; uint32_t *d_map_cursor;   /* cursor[R], then status[1] */
+  uint32_t *d_map_cells; uint32_t *d_map_items; uint32_t *d_map_cursor;   /* cursor[R], then status[1], then inv_step[R] (float) */
   size_t cap_map_cells, cap_map_items, cap_map_cursor;
   uint32_t map_G, map_items_per_rx, map_R; bool map_valid;
   uint64_t map_key, scene_version;
@@ -878,14 +879,23 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
     if (R * (size_t)per_rx >= ((size_t)1 << 32)) break;          /* beyond the kernels' 32-bit item index: walk the BVH */
     if (ctx->cap_map_cells < cells) { dev_free(ctx->d_map_cells); ctx->cap_map_cells = 0; CK(dev_alloc(&ctx->d_map_cells, cells)); ctx->cap_map_cells = cells; }
     if (ctx->cap_map_items < R * (size_t)per_rx) { dev_free(ctx->d_map_items); ctx->cap_map_items = 0; CK(dev_alloc(&ctx->d_map_items, R * (size_t)per_rx)); ctx->cap_map_items = R * (size_t)per_rx; }
-    if (ctx->cap_map_cursor < R + 1) { dev_free(ctx->d_map_cursor); ctx->cap_map_cursor = 0; CK(dev_alloc(&ctx->d_map_cursor, R + 1)); ctx->cap_map_cursor = R + 1; }
+    if (ctx->cap_map_cursor < 2 * R + 1) { dev_free(ctx->d_map_cursor); ctx->cap_map_cursor = 0; CK(dev_alloc(&ctx->d_map_cursor, 2 * R + 1)); ctx->cap_map_cursor = 2 * R + 1; }
     if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); }
     CK(cudaMemsetAsync(ctx->d_map_cursor, 0, (R + 1) * 4, st));
+    {
+      /* depth quantisation per receiver: 255 steps up to the farthest corner of the scene's bounds */
+      std::vector<float> is(R);
+      const V3 lo = v3(ctx->scene_lo[0], ctx->scene_lo[1], ctx->scene_lo[2]), hi = v3(ctx->scene_hi[0], ctx->scene_hi[1], ctx->scene_hi[2]);
+      for (size_t r = 0; r < R; ++r) is[r] = hrt_rxmap_inv_step(v3(p->rx_pos[r].x, p->rx_pos[r].y, p->rx_pos[r].z), lo, hi);
+      CK(cudaMemcpyAsync(ctx->d_map_cursor + R + 1, is.data(), R * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));               /* `is` is a temporary */
+    }
     CK(cudaEventRecord(e0, st));
     const SceneDev sc = scene_dev(ctx);
     const uint32_t nb = G / HRT_RXMAP_BLOCK;
     k_rxmap_build<<<dim3(nb * nb, 6, (unsigned)R), 64, 0, st>>>(sc, d_rx, G, 4.f * ctx->pad, ctx->d_map_cells, ctx->d_map_items,
-                                                               per_rx, ctx->d_map_cursor, ctx->d_map_cursor + R);
+                                                               per_rx, (const float *)(ctx->d_map_cursor + R + 1),
+                                                               ctx->d_map_cursor, ctx->d_map_cursor + R);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
     uint32_t status = 0;
@@ -1379,6 +1389,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     if (want && smem && !brute) { rc = ensure_rxmap(ctx, p, d_rx, st, &use_map); if (rc) return rc; }
   }
   rd.map.cells = ctx->d_map_cells; rd.map.items = ctx->d_map_items; rd.map.G = ctx->map_G; rd.map.items_per_rx = ctx->map_items_per_rx;
+  rd.map.inv_step = (const float *)(ctx->d_map_cursor + p->num_rx + 1);
   const ScatterFn f_scatter = use_map ? (lean ? scatter_fn_map_lean(warp_mode) : scatter_fn_map(warp_mode, count))
                                       : lean ? scatter_fn_lean(smem, warp_mode) : scatter_fn(smem, brute, warp_mode, count);
   S.rx_map = use_map; S.rx_map_build_ms = use_map ? ctx->map_build_ms : 0.f; S.rx_map_cells = use_map ? ctx->map_G : 0;

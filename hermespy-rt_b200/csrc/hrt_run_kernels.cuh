@@ -97,9 +97,11 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
  * (hrt_rxmap.cuh).  Cell word: (offset of the cell's list inside the receiver's
  * item range << 8) | length; items are leaf slots (uint16). */
 /* shadow query through the map of receiver r: exact tests of the candidates of
- * cell (-d) -- between hit point and receiver, and behind the hit point -- and,
- * unless that already produced a hit in front of the receiver (dist: distance
- * to it), of cell (+d), beyond the receiver.  Triangle records staged in shared
+ * cell (-d) -- between hit point and receiver -- nearest to the hit point first,
+ * without the ones that lie entirely behind it and stopping once nothing left can
+ * be closer than the best hit (depth bounds of the items, hrt_rxmap.cuh); then,
+ * unless that already produced a hit in front of the receiver (dist: distance to
+ * it), of cell (+d), beyond the receiver.  Triangle records staged in shared
  * memory at offset 0. */
 template <class Cnt>
 __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, float dist, Cnt &cnt,
@@ -111,21 +113,28 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
   const uint32_t gid_addr = m.tri_addr + sc.num_tris * 48u;
   /* 32-bit index arithmetic (the host checks that R * 6 G^2 and R * items_per_rx fit) */
   const uint32_t cell0 = r * (6u * mp.G * mp.G);
-  const uint16_t *items = mp.items + r * mp.items_per_rx;
+  const uint32_t *items = mp.items + r * mp.items_per_rx;
   uint32_t c_pos, c_neg;
   hrt_rxmap_cells2(d, mp.G, &c_pos, &c_neg);
   uint32_t w = __ldg(&mp.cells[cell0 + c_neg]);
   const uint32_t w_pos = __ldg(&mp.cells[cell0 + c_pos]);
+  const HrtMapDepth md = hrt_rxmap_query_depth(dist, __ldg(&mp.inv_step[r]));
+  int q_stop = -1;
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
-    const uint16_t *it = items + (w >> 8), *end = it + (w & 255u);
+    const uint32_t *it = items + (w >> 8), *end = it + (w & 255u);
 #pragma unroll 1
     for (; it != end; ++it) {
-      const uint32_t s = __ldg(it);
+      const uint32_t iw = __ldg(it), s = iw & 0xFFFFu;
+      if (side == 0) {
+        if ((int)((iw >> 16) & 255u) < q_stop) break;          /* everything left is farther from o than the best hit */
+        if ((int)(iw >> 24) > md.q_behind) continue;           /* entirely behind o */
+      }
       float t;
       if (hrt_mt_test<Cnt, true>(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, 0u, 0u, &t, cnt)) {
         const uint32_t gid = lds32(gid_addr + 4u * s);
         if (t < h.t || gid < h.gid) { h.t = t; h.gid = gid; h.slot = s; }     /* t == h.t: lowest id wins (:275) */
+        if (side == 0) q_stop = hrt_rxmap_stop(md, h.t);
       }
     }
     /* a hit clearly in front of the receiver: nothing beyond it can be closer */
@@ -142,8 +151,8 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
  * back to the BVH for this run). */
 #define HRT_RXMAP_CAND 1024
 __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx_pos, uint32_t G, float pad,
-                                                    uint32_t *cells, uint16_t *items, uint32_t items_per_rx,
-                                                    uint32_t *cursor, uint32_t *status)
+                                                    uint32_t *cells, uint32_t *items, uint32_t items_per_rx,
+                                                    const float *inv_step, uint32_t *cursor, uint32_t *status)
 {
   __shared__ uint16_t cand[HRT_RXMAP_CAND];
   __shared__ uint32_t ncand, base, wtot[2];
@@ -189,13 +198,18 @@ __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx
   if (!fits) atomicOr(status, 1u);
   cells[((size_t)(r * 6u + face) * G + j) * G + i] = fits ? ((off << 8) | count) : 0u;
   if (!fits) return;
-  uint16_t *dst = items + (size_t)r * items_per_rx + off;
+  uint32_t *dst = items + (size_t)r * items_per_rx + off, nw = 0;
+  const float is = inv_step[r];
   for (uint32_t k = 0; k < nc; ++k) {
     const uint32_t s = cand[k];
     V3 va, vb, vc;
     hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
-    if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) *dst++ = (uint16_t)s;
+    if (!hrt_rxmap_overlap(cp, va, vb, vc, pad)) continue;
+    float dl, dh;
+    hrt_rxmap_depth(cp, va, vb, vc, pad, G, &dl, &dh);
+    dst[nw++] = hrt_rxmap_item(s, dl, dh, is);
   }
+  hrt_rxmap_sort_items(dst, nw);                           /* nearest to a hit point on the far side first */
 }
 
 template <bool COUNT> struct CntSel { typedef HrtNoCount type; };

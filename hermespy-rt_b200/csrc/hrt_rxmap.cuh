@@ -163,3 +163,114 @@ HRT_HD void hrt_rxmap_corners(float4 q0, float4 q1, float4 q2, V3 r, V3 *va, V3 
   *vb = v3(a.x + q0.w, a.y + q1.x, a.z + q1.y);
   *vc = v3(a.x + q1.z, a.y + q1.w, a.z + q2.x);
 }
+
+/* ---- depth bounds of a list item ----
+ * Every item of a cell's list carries conservative bounds [d_lo, d_hi] on the
+ * distance from the receiver at which a line inside the cell can touch the
+ * triangle, quantised to 8 bits each with a per-receiver step.  A query walking
+ * from the hit point o (at distance D from the receiver) towards the receiver
+ *   - skips items that lie entirely behind o (d_lo > D): they could only give t < 0;
+ *   - visits the rest nearest-to-o first (lists are sorted by d_hi, descending) and
+ *     stops as soon as the best hit so far is closer to o than anything left.
+ * Item word: slot | q_hi << 16 | q_lo << 24.  Bounds: the triangle as a whole
+ * (exact point-triangle distance, farthest corner), tightened by the distances at
+ * which the cell's corner rays meet the triangle's plane when all four do so at a
+ * non-grazing angle. */
+HRT_HD float hrt_point_tri_dist2(V3 a, V3 b, V3 c)     /* squared distance of the origin from triangle (a, b, c) (Ericson, RTCD 5.1.5) */
+{
+  const V3 ab = v3(b.x - a.x, b.y - a.y, b.z - a.z), ac = v3(c.x - a.x, c.y - a.y, c.z - a.z);
+  const V3 ap = v3(-a.x, -a.y, -a.z);
+  const float d1 = hrt_dot3(ab, ap), d2 = hrt_dot3(ac, ap);
+  if (d1 <= 0.f && d2 <= 0.f) return hrt_dot3(a, a);
+  const V3 bp = v3(-b.x, -b.y, -b.z);
+  const float d3 = hrt_dot3(ab, bp), d4 = hrt_dot3(ac, bp);
+  if (d3 >= 0.f && d4 <= d3) return hrt_dot3(b, b);
+  const float vc = d1 * d4 - d3 * d2;
+  if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const float v = d1 / (d1 - d3); const V3 q = v3(a.x + v * ab.x, a.y + v * ab.y, a.z + v * ab.z); return hrt_dot3(q, q); }
+  const V3 cp = v3(-c.x, -c.y, -c.z);
+  const float d5 = hrt_dot3(ab, cp), d6 = hrt_dot3(ac, cp);
+  if (d6 >= 0.f && d5 <= d6) return hrt_dot3(c, c);
+  const float vb = d5 * d2 - d1 * d6;
+  if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const float w = d2 / (d2 - d6); const V3 q = v3(a.x + w * ac.x, a.y + w * ac.y, a.z + w * ac.z); return hrt_dot3(q, q); }
+  const float va = d3 * d6 - d5 * d4;
+  if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+    const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    const V3 q = v3(b.x + w * (c.x - b.x), b.y + w * (c.y - b.y), b.z + w * (c.z - b.z));
+    return hrt_dot3(q, q);
+  }
+  const float den = 1.f / (va + vb + vc), v = vb * den, w = vc * den;
+  const V3 q = v3(a.x + ab.x * v + ac.x * w, a.y + ab.y * v + ac.y * w, a.z + ab.z * v + ac.z * w);
+  return hrt_dot3(q, q);
+}
+
+/* conservative [d_lo, d_hi] for triangle (va, vb, vc: corners relative to the apex) inside pyramid p
+ * of a G-cell map; pad as in hrt_rxmap_overlap */
+HRT_HD void hrt_rxmap_depth(const HrtPyramid &p, V3 va, V3 vb, V3 vc, float pad, uint32_t G, float *d_lo, float *d_hi)
+{
+  float lo = sqrtf(fmaxf(hrt_point_tri_dist2(va, vb, vc), 0.f)) * 0.9999f - pad;
+  float hi = sqrtf(fmaxf(hrt_dot3(va, va), fmaxf(hrt_dot3(vb, vb), hrt_dot3(vc, vc)))) * 1.0001f + pad;
+  const V3 e1 = v3(vb.x - va.x, vb.y - va.y, vb.z - va.z), e2 = v3(vc.x - va.x, vc.y - va.y, vc.z - va.z);
+  V3 n = v3(e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x);
+  const float nl = sqrtf(hrt_dot3(n, n));
+  if (nl > 0.f) {
+    n = v3(n.x / nl, n.y / nl, n.z / nl);
+    float h = hrt_dot3(va, n);                       /* signed distance of the plane from the apex */
+    if (h < 0.f) { h = -h; n = v3(-n.x, -n.y, -n.z); }
+    float cmin = 2.f, cmax = -2.f;
+    for (int k = 0; k < 4; ++k) { const float c = hrt_dot3(p.c[k], n); cmin = fminf(cmin, c); cmax = fmaxf(cmax, c); }
+    if (cmin > 0.05f && h > 8.f * pad) {
+      /* all four corner rays meet the plane in front of the apex, none at a grazing angle: inside the
+       * pyramid the plane is met between h / (largest cosine) and h / (smallest cosine); the largest
+       * cosine inside the cell exceeds the corners' by at most the cell's angular diameter (< 3 / G) */
+      const float far_ = (h + pad) / cmin * 1.0001f;
+      const float near_ = (h - pad) / fminf(1.f, cmax + 3.f / (float)G) * 0.9999f;
+      hi = fminf(hi, far_); lo = fmaxf(lo, near_);
+    }
+  }
+  *d_lo = fmaxf(lo, 0.f); *d_hi = hi;
+}
+
+/* item word from a slot and its bounds; inv_step = 255 / (largest distance in the receiver's map) */
+HRT_HD uint32_t hrt_rxmap_item(uint32_t slot, float d_lo, float d_hi, float inv_step)
+{
+  const float ql = floorf(fminf(fmaxf(d_lo * inv_step, 0.f), 255.f));
+  const float qh = ceilf(fminf(fmaxf(d_hi * inv_step, 0.f), 255.f));
+  return slot | ((uint32_t)qh << 16) | ((uint32_t)ql << 24);
+}
+
+/* 255 / (distance from the apex to the farthest corner of the scene's bounding box, plus a metre) */
+HRT_HD float hrt_rxmap_inv_step(V3 apex, V3 lo, V3 hi)
+{
+  const float dx = fmaxf(fabsf(lo.x - apex.x), fabsf(hi.x - apex.x)), dy = fmaxf(fabsf(lo.y - apex.y), fabsf(hi.y - apex.y));
+  const float dz = fmaxf(fabsf(lo.z - apex.z), fabsf(hi.z - apex.z));
+  return 255.f / (sqrtf(dx * dx + dy * dy + dz * dz) + 1.f);
+}
+
+/* a cell's items by d_hi, descending (insertion sort: the lists are a handful of items) */
+HRT_HD void hrt_rxmap_sort_items(uint32_t *it, uint32_t n)
+{
+  for (uint32_t i = 1; i < n; ++i) {
+    const uint32_t w = it[i], key = (w >> 16) & 255u;
+    uint32_t j = i;
+    while (j > 0 && ((it[j - 1] >> 16) & 255u) < key) { it[j] = it[j - 1]; --j; }
+    it[j] = w;
+  }
+}
+
+/* Query-side thresholds in quantised units.  Margins: one quantisation step is already in the
+ * floor / ceil of the item bounds; on top 5 cm + 0.5 % of the distance cover the fp32 error of a
+ * computed t (up to ~1e-2 m for rays within 1e-3 rad of a plane; phantom hits excepted as always). */
+struct HrtMapDepth { float dist, inv_step; int q_behind; };
+HRT_HD HrtMapDepth hrt_rxmap_query_depth(float dist, float inv_step)
+{
+  HrtMapDepth m; m.dist = dist; m.inv_step = inv_step;
+  m.q_behind = (int)ceilf(fminf((dist * 1.005f + 0.05f) * inv_step, 300.f));    /* q_lo above this: entirely behind the hit point */
+  return m;
+}
+/* after a hit at distance t from o (between o and the receiver): items whose q_hi is below the result
+ * lie entirely farther from o than that hit */
+HRT_HD int hrt_rxmap_stop(const HrtMapDepth &m, float t)
+{
+  const float s = (m.dist - t) * 0.995f - 0.05f;                 /* distance of the hit from the receiver, less the margin */
+  return s > 0.f ? (int)floorf(fminf(s * m.inv_step, 300.f)) : -1;
+}

@@ -139,15 +139,26 @@ static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
 
 /* receiver maps (hrt_rxmap.cuh), built serially with the same two-level scheme and
  * element functions as the kernels k_rxmap_* */
-struct EmulRxMap { uint32_t G = 0; std::vector<uint32_t> start, count; std::vector<uint16_t> items; };
+struct EmulRxMap { uint32_t G = 0; std::vector<uint32_t> start, count; std::vector<uint32_t> items; std::vector<float> inv_step; };
 
 static void build_rxmap(const EmulScene &E, const Vec3 *rx, size_t R, uint32_t G, float pad, EmulRxMap &M)
 {
-  M.G = G; M.start.assign(R * 6 * G * G, 0); M.count.assign(R * 6 * G * G, 0); M.items.clear();
+  M.G = G; M.start.assign(R * 6 * G * G, 0); M.count.assign(R * 6 * G * G, 0); M.items.clear(); M.inv_step.assign(R, 0.f);
   const uint32_t nb = G / HRT_RXMAP_BLOCK;
   std::vector<uint32_t> cand;
+  /* scene bounds: the per-receiver quantisation step covers the farthest corner of the bounding box */
+  V3 lo = v3(3e38f, 3e38f, 3e38f), hi = v3(-3e38f, -3e38f, -3e38f);
+  for (uint32_t s = 0; s < E.n; ++s) {
+    const float4 q0 = E.tris[3 * s], q1 = E.tris[3 * s + 1], q2 = E.tris[3 * s + 2];
+    const V3 c[3] = { v3(q0.x, q0.y, q0.z), v3(q0.x + q0.w, q0.y + q1.x, q0.z + q1.y), v3(q0.x + q1.z, q0.y + q1.w, q0.z + q2.x) };
+    for (int k = 0; k < 3; ++k) {
+      lo = v3(fminf(lo.x, c[k].x), fminf(lo.y, c[k].y), fminf(lo.z, c[k].z));
+      hi = v3(fmaxf(hi.x, c[k].x), fmaxf(hi.y, c[k].y), fmaxf(hi.z, c[k].z));
+    }
+  }
   for (size_t r = 0; r < R; ++r) {
     const V3 apex = v3(rx[r].x, rx[r].y, rx[r].z);
+    M.inv_step[r] = hrt_rxmap_inv_step(apex, lo, hi);
     for (uint32_t f = 0; f < 6; ++f)
       for (uint32_t bj = 0; bj < nb; ++bj)
         for (uint32_t bi = 0; bi < nb; ++bi) {
@@ -165,29 +176,39 @@ static void build_rxmap(const EmulScene &E, const Vec3 *rx, size_t R, uint32_t G
               M.start[cell] = (uint32_t)M.items.size();
               for (uint32_t s : cand) {
                 V3 va, vb, vc; hrt_rxmap_corners(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], apex, &va, &vb, &vc);
-                if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) M.items.push_back((uint16_t)s);
+                if (!hrt_rxmap_overlap(cp, va, vb, vc, pad)) continue;
+                float dl, dh; hrt_rxmap_depth(cp, va, vb, vc, pad, G, &dl, &dh);
+                M.items.push_back(hrt_rxmap_item(s, dl, dh, M.inv_step[r]));
               }
               M.count[cell] = (uint32_t)M.items.size() - M.start[cell];
+              hrt_rxmap_sort_items(&M.items[M.start[cell]], M.count[cell]);
             }
         }
   }
 }
 
-/* shadow query through the receiver map: the exact test of the candidates of cells (+d) and (-d) */
+/* shadow query through the receiver map, exactly as query_map in hrt_run_kernels.cuh */
 static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, V3 d, float dist, unsigned long long *tests = nullptr)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   HrtNoCount nc;
   uint32_t c_pos, c_neg;
-  hrt_rxmap_cells2(d, M.G, &c_pos, &c_neg);          /* as the kernel: (-d) first, (+d) only if nothing in front of the receiver */
+  hrt_rxmap_cells2(d, M.G, &c_pos, &c_neg);          /* (-d) first, (+d) only if nothing in front of the receiver */
+  const HrtMapDepth md = hrt_rxmap_query_depth(dist, M.inv_step[r]);
+  int q_stop = -1;
   for (int side = 0; side < 2; ++side) {
     const size_t cell = r * 6 * M.G * M.G + (side ? c_pos : c_neg);
     for (uint32_t k = 0; k < M.count[cell]; ++k) {
-      const uint32_t s = M.items[M.start[cell] + k];
+      const uint32_t w = M.items[M.start[cell] + k], s = w & 0xFFFFu;
+      if (side == 0) {
+        if ((int)((w >> 16) & 255u) < q_stop) break;           /* everything left is farther from o than the best hit */
+        if ((int)(w >> 24) > md.q_behind) continue;            /* entirely behind o */
+      }
       float t;
       if (tests) ++*tests;
       if (hrt_mt_test<HrtNoCount, true>(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], o, d, h.t, 0u, 0u, &t, nc)) {
         if (t < h.t || E.gid[s] < h.gid) { h.t = t; h.gid = E.gid[s]; h.slot = s; }
+        if (side == 0) q_stop = hrt_rxmap_stop(md, h.t);
       }
     }
     if (h.t < dist * 0.999f) break;
