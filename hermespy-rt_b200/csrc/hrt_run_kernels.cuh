@@ -113,7 +113,7 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
   const uint32_t gid_addr = m.tri_addr + sc.num_tris * 48u;
   /* 32-bit index arithmetic (the host checks that R * 6 G^2 and R * items_per_rx fit) */
   const uint32_t cell0 = r * (6u * mp.G * mp.G);
-  const uint32_t *items = mp.items + r * mp.items_per_rx;
+  const uint32_t item0 = r * mp.items_per_rx;
   uint32_t c_pos, c_neg;
   hrt_rxmap_cells2(d, mp.G, &c_pos, &c_neg);
   uint32_t w = __ldg(&mp.cells[cell0 + c_neg]);
@@ -122,10 +122,11 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
   int q_stop = -1;
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
-    const uint32_t *it = items + (w >> 8), *end = it + (w & 255u);
+    uint32_t k = item0 + (w >> 8);
+    const uint32_t kend = k + (w & 255u);
 #pragma unroll 1
-    for (; it != end; ++it) {
-      const uint32_t iw = __ldg(it), s = iw & 0xFFFFu;
+    for (; k != kend; ++k) {
+      const uint32_t iw = __ldg(&mp.items[k]), s = iw & 0xFFFFu;
       if (side == 0) {
         if ((int)((iw >> 16) & 255u) < q_stop) break;          /* everything left is farther from o than the best hit */
         if ((int)(iw >> 24) > md.q_behind) continue;           /* entirely behind o */
@@ -615,6 +616,16 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
     sincosf(theta_p, &si_p, &ci_p);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
     const uint64_t hkey = hrt_mix64((path << 32) | gid);
+    /* thread-per-hit summary: the warp's total of the hit keys, once per batch -- it is the hash sum of
+     * every receiver for which all 32 lanes have a valid path (most of them) */
+    unsigned long long hkey_all = 0ull;
+    if (!WARP && summary) {
+      const unsigned long long hk = valid ? hkey : 0ull;
+      hkey_all = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk & 0xFFFFu))
+               + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 16) & 0xFFFFu)) << 16)
+               + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 32) & 0xFFFFu)) << 32)
+               + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk >> 48)) << 48);
+    }
 
     const uint32_t step = WARP ? 32u : 1u;
     for (uint32_t r0 = 0; r0 < R; r0 += step) {
@@ -742,6 +753,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
             /* integer sums: one REDUX per 16-bit digit (32 x 65535 fits 32 bits) */
             const unsigned long long hk = ok ? hkey : 0ull;
             const unsigned tb = ok ? __float_as_uint(p.tau) : 0u;
+            if (m_ok == 0xFFFFFFFFu) hsum = hkey_all;
+            else
             hsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(hk & 0xFFFFu))
                  + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 16) & 0xFFFFu)) << 16)
                  + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)((hk >> 32) & 0xFFFFu)) << 32)

@@ -264,13 +264,23 @@ struct HrtMapDepth { float dist, inv_step; int q_behind; };
 HRT_HD HrtMapDepth hrt_rxmap_query_depth(float dist, float inv_step)
 {
   HrtMapDepth m; m.dist = dist; m.inv_step = inv_step;
-  m.q_behind = (int)ceilf(fminf((dist * 1.005f + 0.05f) * inv_step, 300.f));    /* q_lo above this: entirely behind the hit point */
+  const float q = fminf(HRT_FMA(dist, 1.005f, 0.05f) * inv_step, 300.f);        /* q_lo above this: entirely behind the hit point */
+#if defined(__CUDA_ARCH__)
+  m.q_behind = __float2int_ru(q);
+#else
+  m.q_behind = (int)ceilf(q);
+#endif
   return m;
 }
 /* after a hit at distance t from o (between o and the receiver): items whose q_hi is below the result
  * lie entirely farther from o than that hit */
 HRT_HD int hrt_rxmap_stop(const HrtMapDepth &m, float t)
 {
-  const float s = (m.dist - t) * 0.995f - 0.05f;                 /* distance of the hit from the receiver, less the margin */
-  return s > 0.f ? (int)floorf(fminf(s * m.inv_step, 300.f)) : -1;
+  const float s = HRT_FMA(m.dist - t, 0.995f, -0.05f);           /* distance of the hit from the receiver, less the margin */
+  const float q = fminf(s * m.inv_step, 300.f);                  /* s <= 0: q <= 0, nothing is below it */
+#if defined(__CUDA_ARCH__)
+  return __float2int_rd(q);
+#else
+  return (int)floorf(q);
+#endif
 }
