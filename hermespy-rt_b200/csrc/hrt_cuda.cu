@@ -234,7 +234,7 @@ struct hrt_ctx {
   uint32_t *d_map_cells; uint32_t *d_map_items; uint32_t *d_map_cursor;   /* cursor[R], then status[1], then inv_step[R] (float) */
   size_t cap_map_cells, cap_map_items, cap_map_cursor;
   uint32_t map_G, map_items_per_rx, map_R; bool map_valid;
-  uint64_t map_key, scene_version;
+  uint64_t map_key, map_failed_key, scene_version;
   float map_build_ms;
 
   bool have_mats;
@@ -870,6 +870,7 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
   uint64_t key = hash_bytes(p->rx_pos, R * sizeof(Vec3), 0xCBF29CE484222325ull);
   key = hash_bytes(&ctx->scene_version, 8, key); key = hash_bytes(&G, 4, key);
   if (ctx->map_valid && ctx->map_key == key && ctx->map_R == R && ctx->map_G == G) { *use = true; return HRT_OK; }
+  if (ctx->map_failed_key == key) return HRT_OK;                  /* did not fit last time either: walk the BVH */
   ctx->map_valid = false;
   uint32_t per_rx = (uint32_t)(6 * (size_t)G * G * 4);            /* items per receiver: 4 per cell on average, grown on overflow */
   if (const char *e = getenv("HRT_RXMAP_ITEMS_PER_CELL")) { int v = atoi(e); if (v >= 1 && v <= 64) per_rx = (uint32_t)(6 * (size_t)G * G * v); }
@@ -910,6 +911,7 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
     }
     per_rx *= 4;                                                   /* some list did not fit: more room, once or twice */
   }
+  if (!*use) ctx->map_failed_key = key;
   if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
   return HRT_OK;
 }
