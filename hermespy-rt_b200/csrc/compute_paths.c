@@ -21,6 +21,10 @@
  *   HRT_DEVICE=<n>        single CUDA device (default 0)
  *   HRT_NO_RAYSINFO=1     do not fill raysInfo_scat (saves the largest copy)
  *   HRT_NO_SCENE_CACHE=1  re-upload the scene and rebuild the BVH on every call
+ *   HRT_STRICT_UNTOUCHED=1  leave every word of the scatter gains, delays and directions that the
+ *                         reference leaves untouched (slots of rays that left the scene, directions of
+ *                         occluded slots) untouched as well, instead of writing 0 -- costs a second
+ *                         host copy of those arrays ("Unwritten outputs")
  */
 #include "../../include/hrt_cuda.h"
 
@@ -156,7 +160,39 @@ static void run_dense(
   p.los = chanInfo_los; p.rays_los = raysInfo_los;
   p.scat = chanInfo_scat; p.rays_scat = raysInfo_scat;
   if (a_te_c64) { p.flags |= HRT_FLAG_DENSE_C64; p.scat_a_te_c64 = a_te_c64; p.scat_a_tm_c64 = a_tm_c64; }
+  if (!getenv("HRT_STRICT_UNTOUCHED")) {
+    if (hrt_multi_run(ctx, &p) != HRT_OK) die("compute_paths failed", hrt_multi_last_error(ctx));
+    return;
+  }
+  /* Strict mode: the run fills temporaries, then only the words the reference writes are merged into
+   * the caller's arrays -- gains and delay where the ray was alive (:685-709), the arrival direction
+   * where the receiver was not occluded (:707).  freq_shift is written in full by the reference as well
+   * (its memcpy chain, :494-508) and RaysInfo rows are copied whole (:732-743): those go straight out. */
+  const size_t n = num_rx * num_tx * num_bounces * num_rays;
+  float *tmp = (float *)malloc((n ? n : 1) * 8 * sizeof(float));     /* 4 gains (or 2 x complex), tau, 3 direction words */
+  uint8_t *state = (uint8_t *)calloc(n ? n : 1, 1);
+  if (!tmp || !state) die("compute_paths", "out of memory (strict mode)");
+  ChannelInfo t = *chanInfo_scat;
+  t.a_te_re = tmp; t.a_te_im = tmp + n; t.a_tm_re = tmp + 2 * n; t.a_tm_im = tmp + 3 * n;
+  t.tau = tmp + 4 * n; t.directions_rx = (Vec3 *)(tmp + 5 * n);
+  p.scat = &t;
+  if (a_te_c64) { p.scat_a_te_c64 = tmp; p.scat_a_tm_c64 = tmp + 2 * n; }
+  p.flags |= HRT_FLAG_TRACE;
+  p.trace_slot_state = state;
   if (hrt_multi_run(ctx, &p) != HRT_OK) die("compute_paths failed", hrt_multi_last_error(ctx));
+  for (size_t i = 0; i < n; ++i) {
+    if (!state[i]) continue;                                   /* ray no longer alive: nothing written */
+    if (a_te_c64) {
+      a_te_c64[2 * i] = tmp[2 * i]; a_te_c64[2 * i + 1] = tmp[2 * i + 1];
+      a_tm_c64[2 * i] = tmp[2 * n + 2 * i]; a_tm_c64[2 * i + 1] = tmp[2 * n + 2 * i + 1];
+    } else {
+      chanInfo_scat->a_te_re[i] = t.a_te_re[i]; chanInfo_scat->a_te_im[i] = t.a_te_im[i];
+      chanInfo_scat->a_tm_re[i] = t.a_tm_re[i]; chanInfo_scat->a_tm_im[i] = t.a_tm_im[i];
+    }
+    chanInfo_scat->tau[i] = t.tau[i];
+    if (state[i] == 1) chanInfo_scat->directions_rx[i] = t.directions_rx[i];   /* 2: occluded, direction untouched */
+  }
+  free(tmp); free(state);
 }
 
 void compute_paths(

@@ -892,3 +892,41 @@ def test_complex64_entry_and_scene_cache(tmp_path):
     os_ = __import__("os"); os_.utime(path, None)
     b1 = rt.compute_paths(path, np.array([[0.0, 0.0, 0.15]]), np.array([[0.0, 0.0, 0.151]]), *args[2:])[1]
     assert not np.array_equal(a1.tau, b1.tau) and int((b1.tau > 0).sum()) > 1000
+
+
+def test_strict_untouched_mode():
+    """HRT_STRICT_UNTOUCHED=1 (SURVEY 8(b) "Unwritten outputs"): compute_paths() leaves exactly the
+    words of gains, delays and arrival directions untouched that the reference leaves untouched --
+    pre-filled with 0x5A, they still hold 0x5A afterwards wherever the oracle's do -- and writes the
+    reference's values everywhere else."""
+    import os
+    scene, rx, tx, f = tl.CONFIGS["canyon_moving"]
+    rx = list(rx) + [[20.0, 2.0, 1.5]]
+    rxv, txv = [[0.5, -1.0, 0.25], [0, 0, 0]], [[3.0, 1.0, -0.5]]
+    P, B = 20000, 5
+    a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B, fill=0x5A)
+    L = hrt.lib()
+    sc = L.scene_load(tl.scene_path(scene).encode())
+    os.environ["HRT_STRICT_UNTOUCHED"] = "1"
+    try:
+        o = abi.call_compute_paths(L, sc, rx, tx, rxv, txv, f, P, B, fill=0x5A)
+    finally:
+        del os.environ["HRT_STRICT_UNTOUCHED"]
+        abi.free_scene(sc)
+    st = tr["slot_state"].reshape(-1)
+    fill = np.uint32(0x5A5A5A5A)
+    for k in ("a_te_re", "a_te_im", "a_tm_re", "a_tm_im", "tau"):
+        w = o.scat[k].reshape(-1).view(np.uint32)
+        assert (w[st == 0] == fill).all(), k                     # dead rays: untouched
+        assert (a.scat[k].reshape(-1).view(np.uint32)[st == 0] == fill).all()
+    d = o.scat["directions_rx"].reshape(-1, 3).view(np.uint32)
+    assert (d[st != 1] == fill).all() and (a.scat["directions_rx"].reshape(-1, 3).view(np.uint32)[st != 1] == fill).all()
+    assert np.array_equal(o.scat["tau"].reshape(-1).view(np.uint32)[st != 0], a.scat["tau"].reshape(-1).view(np.uint32)[st != 0])
+    assert np.array_equal(d[st == 1], a.scat["directions_rx"].reshape(-1, 3).view(np.uint32)[st == 1])
+    assert np.array_equal(o.scat["freq_shift"].view(np.uint32), a.scat["freq_shift"].view(np.uint32))      # T = 1: fully determined
+    wr = st != 0
+    for pol in ("te", "tm"):
+        ar = a.scat[f"a_{pol}_re"].reshape(-1)[wr].astype(np.float64); ai = a.scat[f"a_{pol}_im"].reshape(-1)[wr].astype(np.float64)
+        br = o.scat[f"a_{pol}_re"].reshape(-1)[wr].astype(np.float64); bi = o.scat[f"a_{pol}_im"].reshape(-1)[wr].astype(np.float64)
+        assert (np.hypot(ar - br, ai - bi) <= tl.GAIN_RTOL * np.hypot(ar, ai) + 1e-38).all()
+    assert (st == 0).sum() > 10000 and (st == 2).sum() > 0 and (st == 1).sum() > 50000
