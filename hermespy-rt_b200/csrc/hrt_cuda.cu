@@ -1443,6 +1443,9 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   /* hit order matters for the thread-per-hit mapping (lanes = neighbouring hits);
    * with a warp per hit the lanes share their origin anyway, and small runs are
    * better off without the per-depth count read-back the sort needs */
+  /* the top 24 of the 30 Morton bits (8 per axis) order the hits: three 8-bit radix passes instead of four */
+  int hit_sort_low_bit = 6;
+  if (const char *e = getenv("HRT_HIT_SORT_LOW_BIT")) { int v = atoi(e); if (v >= 0 && v <= 22) hit_sort_low_bit = v; }
   const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT") && (!warp_mode || getenv("HRT_HIT_SORT_ALWAYS"));
   if (sort_hits) {
     /* the chunk's direction sort below needs less: same pair types, 32 key bits */
@@ -1578,7 +1581,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
           if (h_counts[t] == 0) continue;
           size_t tb = ctx->sort_tmp_bytes;
           CKR(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tb, rd.qkey + off, rd.qkey_alt + off, qcur + off,
-                                              rd.queue_alt + off, (int)h_counts[t], 0, 30, st));
+                                              rd.queue_alt + off, (int)h_counts[t], hit_sort_low_bit, 30, st));
           S.kernel_launches += 4;
         }
         uint32_t *tmpq = qcur; qcur = rd.queue_alt; rd.queue_alt = tmpq;
