@@ -58,6 +58,7 @@ __constant__ HrtExtTable c_ext;
 #define HRT_SMEM_SCENE_LIMIT (100 * 1024)  /* stage 8 octant node copies + triangles in shared memory below this */
 #define HRT_AMB_CAP 65536
 
+#define HRT_SORT_STREAMS 4
 static char g_create_error[256] = "";
 
 struct SceneDev {
@@ -218,6 +219,7 @@ struct hrt_ctx {
   int *d_kl, *d_kr, *d_kfirst, *d_klast, *d_newidx;
   float *d_box;            /* [(2n-1)][6] lo.xyz hi.xyz; inner nodes then leaves */
   bool sah;                /* tree built by the binned-SAH builder (raw arrays below) */
+  uint32_t cap_raw, cap_nodes;   /* capacities (triangles) of d_raw_* and d_nodes: rebuilds reuse them */
   int2 *d_raw_ref;         /* [num_nodes] child refs */
   float *d_raw_box;        /* [num_nodes][12] both children's boxes, unpadded */
   float build_ms; int build_levels;
@@ -246,6 +248,10 @@ struct hrt_ctx {
   float *d_pos;            /* rx_pos, tx_pos, rx_vel, tx_vel */
   size_t cap_pos;
   void *sort_tmp; size_t sort_tmp_bytes;
+  /* side streams for the per-transmitter hit sorts of one depth (small sorts overlap), each with its
+   * own CUB scratch of sort_side_bytes */
+  cudaStream_t sort_stream[HRT_SORT_STREAMS]; void *sort_side_tmp[HRT_SORT_STREAMS]; size_t sort_side_bytes;
+  cudaEvent_t sort_fork, sort_join[HRT_SORT_STREAMS];
   void *d_los;             /* HrtLosOut[R*T] */
   size_t cap_los;
   float *d_cir; size_t cap_cir;
@@ -316,6 +322,16 @@ extern "C" int hrt_ctx_create(int device, hrt_ctx **out)
     free(c); return HRT_E_CUDA;
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+  {
+    /* the builder's scratch comes from the device's default memory pool (build_sah): keep up to
+     * 1 GB of it cached between rebuilds instead of returning it at every synchronisation */
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+      uint64_t keep = 1ull << 30;
+      cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   *out = c;
   (void)ctx;
   return HRT_OK;
@@ -326,7 +342,7 @@ static void free_scene_dev(hrt_ctx *c)
   dev_free(c->d_tris); dev_free(c->d_tri_gid); dev_free(c->d_mesh_of); dev_free(c->d_mesh_mat);
   dev_free(c->d_mesh_vel); dev_free(c->d_nodes); dev_free(c->d_kl); dev_free(c->d_kr);
   dev_free(c->d_kfirst); dev_free(c->d_klast); dev_free(c->d_newidx); dev_free(c->d_box);
-  dev_free(c->d_raw_ref); dev_free(c->d_raw_box);
+  dev_free(c->d_raw_ref); dev_free(c->d_raw_box); c->cap_raw = c->cap_nodes = 0;
   dev_free(c->d_verts); dev_free(c->d_idx3); dev_free(c->d_vmesh); dev_free(c->d_recs); dev_free(c->d_tboxes); dev_free(c->d_bounds);
   dev_free(c->d_wnodes); dev_free(c->d_wparent); dev_free(c->d_weven); dev_free(c->d_widx); dev_free(c->d_wtotal);
   c->cap_wnodes = c->cap_wscratch = 0; c->num_wide = 0;
@@ -367,6 +383,11 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
   delete c->pool; c->pool = nullptr;
   for (int k = 0; k < 2; ++k) if (c->stage[k]) { cudaFreeHost(c->stage[k]); cudaEventDestroy(c->stage_ev[k]); c->stage[k] = nullptr; }
   if (c->sort_tmp) { cudaFree(c->sort_tmp); c->sort_tmp = nullptr; }
+  for (int k = 0; k < HRT_SORT_STREAMS; ++k) {
+    if (c->sort_side_tmp[k]) { cudaFree(c->sort_side_tmp[k]); c->sort_side_tmp[k] = nullptr; }
+    if (c->sort_stream[k]) { cudaStreamDestroy(c->sort_stream[k]); c->sort_stream[k] = nullptr; cudaEventDestroy(c->sort_join[k]); }
+  }
+  if (c->sort_fork) { cudaEventDestroy(c->sort_fork); c->sort_fork = nullptr; }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
   free(c->evpool);
@@ -444,11 +465,17 @@ static int build_sah(hrt_ctx *ctx, uint32_t n, const float *d_boxes, const float
 #define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, HRT_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto out; } } while (0)
   CKB(cudaEventCreate(&e0)); CKB(cudaEventCreate(&e1));
   CKB(cudaEventRecord(e0, st));
-  for (int k = 0; k < 2; ++k) {
-    CKB(dev_alloc(&d_idx[k], n)); CKB(dev_alloc(&d_wof[k], n)); CKB(dev_alloc(&d_work[k], max_work));
+  /* scratch from the stream's memory pool: a rebuild next to GBs of live run buffers must not pay
+   * cudaMalloc / cudaFree (measured: 0.7 s instead of 50 ms on the 958k-triangle scene) */
+#define SCRATCH(ptr, count) CKB(cudaMallocAsync((void **)&(ptr), (size_t)(count) * sizeof(*(ptr)), st))
+  for (int k = 0; k < 2; ++k) { SCRATCH(d_idx[k], n); SCRATCH(d_wof[k], n); SCRATCH(d_work[k], max_work); }
+  SCRATCH(d_bins, max_work * 3 * SAH_BINS); SCRATCH(d_cnt, 2);
+#undef SCRATCH
+  if (ctx->cap_raw < n) {
+    dev_free(ctx->d_raw_ref); dev_free(ctx->d_raw_box); ctx->cap_raw = 0;
+    CKB(dev_alloc(&ctx->d_raw_ref, n)); CKB(dev_alloc(&ctx->d_raw_box, (size_t)n * 12));
+    ctx->cap_raw = n;
   }
-  CKB(dev_alloc(&d_bins, max_work * 3 * SAH_BINS)); CKB(dev_alloc(&d_cnt, 2));
-  CKB(dev_alloc(&ctx->d_raw_ref, n)); CKB(dev_alloc(&ctx->d_raw_box, (size_t)n * 12));
   {
     SahWork root; memset(&root, 0, sizeof root);
     root.start = 0; root.end = n; root.inner = 0;
@@ -487,8 +514,8 @@ static int build_sah(hrt_ctx *ctx, uint32_t n, const float *d_boxes, const float
   ctx->build_levels = level;
 out:
 #undef CKB
-  for (int k = 0; k < 2; ++k) { cudaFree(d_idx[k]); cudaFree(d_wof[k]); cudaFree(d_work[k]); }
-  cudaFree(d_bins); cudaFree(d_cnt);
+  for (int k = 0; k < 2; ++k) { cudaFreeAsync(d_idx[k], st); cudaFreeAsync(d_wof[k], st); cudaFreeAsync(d_work[k], st); }
+  cudaFreeAsync(d_bins, st); cudaFreeAsync(d_cnt, st);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   return rc;
@@ -586,7 +613,7 @@ extern "C" int hrt_scene_upload(hrt_ctx *ctx, const Scene *scene, Vec3 *normals_
         const int brc = build_sah(ctx, n, d_boxes, d_recs);
         if (brc) { rc = brc; goto done; }
         ctx->octants = 1;
-        CKG(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
+        CKG(dev_alloc(&ctx->d_nodes, (size_t)n * 4)); ctx->cap_nodes = n;      /* <= n - 1 inner nodes: a rebuild reuses it */
         goto built;
       }
       /* Morton/Karras builder (HRT_BVH_LBVH=1, and scenes of <= leaf_max triangles) */
@@ -684,12 +711,14 @@ extern "C" int hrt_scene_advance(hrt_ctx *ctx, float dt_s, int rebuild)
   ctx->scene_max_abs = max_abs;
   const float pad = fmaxf(ctx->pad, hrt_box_pad(max_abs, ctx->pad_ulps));
   if (rebuild && (int)n > ctx->leaf_max) {
-    dev_free(ctx->d_raw_ref); dev_free(ctx->d_raw_box); dev_free(ctx->d_nodes);
     ctx->sah = true;
     const int rc = build_sah(ctx, n, ctx->d_tboxes, ctx->d_recs);
     if (rc) { ctx->have_scene = false; return rc; }
     ctx->octants = 1;
-    CK(dev_alloc(&ctx->d_nodes, (size_t)ctx->num_nodes * 4 * ctx->octants));
+    if (ctx->cap_nodes < n) {
+      dev_free(ctx->d_nodes); ctx->cap_nodes = 0;
+      CK(dev_alloc(&ctx->d_nodes, (size_t)n * 4)); ctx->cap_nodes = n;
+    }
     ctx->root_ref = 0;
   } else {
     /* same leaf order: refresh the triangle records, then the boxes */
@@ -1456,7 +1485,27 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       ctx->sort_tmp = nullptr; ctx->sort_tmp_bytes = 0;
       CK(cudaMalloc(&ctx->sort_tmp, tb)); ctx->sort_tmp_bytes = tb;
     }
+    /* several transmitters: their sorts of one depth run side by side (HRT_SORT_SERIAL=1: one after the other) */
+    if (T > 1 && !getenv("HRT_SORT_SERIAL")) {
+      if (!ctx->sort_fork) {
+        CK(cudaEventCreateWithFlags(&ctx->sort_fork, cudaEventDisableTiming));
+        for (int k = 0; k < HRT_SORT_STREAMS; ++k) {
+          CK(cudaStreamCreateWithFlags(&ctx->sort_stream[k], cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&ctx->sort_join[k], cudaEventDisableTiming));
+        }
+      }
+      if (tb > ctx->sort_side_bytes) {
+        for (int k = 0; k < HRT_SORT_STREAMS; ++k) {
+          if (ctx->sort_side_tmp[k]) cudaFree(ctx->sort_side_tmp[k]);
+          ctx->sort_side_tmp[k] = nullptr;
+        }
+        ctx->sort_side_bytes = 0;
+        for (int k = 0; k < HRT_SORT_STREAMS; ++k) CK(cudaMalloc(&ctx->sort_side_tmp[k], tb));
+        ctx->sort_side_bytes = tb;
+      }
+    }
   }
+  const bool sort_side = sort_hits && T > 1 && ctx->sort_fork && ctx->sort_side_bytes && !getenv("HRT_SORT_SERIAL");
 
   const float host_setup = host_ms();
   CK(cudaEventRecord(ctx->ev[0], st));
@@ -1576,14 +1625,24 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
         CKR(cudaMemcpyAsync(h_counts, rd.qcount + (size_t)(b + 1) * T, T * 4, cudaMemcpyDeviceToHost, st));
         CKR(cudaStreamSynchronize(st));
         uint32_t *&qcur = rd.queue[(b + 1) & 1];
+        if (sort_side) CKR(cudaEventRecord(ctx->sort_fork, st));
+        unsigned side_used = 0;
         for (size_t t = 0; t < T; ++t) {
           const size_t off = t * (size_t)rd.n_alloc;
           if (h_counts[t] == 0) continue;
-          size_t tb = ctx->sort_tmp_bytes;
-          CKR(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tb, rd.qkey + off, rd.qkey_alt + off, qcur + off,
-                                              rd.queue_alt + off, (int)h_counts[t], hit_sort_low_bit, 30, st));
+          const int k = (int)(t % HRT_SORT_STREAMS);
+          cudaStream_t ss = sort_side ? ctx->sort_stream[k] : st;
+          if (sort_side && !(side_used & (1u << k))) { CKR(cudaStreamWaitEvent(ss, ctx->sort_fork, 0)); side_used |= 1u << k; }
+          size_t tb = sort_side ? ctx->sort_side_bytes : ctx->sort_tmp_bytes;
+          CKR(cub::DeviceRadixSort::SortPairs(sort_side ? ctx->sort_side_tmp[k] : ctx->sort_tmp, tb, rd.qkey + off, rd.qkey_alt + off,
+                                              qcur + off, rd.queue_alt + off, (int)h_counts[t], hit_sort_low_bit, 30, ss));
           S.kernel_launches += 4;
         }
+        for (int k = 0; k < HRT_SORT_STREAMS; ++k)
+          if (side_used & (1u << k)) {
+            CKR(cudaEventRecord(ctx->sort_join[k], ctx->sort_stream[k]));
+            CKR(cudaStreamWaitEvent(st, ctx->sort_join[k], 0));
+          }
         uint32_t *tmpq = qcur; qcur = rd.queue_alt; rd.queue_alt = tmpq;
       }
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st));
