@@ -252,6 +252,9 @@ struct hrt_ctx {
    * own CUB scratch of sort_side_bytes */
   cudaStream_t sort_stream[HRT_SORT_STREAMS]; void *sort_side_tmp[HRT_SORT_STREAMS]; size_t sort_side_bytes;
   cudaEvent_t sort_fork, sort_join[HRT_SORT_STREAMS];
+  /* k_scatter of depth b runs on scat_stream[b & 1]: its ragged end overlaps the next depth's k_bounce, sort and
+   * the start of the next k_scatter.  scat_ready: hits of a depth are in order; scat_done[k]: last k_scatter on stream k */
+  cudaStream_t scat_stream[2]; cudaEvent_t scat_ready, scat_done[2];
   void *d_los;             /* HrtLosOut[R*T] */
   size_t cap_los;
   float *d_cir; size_t cap_cir;
@@ -388,6 +391,10 @@ extern "C" void hrt_ctx_destroy(hrt_ctx *c)
     if (c->sort_stream[k]) { cudaStreamDestroy(c->sort_stream[k]); c->sort_stream[k] = nullptr; cudaEventDestroy(c->sort_join[k]); }
   }
   if (c->sort_fork) { cudaEventDestroy(c->sort_fork); c->sort_fork = nullptr; }
+  if (c->scat_ready) {
+    cudaEventDestroy(c->scat_ready); c->scat_ready = nullptr;
+    for (int k = 0; k < 2; ++k) { cudaStreamDestroy(c->scat_stream[k]); cudaEventDestroy(c->scat_done[k]); c->scat_stream[k] = nullptr; }
+  }
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   for (size_t i = 0; i < c->evpool_n; ++i) cudaEventDestroy(c->evpool[i]);
   free(c->evpool);
@@ -1506,6 +1513,16 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     }
   }
   const bool sort_side = sort_hits && T > 1 && ctx->sort_fork && ctx->sort_side_bytes && !getenv("HRT_SORT_SERIAL");
+  /* depth pipeline: k_bounce(b + 1) needs k_bounce(b) only, so k_scatter(b) runs beside it on a stream of its own
+   * (buffers alternate by depth parity: k_bounce(b) waits for k_scatter(b - 2)).  HRT_NO_OVERLAP=1: one stream */
+  const bool overlap = B > 1 && !getenv("HRT_NO_OVERLAP");
+  if (overlap && !ctx->scat_ready) {
+    CK(cudaEventCreateWithFlags(&ctx->scat_ready, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaStreamCreateWithFlags(&ctx->scat_stream[k], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ctx->scat_done[k], cudaEventDisableTiming));
+    }
+  }
 
   const float host_setup = host_ms();
   CK(cudaEventRecord(ctx->ev[0], st));
@@ -1526,7 +1543,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   float ms_bounce = 0.f, ms_scatter = 0.f;
   /* per-launch timing: three events per (chunk, bounce), resolved after the
    * run -- no synchronisation inside the loop */
-  const size_t EV_CAP = 4 * 512;
+  const size_t EV_CAP = 5 * 512;
   size_t ev_used = 0;
   uint8_t tail_dead[8] = {255, 255, 255, 255, 255, 255, 255, 255};  /* TX 1, paths 0..7 */
   rc = HRT_OK;
@@ -1607,16 +1624,18 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
                             T * (size_t)rd.n_alloc * sizeof(Ray), cudaMemcpyDeviceToDevice, st));
       /* persistent grids: enough blocks to fill the machine, grid-stride inside */
       const dim3 gb((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), ((size_t)rd.n + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      const bool timed = ev_used + 4 <= EV_CAP;
+      const bool timed = ev_used + 5 <= EV_CAP;
       if (timed) {
-        if (ctx->evpool_n < ev_used + 4) {
-          cudaEvent_t *np_ = (cudaEvent_t *)realloc(ctx->evpool, (ev_used + 4) * sizeof(cudaEvent_t));
+        if (ctx->evpool_n < ev_used + 5) {
+          cudaEvent_t *np_ = (cudaEvent_t *)realloc(ctx->evpool, (ev_used + 5) * sizeof(cudaEvent_t));
           if (!np_) { rc = fail(ctx, HRT_E_NOMEM, "out of host memory"); goto run_done; }
           ctx->evpool = np_;
-          while (ctx->evpool_n < ev_used + 4) CKR(cudaEventCreate(&ctx->evpool[ctx->evpool_n++]));
+          while (ctx->evpool_n < ev_used + 5) CKR(cudaEventCreate(&ctx->evpool[ctx->evpool_n++]));
         }
-        CKR(cudaEventRecord(ctx->evpool[ev_used], st));
       }
+      /* this k_bounce overwrites the queue and records k_scatter(b - 2) reads */
+      if (overlap && b >= 2) CKR(cudaStreamWaitEvent(st, ctx->scat_done[b & 1], 0));
+      if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used], st));
       f_bounce<<<gb, HRT_BLOCK, smem ? scene_sb : 0, st>>>(rd, sc, ctx->mats, b);
       CKR(cudaGetLastError());
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 1], st));
@@ -1646,12 +1665,21 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
         uint32_t *tmpq = qcur; qcur = rd.queue_alt; rd.queue_alt = tmpq;
       }
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 2], st));
+      cudaStream_t ss = overlap ? ctx->scat_stream[b & 1] : st;
+      if (overlap) { CKR(cudaEventRecord(ctx->scat_ready, st)); CKR(cudaStreamWaitEvent(ss, ctx->scat_ready, 0)); }
+      if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 3], ss));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      f_scatter<<<gs, HRT_BLOCK, scat_sb, st>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+      f_scatter<<<gs, HRT_BLOCK, scat_sb, ss>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
-      if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 3], st)); ev_used += 4; }
+      if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 4], ss)); ev_used += 5; }
+      if (overlap) CKR(cudaEventRecord(ctx->scat_done[b & 1], ss));
+    }
+    /* everything after the depth loop (and the next chunk) comes after every k_scatter of this chunk */
+    if (overlap) {
+      CKR(cudaStreamWaitEvent(st, ctx->scat_done[(B - 1) & 1], 0));
+      CKR(cudaStreamWaitEvent(st, ctx->scat_done[B & 1], 0));
     }
 
     if (flags & HRT_FLAG_SUMMARY) {
@@ -1763,15 +1791,17 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[2]);
     cudaEventElapsedTime(&b, ctx->ev[0], ctx->ev[1]);
     float ms_sort = 0.f;
-    for (size_t e = 0; e + 4 <= ev_used; e += 4) {
+    /* with the depth pipeline a k_bounce / sort interval may contain the ragged end of the previous k_scatter,
+     * and a k_scatter interval the start-up of the next one: the three sums can exceed ms_total slightly */
+    for (size_t e = 0; e + 5 <= ev_used; e += 5) {
       float x = 0.f, y = 0.f, z = 0.f;
       cudaEventElapsedTime(&x, ctx->evpool[e], ctx->evpool[e + 1]);
       cudaEventElapsedTime(&z, ctx->evpool[e + 1], ctx->evpool[e + 2]);
-      cudaEventElapsedTime(&y, ctx->evpool[e + 2], ctx->evpool[e + 3]);
+      cudaEventElapsedTime(&y, ctx->evpool[e + 3], ctx->evpool[e + 4]);
       ms_bounce += x; ms_scatter += y; ms_sort += z;
     }
     S.ms_sort = ms_sort;
-    S.n_bounce_launches = S.n_scatter_launches = (uint32_t)(ev_used / 4);
+    S.n_bounce_launches = S.n_scatter_launches = (uint32_t)(ev_used / 5);
     S.ms_total = a; S.ms_bounce = ms_bounce; S.ms_scatter = ms_scatter;
     S.ms_other = b;
     S.host_ms_setup = host_setup; S.host_ms_total = host_ms();

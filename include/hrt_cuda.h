@@ -203,7 +203,11 @@ typedef struct {
   uint64_t ambiguous_dirs;     /* launch directions recomputed on the host        */
   uint64_t kernel_launches;    /* kernels of this library launched by the run     */
   float    ms_total;           /* CUDA-event time of the whole run on its stream  */
-  float    ms_bounce;          /* sum over k_bounce launches                      */
+  float    ms_bounce;          /* sum over k_bounce launches.  By default k_scatter of
+                                  depth b runs beside k_bounce / the sort of depth b+1
+                                  (depth pipeline): the event interval of a k_bounce
+                                  then includes its wait for SM slots; HRT_NO_OVERLAP=1
+                                  puts every kernel on one stream (per-kernel times)   */
   float    ms_scatter;         /* sum over k_scatter launches (dominant kernel)   */
   float    ms_other;
   uint32_t n_bounce_launches;  /* launches behind ms_bounce / ms_scatter           */

@@ -6,6 +6,7 @@ With world > 1 the run is shard 0 of `world` of the job (blocks of `block` paths
 dealt round-robin, as bench.py --gpus N deals them): rays_per_tx = 6.25e7 and
 world = 64 is 1/64 of the full C5 job at its true ray density."""
 import json, os, sys, time
+os.environ.setdefault("HRT_NO_OVERLAP", "1")      # clean per-kernel event intervals (ms_bounce, ms_scatter)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "hermespy-rt_b200"))
 import numpy as np
