@@ -192,6 +192,36 @@ HRT_HD bool hrt_mt_test(float4 q0, float4 q1, float4 q2, V3 o, V3 d,
   return false;
 }
 
+/* The triangle a shadow ray starts on is a candidate of every one of its queries, and nearly always a
+ * miss by "t <= 0" (the ray leaves the surface; it hits only when the receiver lies behind it).  That
+ * decision needs, of the ray's direction, only the sign of det: t's numerator nt = ac . ((o - a) x ab)
+ * (:269, :274) depends on the origin alone.  hrt_mt_self_nt forms it once per hit point with the very
+ * operations of hrt_mt_test; hrt_mt_self_miss then answers most queries from stage A (p = d x ac, det)
+ * alone: true = hrt_mt_test is certain to return false (its det and t <= 0 exits, which no earlier exit
+ * can turn into a hit); false = undecided, run hrt_mt_test. */
+HRT_HD float hrt_mt_self_nt(float4 q0, float4 q1, float4 q2, V3 o)
+{
+  const V3 a  = v3(q0.x, q0.y, q0.z);
+  const V3 ab = v3(q0.w, q1.x, q1.y);
+  const V3 ac = v3(q1.z, q1.w, q2.x);
+  const V3 sv = v3_sub(o, a);
+  const V3 qv = v3_cross(sv, ab);
+  return v3_dot(ac, qv);
+}
+
+template <class Cnt>
+HRT_HD bool hrt_mt_self_miss(float4 q0, float4 q1, float4 q2, V3 d, float nt, Cnt &cnt)
+{
+  const V3 ab = v3(q0.w, q1.x, q1.y);
+  const V3 ac = v3(q1.z, q1.w, q2.x);
+  const V3 pv = v3_cross(d, ac);
+  const float det = v3_dot(ab, pv);
+  if (det > -HRT_EPS && det < HRT_EPS) { cnt.tri(0); return true; }
+  const float snt = HRT_MUL(nt, det);
+  if (!(snt > 0.f) && nt == nt) { cnt.tri(0); return true; }
+  return false;
+}
+
 /* Ray/box culling state.  Conservative by construction: boxes are padded by
  * the builder, the far bound carries slack, NaNs never reject. */
 struct HrtRayCull {

@@ -95,7 +95,7 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
 
 /* ------------------------------------------------------- receiver maps
  * (hrt_rxmap.cuh).  Cell word: (offset of the cell's list inside the receiver's
- * item range << 8) | length; items are leaf slots (uint16). */
+ * item range << 8) | "sure" bit | length; items: leaf slot | depth bounds. */
 /* shadow query through the map of receiver r: exact tests of the candidates of
  * cell (-d) -- between hit point and receiver -- nearest to the hit point first,
  * without the ones that lie entirely behind it and stopping once nothing left can
@@ -105,7 +105,7 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
  * memory at offset 0. */
 template <class Cnt>
 __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &mp, uint32_t r, V3 o, V3 d, float dist, Cnt &cnt,
-                                            uint32_t smem0)
+                                            uint32_t smem0, uint32_t self_slot, float self_nt)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   HrtSharedMem m;
@@ -123,13 +123,23 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
     uint32_t k = item0 + (w >> 8);
-    const uint32_t kend = k + (w & 255u);
+    const uint32_t kend = k + (w & HRT_RXMAP_MAX_LIST);
+    if (side == 1 && (w & HRT_RXMAP_SURE) && h.gid == HRT_NONE && dist > 1.001f) {
+      /* "sure" cell (hrt_rxmap.cuh): nothing between hit point and receiver, and beyond the receiver the ray
+       * is certain to hit the cell's only triangle.  t is not computed: it exceeds dist > 1, which is all the
+       * caller asks of it (src/compute_paths.c:683) */
+      const uint32_t s = __ldg(&mp.items[k]) & 0xFFFFu;
+      h.gid = lds32(gid_addr + 4u * s); h.slot = s; h.t = dist;
+      break;
+    }
 #pragma unroll 1
     for (; k != kend; ++k) {
       const uint32_t iw = __ldg(&mp.items[k]), s = iw & 0xFFFFu;
       if (side == 0) {
         if ((int)((iw >> 16) & 255u) < q_stop) break;          /* everything left is farther from o than the best hit */
         if ((int)(iw >> 24) > md.q_behind) continue;           /* entirely behind o */
+        /* the triangle the ray starts on: a miss by t <= 0 unless the receiver is behind it (hrt_core.cuh) */
+        if (s == self_slot && hrt_mt_self_miss(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), d, self_nt, cnt)) continue;
       }
       float t;
       if (hrt_mt_test<Cnt, true>(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, 0u, 0u, &t, cnt)) {
@@ -179,12 +189,19 @@ __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx
   if (nc > HRT_RXMAP_CAND) { if (tid == 0) atomicOr(status, 1u); nc = HRT_RXMAP_CAND; }
   const uint32_t i = bi * HRT_RXMAP_BLOCK + (tid & 7u), j = bj * HRT_RXMAP_BLOCK + (tid >> 3);
   const HrtPyramid cp = hrt_rxmap_pyramid(face, G, i, i + 1u, j, j + 1u);
-  uint32_t count = 0;
+  uint32_t count = 0, only = 0;
   for (uint32_t k = 0; k < nc; ++k) {
     const uint32_t s = cand[k];
     V3 va, vb, vc;
     hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
-    count += hrt_rxmap_overlap(cp, va, vb, vc, pad) ? 1u : 0u;
+    if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) { ++count; only = s; }
+  }
+  const float is = inv_step[r];
+  uint32_t sure = 0;
+  if (count == 1u) {
+    V3 va, vb, vc;
+    hrt_rxmap_corners(__ldg(&sc.tris[3 * only]), __ldg(&sc.tris[3 * only + 1]), __ldg(&sc.tris[3 * only + 2]), apex, &va, &vb, &vc);
+    if (hrt_rxmap_sure(cp, va, vb, vc, pad, 510.f / is)) sure = HRT_RXMAP_SURE;   /* reach: twice the farthest corner of the scene */
   }
   /* exclusive scan of the 64 counts */
   uint32_t incl = count;
@@ -195,12 +212,11 @@ __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx
   if (tid == 0) base = atomicAdd(&cursor[r], total);
   __syncthreads();
   const uint32_t off = base + my;
-  const bool fits = base + total <= items_per_rx && off < (1u << 24) && count <= 255u;
+  const bool fits = base + total <= items_per_rx && off < (1u << 24) && count <= HRT_RXMAP_MAX_LIST;
   if (!fits) atomicOr(status, 1u);
-  cells[((size_t)(r * 6u + face) * G + j) * G + i] = fits ? ((off << 8) | count) : 0u;
+  cells[((size_t)(r * 6u + face) * G + j) * G + i] = fits ? ((off << 8) | sure | count) : 0u;
   if (!fits) return;
   uint32_t *dst = items + (size_t)r * items_per_rx + off, nw = 0;
-  const float is = inv_step[r];
   for (uint32_t k = 0; k < nc; ++k) {
     const uint32_t s = cand[k];
     V3 va, vb, vc;
@@ -612,6 +628,9 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
      * product n.d of the most recent shadow hit (what the reference feeds to acos,
      * :281); 2 = "none yet: the primary angle theta_p" */
     const float theta_p = r2.w;
+    /* receiver maps: t's numerator for the triangle this hit lies on, once for all receivers (hrt_mt_self_nt) */
+    float self_nt = 0.f;
+    if (MAP) self_nt = hrt_mt_self_nt(lds128(smem0 + slot * 48u), lds128(smem0 + slot * 48u + 16u), lds128(smem0 + slot * 48u + 32u), s.o);
     float cx_carry = HRT_CX_PRIMARY, ci_p, si_p;
     sincosf(theta_p, &si_p, &ci_p);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
@@ -636,7 +655,7 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc, smem0) : query<SMEM, BRUTE>(sc, s.o, sd, wc, smem0);   /* :682 */
+        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc, smem0, slot, self_nt) : query<SMEM, BRUTE>(sc, s.o, sd, wc, smem0);   /* :682 */
         if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM, MAP>(sc, h.slot, smem0), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;

@@ -155,6 +155,54 @@ HRT_HD bool hrt_rxmap_overlap(const HrtPyramid &p, V3 va, V3 vb, V3 vc, float pa
   return true;
 }
 
+/* ---- "sure" cells ----
+ * Cell word: offset << 8 | HRT_RXMAP_SURE | length (<= HRT_RXMAP_MAX_LIST).  A cell is "sure" when its list has
+ * exactly ONE triangle and every line through the apex inside the (enlarged) cell, followed AWAY from the apex,
+ * meets that triangle well inside it and at a non-grazing angle.  The far side of a shadow query (beyond the
+ * receiver) then needs no exact test: the reference's test is certain to accept the triangle, no other
+ * triangle is listed, and of the hit only its existence, its triangle and "t > 1" matter to the caller (t is
+ * at least the distance to the receiver).  "Well inside": all four corner rays of the cell meet the plane in
+ * front of the apex with cosine >= c_min >= 0.01 to the normal, at barycentric coordinates (u, v) with
+ *   u, v >= m,  u + v <= 1 - m,   m = 0.01 + 8 x (e_fp + e_pad)
+ * (the image of the cell on the plane is the convex hull of the four points).  e_fp bounds the fp32 error of
+ * the reference's u and v (src/compute_paths.c:264-271) for origins up to `reach` metres from the triangle:
+ * u = (s . p) / det with p = d x e2, s = o - a; rounding leaves |err(s . p)| <= 3.6e-7 |s| |e2| + 4e-6 |e2|
+ * (three products and two sums at 6e-8 relative each, plus the subtraction that formed s at coordinates of
+ * ~100 m) and |det| = |d . n^| |e1 x e2| >= c_min |e1| |e2| sin(phi), so err(u) <= (3.6e-7 reach + 4e-6) /
+ * (c_min h_min), h_min the triangle's smallest height; the same for v.  e_pad = pad / (c_min h_min) is the
+ * shift of the hit point when the ray misses the apex by pad (the fp32 direction normalize(R - o), see the
+ * file header).  Nothing is "sure" when the apex is within 64 pad of the plane or m >= 0.25. */
+#define HRT_RXMAP_SURE 0x80u
+#define HRT_RXMAP_MAX_LIST 127u
+
+HRT_HD bool hrt_rxmap_sure(const HrtPyramid &p, V3 va, V3 vb, V3 vc, float pad, float reach)
+{
+  const V3 e1 = v3(vb.x - va.x, vb.y - va.y, vb.z - va.z), e2 = v3(vc.x - va.x, vc.y - va.y, vc.z - va.z);
+  const V3 e3 = v3(vc.x - vb.x, vc.y - vb.y, vc.z - vb.z);
+  const V3 n = v3(e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x);
+  const float nl2 = hrt_dot3(n, n), nl = sqrtf(nl2);
+  if (!(nl > 1e-3f)) return false;                          /* |det| = |d . n^| nl stays far above FLT_EPSILON */
+  float h = hrt_dot3(va, n) / nl, sg = 1.f;                 /* distance of the plane from the apex */
+  if (h < 0.f) { h = -h; sg = -1.f; }
+  const float lmax = sqrtf(fmaxf(hrt_dot3(e1, e1), fmaxf(hrt_dot3(e2, e2), hrt_dot3(e3, e3))));
+  const float hmin = nl / lmax;
+  float cmin = 2.f;
+  for (int k = 0; k < 4; ++k) cmin = fminf(cmin, sg * hrt_dot3(p.c[k], n) / nl);
+  if (!(cmin >= 0.01f) || !(h > 64.f * pad)) return false;
+  const float m = 0.01f + 8.f * ((3.6e-7f * reach + 4e-6f) + pad) / (cmin * hmin);
+  if (!(m < 0.25f)) return false;
+  for (int k = 0; k < 4; ++k) {
+    const float c = sg * hrt_dot3(p.c[k], n) / nl;
+    const float tq = h / c;
+    const V3 w = v3(p.c[k].x * tq - va.x, p.c[k].y * tq - va.y, p.c[k].z * tq - va.z);
+    const V3 we2 = v3(w.y * e2.z - w.z * e2.y, w.z * e2.x - w.x * e2.z, w.x * e2.y - w.y * e2.x);
+    const V3 e1w = v3(e1.y * w.z - e1.z * w.y, e1.z * w.x - e1.x * w.z, e1.x * w.y - e1.y * w.x);
+    const float u = hrt_dot3(we2, n) / nl2, v = hrt_dot3(e1w, n) / nl2;
+    if (!(u >= m && v >= m && u + v <= 1.f - m)) return false;
+  }
+  return true;
+}
+
 /* corners of triangle record (q0, q1, q2) relative to apex r */
 HRT_HD void hrt_rxmap_corners(float4 q0, float4 q1, float4 q2, V3 r, V3 *va, V3 *vb, V3 *vc)
 {

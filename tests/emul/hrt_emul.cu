@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <vector>
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "../../include/hrt_cuda.h"
@@ -139,11 +140,11 @@ static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
 
 /* receiver maps (hrt_rxmap.cuh), built serially with the same two-level scheme and
  * element functions as the kernels k_rxmap_* */
-struct EmulRxMap { uint32_t G = 0; std::vector<uint32_t> start, count; std::vector<uint32_t> items; std::vector<float> inv_step; };
+struct EmulRxMap { uint32_t G = 0; std::vector<uint32_t> start, count; std::vector<uint8_t> sure; std::vector<uint32_t> items; std::vector<float> inv_step; };
 
 static void build_rxmap(const EmulScene &E, const Vec3 *rx, size_t R, uint32_t G, float pad, EmulRxMap &M)
 {
-  M.G = G; M.start.assign(R * 6 * G * G, 0); M.count.assign(R * 6 * G * G, 0); M.items.clear(); M.inv_step.assign(R, 0.f);
+  M.G = G; M.start.assign(R * 6 * G * G, 0); M.count.assign(R * 6 * G * G, 0); M.sure.assign(R * 6 * G * G, 0); M.items.clear(); M.inv_step.assign(R, 0.f);
   const uint32_t nb = G / HRT_RXMAP_BLOCK;
   std::vector<uint32_t> cand;
   /* scene bounds: the per-receiver quantisation step covers the farthest corner of the bounding box */
@@ -182,14 +183,22 @@ static void build_rxmap(const EmulScene &E, const Vec3 *rx, size_t R, uint32_t G
               }
               M.count[cell] = (uint32_t)M.items.size() - M.start[cell];
               hrt_rxmap_sort_items(&M.items[M.start[cell]], M.count[cell]);
+              if (M.count[cell] == 1) {
+                const uint32_t s = M.items[M.start[cell]] & 0xFFFFu;
+                V3 va, vb, vc; hrt_rxmap_corners(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], apex, &va, &vb, &vc);
+                M.sure[cell] = hrt_rxmap_sure(cp, va, vb, vc, pad, 510.f / M.inv_step[r]) ? 1 : 0;
+              }
             }
         }
   }
 }
 
+static unsigned long long *g_dbg = nullptr;   /* lab counters: tests on the origin's own plane / elsewhere, per side; accepted per side */
 /* shadow query through the receiver map, exactly as query_map in hrt_run_kernels.cuh */
-static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, V3 d, float dist, unsigned long long *tests = nullptr)
+static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, V3 d, float dist, uint32_t self_slot, float self_nt,
+                        unsigned long long *tests = nullptr, bool *took_sure = nullptr)
 {
+  if (took_sure) *took_sure = false;
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   HrtNoCount nc;
   uint32_t c_pos, c_neg;
@@ -198,15 +207,28 @@ static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, 
   int q_stop = -1;
   for (int side = 0; side < 2; ++side) {
     const size_t cell = r * 6 * M.G * M.G + (side ? c_pos : c_neg);
+    if (side == 1 && M.sure[cell] && h.gid == HRT_NONE && dist > 1.001f) {     /* "sure" cell: no test, t not computed */
+      const uint32_t s = M.items[M.start[cell]] & 0xFFFFu;
+      h.gid = E.gid[s]; h.slot = s; h.t = dist;
+      if (took_sure) *took_sure = true;
+      break;
+    }
     for (uint32_t k = 0; k < M.count[cell]; ++k) {
       const uint32_t w = M.items[M.start[cell] + k], s = w & 0xFFFFu;
       if (side == 0) {
         if ((int)((w >> 16) & 255u) < q_stop) break;           /* everything left is farther from o than the best hit */
         if ((int)(w >> 24) > md.q_behind) continue;            /* entirely behind o */
+        if (s == self_slot && hrt_mt_self_miss(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], d, self_nt, nc)) continue;
       }
       float t;
       if (tests) ++*tests;
+      if (g_dbg) {
+        const float4 q0 = E.tris[3 * s], q2 = E.tris[3 * s + 2];
+        const float pd = fabsf((o.x - q0.x) * q2.y + (o.y - q0.y) * q2.z + (o.z - q0.z) * q2.w);
+        g_dbg[side * 2 + (pd < 3e-4f ? 0 : 1)]++;
+      }
       if (hrt_mt_test<HrtNoCount, true>(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], o, d, h.t, 0u, 0u, &t, nc)) {
+        if (g_dbg) g_dbg[4 + side]++;
         if (t < h.t || E.gid[s] < h.gid) { h.t = t; h.gid = E.gid[s]; h.slot = s; }
         if (side == 0) q_stop = hrt_rxmap_stop(md, h.t);
       }
@@ -318,11 +340,12 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
         hrt_bounce_update(s, mat, k, h.t, n, theta);
         float carry = theta, cx_carry = HRT_CX_PRIMARY;
         const float ci_p = cosf(theta), si_p = sinf(theta);
+        const float self_nt = hrt_mt_self_nt(E.tris[3 * h.slot], E.tris[3 * h.slot + 1], E.tris[3 * h.slot + 2], s.o);   /* as k_scatter */
         for (size_t r = 0; r < R; ++r) {
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
-          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist) : query(E, s.o, sd, brute);
+          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist, h.slot, self_nt) : query(E, s.o, sd, brute);
           if (sh.gid != HRT_NONE) { carry = hrt_theta_fold(nrm(E, sh.slot), sd); cx_carry = v3_dot(nrm(E, sh.slot), sd); }
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
           /* closed_form: what k_scatter runs (hrt_scatter_path_auto); else the reference's formulas line by line */
@@ -475,7 +498,7 @@ extern "C" int emul_scatter_cf_vs_exact(size_t n, uint32_t seed, float f_ghz, do
  * return the same (triangle, t).  Returns the number of differing queries;
  * *avg_tests = triangle tests per query through the map. */
 extern "C" long emul_rxmap_vs_brute(const Scene *sc, const Vec3 *rx, size_t R, const Vec3 *origins, size_t n,
-                                    uint32_t G, double *avg_tests, double *avg_list)
+                                    uint32_t G, double *avg_tests, double *avg_list, const uint32_t *origin_gid)
 {
   EmulScene E;
   float ma = 0.f;
@@ -484,21 +507,53 @@ extern "C" long emul_rxmap_vs_brute(const Scene *sc, const Vec3 *rx, size_t R, c
   build(sc, E, 2, 64.f, ma);
   EmulRxMap M;
   build_rxmap(E, rx, R, G, 4.f * E.pad, M);
-  unsigned long long tests = 0; long bad = 0;
+  unsigned long long tests = 0, n_sure = 0; long bad = 0;
+  static unsigned long long dbg[6]; if (getenv("EMUL_RXMAP_VERBOSE")) { memset(dbg, 0, sizeof dbg); g_dbg = dbg; }
   HrtNoCount nc;
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
-  for (size_t i = 0; i < n; ++i)
+  for (size_t i = 0; i < n; ++i) {
+    /* "own" triangle of the origin, for the early-out of the triangle a ray starts on (valid for any triangle:
+     * the one the caller names, else the one whose plane is nearest) */
+    uint32_t own = 0; float own_pd = 3e38f;
+    if (origin_gid && origin_gid[i] != HRT_NONE) {
+      for (uint32_t s = 0; s < E.n; ++s) if (E.gid[s] == origin_gid[i]) own = s;      /* the triangle the origin was placed on */
+    } else
+    for (uint32_t s = 0; s < E.n; ++s) {
+      const float4 q0 = E.tris[3 * s], q2 = E.tris[3 * s + 2];
+      const float pd = fabsf((origins[i].x - q0.x) * q2.y + (origins[i].y - q0.y) * q2.z + (origins[i].z - q0.z) * q2.w);
+      if (pd < own_pd) { own_pd = pd; own = s; }
+    }
+    const float own_nt = hrt_mt_self_nt(E.tris[3 * own], E.tris[3 * own + 1], E.tris[3 * own + 2], tov(origins[i]));
     for (size_t r = 0; r < R; ++r) {
       float dist;
       const V3 o = tov(origins[i]);
       const V3 sd = hrt_shadow_dir(o, tov(rx[r]), &dist);
       if (!(dist > 0.f)) continue;
-      const HrtHit a = query_map(E, M, r, o, sd, dist, &tests);
+      bool sure = false;
+      const HrtHit a = query_map(E, M, r, o, sd, dist, own, own_nt, &tests, &sure);
       const HrtHit b = hrt_closest_hit_brute(m, E.gid.data(), E.n, o, sd, nc);
-      if (a.gid != b.gid || (a.gid != HRT_NONE && memcmp(&a.t, &b.t, 4))) ++bad;
+      n_sure += sure;
+      if (getenv("EMUL_RXMAP_VERBOSE")) {
+        static unsigned long long cat[6]; static unsigned long long seen = 0;
+        uint32_t cp_, cn_; hrt_rxmap_cells2(sd, M.G, &cp_, &cn_);
+        const size_t cell = r * 6 * M.G * M.G + cp_;
+        const bool near_hit = b.gid != HRT_NONE && b.t < dist * 0.999f;
+        if (near_hit) ++cat[0];
+        else if (M.count[cell] == 0) ++cat[1];
+        else if (M.count[cell] == 1 && M.sure[cell]) ++cat[2];
+        else if (M.count[cell] == 1) ++cat[3];
+        else if (M.count[cell] == 2) ++cat[4];
+        else ++cat[5];
+        if (++seen == n * R) fprintf(stderr, "far side: near hit %llu, empty %llu, sure %llu, single not sure %llu, two %llu, more %llu\n", cat[0], cat[1], cat[2], cat[3], cat[4], cat[5]);
+      }
+      /* a "sure" answer names the triangle and promises t >= dist > 1 without computing t */
+      if (sure ? (a.gid != b.gid || !(b.t > 1.f) || !(b.t >= dist * 0.999f)) : (a.gid != b.gid || (a.gid != HRT_NONE && memcmp(&a.t, &b.t, 4)))) ++bad;
     }
+  }
   *avg_tests = (double)tests / (double)(n * R);
   *avg_list = (double)M.items.size() / (double)M.start.size();
+  if (g_dbg) { fprintf(stderr, "near side: own-plane tests %llu, other %llu, accepted %llu; far side: own-plane %llu, other %llu, accepted %llu\n", dbg[0], dbg[1], dbg[4], dbg[2], dbg[3], dbg[5]); g_dbg = nullptr; }
+  if (const char *e = getenv("EMUL_RXMAP_VERBOSE")) { (void)e; fprintf(stderr, "rxmap: %llu of %zu queries answered by a sure cell\n", n_sure, n * R); }
   return bad;
 }
 

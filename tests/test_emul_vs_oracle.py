@@ -143,13 +143,14 @@ def test_receiver_maps_are_conservative(scene, G):
     lib = tl.emul_lib()
     lib.emul_rxmap_vs_brute.restype = C.c_long
     lib.emul_rxmap_vs_brute.argtypes = [C.POINTER(abi.Scene), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                        C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+                                        C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
     T = tl.scene_triangles(scene)
     rng = np.random.default_rng(17)
     lo, hi = T.reshape(-1, 3).min(0), T.reshape(-1, 3).max(0)
     n = 1500
     w = rng.random((n, 3)); w /= w.sum(1, keepdims=True)
-    tt = T[rng.integers(0, len(T), n)]
+    on_tri = rng.integers(0, len(T), n)
+    tt = T[on_tri]
     nrm = np.cross(tt[:, 1] - tt[:, 0], tt[:, 2] - tt[:, 0]); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     on_surface = (tt * w[:, :, None]).sum(1) + nrm * (1e-4 * rng.choice([-1, 1], n))[:, None]   # the reference's 1e-4 offset
     volume = lo + rng.random((n // 2, 3)) * (hi - lo)
@@ -160,8 +161,13 @@ def test_receiver_maps_are_conservative(scene, G):
     origins = np.ascontiguousarray(np.concatenate([on_surface, volume, near_rx]).astype(np.float32))
     sc = lib.scene_load(tl.scene_path(scene).encode())
     avg, lst = C.c_double(0), C.c_double(0)
+    # the triangle each surface origin sits on (k_scatter hands it to the query for its early-out of the own triangle);
+    # every third one deliberately names a wrong triangle: the early-out must be exact for any triangle
+    own = np.full(len(origins), 0xFFFFFFFF, np.uint32)
+    own[:n] = on_tri
+    own[2:n:3] = rng.integers(0, len(T), len(own[2:n:3]))
     bad = lib.emul_rxmap_vs_brute(C.byref(sc), rx.ctypes.data, len(rx), origins.ctypes.data, len(origins), G,
-                                  C.byref(avg), C.byref(lst))
+                                  C.byref(avg), C.byref(lst), own.ctypes.data)
     abi.free_scene(sc)
     assert bad == 0, bad
     assert avg.value < 0.6 * len(T) + 4, avg.value     # the lists really are short
