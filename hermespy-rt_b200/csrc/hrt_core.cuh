@@ -383,9 +383,12 @@ HRT_HD HrtHit hrt_closest_hit(const Mem &mem, const Gid tri_gid, int root_ref,
  * root_ref: wide node index, a leaf ref, or anything with num_tris == 0. */
 #define HRT_WSTACK 96   /* 3 pushes per level, depth <= (32 + log2 n) / 2 + 1 */
 #define HRT_WIDE_EMPTY ((int)0x80000000)   /* ref of an unused child slot */
-template <bool SORTED, class Mem, class Gid, class Cnt>
+/* SELF: the ray starts on triangle slot `self_slot` (a shadow ray leaving a hit point); self_nt = hrt_mt_self_nt
+ * of that triangle and origin: its test is decided from stage A alone whenever possible (hrt_mt_self_miss). */
+template <bool SORTED, bool SELF = false, class Mem, class Gid, class Cnt>
 HRT_HD HrtHit hrt_closest_hit_wide(const Mem &mem_in, const Gid tri_gid, int root_ref,
-                                   uint32_t num_tris, V3 o, V3 d, Cnt &cnt, size_t oct_stride4 = 0)
+                                   uint32_t num_tris, V3 o, V3 d, Cnt &cnt, size_t oct_stride4 = 0,
+                                   uint32_t self_slot = HRT_NONE, float self_nt = 0.f)
 {
   HrtHit h; h.t = HRT_T_MAX; h.gid = HRT_NONE; h.slot = HRT_NONE;
   if (num_tris == 0) return h;
@@ -470,6 +473,7 @@ HRT_HD HrtHit hrt_closest_hit_wide(const Mem &mem_in, const Gid tri_gid, int roo
       for (uint32_t k = 0; k < ntri; ++k) {
         const uint32_t s = first + k;
         float t;
+        if (SELF && s == self_slot && hrt_mt_self_miss(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), d, self_nt, cnt)) continue;
         const uint32_t gid = tri_gid[s];
         if (hrt_mt_test(mem.tri(s, 0), mem.tri(s, 1), mem.tri(s, 2), o, d, h.t, h.gid, gid, &t, cnt)) {
           h.t = t; h.gid = gid; h.slot = s;

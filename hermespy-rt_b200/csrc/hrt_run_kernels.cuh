@@ -73,8 +73,9 @@ static size_t scene_smem_bytes(uint32_t num_wide, uint32_t num_tris, uint32_t oc
 __device__ __forceinline__ uint32_t scene_tri_off(const SceneDev &sc) { return sc.num_wide * 112u * sc.wide_octants; }
 
 /* smem0: shared-window address of the staged scene; kernels compute it once and keep it in a register */
-template <bool SMEM, bool BRUTE, class Cnt>
-__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, uint32_t smem0 = smem_base_addr())
+template <bool SMEM, bool BRUTE, bool SELF = false, class Cnt>
+__device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, uint32_t smem0 = smem_base_addr(),
+                                        uint32_t self_slot = HRT_NONE, float self_nt = 0.f)
 {
   const size_t stride4 = (size_t)sc.num_wide * HRT_WIDE_F4;
   if (SMEM) {
@@ -84,12 +85,12 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
     HrtSharedGid gid; gid.addr = m.tri_addr + sc.num_tris * 48u;
     asm volatile("" : "+r"(m.tri_addr), "+r"(gid.addr));   /* keep both bases in registers across the leaf loop */
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
-    return hrt_closest_hit_wide<true>(m, gid, sc.wroot, sc.num_tris, o, d, cnt, stride4);
+    return hrt_closest_hit_wide<true, SELF>(m, gid, sc.wroot, sc.num_tris, o, d, cnt, stride4, self_slot, self_nt);
   } else {
     HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris; m.wnodes = sc.wnodes;
     if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
-    if (sc.wide_octants == 8) return hrt_closest_hit_wide<true>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt, stride4);
-    return hrt_closest_hit_wide<false>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt);
+    if (sc.wide_octants == 8) return hrt_closest_hit_wide<true, SELF>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt, stride4, self_slot, self_nt);
+    return hrt_closest_hit_wide<false, SELF>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt, 0, self_slot, self_nt);
   }
 }
 
@@ -628,9 +629,14 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
      * product n.d of the most recent shadow hit (what the reference feeds to acos,
      * :281); 2 = "none yet: the primary angle theta_p" */
     const float theta_p = r2.w;
-    /* receiver maps: t's numerator for the triangle this hit lies on, once for all receivers (hrt_mt_self_nt) */
+    /* t's numerator for the triangle this hit lies on, once for all receivers (hrt_mt_self_nt) */
     float self_nt = 0.f;
-    if (MAP) self_nt = hrt_mt_self_nt(lds128(smem0 + slot * 48u), lds128(smem0 + slot * 48u + 16u), lds128(smem0 + slot * 48u + 32u), s.o);
+    if (SMEM && !BRUTE) {
+      /* (shared-memory scenes only: in the global-memory kernel the extra live values cost more in spills than
+       * the early-out saves -- C5: 667 -> 699 ms) */
+      const uint32_t ta = smem0 + (MAP ? 0u : scene_tri_off(sc)) + slot * 48u;
+      self_nt = hrt_mt_self_nt(lds128(ta), lds128(ta + 16u), lds128(ta + 32u), s.o);
+    }
     float cx_carry = HRT_CX_PRIMARY, ci_p, si_p;
     sincosf(theta_p, &si_p, &ci_p);
     const uint64_t path = hrt_gpath(rd.l0 + l, rd.rank, rd.world, rd.blk);
@@ -655,7 +661,8 @@ k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_
       HrtHit h; h.gid = HRT_NONE; h.t = -1.f; h.slot = 0;
       if (act) {
         sd = hrt_shadow_dir(s.o, ld3(rxp, r), &dist);                          /* :676-678 */
-        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc, smem0, slot, self_nt) : query<SMEM, BRUTE>(sc, s.o, sd, wc, smem0);   /* :682 */
+        h = MAP ? query_map(sc, rd.map, r, s.o, sd, dist, wc, smem0, slot, self_nt)
+                : query<SMEM, BRUTE, SMEM>(sc, s.o, sd, wc, smem0, slot, self_nt);                                   /* :682 */
         if (h.gid != HRT_NONE) cx_sh = v3_dot(tri_normal<SMEM, MAP>(sc, h.slot, smem0), sd);   /* :281, argument of acos */
       }
       const bool shit = act && h.gid != HRT_NONE;

@@ -128,13 +128,15 @@ static void build(const Scene *sc, EmulScene &E, int leaf_max, float pad_ulps, f
   collapse_wide(E);
 }
 
-static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute)
+static HrtHit query(const EmulScene &E, V3 o, V3 d, int brute, uint32_t self_slot = HRT_NONE, float self_nt = 0.f)
 {
   HrtGlobalMem m; m.nodes = E.nodes.data(); m.tris = E.tris.data(); m.wnodes = E.wnodes.data();
   HrtNoCount nc;
   if (brute == 1) return hrt_closest_hit_brute(m, E.gid.data(), E.n, o, d, nc);
   if (brute == 2) return hrt_closest_hit(m, E.gid.data(), E.root, E.n, o, d, nc);                        /* binary tree as built */
   if (brute == 4) return hrt_closest_hit_wide<false>(m, E.gid.data(), E.wroot, E.n, o, d, nc);        /* 4-wide, plain copy (octant 0) */
+  if (self_slot != HRT_NONE)                                                                          /* shadow rays, as k_scatter */
+    return hrt_closest_hit_wide<true, true>(m, E.gid.data(), E.wroot, E.n, o, d, nc, (size_t)E.num_wide * HRT_WIDE_F4, self_slot, self_nt);
   return hrt_closest_hit_wide<true>(m, E.gid.data(), E.wroot, E.n, o, d, nc, (size_t)E.num_wide * HRT_WIDE_F4);  /* 4-wide: what the kernels run */
 }
 
@@ -345,7 +347,8 @@ extern "C" int emul_compute_paths(const Scene *sc, const Vec3 *rx_pos, const Vec
           const size_t so = ((r * T + t) * B + b) * P + p;
           float dist;
           const V3 sd = hrt_shadow_dir(s.o, tov(rx_pos[r]), &dist);
-          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist, h.slot, self_nt) : query(E, s.o, sd, brute);
+          const HrtHit sh = use_map ? query_map(E, M, r, s.o, sd, dist, h.slot, self_nt)
+                                    : query(E, s.o, sd, brute, brute == 0 ? h.slot : HRT_NONE, self_nt);
           if (sh.gid != HRT_NONE) { carry = hrt_theta_fold(nrm(E, sh.slot), sd); cx_carry = v3_dot(nrm(E, sh.slot), sd); }
           if (sh.gid != HRT_NONE && sh.t <= 1.f) { tr_state[so] = 2; continue; }
           /* closed_form: what k_scatter runs (hrt_scatter_path_auto); else the reference's formulas line by line */
