@@ -539,6 +539,11 @@ def main_gpu(args):
                           "query performs no box test at all, so the counted work per query is a third of the BVH walk's while the "
                           "kernel finishes sooner: compare bvh_mode (same step, HRT_RXMAP=0)",
             "bvh_mode": bvh_mode,
+            "reference_equivalent": {
+                "note": "for context (SURVEY 8(d), last line): the reference tests every triangle for every query, "
+                        "~29 flops x N triangles; the same queries at that cost per second",
+                "flops_per_query": 29.0 * s0["num_tris"],
+                "tflops": 29.0 * s0["num_tris"] * shadow_rank0 / (ms_scatter * 1e-3) / 1e12 if ms_scatter else None},
             "intersection_share_of_issue_slots": isect_share,
             "frac_of_intersection_slots": (achieved / peak_unfused / isect_share) if achieved and peak_unfused and isect_share else None,
             "intersection_note": isect_note,

@@ -574,3 +574,54 @@ extern "C" void emul_ext_refr_coefs(uint32_t material, float f_ghz, float theta1
 extern "C" float emul_ext_pattern_pi(float s1, float s2, float s3, int a1, int a3, const float ki[3], const float ks[3], const float n[3])
 { return hrt_scat_pattern_pi(s1, s2, s3, a1, a3, v3(ki[0], ki[1], ki[2]), v3(ks[0], ks[1], ks[2]), v3(n[0], n[1], n[2])); }
 extern "C" float emul_ext_lobe_norm(int alpha, float cos_i, float sin_i) { return hrt_lobe_norm(alpha, cos_i, sin_i); }
+
+/* "Sure" cells (hrt_rxmap_sure) against the exact test: random receivers, triangles and cells; for every cell
+ * the predicate accepts, rays from random origins on the far side of the receiver (up to `reach` away), aimed at
+ * the receiver with the kernels' own fp32 direction and continuing through the cell, must be accepted by
+ * hrt_mt_test with t >= the distance to the receiver.  Returns the number of violations; *n_sure = cells accepted,
+ * *n_rays = rays tested. */
+extern "C" long emul_sure_check(size_t n, uint32_t seed, float scale, unsigned long long *n_sure, unsigned long long *n_rays)
+{
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 12345u;
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (float)((st >> 11) & 0xFFFFFF) / 16777216.f; };
+  long bad = 0; *n_sure = 0; *n_rays = 0;
+  HrtNoCount nc;
+  for (size_t i = 0; i < n; ++i) {
+    const V3 apex = v3((rnd() - 0.5f) * scale, (rnd() - 0.5f) * scale, rnd() * 0.1f * scale);
+    const uint32_t G = 32u << (uint32_t)(rnd() * 3.99f);                 /* 32 .. 256 */
+    const uint32_t face = (uint32_t)(rnd() * 5.99f), ci = (uint32_t)(rnd() * (G - 0.01f)), cj = (uint32_t)(rnd() * (G - 0.01f));
+    const HrtPyramid cp = hrt_rxmap_pyramid(face, G, ci, ci + 1, cj, cj + 1);
+    /* a triangle around the cell's centre ray at a random distance, random orientation and size */
+    const V3 mid = v3((cp.c[0].x + cp.c[2].x) * 0.5f, (cp.c[0].y + cp.c[2].y) * 0.5f, (cp.c[0].z + cp.c[2].z) * 0.5f);
+    const float dist = 0.05f * scale * (0.02f + rnd());
+    const V3 ctr = v3(apex.x + mid.x * dist, apex.y + mid.y * dist, apex.z + mid.z * dist);
+    const float size = dist * (4.f + 200.f * rnd()) / (float)G;
+    V3 p[3];
+    for (int k = 0; k < 3; ++k) p[k] = v3(ctr.x + (rnd() - 0.5f) * size, ctr.y + (rnd() - 0.5f) * size, ctr.z + (rnd() - 0.5f) * size);
+    const HrtTriSetup S = hrt_tri_setup(p[0], p[1], p[2]);
+    V3 va, vb, vc; hrt_rxmap_corners(S.q0, S.q1, S.q2, apex, &va, &vb, &vc);
+    const float max_abs = scale;                                        /* coordinates stay within +-scale */
+    const float pad = 4.f * hrt_box_pad(max_abs, 64.f), reach = 2.f * scale * 1.8f;
+    if (!hrt_rxmap_sure(cp, va, vb, vc, pad, reach)) continue;
+    ++*n_sure;
+    for (int r = 0; r < 64; ++r) {
+      /* a direction inside the cell (bilinear mix of the corner directions), an origin on the other side of the apex */
+      const float a = rnd(), b = rnd();
+      V3 w = v3((cp.c[0].x * (1 - a) + cp.c[1].x * a) * (1 - b) + (cp.c[3].x * (1 - a) + cp.c[2].x * a) * b,
+                (cp.c[0].y * (1 - a) + cp.c[1].y * a) * (1 - b) + (cp.c[3].y * (1 - a) + cp.c[2].y * a) * b,
+                (cp.c[0].z * (1 - a) + cp.c[1].z * a) * (1 - b) + (cp.c[3].z * (1 - a) + cp.c[2].z * a) * b);
+      const float back = 1.01f + rnd() * rnd() * scale * 0.9f;
+      const V3 o = v3(apex.x - w.x * back, apex.y - w.y * back, apex.z - w.z * back);
+      float dd;
+      const V3 d = hrt_shadow_dir(o, apex, &dd);
+      if (!(dd > 1.001f)) continue;
+      uint32_t c_pos, c_neg; hrt_rxmap_cells2(d, G, &c_pos, &c_neg);
+      if (c_pos != (face * G + cj) * G + ci) continue;                  /* rounded into a neighbouring cell: not this cell's query */
+      ++*n_rays;
+      float t = 0.f;
+      const bool hit = hrt_mt_test<HrtNoCount, true>(S.q0, S.q1, S.q2, o, d, HRT_T_MAX, 0u, 0u, &t, nc);
+      if (!hit || !(t >= dd * 0.999f) || !(t > 1.f)) ++bad;
+    }
+  }
+  return bad;
+}

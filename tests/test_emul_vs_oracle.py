@@ -187,3 +187,18 @@ def test_compute_paths_receiver_maps_match_golden(name):
     tl.assert_gains_close(ref, mask, w, rtol=1e-5)
     assert np.array_equal(tr["slot_state"], g["trace.slot_state"])
     assert np.array_equal(tr["hit_tri"], g["trace.hit_tri"])
+
+
+@pytest.mark.parametrize("scale", [20.0, 300.0, 3000.0])
+def test_sure_cells_imply_a_hit(scale):
+    """hrt_rxmap_sure: wherever the predicate lets the far side of a shadow query skip the exact test, the exact
+    test (hrt_mt_test, the reference's arithmetic) accepts the triangle for every ray through the receiver in that
+    cell, with t beyond the receiver -- random receivers, triangles, cells and origins up to `scale` metres away."""
+    import ctypes as C
+    lib = tl.emul_lib()
+    lib.emul_sure_check.restype = C.c_long
+    lib.emul_sure_check.argtypes = [C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    n_sure, n_rays = C.c_ulonglong(0), C.c_ulonglong(0)
+    bad = lib.emul_sure_check(100000, 7, scale, C.byref(n_sure), C.byref(n_rays))
+    assert n_sure.value > 3000 and n_rays.value > 100000, (n_sure.value, n_rays.value)    # not vacuous
+    assert bad == 0, (bad, n_sure.value, n_rays.value)
