@@ -191,11 +191,12 @@ __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx
   const uint32_t i = bi * HRT_RXMAP_BLOCK + (tid & 7u), j = bj * HRT_RXMAP_BLOCK + (tid >> 3);
   const HrtPyramid cp = hrt_rxmap_pyramid(face, G, i, i + 1u, j, j + 1u);
   uint32_t count = 0, only = 0;
+  unsigned long long keep = 0ull;                 /* verdicts of the first 64 candidates, for the writing pass */
   for (uint32_t k = 0; k < nc; ++k) {
     const uint32_t s = cand[k];
     V3 va, vb, vc;
     hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
-    if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) { ++count; only = s; }
+    if (hrt_rxmap_overlap(cp, va, vb, vc, pad)) { ++count; only = s; if (k < 64u) keep |= 1ull << k; }
   }
   const float is = inv_step[r];
   uint32_t sure = 0;
@@ -219,10 +220,11 @@ __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx
   if (!fits) return;
   uint32_t *dst = items + (size_t)r * items_per_rx + off, nw = 0;
   for (uint32_t k = 0; k < nc; ++k) {
+    if (k < 64u && !((keep >> k) & 1ull)) continue;
     const uint32_t s = cand[k];
     V3 va, vb, vc;
     hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);
-    if (!hrt_rxmap_overlap(cp, va, vb, vc, pad)) continue;
+    if (k >= 64u && !hrt_rxmap_overlap(cp, va, vb, vc, pad)) continue;
     float dl, dh;
     hrt_rxmap_depth(cp, va, vb, vc, pad, G, &dl, &dh);
     dst[nw++] = hrt_rxmap_item(s, dl, dh, is);
