@@ -521,10 +521,11 @@ def main_gpu(args):
                             "bound; its DRAM traffic is the gather of per-hit state and the receiver-map cells" % (tj["source"], l0["duration_ms"]))
         except Exception:
             pass
-        isect_share, isect_note = None, None
+        isect_share, isect_note, issue_pct, lanes = None, None, None, None
         try:
             sj = json.load(open(os.path.join(ROOT, "profiles", "k_scatter_shares.json")))
             isect_share = sj["intersection_share_of_issue_slots"]
+            issue_pct, lanes = sj.get("issue_active_pct"), sj.get("active_threads_per_instruction")
             isect_note = ("k_scatter fuses the reference's per-path scattering math (0 counted flops) with the closest-hit "
                           "query; by ncu source-level instruction counts (%s) %.0f %% of its issue slots are the query. "
                           "frac_of_intersection_slots = frac / that share" % (sj["source"], 100 * isect_share))
@@ -544,6 +545,10 @@ def main_gpu(args):
                         "~29 flops x N triangles; the same queries at that cost per second",
                 "flops_per_query": 29.0 * s0["num_tris"],
                 "tflops": 29.0 * s0["num_tris"] * shadow_rank0 / (ms_scatter * 1e-3) / 1e12 if ms_scatter else None},
+            "issue_slots_busy_pct_ncu": issue_pct, "active_lanes_per_instruction_ncu": lanes,
+            "issue_note": "the kernel is bound by instruction issue, not by a memory level or the fp32 pipe alone: share of "
+                          "issue slots in use and lanes active per issued instruction, from the committed ncu capture of this "
+                          "kernel (profiles/k_scatter_shares.json -> source)",
             "intersection_share_of_issue_slots": isect_share,
             "frac_of_intersection_slots": (achieved / peak_unfused / isect_share) if achieved and peak_unfused and isect_share else None,
             "intersection_note": isect_note,

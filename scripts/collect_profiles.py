@@ -79,7 +79,8 @@ def source_shares(rep, kernel_substr, out_path):
     INTERSECTION = {"hrt_closest_hit", "hrt_mt_test", "hrt_slab_sorted", "hrt_slab", "hrt_fma_pair", "v3_dot", "v3_cross",
                     "v3_sub", "lds128", "lds32", "smem_base_addr", "node", "tri", "child_at", "child_ref", "cache_word",
                     "hrt_safe_inv", "hrt_octant", "hrt_ray_cull", "hrt_origin_chain", "select_octant", "query", "origin_chain",
-                    "hrt_closest_hit_wide", "wide", "select_wide_octant", "scene_tri_off"}
+                    "hrt_closest_hit_wide", "wide", "select_wide_octant", "scene_tri_off",
+                    "query_map", "hrt_rxmap_cells2", "hrt_rxmap_query_depth", "hrt_rxmap_stop", "hrt_mt_self_miss", "hrt_mt_self_nt"}
     share = sum(c for fn, c in fa.items() if fn in INTERSECTION) / max(tot, 1)
     json.dump({"kernel": kernel_substr, "intersection_share_of_issue_slots": share,
                "functions": {fn: c / tot for fn, c in fa.most_common(30)},
@@ -130,6 +131,14 @@ for rep, kern, tag in (("prof_scatter.ncu-rep", os.environ.get("HRT_PROF_KERNEL"
         tr.append({"kernel": r.get("Kernel Name"), "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                    "duration_ms": dur * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(du, 1) if dur is not None else None})
     json.dump({"source": f"ncu --set full --clock-control none, {rep}", "launches": tr}, open(os.path.join(OUT, f"{tag}_traffic.json"), "w"), indent=1)
+    # issue-slot utilisation and lane occupancy of the first captured launch, next to the shares
+    sj_path = os.path.join(OUT, f"{tag}_shares.json")
+    sj = json.load(open(sj_path))
+    if rows:
+        sj["issue_active_pct"] = fnum(rows[0].get("smsp__issue_active.avg.pct_of_peak_sustained_active", ""))
+        sj["active_threads_per_instruction"] = fnum(rows[0].get("smsp__thread_inst_executed_per_inst_executed.ratio", ""))
+        sj["registers_per_thread"] = fnum(rows[0].get("launch__registers_per_thread", ""))
+    json.dump(sj, open(sj_path, "w"), indent=1)
     if tag == "k_scatter":
         shutil.copy(os.path.join(OUT, "k_scatter_shares.json"), os.path.join(ROOT, "profiles", "k_scatter_shares.json"))
     if tag == "k_scatter":   # what bench.py reports as roofline.traffic
