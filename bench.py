@@ -147,7 +147,8 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    P = int(os.environ.get("HRT_REF_PATHS", str(2500 * max(1, min((os.cpu_count() or 1) // NUM_TX, 32)))))
+    # per step: 10,000 rays per process (~2 s of the reference each), one process per host core
+    P = int(os.environ.get("HRT_REF_PATHS", str(10000 * max(1, min((os.cpu_count() or 1) // NUM_TX, 32)))))
     for _ in range(args.warmup):
         run_reference_sample(max(P // 10, 100), True)
     tot_rb, tot_s = 0, 0.0
@@ -567,10 +568,10 @@ def main_gpu(args):
         # ---- CPU baseline: the unmodified reference on a bounded sample, one core
         cpu = None
         if world == 1:
-            r = run_reference_sample(int(os.environ.get("HRT_REF_PATHS", "1000")), False)
+            r = run_reference_sample(int(os.environ.get("HRT_REF_PATHS", "12000")), False)     # ~10 s on one core
             if r:
                 cpu = {"value": r[0] / r[1], "unit": "ray-bounces/s", "cores": 1, "kind": "reference",
-                       "sample": f"same scene/TX/RX/bounces, {os.environ.get('HRT_REF_PATHS', '1000')} rays per TX "
+                       "sample": f"same scene/TX/RX/bounces, {os.environ.get('HRT_REF_PATHS', '12000')} rays per TX "
                                  f"({r[0]} ray-bounces, {r[1]:.1f} s of compute_paths())"}
         # ---- the drop-in entry itself on configs[1] and configs[2] (N = 1 only: host-memory heavy)
         dense = None

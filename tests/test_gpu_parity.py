@@ -930,3 +930,33 @@ def test_strict_untouched_mode():
         br = o.scat[f"a_{pol}_re"].reshape(-1)[wr].astype(np.float64); bi = o.scat[f"a_{pol}_im"].reshape(-1)[wr].astype(np.float64)
         assert (np.hypot(ar - br, ai - bi) <= tl.GAIN_RTOL * np.hypot(ar, ai) + 1e-38).all()
     assert (st == 0).sum() > 10000 and (st == 2).sum() > 0 and (st == 1).sum() > 50000
+
+
+@pytest.mark.parametrize("scene", SCENES + ["canyon_moving"])
+def test_receiver_maps_vs_brute_force_random_configs(ctx, scene, monkeypatch):
+    """Receiver maps with their exact shortcuts ("sure" cells, own-triangle early-out; hrt_rxmap.cuh) against the
+    brute-force kernel (every triangle for every query = the reference's loop) on random receiver / transmitter
+    sets in, around and just above the floor of the scene: every dense output word and slot state identical.
+    (scripts/soak_maps.py is the long version: 200 configurations, 7e8 queries.)"""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(scene.encode()))
+    ctx.load_scene(tl.scene_path(scene))
+    T3 = tl.scene_triangles(scene).reshape(-1, 3)
+    lo, hi = T3.min(0), T3.max(0)
+    ext = np.maximum(hi - lo, 1.0)
+    for G in (64, 256):
+        R, T, B, P = int(rng.integers(8, 33)), int(rng.integers(1, 3)), int(rng.integers(2, 5)), 6000
+        rx = lo + rng.random((R, 3)) * ext
+        rx[: R // 4] = lo - 0.3 * ext + rng.random((R // 4, 3)) * 1.6 * ext
+        rx[R // 4: R // 2, 2] = lo[2] + rng.random(R // 2 - R // 4) * 0.02 * ext[2] + 1e-3
+        tx = lo + (0.2 + 0.6 * rng.random((T, 3))) * ext
+        rxv, txv = rng.uniform(-3, 3, rx.shape), rng.uniform(-10, 10, tx.shape)
+        monkeypatch.setenv("HRT_RXMAP", "1"); monkeypatch.setenv("HRT_RXMAP_G", str(G))
+        a = ctx.run(rx, tx, rxv, txv, 3.5, P, B, dense=True, trace=True)
+        assert a["stats"]["rx_map"] == 1
+        monkeypatch.setenv("HRT_RXMAP", "0"); monkeypatch.delenv("HRT_RXMAP_G")
+        b = ctx.run(rx, tx, rxv, txv, 3.5, P, B, dense=True, trace=True, brute_force=True)
+        wa, wb = tl.outputs_words(a["out"]), tl.outputs_words(b["out"])
+        assert np.array_equal(a["trace"]["slot_state"], b["trace"]["slot_state"])
+        for key in ("scat.a_te_re", "scat.a_te_im", "scat.a_tm_re", "scat.a_tm_im", "scat.tau", "scat.freq_shift"):
+            assert np.array_equal(wa[key], wb[key]), (key, G)
