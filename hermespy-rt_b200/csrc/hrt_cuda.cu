@@ -1734,8 +1734,14 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
        * for T > 1 the first bits of TX 1 in the last byte (appendix A-9). */
       uint8_t *A = p->rays_scat->rays_active;
       const size_t rowb = P / 8 + 1;
-      uint64_t L = 0;
-      while (L < rd.n) {
+      /* big chunks: the copy threads share the loop, each a range of whole bytes (chunks and shard blocks start at
+       * multiples of 32 paths, so no byte is written by two of them) */
+      const bool par = rd.n >= (1u << 18) && ctx->pool;
+      const int parts = par ? ctx->pool->n : 1;
+      auto mask_range = [&](int w) {
+      const uint64_t L_end = w + 1 == parts ? rd.n : ((uint64_t)rd.n * (uint64_t)(w + 1) / (uint64_t)parts) & ~(uint64_t)31;
+      uint64_t L = ((uint64_t)rd.n * (uint64_t)w / (uint64_t)parts) & ~(uint64_t)31;
+      while (L < L_end) {
         const uint64_t g = hrt_gpath(l0 + L, rank, world, blk);
         /* whole bytes: 8 consecutive paths of one shard block (blocks are multiples of 32) */
         const bool whole = (g & 7) == 0 && L + 8 <= rd.n && (world <= 1 || (l0 + L) % blk + 8 <= blk);
@@ -1757,6 +1763,9 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
           }
         ++L;
       }
+      };
+      if (par) ctx->pool->run([&](int w, int) { mask_range(w); });
+      else mask_range(0);
     }
   }
   S.shadow_queries = S.primary_hits * R;
