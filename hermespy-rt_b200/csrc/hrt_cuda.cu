@@ -1482,7 +1482,10 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
   /* all 30 Morton bits order the hits (sorting 24 saves a radix pass, 2 ms, and costs k_scatter as much in coherence) */
   int hit_sort_low_bit = 0;
   if (const char *e = getenv("HRT_HIT_SORT_LOW_BIT")) { int v = atoi(e); if (v >= 0 && v <= 22) hit_sort_low_bit = v; }
-  const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT") && (!warp_mode || getenv("HRT_HIT_SORT_ALWAYS"));
+  /* tiny runs (< 2^22 path x receiver slots per depth, k_scatter < ~0.1 ms): ordering the work costs more than it
+   * saves -- a dozen launches of ~0.2 ms in total (configs[0]: 0.79 -> 0.55 ms per call) */
+  const bool tiny = (uint64_t)T * n_shard * (R ? R : 1) < (1ull << 22) && !getenv("HRT_SORT_ALWAYS");
+  const bool sort_hits = !getenv("HRT_NO_HIT_SORT") && !getenv("HRT_NO_SORT") && !tiny && (!warp_mode || getenv("HRT_HIT_SORT_ALWAYS"));
   if (sort_hits) {
     /* the chunk's direction sort below needs less: same pair types, 32 key bits */
     size_t tb = 0;
@@ -1600,7 +1603,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
 
     /* order the chunk's paths by launch direction */
     if (flags & HRT_FLAG_HOST_DIRS) { k_dirkeys<<<g1, 256, 0, st>>>(rd); CKR(cudaGetLastError()); S.kernel_launches++; }
-    if (getenv("HRT_NO_SORT")) {
+    if (tiny || getenv("HRT_NO_SORT")) {
       CKR(cudaMemcpyAsync(rd.perm2, rd.perm, (size_t)rd.n * 4, cudaMemcpyDeviceToDevice, st));
     } else {
       size_t tb = 0;

@@ -24,6 +24,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(autouse=True)
+def _order_the_work_at_test_sizes(monkeypatch):
+    """hrt_run skips the direction / hit sorts for tiny runs (< 2^22 path x receiver slots); the tests are that
+    small, so they force the sorts on to exercise the full-size path.  test_tiny_runs_skip_ordering covers the
+    other branch."""
+    monkeypatch.setenv("HRT_SORT_ALWAYS", "1")
+
+
 def _ulps(a, b):
     """distance in fp32 representable values (+0 and -0 coincide)"""
     def key(x):
@@ -960,3 +968,23 @@ def test_receiver_maps_vs_brute_force_random_configs(ctx, scene, monkeypatch):
         assert np.array_equal(a["trace"]["slot_state"], b["trace"]["slot_state"])
         for key in ("scat.a_te_re", "scat.a_te_im", "scat.a_tm_re", "scat.a_tm_im", "scat.tau", "scat.freq_shift"):
             assert np.array_equal(wa[key], wb[key]), (key, G)
+
+
+@pytest.mark.parametrize("name", ["reflector_testc", "canyon_3rx", "box_generic"])
+def test_tiny_runs_skip_ordering(ctx, name, monkeypatch):
+    """Small runs do without the direction and hit sorts (fewer launches); the outputs are the same bits."""
+    g = tl.load_golden(name)
+    ctx.load_scene(tl.scene_path(g["scene"]))
+    args = (g["rx"], g["tx"], g["rxv"], g["txv"], float(g["f"]), int(g["P"]), int(g["B"]))
+    a = ctx.run(*args, dense=True, raysinfo=True, trace=True)                   # sorts forced on (fixture)
+    monkeypatch.delenv("HRT_SORT_ALWAYS")
+    b = ctx.run(*args, dense=True, raysinfo=True, trace=True)
+    assert b["stats"]["kernel_launches"] < a["stats"]["kernel_launches"]
+    wa, wb = tl.outputs_words(a["out"]), tl.outputs_words(b["out"])
+    for k in wa:
+        assert np.array_equal(wa[k], wb[k]), k
+    assert np.array_equal(a["trace"]["slot_state"], b["trace"]["slot_state"])
+    ref = {k[4:]: v for k, v in g.items() if k.startswith("out.")}
+    mask = {k[5:]: v for k, v in g.items() if k.startswith("mask.")}
+    tl.assert_exact(ref, mask, wb)
+    tl.assert_gains_close(ref, mask, wb)
