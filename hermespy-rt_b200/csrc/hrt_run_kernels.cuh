@@ -121,6 +121,8 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
   const uint32_t w_pos = __ldg(&mp.cells[cell0 + c_pos]);
   const HrtMapDepth md = hrt_rxmap_query_depth(dist, __ldg(&mp.inv_step[r]));
   int q_stop = -1;
+  /* the triangle the ray starts on is in every near-side list: decided here, by all lanes together */
+  const bool self_out = hrt_mt_self_miss(m.tri(self_slot, 0), m.tri(self_slot, 1), m.tri(self_slot, 2), d, self_nt, cnt);
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
     uint32_t k = item0 + (w >> 8);
@@ -140,7 +142,7 @@ __device__ __forceinline__ HrtHit query_map(const SceneDev &sc, const RxMapDev &
         if ((int)((iw >> 16) & 255u) < q_stop) break;          /* everything left is farther from o than the best hit */
         if ((int)(iw >> 24) > md.q_behind) continue;           /* entirely behind o */
         /* the triangle the ray starts on: a miss by t <= 0 unless the receiver is behind it (hrt_core.cuh) */
-        if (s == self_slot && hrt_mt_self_miss(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), d, self_nt, cnt)) continue;
+        if (s == self_slot && self_out) continue;
       }
       float t;
       if (hrt_mt_test<Cnt, true>(m.tri(s, 0), m.tri(s, 1), m.tri(s, 2), o, d, h.t, 0u, 0u, &t, cnt)) {

@@ -207,6 +207,8 @@ static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, 
   hrt_rxmap_cells2(d, M.G, &c_pos, &c_neg);          /* (-d) first, (+d) only if nothing in front of the receiver */
   const HrtMapDepth md = hrt_rxmap_query_depth(dist, M.inv_step[r]);
   int q_stop = -1;
+  const bool self_out = self_slot != HRT_NONE &&
+                        hrt_mt_self_miss(E.tris[3 * self_slot], E.tris[3 * self_slot + 1], E.tris[3 * self_slot + 2], d, self_nt, nc);
   for (int side = 0; side < 2; ++side) {
     const size_t cell = r * 6 * M.G * M.G + (side ? c_pos : c_neg);
     if (side == 1 && M.sure[cell] && h.gid == HRT_NONE && dist > 1.001f) {     /* "sure" cell: no test, t not computed */
@@ -220,7 +222,7 @@ static HrtHit query_map(const EmulScene &E, const EmulRxMap &M, size_t r, V3 o, 
       if (side == 0) {
         if ((int)((w >> 16) & 255u) < q_stop) break;           /* everything left is farther from o than the best hit */
         if ((int)(w >> 24) > md.q_behind) continue;            /* entirely behind o */
-        if (s == self_slot && hrt_mt_self_miss(E.tris[3 * s], E.tris[3 * s + 1], E.tris[3 * s + 2], d, self_nt, nc)) continue;
+        if (s == self_slot && self_out) continue;
       }
       float t;
       if (tests) ++*tests;
