@@ -784,7 +784,8 @@ def test_c4_geometry_vs_oracle(ctx):
     assert rx.shape == (64, 3) and tx.shape == (4, 3)
     rng = np.random.default_rng(21)
     rxv, txv = rng.uniform(-3, 3, rx.shape), rng.uniform(-10, 10, tx.shape)
-    P, B, f = 2000, 5, 3.5
+    import os
+    P, B, f = int(os.environ.get("HRT_TEST_C4_RAYS", "2000")), 5, 3.5       # (a soak sets more rays: profiles/r2_v3/soak_c4.log)
     a, tr = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B, fill=0x00)
     b, _ = tl.run_oracle(scene, rx, tx, rxv, txv, f, P, B, fill=0x5A, trace=False)
     mask = tl.written_mask(a, b)
