@@ -236,7 +236,7 @@ struct hrt_ctx {
   uint32_t *d_map_cells; uint32_t *d_map_items; uint32_t *d_map_cursor;   /* cursor[R], then status[1], then inv_step[R] (float) */
   size_t cap_map_cells, cap_map_items, cap_map_cursor;
   uint32_t map_G, map_items_per_rx, map_R; bool map_valid;
-  uint64_t map_key, map_failed_key, scene_version;
+  uint64_t map_key, map_failed_key, scene_version; uint64_t map_key0;   /* receivers + scene version, without G */
   float map_build_ms;
 
   bool have_mats;
@@ -892,20 +892,41 @@ static uint64_t hash_bytes(const void *p, size_t n, uint64_t h)
   return h;
 }
 
-static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, cudaStream_t st, bool *use)
+/* Cost model of the shadow queries of one run (C4-like scenes, measured on B200; ms): the BVH walk, or a map
+ * of G cells per face edge -- its build (once per receiver set and scene; counted at a quarter, on the
+ * assumption that a receiver set is used for a few calls) plus the queries through it. */
+static double rxmap_query_ms(uint32_t G, double Q) { return Q * (G >= 256 ? 2.05e-8 : G >= 128 ? 2.15e-8 : 2.5e-8); }
+static double rxmap_build_ms(uint32_t G, size_t R, uint32_t num_tris)
+{ return 0.05 * (double)R * ((double)G / 256.0) * ((double)G / 256.0) * (0.5 + 0.5 * (double)num_tris / 234.0); }
+static double bvh_query_ms(double Q) { return Q * 3.8e-8; }
+
+/* G = 0: choose by the cost model for Q expected shadow queries (may decide for the BVH: *use stays false) */
+static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, cudaStream_t st, bool *use, uint32_t G, double Q)
 {
   *use = false;
   const size_t R = p->num_rx;
-  /* cells per cube-map face edge: the finest of 256 / 128 / 64 whose cell words stay below 1 GB
-   * (measured on C4, 64 receivers: 4.0 / 4.8 / 6.5 candidate tests per query, 8.27 / 7.95 / 6.9e8 rb/s) */
-  uint32_t G = 256;
-  while (G > 64 && R * 6 * (size_t)G * G * 4 > ((size_t)1 << 30)) G >>= 1;
-  if (const char *e = getenv("HRT_RXMAP_G")) { int v = atoi(e); if (v >= 8 && v <= 1024) G = (uint32_t)v & ~7u; }
+  if (ctx->num_tris == 0 || ctx->num_tris > 65535) return HRT_OK;
+  uint64_t key0 = hash_bytes(p->rx_pos, R * sizeof(Vec3), 0xCBF29CE484222325ull);
+  key0 = hash_bytes(&ctx->scene_version, 8, key0);
+  const bool cached = ctx->map_valid && ctx->map_key0 == key0 && ctx->map_R == R;
+  if (G == 0) {
+    /* the finest of 256 / 128 / 64 whose cell words stay below 1 GB, or coarser when the run is too short for the
+     * finer build to pay (measured on C4, 64 receivers: k_scatter 237 / 248 / 290 ms, builds 3.1 / 0.8 / 0.2 ms) */
+    uint32_t Gmax = 256;
+    while (Gmax > 64 && R * 6 * (size_t)Gmax * Gmax * 4 > ((size_t)1 << 30)) Gmax >>= 1;
+    double best = bvh_query_ms(Q);
+    for (uint32_t g = Gmax; g >= 64; g >>= 1) {
+      const double c = rxmap_build_ms(g, R, ctx->num_tris) * 0.25 + rxmap_query_ms(g, Q);
+      if (c < best) { best = c; G = g; }
+    }
+    /* a map of these receivers and this scene is there already: free of charge */
+    if (cached && rxmap_query_ms(ctx->map_G, Q) <= best) { *use = true; return HRT_OK; }
+    if (G == 0) return HRT_OK;
+  }
   const size_t cells = R * 6 * (size_t)G * G;
-  if (ctx->num_tris == 0 || ctx->num_tris > 65535 || cells * 4 > ((size_t)2 << 30)) return HRT_OK;   /* (k_scatter indexes cells and items with 32 bits) */
-  uint64_t key = hash_bytes(p->rx_pos, R * sizeof(Vec3), 0xCBF29CE484222325ull);
-  key = hash_bytes(&ctx->scene_version, 8, key); key = hash_bytes(&G, 4, key);
-  if (ctx->map_valid && ctx->map_key == key && ctx->map_R == R && ctx->map_G == G) { *use = true; return HRT_OK; }
+  if (cells * 4 > ((size_t)2 << 30)) return HRT_OK;   /* (k_scatter indexes cells and items with 32 bits) */
+  uint64_t key = hash_bytes(&G, 4, key0);
+  if (cached && ctx->map_G == G) { *use = true; return HRT_OK; }
   if (ctx->map_failed_key == key) return HRT_OK;                  /* did not fit last time either: walk the BVH */
   ctx->map_valid = false;
   uint32_t per_rx = (uint32_t)(6 * (size_t)G * G * 4);            /* items per receiver: 4 per cell on average, grown on overflow */
@@ -941,7 +962,7 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
     cudaEventElapsedTime(&ctx->map_build_ms, e0, e1);
     ctx->stats.kernel_launches++;
     if (!status) {
-      ctx->map_valid = true; ctx->map_key = key; ctx->map_R = (uint32_t)R; ctx->map_G = G; ctx->map_items_per_rx = per_rx;
+      ctx->map_valid = true; ctx->map_key = key; ctx->map_key0 = key0; ctx->map_R = (uint32_t)R; ctx->map_G = G; ctx->map_items_per_rx = per_rx;
       *use = true;
       break;
     }
@@ -1423,8 +1444,21 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
     size_t min_rx = 8;
     if (const char *e = getenv("HRT_RXMAP_MIN_RX")) min_rx = (size_t)atoll(e);
     const char *force = getenv("HRT_RXMAP");          /* 0: never, 1: whenever possible */
-    const bool want = force ? force[0] == '1' : (R >= min_rx && (uint64_t)T * P * R >= (1ull << 22));
-    if (want && smem && !brute) { rc = ensure_rxmap(ctx, p, d_rx, st, &use_map); if (rc) return rc; }
+    uint32_t G = 0;                                   /* 0: by the cost model of ensure_rxmap */
+    if (const char *e = getenv("HRT_RXMAP_G")) { int v = atoi(e); if (v >= 8 && v <= 1024) G = (uint32_t)v & ~7u; }
+    if (force && force[0] == '1' && G == 0) {         /* forced: the finest that fits */
+      G = 256;
+      while (G > 64 && R * 6 * (size_t)G * G * 4 > ((size_t)1 << 30)) G >>= 1;
+    }
+    /* expected shadow queries: about half of the rays survive each bounce */
+    const double Q = (double)T * (double)n_shard * (double)R * (B < 3 ? (double)B : 2.5);
+    /* below ~1e8 expected queries the map does not pay: measured crossover of a steady state ~3e7, of a first call
+     * (build + allocations) ~3e8 (scripts/probe_mapsize.py) */
+    double min_q = 1e8;
+    if (const char *e = getenv("HRT_RXMAP_MIN_QUERIES")) min_q = atof(e);
+    bool want = force ? force[0] == '1' : (R >= min_rx && Q >= min_q);
+    if (!force && G != 0 && bvh_query_ms(Q) <= rxmap_build_ms(G, R, ctx->num_tris) * 0.25 + rxmap_query_ms(G, Q)) want = false;
+    if (want && smem && !brute) { rc = ensure_rxmap(ctx, p, d_rx, st, &use_map, G, Q); if (rc) return rc; }
   }
   rd.map.cells = ctx->d_map_cells; rd.map.items = ctx->d_map_items; rd.map.G = ctx->map_G; rd.map.items_per_rx = ctx->map_items_per_rx;
   rd.map.inv_step = (const float *)(ctx->d_map_cursor + p->num_rx + 1);
