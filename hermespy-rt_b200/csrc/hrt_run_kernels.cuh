@@ -45,14 +45,52 @@ struct HrtSharedGid {
 
 /* copies nodes, triangle records and ids into shared memory; returns the
  * first free float4 slot after them */
+/* HRT_STAGE_BULK (default): one thread hands the three arrays to the copy engine (cp.async.bulk, completion
+ * counted in bytes on an mbarrier), every thread waits on the barrier; 0: a plain load / store loop. */
+#ifndef HRT_STAGE_BULK
+#define HRT_STAGE_BULK 1
+#endif
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 template <bool NODES = true>
 __device__ __forceinline__ uint32_t stage_scene(const SceneDev &sc)
 {
   const uint32_t nn = NODES ? sc.num_wide * HRT_WIDE_F4 * sc.wide_octants : 0u, nt = sc.num_tris * 3u;
+  uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
+#if HRT_STAGE_BULK
+  __shared__ __align__(8) unsigned long long stage_bar;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar), dst0 = smem_base_addr();
+  const uint32_t gid_bulk = sc.num_tris & ~3u;                     /* ids in whole 16-byte pieces; the rest by hand */
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (nn + nt) * 16u + gid_bulk * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    if (nn) bulk_g2s(dst0, sc.wnodes, nn * 16u, bar);
+    if (nt) bulk_g2s(dst0 + nn * 16u, sc.tris, nt * 16u, bar);
+    if (gid_bulk) bulk_g2s(dst0 + (nn + nt) * 16u, sc.tri_gid, gid_bulk * 4u, bar);
+  }
+  for (uint32_t i = gid_bulk + threadIdx.x; i < sc.num_tris; i += blockDim.x) gid[i] = sc.tri_gid[i];
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "STAGE_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+               "@p bra STAGE_DONE;\n"
+               "bra STAGE_WAIT;\n"
+               "STAGE_DONE:\n"
+               "}" :: "r"(bar) : "memory");
+#else
   for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) hrt_smem4[i] = sc.wnodes[i];
   for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) hrt_smem4[nn + i] = sc.tris[i];
-  uint32_t *gid = (uint32_t *)(hrt_smem4 + nn + nt);
   for (uint32_t i = threadIdx.x; i < sc.num_tris; i += blockDim.x) gid[i] = sc.tri_gid[i];
+#endif
   return nn + nt + (sc.num_tris + 3u) / 4u;
 }
 
