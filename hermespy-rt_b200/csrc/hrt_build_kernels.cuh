@@ -403,11 +403,11 @@ __global__ void __launch_bounds__(1024) k_wide_scan(int n, const uint8_t *even, 
 }
 
 __global__ void k_wide_emit(const float4 *bn, int n, const uint8_t *even, const uint32_t *widx,
-                            float4 *wnodes, size_t oct_stride4, uint32_t octants)
+                            float4 *wnodes, size_t oct_stride4, uint32_t octants, uint32_t node_stride4)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !even[i]) return;
   HrtWideChild ch[4];
   const int c = hrt_wide_children(bn, i, widx, ch);
-  hrt_wide_emit(wnodes, oct_stride4, octants, widx[i], ch, c);
+  hrt_wide_emit(wnodes, oct_stride4, octants, widx[i], ch, c, node_stride4);
 }

@@ -162,7 +162,7 @@ struct HrtWideChild { int ref; V3 lo, hi; };
 
 /* writes the `octants` copies of wide node `w`; copies are `oct_stride4` float4s apart */
 HRT_HD void hrt_wide_emit(float4 *nodes, size_t oct_stride4, uint32_t octants, uint32_t w,
-                          const HrtWideChild *ch, int n)
+                          const HrtWideChild *ch, int n, uint32_t node_stride4 = HRT_WIDE_F4)
 {
   for (uint32_t oct = 0; oct < octants; ++oct) {
     /* front-to-back order for this octant: ascending centre along (+-1, +-1, +-1) */
@@ -191,7 +191,7 @@ HRT_HD void hrt_wide_emit(float4 *nodes, size_t oct_stride4, uint32_t octants, u
       v[4][s] = (oct & 4u) ? ch[k].hi.z : ch[k].lo.z; v[5][s] = (oct & 4u) ? ch[k].lo.z : ch[k].hi.z;
       v[6][s] = hrt_int_as_float(ch[k].ref);
     }
-    float4 *dst = nodes + (size_t)oct * oct_stride4 + (size_t)w * HRT_WIDE_F4;
+    float4 *dst = nodes + (size_t)oct * oct_stride4 + (size_t)w * node_stride4;
     for (int q = 0; q < 7; ++q) { dst[q].x = v[q][0]; dst[q].y = v[q][1]; dst[q].z = v[q][2]; dst[q].w = v[q][3]; }
   }
 }

@@ -295,12 +295,13 @@ struct HrtGlobalMem {
   }
   /* 4-wide nodes (hrt_bvh.cuh): float4 k of wide node i of the selected octant copy */
   const float4 *wnodes;
+  uint32_t wstride = 7u;       /* float4s from one wide node to the next: 7, or 8 (128-byte aligned nodes, scenes read from global memory) */
   HRT_HD float4 wide(int i, int k) const
   {
 #if defined(__CUDA_ARCH__)
-    return __ldg(&wnodes[7 * (size_t)i + k]);
+    return __ldg(&wnodes[(size_t)wstride * (size_t)i + k]);
 #else
-    return wnodes[7 * (size_t)i + k];
+    return wnodes[(size_t)wstride * (size_t)i + k];
 #endif
   }
   HRT_HD void select_wide_octant(uint32_t oct, size_t stride4)

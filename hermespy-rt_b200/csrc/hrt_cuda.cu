@@ -73,6 +73,7 @@ struct SceneDev {
   int root_ref;
   const float4 *wnodes;        /* 4-wide nodes the kernels traverse (hrt_bvh.cuh), wide_octants copies */
   uint32_t num_wide, wide_octants;   /* copies: 8 (one per direction octant) or 1 */
+  uint32_t wstride;                  /* float4s per node slot: 7 (scenes staged in shared memory) or 8 (128-byte aligned) */
   int wroot;
   float key_lo[3], key_scale[3];   /* vertex bounds -> 10-bit grid of the hit-order keys */
   float key_log;                   /* > 0: logarithmic x/y grid around the TX, cells per octave */
@@ -214,7 +215,7 @@ struct hrt_ctx {
   /* 4-wide nodes collapsed from d_nodes (build_wide) and the collapse scratch */
   float4 *d_wnodes; size_t cap_wnodes;
   int *d_wparent; uint8_t *d_weven; uint32_t *d_widx, *d_wtotal; size_t cap_wscratch;
-  uint32_t num_wide, wide_octants; int wroot;
+  uint32_t num_wide, wide_octants, wstride; int wroot;
   /* builder arrays kept for re-padding */
   int *d_kl, *d_kr, *d_kfirst, *d_klast, *d_newidx;
   float *d_box;            /* [(2n-1)][6] lo.xyz hi.xyz; inner nodes then leaves */
@@ -428,13 +429,17 @@ static int build_wide(hrt_ctx *ctx, cudaStream_t st)
   CK(cudaStreamSynchronize(st));
   ctx->num_wide = total;
   ctx->wide_octants = octant_copies(total);
-  const size_t need = (size_t)total * HRT_WIDE_F4 * ctx->wide_octants;
+  /* scenes that are read from global memory get 128-byte node slots: a visit touches 4 sectors instead of
+   * up to 5 of a node that straddles them (the shared-memory layout stays packed: bank spread, capacity) */
+  ctx->wstride = (ctx->wide_octants == 8 && scene_smem_bytes(total, ctx->num_tris, 8) <= HRT_SMEM_SCENE_LIMIT) || getenv("HRT_WIDE_PACKED")
+                   ? HRT_WIDE_F4 : 8u;
+  const size_t need = (size_t)total * ctx->wstride * ctx->wide_octants;
   if (ctx->cap_wnodes < need) {
     dev_free(ctx->d_wnodes); ctx->cap_wnodes = 0;
     CK(dev_alloc(&ctx->d_wnodes, need)); ctx->cap_wnodes = need;
   }
   k_wide_emit<<<nblk(n), 256, 0, st>>>(ctx->d_nodes, (int)n, ctx->d_weven, ctx->d_widx, ctx->d_wnodes,
-                                       (size_t)total * HRT_WIDE_F4, ctx->wide_octants);
+                                       (size_t)total * ctx->wstride, ctx->wide_octants, ctx->wstride);
   CK(cudaGetLastError());
   ctx->wroot = 0;
   return HRT_OK;
@@ -801,6 +806,7 @@ static SceneDev scene_dev(const hrt_ctx *c)
     s.key_log = (ext > 256.f && !getenv("HRT_KEY_UNIFORM")) ? 511.f / log2f(1.f + 2.f * ext * 20.f) : 0.f;
   }
   s.wnodes = c->d_wnodes; s.num_wide = c->num_wide; s.wide_octants = c->wide_octants; s.wroot = c->wroot;
+  s.wstride = c->wstride ? c->wstride : HRT_WIDE_F4;
   return s;
 }
 

@@ -115,7 +115,7 @@ template <bool SMEM, bool BRUTE, bool SELF = false, class Cnt>
 __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt, uint32_t smem0 = smem_base_addr(),
                                         uint32_t self_slot = HRT_NONE, float self_nt = 0.f)
 {
-  const size_t stride4 = (size_t)sc.num_wide * HRT_WIDE_F4;
+  const size_t stride4 = (size_t)sc.num_wide * sc.wstride;
   if (SMEM) {
     HrtSharedMem m;
     m.wnode_addr = smem0;
@@ -125,7 +125,7 @@ __device__ __forceinline__ HrtHit query(const SceneDev &sc, V3 o, V3 d, Cnt &cnt
     if (BRUTE) return hrt_closest_hit_brute(m, gid, sc.num_tris, o, d, cnt);
     return hrt_closest_hit_wide<true, SELF>(m, gid, sc.wroot, sc.num_tris, o, d, cnt, stride4, self_slot, self_nt);
   } else {
-    HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris; m.wnodes = sc.wnodes;
+    HrtGlobalMem m; m.nodes = sc.nodes; m.tris = sc.tris; m.wnodes = sc.wnodes; m.wstride = sc.wstride;
     if (BRUTE) return hrt_closest_hit_brute(m, sc.tri_gid, sc.num_tris, o, d, cnt);
     if (sc.wide_octants == 8) return hrt_closest_hit_wide<true, SELF>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt, stride4, self_slot, self_nt);
     return hrt_closest_hit_wide<false, SELF>(m, sc.tri_gid, sc.wroot, sc.num_tris, o, d, cnt, 0, self_slot, self_nt);
