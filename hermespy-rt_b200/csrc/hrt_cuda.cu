@@ -903,7 +903,7 @@ static uint64_t hash_bytes(const void *p, size_t n, uint64_t h)
  * assumption that a receiver set is used for a few calls) plus the queries through it. */
 static double rxmap_query_ms(uint32_t G, double Q) { return Q * (G >= 256 ? 2.05e-8 : G >= 128 ? 2.15e-8 : 2.5e-8); }
 static double rxmap_build_ms(uint32_t G, size_t R, uint32_t num_tris)
-{ return 0.05 * (double)R * ((double)G / 256.0) * ((double)G / 256.0) * (0.5 + 0.5 * (double)num_tris / 234.0); }
+{ return (double)R * (0.0075 + 0.037 * ((double)G / 256.0) * ((double)G / 256.0)) * (0.5 + 0.5 * (double)num_tris / 234.0); }   /* 64 RX: 2.85 / 1.09 / 0.63 ms at G = 256 / 128 / 64 */
 static double bvh_query_ms(double Q) { return Q * 3.8e-8; }
 
 /* G = 0: choose by the cost model for Q expected shadow queries (may decide for the BVH: *use stays false) */
@@ -917,7 +917,7 @@ static int ensure_rxmap(hrt_ctx *ctx, const HrtRunParams *p, const float *d_rx, 
   const bool cached = ctx->map_valid && ctx->map_key0 == key0 && ctx->map_R == R;
   if (G == 0) {
     /* the finest of 256 / 128 / 64 whose cell words stay below 1 GB, or coarser when the run is too short for the
-     * finer build to pay (measured on C4, 64 receivers: k_scatter 237 / 248 / 290 ms, builds 3.1 / 0.8 / 0.2 ms) */
+     * finer build to pay (measured on C4, 64 receivers: k_scatter 237 / 248 / 290 ms, builds 2.85 / 1.09 / 0.63 ms) */
     uint32_t Gmax = 256;
     while (Gmax > 64 && R * 6 * (size_t)Gmax * Gmax * 4 > ((size_t)1 << 30)) Gmax >>= 1;
     double best = bvh_query_ms(Q);

@@ -211,11 +211,15 @@ __global__ void __launch_bounds__(64) k_rxmap_build(SceneDev sc, const float *rx
   const uint32_t nb = G / HRT_RXMAP_BLOCK, face = blockIdx.y, r = blockIdx.z;
   const uint32_t bi = blockIdx.x % nb, bj = blockIdx.x / nb, tid = threadIdx.x;
   const V3 apex = v3(rx_pos[3 * r], rx_pos[3 * r + 1], rx_pos[3 * r + 2]);
-  if (tid == 0) ncand = 0;
+  __shared__ HrtPyramid s_bp;                      /* the block's pyramid: built once, not by each of the 64 threads */
+  if (tid == 0) {
+    ncand = 0;
+    s_bp = hrt_rxmap_pyramid(face, G, bi * HRT_RXMAP_BLOCK, (bi + 1u) * HRT_RXMAP_BLOCK,
+                             bj * HRT_RXMAP_BLOCK, (bj + 1u) * HRT_RXMAP_BLOCK);
+  }
   __syncthreads();
   {
-    const HrtPyramid bp = hrt_rxmap_pyramid(face, G, bi * HRT_RXMAP_BLOCK, (bi + 1u) * HRT_RXMAP_BLOCK,
-                                            bj * HRT_RXMAP_BLOCK, (bj + 1u) * HRT_RXMAP_BLOCK);
+    const HrtPyramid bp = s_bp;
     for (uint32_t s = tid; s < sc.num_tris; s += 64u) {
       V3 va, vb, vc;
       hrt_rxmap_corners(__ldg(&sc.tris[3 * s]), __ldg(&sc.tris[3 * s + 1]), __ldg(&sc.tris[3 * s + 2]), apex, &va, &vb, &vc);

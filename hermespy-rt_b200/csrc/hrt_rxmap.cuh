@@ -97,6 +97,18 @@ HRT_HD V3 hrt_rxmap_dir(uint32_t face, float a, float b)
  * directions */
 struct HrtPyramid { V3 m[4]; V3 c[4]; };
 
+/* 1 / sqrt(x) to ~1 ulp: the approximate reciprocal square root and one Newton step on the device (the build kernel
+ * spent a seventh of its instructions on the IEEE square roots and divisions of its pyramids) */
+HRT_HD float hrt_rxmap_rsqrt(float x)
+{
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * (1.5f - 0.5f * x * r * r);
+#else
+  return 1.f / sqrtf(x);
+#endif
+}
+
 HRT_HD HrtPyramid hrt_rxmap_pyramid(uint32_t face, uint32_t G, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1)
 {
   const float g = 2.f / (float)G;
@@ -109,13 +121,13 @@ HRT_HD HrtPyramid hrt_rxmap_pyramid(uint32_t face, uint32_t G, uint32_t i0, uint
   for (int k = 0; k < 4; ++k) {
     const V3 u = p.c[k], v = p.c[(k + 1) & 3];
     V3 n = v3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
-    const float l = 1.f / sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    const float l = hrt_rxmap_rsqrt(n.x * n.x + n.y * n.y + n.z * n.z);
     const float sgn = (n.x * mid.x + n.y * mid.y + n.z * mid.z) < 0.f ? -l : l;
     p.m[k] = v3(n.x * sgn, n.y * sgn, n.z * sgn);
   }
   for (int k = 0; k < 4; ++k) {
     const V3 u = p.c[k];
-    const float l = 1.f / sqrtf(u.x * u.x + u.y * u.y + u.z * u.z);
+    const float l = hrt_rxmap_rsqrt(u.x * u.x + u.y * u.y + u.z * u.z);
     p.c[k] = v3(u.x * l, u.y * l, u.z * l);
   }
   return p;
