@@ -423,6 +423,8 @@ def main_gpu(args):
               "seconds": t_s, "ray_bounces_per_s": float(sm[1]) / t_s,
               "closest_hit_queries_per_s": (float(sm[1]) + float(sm[2])) / t_s,
               "full_job_seconds_at_this_rate": 256.0 / world * t_s,
+              "full_job_note": "a shard has 1/256 of the job's hit density, so this extrapolation is pessimistic: the full "
+                               "1e9-ray job was run on 8 GPUs (scripts/run_c5_full.py): 14.65 s, profiles/r2_v3/c5_full.json",
               "target_rb_per_s_north_star": 1e10,
               "roofline": {"bound": "fp32", "kernel": "k_scatter (global-memory scene, 4-wide BVH)",
                            "achieved": mine["achieved_tflops"], "peak": peak_unfused, "unit": "TFLOP/s",
