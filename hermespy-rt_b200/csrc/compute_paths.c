@@ -80,9 +80,28 @@ static hrt_multi *implicit_ctx(void)
   return g_ctx;
 }
 
+/* change detection, not cryptography: four independent xor-rotate-multiply lanes over 32-byte pieces (a byte-wise
+ * FNV chain runs at < 1 GB/s -- 30 ms per call on a million-triangle scene), FNV-1a for the tail */
 static uint64_t fnv(const void *p, size_t n, uint64_t h)
 {
   const unsigned char *b = (const unsigned char *)p;
+  if (n >= 64) {
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t a0 = h ^ 0x243F6A8885A308D3ull, a1 = h + 0x13198A2E03707344ull, a2 = ~h, a3 = h * 0x100000001B3ull + 1u;
+    while (n >= 32) {
+      uint64_t w[4];
+      memcpy(w, b, 32);
+      a0 ^= w[0]; a0 = (a0 << 29 | a0 >> 35) * K;
+      a1 ^= w[1]; a1 = (a1 << 31 | a1 >> 33) * K;
+      a2 ^= w[2]; a2 = (a2 << 27 | a2 >> 37) * K;
+      a3 ^= w[3]; a3 = (a3 << 33 | a3 >> 31) * K;
+      b += 32; n -= 32;
+    }
+    h = (a0 ^ (a1 << 17 | a1 >> 47)) * K;
+    h = (h ^ (a2 << 31 | a2 >> 33)) * K;
+    h = (h ^ (a3 << 45 | a3 >> 19)) * K;
+    h ^= h >> 29;
+  }
   for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
   return h;
 }
