@@ -52,6 +52,11 @@ __constant__ HrtExtTable c_ext;
 #ifndef HRT_BLOCK
 #define HRT_BLOCK 512   /* 2 blocks of 512 threads per SM: 64 registers, ~85 KB shared memory each */
 #endif
+#ifndef HRT_MAP_BLOCK
+#define HRT_MAP_BLOCK 576   /* k_scatter with receiver maps: 2 blocks of 576 threads, 56 registers, 36 warps per SM.  Sweep (k_scatter ms on C4):
+                               512 / 576 / 640 / 672 threads x 2, 1024 x 1 -> 237.6 / 231.4 / 232.2 / 237.6 / 235.4.  The tree-walking kernels
+                               stay at 512 (576: C5 663 -> 681 ms, C4 through the BVH 436 -> 444 ms: spills) */
+#endif
 #ifndef HRT_MIN_BLOCKS
 #define HRT_MIN_BLOCKS 2   /* => 64 registers (1024 threads/SM): best of the sweep in profiles/r1_sweeps.md; __launch_bounds__ min blocks/SM of the two traversal kernels */
 #endif
@@ -1713,7 +1718,7 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 3], ss));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
       const dim3 gs((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
-      f_scatter<<<gs, HRT_BLOCK, scat_sb, ss>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+      f_scatter<<<gs, use_map ? HRT_MAP_BLOCK : HRT_BLOCK, scat_sb, ss>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
       if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 4], ss)); ev_used += 5; }
