@@ -57,6 +57,9 @@ __constant__ HrtExtTable c_ext;
                                512 / 576 / 640 / 672 threads x 2, 1024 x 1 -> 237.6 / 231.4 / 232.2 / 237.6 / 235.4.  The tree-walking kernels
                                stay at 512 (576: C5 663 -> 681 ms, C4 through the BVH 436 -> 444 ms: spills) */
 #endif
+#ifndef HRT_MAP_MIN_BLOCKS
+#define HRT_MAP_MIN_BLOCKS 2   /* (same 36 warps in smaller blocks, 384 x 3 / 288 x 4 / 192 x 6: 232.0 / 232.9 / 232.7 ms against 231.5) */
+#endif
 #ifndef HRT_MIN_BLOCKS
 #define HRT_MIN_BLOCKS 2   /* => 64 registers (1024 threads/SM): best of the sweep in profiles/r1_sweeps.md; __launch_bounds__ min blocks/SM of the two traversal kernels */
 #endif
@@ -1717,7 +1720,8 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       if (overlap) { CKR(cudaEventRecord(ctx->scat_ready, st)); CKR(cudaStreamWaitEvent(ss, ctx->scat_ready, 0)); }
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 3], ss));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
-      const dim3 gs((unsigned)min((size_t)((sms * HRT_MIN_BLOCKS + T - 1) / T), (units + HRT_BLOCK - 1) / HRT_BLOCK), (unsigned)T);
+      const size_t sblk = use_map ? HRT_MAP_BLOCK : HRT_BLOCK, smin = use_map ? HRT_MAP_MIN_BLOCKS : HRT_MIN_BLOCKS;
+      const dim3 gs((unsigned)min((size_t)((sms * smin + T - 1) / T), (units + sblk - 1) / sblk), (unsigned)T);
       f_scatter<<<gs, use_map ? HRT_MAP_BLOCK : HRT_BLOCK, scat_sb, ss>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
