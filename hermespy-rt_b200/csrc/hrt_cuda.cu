@@ -57,6 +57,10 @@ __constant__ HrtExtTable c_ext;
                                512 / 576 / 640 / 672 threads x 2, 1024 x 1 -> 237.6 / 231.4 / 232.2 / 237.6 / 235.4.  The tree-walking kernels
                                stay at 512 (576: C5 663 -> 681 ms, C4 through the BVH 436 -> 444 ms: spills) */
 #endif
+#ifndef HRT_GLOBAL_BLOCK
+#define HRT_GLOBAL_BLOCK 448   /* k_scatter walking a scene in global memory (C5): 2 blocks of 448 threads, 72 registers: 671 -> 654 ms
+                                  (512 x 2 at 64 registers spills more; 384 x 3 at 56: 696 ms) */
+#endif
 #ifndef HRT_MAP_MIN_BLOCKS
 #define HRT_MAP_MIN_BLOCKS 2   /* (same 36 warps in smaller blocks, 384 x 3 / 288 x 4 / 192 x 6: 232.0 / 232.9 / 232.7 ms against 231.5) */
 #endif
@@ -1720,9 +1724,9 @@ extern "C" int hrt_run(hrt_ctx *ctx, const HrtRunParams *p)
       if (overlap) { CKR(cudaEventRecord(ctx->scat_ready, st)); CKR(cudaStreamWaitEvent(ss, ctx->scat_ready, 0)); }
       if (timed) CKR(cudaEventRecord(ctx->evpool[ev_used + 3], ss));
       const size_t units = warp_mode ? (size_t)rd.n * 32 : rd.n;
-      const size_t sblk = use_map ? HRT_MAP_BLOCK : HRT_BLOCK, smin = use_map ? HRT_MAP_MIN_BLOCKS : HRT_MIN_BLOCKS;
+      const size_t sblk = use_map ? HRT_MAP_BLOCK : smem ? HRT_BLOCK : HRT_GLOBAL_BLOCK, smin = use_map ? HRT_MAP_MIN_BLOCKS : HRT_MIN_BLOCKS;
       const dim3 gs((unsigned)min((size_t)((sms * smin + T - 1) / T), (units + sblk - 1) / sblk), (unsigned)T);
-      f_scatter<<<gs, use_map ? HRT_MAP_BLOCK : HRT_BLOCK, scat_sb, ss>>>(rd, sc, ctx->mats, b, smem_rx_ok);
+      f_scatter<<<gs, (unsigned)sblk, scat_sb, ss>>>(rd, sc, ctx->mats, b, smem_rx_ok);
       CKR(cudaGetLastError());
       S.kernel_launches += 2;
       if (timed) { CKR(cudaEventRecord(ctx->evpool[ev_used + 4], ss)); ev_used += 5; }

@@ -612,7 +612,7 @@ struct PairAcc {
 /* MAP: shadow queries through receiver maps (rd.map, hrt_rxmap.cuh) instead of the
  * tree walk; only the triangle records are staged in shared memory. */
 template <bool SMEM, bool BRUTE, bool WARP, bool COUNT, bool LEAN = false, bool MAP = false>
-__global__ void __launch_bounds__(MAP ? HRT_MAP_BLOCK : HRT_BLOCK, MAP ? HRT_MAP_MIN_BLOCKS : HRT_MIN_BLOCKS)
+__global__ void __launch_bounds__(MAP ? HRT_MAP_BLOCK : SMEM ? HRT_BLOCK : HRT_GLOBAL_BLOCK, MAP ? HRT_MAP_MIN_BLOCKS : HRT_MIN_BLOCKS)
 k_scatter(RunDev rd, SceneDev sc, HrtMaterialTable mats, uint32_t depth, uint32_t smem_rx_ok)
 {
   typename CntSel<COUNT>::type wc; cnt_init(wc);
