@@ -202,3 +202,14 @@ def test_sure_cells_imply_a_hit(scale):
     bad = lib.emul_sure_check(100000, 7, scale, C.byref(n_sure), C.byref(n_rays))
     assert n_sure.value > 3000 and n_rays.value > 100000, (n_sure.value, n_rays.value)    # not vacuous
     assert bad == 0, (bad, n_sure.value, n_rays.value)
+
+
+def test_receiver_maps_c4_receivers_hit_points():
+    """The maps as the C4 workload uses them: all 64 receivers, G = 256, origins = primary hit points of rays from the
+    four transmitters (offset 1e-4 like the reference's, each with the triangle it lies on for the own-triangle
+    early-out): every query equals the brute-force loop.  (scripts/soak_emul_maps.py is the longer version.)"""
+    import os, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(tl.ROOT, "scripts", "soak_emul_maps.py"),
+                        "simple_street_canyon_with_cars", "3000", "256"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 differ from brute force" in r.stdout
